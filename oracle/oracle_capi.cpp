@@ -15,11 +15,11 @@ extern "C" {
 // C-ABI (include/piqp_b200.h).  Lets the oracle's KKTSystem + IP loop act as "the reference solver"
 // that calls the CUDA backend through the drop-in boundary.
 struct OrcBackendVTable {
-    void* (*create_dense)(int n, int p, int m, const double* P_utri, const double* AT, const double* GT);
-    void* (*create_sparse)(int n, int p, int m,
-                           const int* Pp, const int* Pi, const double* Px,
-                           const int* ATp, const int* ATi, const double* ATx,
-                           const int* GTp, const int* GTi, const double* GTx);
+    int (*create_dense)(void** out, int n, int p, int m, const double* P_utri, const double* AT, const double* GT, int device);
+    int (*create_sparse)(void** out, int n, int p, int m,
+                         const int* Pp, const int* Pi, const double* Px,
+                         const int* ATp, const int* ATi, const double* ATx,
+                         const int* GTp, const int* GTi, const double* GTx, int mode, const int* perm, int device);
     int (*update_data)(void* h, int options, const double* P, const double* AT, const double* GT);
     int (*factor)(void* h, double delta, const double* x_reg, const double* z_reg);
     int (*solve)(void* h, const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz);
@@ -36,7 +36,8 @@ namespace {
 struct ForeignDense : KKTBackend {
     const OrcBackendVTable* vt; void* h; const DenseMatrices& D;
     ForeignDense(const OrcBackendVTable* v, const DenseMatrices& D_) : vt(v), D(D_) {
-        h = vt->create_dense(D.n, D.p, D.m, D.P.data(), D.AT.data(), D.GT.data());
+        h = nullptr;
+        vt->create_dense(&h, D.n, D.p, D.m, D.P.data(), D.AT.data(), D.GT.data(), 0);
     }
     ~ForeignDense() override { if (h) vt->destroy(h); }
     void update_data(int o) override { vt->update_data(h, o, D.P.data(), D.AT.data(), D.GT.data()); }
@@ -50,8 +51,9 @@ struct ForeignDense : KKTBackend {
 struct ForeignSparse : KKTBackend {
     const OrcBackendVTable* vt; void* h; const SparseMatrices& S;
     ForeignSparse(const OrcBackendVTable* v, const SparseMatrices& S_) : vt(v), S(S_) {
-        h = vt->create_sparse(S.n, S.p, S.m, S.P.p.data(), S.P.i.data(), S.P.x.data(), S.AT.p.data(), S.AT.i.data(), S.AT.x.data(),
-                              S.GT.p.data(), S.GT.i.data(), S.GT.x.data());
+        h = nullptr;
+        vt->create_sparse(&h, S.n, S.p, S.m, S.P.p.data(), S.P.i.data(), S.P.x.data(), S.AT.p.data(), S.AT.i.data(), S.AT.x.data(),
+                          S.GT.p.data(), S.GT.i.data(), S.GT.x.data(), 0, S.user_perm.empty() ? nullptr : S.user_perm.data(), 0);
     }
     ~ForeignSparse() override { if (h) vt->destroy(h); }
     void update_data(int o) override { vt->update_data(h, o, S.P.x.data(), S.AT.x.data(), S.GT.x.data()); }

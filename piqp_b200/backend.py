@@ -1,0 +1,128 @@
+"""Host-side mirror of the reference plugin interface `piqp::KKTSolverBase` over the C-ABI.
+
+Same method names, argument meaning and error behaviour as include/piqp/kkt_solver_base.hpp:21-44:
+`update_scalings_and_factor` returns True/False, nothing raises for a failed factorisation.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import dp, ip
+
+
+def _f(a, k=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel())
+    if k is not None and a.size != k:
+        raise ValueError("expected %d elements, got %d" % (k, a.size))
+    return a
+
+
+def _p(a):
+    return a.ctypes.data_as(dp)
+
+
+KKT_UPDATE_NONE, KKT_UPDATE_P, KKT_UPDATE_A, KKT_UPDATE_G = 0, 1, 2, 4
+
+
+class KKTSolverBase:
+    """Owns one b200kkt_handle."""
+
+    def __init__(self):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        self.n = self.p = self.m = 0
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.b200kkt_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def clone(self):
+        o = object.__new__(type(self))
+        o._L = self._L
+        o.n, o.p, o.m = self.n, self.p, self.m
+        o._h = C.c_void_p(self._L.b200kkt_clone(self._h))
+        if not o._h.value:
+            raise RuntimeError("b200kkt_clone failed: " + self._L.b200_last_error().decode())
+        return o
+
+    def update_scalings_and_factor(self, delta, x_reg, z_reg):
+        x_reg, z_reg = _f(x_reg, self.n), _f(z_reg, self.m)
+        r = self._L.b200kkt_factor(self._h, C.c_double(delta), _p(x_reg), _p(z_reg))
+        _lib.check(r, "b200kkt_factor")
+        return r == 1
+
+    def solve(self, rhs_x, rhs_y, rhs_z):
+        rx, ry, rz = _f(rhs_x, self.n), _f(rhs_y, self.p), _f(rhs_z, self.m)
+        lx, ly, lz = np.zeros(self.n), np.zeros(self.p), np.zeros(self.m)
+        _lib.check(self._L.b200kkt_solve(self._h, _p(rx), _p(ry), _p(rz), _p(lx), _p(ly), _p(lz)), "b200kkt_solve")
+        return lx, ly, lz
+
+    def eval_P_x(self, alpha, x):
+        x = _f(x, self.n); z = np.zeros(self.n)
+        _lib.check(self._L.b200kkt_eval_P_x(self._h, C.c_double(alpha), _p(x), _p(z)), "b200kkt_eval_P_x")
+        return z
+
+    def eval_A_xn_and_AT_xt(self, alpha_n, alpha_t, xn, xt):
+        xn, xt = _f(xn, self.n), _f(xt, self.p)
+        zn, zt = np.zeros(self.p), np.zeros(self.n)
+        _lib.check(self._L.b200kkt_eval_A_xn_and_AT_xt(self._h, C.c_double(alpha_n), C.c_double(alpha_t), _p(xn), _p(xt), _p(zn), _p(zt)), "eval_A")
+        return zn, zt
+
+    def eval_G_xn_and_GT_xt(self, alpha_n, alpha_t, xn, xt):
+        xn, xt = _f(xn, self.n), _f(xt, self.m)
+        zn, zt = np.zeros(self.m), np.zeros(self.n)
+        _lib.check(self._L.b200kkt_eval_G_xn_and_GT_xt(self._h, C.c_double(alpha_n), C.c_double(alpha_t), _p(xn), _p(xt), _p(zn), _p(zt)), "eval_G")
+        return zn, zt
+
+    def print_info(self):
+        self._L.b200kkt_print_info(self._h)
+
+
+class DenseKKT(KKTSolverBase):
+    """Twin of piqp::dense::KKT<T> (include/piqp/dense/kkt.hpp:25-177).
+
+    P_utri: (n, n) upper triangular; AT: (n, p); GT: (n, m) -- the members of dense::Data, any memory order.
+    """
+
+    def __init__(self, P_utri, AT=None, GT=None, device=0):
+        super().__init__()
+        P = np.asfortranarray(np.asarray(P_utri, dtype=np.float64))
+        self.n = P.shape[0]
+        AT = np.zeros((self.n, 0)) if AT is None else np.asarray(AT, dtype=np.float64)
+        GT = np.zeros((self.n, 0)) if GT is None else np.asarray(GT, dtype=np.float64)
+        self.p, self.m = AT.shape[1], GT.shape[1]
+        ATf, GTf = np.asfortranarray(AT), np.asfortranarray(GT)
+        _lib.check(self._L.b200kkt_dense_create(C.byref(self._h), self.n, self.p, self.m, _p(P),
+                                                _p(ATf) if self.p else None, _p(GTf) if self.m else None, device),
+                   "b200kkt_dense_create")
+
+    def update_data(self, options, P_utri=None, AT=None, GT=None):
+        P = None if P_utri is None else np.asfortranarray(np.asarray(P_utri, dtype=np.float64))
+        A = None if AT is None else np.asfortranarray(np.asarray(AT, dtype=np.float64))
+        G = None if GT is None else np.asfortranarray(np.asarray(GT, dtype=np.float64))
+        _lib.check(self._L.b200kkt_update_data(self._h, int(options), None if P is None else _p(P),
+                                               None if A is None else _p(A), None if G is None else _p(G)), "b200kkt_update_data")
+
+    def internal_kkt_mat(self, factor=False):
+        K = np.zeros((self.n, self.n), order="F")
+        Lf = np.zeros((self.n, self.n), order="F")
+        _lib.check(self._L.b200kkt_dense_get_kkt(self._h, _p(K), _p(Lf)), "b200kkt_dense_get_kkt")
+        return Lf if factor else K
+
+
+def c_abi_vtable():
+    """Function-pointer table of the C-ABI in the layout oracle/oracle_capi.cpp::OrcBackendVTable expects
+    (used by tests to put the CUDA backend behind the oracle's KKTSystem + IP loop)."""
+    L = _lib.lib()
+
+    def addr(name):
+        return C.cast(getattr(L, name), C.c_void_p).value
+
+    return {
+        "create_dense": addr("b200kkt_dense_create"), "create_sparse": addr("b200kkt_sparse_create"),
+        "update_data": addr("b200kkt_update_data"), "factor": addr("b200kkt_factor"), "solve": addr("b200kkt_solve"),
+        "eval_P_x": addr("b200kkt_eval_P_x"), "eval_A": addr("b200kkt_eval_A_xn_and_AT_xt"),
+        "eval_G": addr("b200kkt_eval_G_xn_and_GT_xt"), "destroy": addr("b200kkt_destroy"),
+    }

@@ -1,0 +1,105 @@
+// piqp_b200/csrc/common.cuh -- shared device/host helpers for libpiqp_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+namespace b200 {
+
+// ---- error handling: CUDA failures become C++ exceptions inside the library and are turned into
+// ---- B200_E_CUDA return codes at the C-ABI (capi.cu); nothing throws across the boundary.
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e != cudaSuccess) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s failed at %s:%d: %s", what, file, line, cudaGetErrorString(e));
+        throw CudaError(buf);
+    }
+}
+#define B200_CUDA(x) ::b200::cuda_check((x), #x, __FILE__, __LINE__)
+
+extern unsigned long long g_launches;  // counted at every kernel launch (b200_kernel_launch_count)
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                         \
+    do {                                                                            \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                 \
+        ++::b200::g_launches;                                                       \
+        B200_CUDA(cudaPeekAtLastError());                                           \
+    } while (0)
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// RAII device buffer
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t n_) { alloc(n_); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void alloc(size_t n_) {
+        release();
+        n = n_;
+        if (n) { B200_CUDA(cudaMalloc(&p, n * sizeof(T))); }
+    }
+    void zero(cudaStream_t s = 0) { if (n) B200_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    T* get() const { return p; }
+};
+
+#ifdef __CUDACC__
+
+constexpr double kInf = 1e30;
+
+// ---- warp / block reductions (deterministic: fixed tree, independent of scheduling) ----
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide reductions of NV values at once; `red` is shared scratch of >= 32*NV doubles.
+// All threads of the block must call; result is returned to all threads.
+enum RedOp { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
+template <int NV>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], const int (&op)[NV], double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        v[i] = op[i] == RED_SUM ? warp_sum(v[i]) : (op[i] == RED_MAX ? warp_max(v[i]) : warp_min(v[i]));
+    }
+    __syncthreads();  // protect `red` from a previous use
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) red[i * 32 + w] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double x = op[i] == RED_SUM ? 0.0 : (op[i] == RED_MAX ? -INFINITY : INFINITY);
+        if (lane < nw) x = red[i * 32 + lane];
+        v[i] = op[i] == RED_SUM ? warp_sum(x) : (op[i] == RED_MAX ? warp_max(x) : warp_min(x));
+    }
+}
+
+__device__ __forceinline__ bool is_finite_d(double x) { return isfinite(x); }
+
+#endif  // __CUDACC__
+
+}  // namespace b200

@@ -1,0 +1,462 @@
+// piqp_b200/csrc/dense_backend.cu -- batched dense KKT backend + dense problem data / Ruiz sweeps.
+#include "dense_backend.hpp"
+#include "dense_kernels.cuh"
+
+namespace b200 {
+
+unsigned long long g_launches = 0;
+
+// =====================================================================================================
+// data packing
+// =====================================================================================================
+void DenseData::alloc(int batch_, int n_, int p_, int m_) {
+    batch = batch_; n = n_; p = p_; m = m_; ld = round_up(n > 0 ? n : 1, 8);
+    Pf.alloc((size_t)batch * ld * n); AT.alloc((size_t)batch * ld * p); GT.alloc((size_t)batch * ld * m);
+    Pf.zero(); AT.zero(); GT.zero();
+}
+
+__global__ void pack_sym_upper_kernel(const double* src, long long sb, long long rs, long long cs, double* Pf, long long sP, int ld, int n) {
+    const int b = blockIdx.z;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r >= n) return;
+    const int i = min(r, c), j = max(r, c);
+    Pf[(size_t)b * sP + (size_t)c * ld + r] = src[(size_t)b * sb + (size_t)i * rs + (size_t)j * cs];
+}
+void dense_pack_sym_upper(const double* src, long long sb, long long rs, long long cs, DenseData& D, cudaStream_t st) {
+    if (D.n == 0) return;
+    dim3 grid(ceil_div(D.n, 128), D.n, D.batch);
+    B200_LAUNCH(pack_sym_upper_kernel, grid, 128, 0, st, src, sb, rs, cs, D.Pf.get(), D.sP(), D.ld, D.n);
+}
+
+__global__ void pack_cols_kernel(const double* src, long long sb, int rows, int ld_src, double* dst, long long sdst, int ld) {
+    const int b = blockIdx.z, c = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    dst[(size_t)b * sdst + (size_t)c * ld + r] = src[(size_t)b * sb + (size_t)c * ld_src + r];
+}
+void dense_pack_cols(const double* src, long long sb, int rows, int cols, int ld_src, double* dst, long long sdst, int ld, int batch, cudaStream_t st) {
+    if (rows == 0 || cols == 0) return;
+    dim3 grid(ceil_div(rows, 128), cols, batch);
+    B200_LAUNCH(pack_cols_kernel, grid, 128, 0, st, src, sb, rows, ld_src, dst, sdst, ld);
+}
+
+__global__ void zero_G_rows_kernel(double* GT, long long sG, int ld, int n, int m, const int* mask) {
+    const int b = blockIdx.z, k = blockIdx.y;
+    if (!mask[(size_t)b * m + k]) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) GT[(size_t)b * sG + (size_t)k * ld + r] = 0.0;
+}
+void dense_zero_G_rows(DenseData& D, const int* row_mask, cudaStream_t st) {
+    if (D.m == 0) return;
+    dim3 grid(ceil_div(D.n, 128), D.m, D.batch);
+    B200_LAUNCH(zero_G_rows_kernel, grid, 128, 0, st, D.GT.get(), D.sG(), D.ld, D.n, D.m, row_mask);
+}
+
+// =====================================================================================================
+// Ruiz equilibration (dense/preconditioner.hpp:64-251), bit-compatible with the oracle's operation order
+// =====================================================================================================
+void RuizState::alloc(int batch_, int n_, int p_, int m_) {
+    batch = batch_; n = n_; p = p_; m = m_;
+    const size_t N = (size_t)n + p + m;
+    delta.alloc(batch * N); delta_inv.alloc(batch * N); it.alloc(batch * N);
+    delta_b.alloc((size_t)batch * n); delta_b_inv.alloc((size_t)batch * n); itb.alloc((size_t)batch * n);
+    c.alloc(batch); c_inv.alloc(batch); done.alloc(batch);
+}
+
+__device__ __forceinline__ double ruiz_limit(double d) { return d < 1e-4 ? 1.0 : (d > 1e4 ? 1e4 : d); }
+
+__global__ void fill_kernel(double* p, size_t n, double v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+static void fill(double* p, size_t n, double v, cudaStream_t st) {
+    if (n) B200_LAUNCH(fill_kernel, (unsigned)((n + 255) / 256), 256, 0, st, p, n, v);
+}
+
+// sweep start: done[b] |= !(max|1 - it| > eps)
+__global__ void ruiz_begin_kernel(const double* it, const double* itb, int N, int n, int* done, double eps) {
+    __shared__ double red[32];
+    const int b = blockIdx.x;
+    double v[1] = {0.0};
+    for (int k = threadIdx.x; k < N; k += blockDim.x) v[0] = fmax(v[0], fabs(1.0 - it[(size_t)b * N + k]));
+    for (int k = threadIdx.x; k < n; k += blockDim.x) v[0] = fmax(v[0], fabs(1.0 - itb[(size_t)b * n + k]));
+    const int op[1] = {RED_MAX};
+    block_reduce<1>(v, op, red);
+    if (threadIdx.x == 0 && !(v[0] > eps)) done[b] = 1;
+}
+
+__global__ void ruiz_rownorm_kernel(const double* Pf, long long sP, const double* AT, long long sA, const double* GT, long long sG,
+                                    int ld, int n, int p, int m, const double* xbs, double* it, double* itb, int N, const int* done) {
+    const int b = blockIdx.y;
+    if (done[b]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = 0.0;
+    const double* P = Pf + (size_t)b * sP;
+    for (int c = 0; c < n; c++) v = fmax(v, fabs(P[(size_t)c * ld + i]));
+    const double* A = AT + (size_t)b * sA;
+    for (int c = 0; c < p; c++) v = fmax(v, fabs(A[(size_t)c * ld + i]));
+    const double* G = GT + (size_t)b * sG;
+    for (int c = 0; c < m; c++) v = fmax(v, fabs(G[(size_t)c * ld + i]));
+    const double xb = xbs[(size_t)b * n + i];
+    it[(size_t)b * N + i] = fmax(v, xb);
+    itb[(size_t)b * n + i] = xb;
+}
+
+__global__ void ruiz_colnorm_kernel(const double* AT, long long sA, const double* GT, long long sG, int ld, int n, int p, int m,
+                                    double* it, int N, const int* done) {
+    const int b = blockIdx.y;
+    if (done[b]) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (k >= p + m) return;
+    const double* col = k < p ? AT + (size_t)b * sA + (size_t)k * ld : GT + (size_t)b * sG + (size_t)(k - p) * ld;
+    double v = 0.0;
+    for (int i = lane; i < n; i += 32) v = fmax(v, fabs(col[i]));
+    v = warp_max(v);
+    if (lane == 0) it[(size_t)b * N + n + k] = v;
+}
+
+__global__ void ruiz_finalize_kernel(double* it, double* itb, int N, int n, double* c, double* xbs, double* delta, double* delta_b, const int* done) {
+    const int b = blockIdx.y;
+    if (done[b]) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const double d = 1.0 / sqrt(ruiz_limit(it[(size_t)b * N + k]));
+    it[(size_t)b * N + k] = d;
+    delta[(size_t)b * N + k] *= d;
+    if (k < n) {
+        const double db = 1.0 / sqrt(ruiz_limit(itb[(size_t)b * n + k]));
+        itb[(size_t)b * n + k] = db;
+        c[(size_t)b * n + k] *= d;
+        xbs[(size_t)b * n + k] *= db * d;
+        delta_b[(size_t)b * n + k] *= db;
+    }
+}
+
+// P <- gamma*P then D P D ; AT <- Dx AT Dy ; GT <- Dx GT Dz, with the oracle's multiplication order
+__global__ void ruiz_scale_kernel(double* Pf, long long sP, double* AT, long long sA, double* GT, long long sG, int ld, int n, int p, int m,
+                                  const double* d, int N, const double* gamma, int gamma_inverse, const int* done) {
+    const int b = blockIdx.z;
+    if (done && done[b]) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int c = blockIdx.y;
+    const double* dv = d + (size_t)b * N;
+    if (c < n) {
+        double v = Pf[(size_t)b * sP + (size_t)c * ld + r];
+        if (gamma) v *= gamma[b];
+        const int i = min(r, c), j = max(r, c);
+        v = (v * dv[j]) * dv[i];
+        Pf[(size_t)b * sP + (size_t)c * ld + r] = v;
+    } else if (c < n + p) {
+        double* e = AT + (size_t)b * sA + (size_t)(c - n) * ld + r;
+        *e = (dv[r] * *e) * dv[c];
+    } else {
+        double* e = GT + (size_t)b * sG + (size_t)(c - n - p) * ld + r;
+        *e = (dv[r] * *e) * dv[c];
+    }
+}
+
+__global__ void ruiz_scaleP_kernel(double* Pf, long long sP, int ld, int n, const double* gamma) {
+    const int b = blockIdx.z, c = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) Pf[(size_t)b * sP + (size_t)c * ld + r] *= gamma[b];
+}
+
+// cost scaling (dense/preconditioner.hpp:141-162): one CTA per instance (rare path, default off)
+__global__ void ruiz_cost_kernel(double* Pf, long long sP, int ld, int n, double* c, double* cscale, const int* done) {
+    __shared__ double red[64];
+    const int b = blockIdx.x;
+    if (done[b]) return;
+    double* P = Pf + (size_t)b * sP;
+    double v[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double r = 0.0;
+        for (int cc = 0; cc < n; cc++) r = fmax(r, fabs(P[(size_t)cc * ld + i]));
+        v[0] += r;
+        v[1] = fmax(v[1], fabs(c[(size_t)b * n + i]));
+    }
+    const int op[2] = {RED_SUM, RED_MAX};
+    block_reduce<2>(v, op, red);
+    double gamma = ruiz_limit(v[0] / double(n));
+    gamma = ruiz_limit(fmax(gamma, v[1]));
+    gamma = 1.0 / gamma;
+    for (int cc = 0; cc < n; cc++)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) P[(size_t)cc * ld + i] *= gamma;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) c[(size_t)b * n + i] *= gamma;
+    if (threadIdx.x == 0) cscale[b] *= gamma;
+}
+
+__global__ void ruiz_inverse_kernel(const double* delta, const double* delta_b, const double* c, double* delta_inv, double* delta_b_inv, double* c_inv, int N, int n) {
+    const int b = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < N) delta_inv[(size_t)b * N + k] = 1.0 / delta[(size_t)b * N + k];
+    if (k < n) delta_b_inv[(size_t)b * n + k] = 1.0 / delta_b[(size_t)b * n + k];
+    if (k == 0) c_inv[b] = 1.0 / c[b];
+}
+
+// bounds: b *= d_y ; h *= d_z ; x_l,x_u *= d_b  (and for the reuse/unscale path: c, x_b_scaling)
+__global__ void ruiz_vectors_kernel(double* c, double* bvec, double* h_l, double* h_u, double* x_l, double* x_u, double* xbs,
+                                    const double* d, const double* db, const double* cs, int n, int p, int m, int N, int scale_c_and_xbs) {
+    const int b = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const double* dv = d + (size_t)b * N;
+    if (k < p) bvec[(size_t)b * p + k] *= dv[n + k];
+    if (k < m) { h_l[(size_t)b * m + k] *= dv[n + p + k]; h_u[(size_t)b * m + k] *= dv[n + p + k]; }
+    if (k < n) {
+        const double dbk = db[(size_t)b * n + k];
+        x_l[(size_t)b * n + k] *= dbk; x_u[(size_t)b * n + k] *= dbk;
+        if (scale_c_and_xbs) {
+            c[(size_t)b * n + k] *= cs[b] * dv[k];
+            xbs[(size_t)b * n + k] *= dbk * dv[k];
+        }
+    }
+}
+
+void dense_ruiz_scale(DenseData& D, RuizState& R, double* c, double* b, double* h_l, double* h_u, double* x_l, double* x_u,
+                      double* xbs, bool reuse_prev, bool scale_cost, int max_iter, cudaStream_t st) {
+    const int n = D.n, p = D.p, m = D.m, N = n + p + m, B = D.batch;
+    const int maxd = std::max(1, std::max(N, n));
+    dim3 gridN(ceil_div(maxd, 256), B);
+    dim3 gridMat(ceil_div(std::max(n, 1), 128), N, B);
+    if (!reuse_prev) {
+        fill(R.c.get(), B, 1.0, st); fill(R.delta.get(), (size_t)B * N, 1.0, st); fill(R.delta_b.get(), (size_t)B * n, 1.0, st);
+        fill(R.it.get(), (size_t)B * N, 0.0, st); fill(R.itb.get(), (size_t)B * n, 0.0, st);
+        B200_CUDA(cudaMemsetAsync(R.done.get(), 0, sizeof(int) * B, st));
+        for (int iter = 0; iter < max_iter; iter++) {
+            B200_LAUNCH(ruiz_begin_kernel, B, 256, 0, st, R.it.get(), R.itb.get(), N, n, R.done.get(), 1e-3);
+            if (n > 0) {
+                dim3 gr(ceil_div(n, 128), B);
+                B200_LAUNCH(ruiz_rownorm_kernel, gr, 128, 0, st, D.Pf.get(), D.sP(), D.AT.get(), D.sA(), D.GT.get(), D.sG(), D.ld, n, p, m, xbs,
+                            R.it.get(), R.itb.get(), N, R.done.get());
+            }
+            if (p + m > 0) {
+                dim3 gc(ceil_div(p + m, 8), B);
+                B200_LAUNCH(ruiz_colnorm_kernel, gc, 256, 0, st, D.AT.get(), D.sA(), D.GT.get(), D.sG(), D.ld, n, p, m, R.it.get(), N, R.done.get());
+            }
+            B200_LAUNCH(ruiz_finalize_kernel, gridN, 256, 0, st, R.it.get(), R.itb.get(), N, n, c, xbs, R.delta.get(), R.delta_b.get(), R.done.get());
+            if (n > 0)
+                B200_LAUNCH(ruiz_scale_kernel, gridMat, 128, 0, st, D.Pf.get(), D.sP(), D.AT.get(), D.sA(), D.GT.get(), D.sG(), D.ld, n, p, m,
+                            R.it.get(), N, (const double*)nullptr, 0, R.done.get());
+            if (scale_cost) B200_LAUNCH(ruiz_cost_kernel, B, 256, 0, st, D.Pf.get(), D.sP(), D.ld, n, c, R.c.get(), R.done.get());
+        }
+        B200_LAUNCH(ruiz_inverse_kernel, gridN, 256, 0, st, R.delta.get(), R.delta_b.get(), R.c.get(), R.delta_inv.get(), R.delta_b_inv.get(), R.c_inv.get(), N, n);
+        B200_LAUNCH(ruiz_vectors_kernel, gridN, 256, 0, st, c, b, h_l, h_u, x_l, x_u, xbs, R.delta.get(), R.delta_b.get(), R.c.get(), n, p, m, N, 0);
+    } else {
+        if (n > 0)
+            B200_LAUNCH(ruiz_scale_kernel, gridMat, 128, 0, st, D.Pf.get(), D.sP(), D.AT.get(), D.sA(), D.GT.get(), D.sG(), D.ld, n, p, m,
+                        R.delta.get(), N, R.c.get(), 0, (const int*)nullptr);
+        B200_LAUNCH(ruiz_vectors_kernel, gridN, 256, 0, st, c, b, h_l, h_u, x_l, x_u, xbs, R.delta.get(), R.delta_b.get(), R.c.get(), n, p, m, N, 1);
+    }
+}
+
+void dense_ruiz_unscale(DenseData& D, RuizState& R, double* c, double* b, double* h_l, double* h_u, double* x_l, double* x_u,
+                        double* xbs, cudaStream_t st) {
+    const int n = D.n, p = D.p, m = D.m, N = n + p + m, B = D.batch;
+    const int maxd = std::max(1, std::max(N, n));
+    dim3 gridN(ceil_div(maxd, 256), B);
+    dim3 gridMat(ceil_div(std::max(n, 1), 128), N, B);
+    if (n > 0)
+        B200_LAUNCH(ruiz_scale_kernel, gridMat, 128, 0, st, D.Pf.get(), D.sP(), D.AT.get(), D.sA(), D.GT.get(), D.sG(), D.ld, n, p, m,
+                    R.delta_inv.get(), N, R.c_inv.get(), 0, (const int*)nullptr);
+    B200_LAUNCH(ruiz_vectors_kernel, gridN, 256, 0, st, c, b, h_l, h_u, x_l, x_u, xbs, R.delta_inv.get(), R.delta_b_inv.get(), R.c_inv.get(), n, p, m, N, 1);
+}
+
+// =====================================================================================================
+// DenseBatchedKKT
+// =====================================================================================================
+__global__ void inv_and_copy_kernel(const double* z_reg, double* zinv, size_t nz, const double* delta_in, double* delta_out, int batch) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nz) zinv[i] = 1.0 / z_reg[i];
+    if (i < (size_t)batch) delta_out[i] = delta_in[i];
+}
+__global__ void fail_to_ok_kernel(const int* fail, const int* active, int* ok, int batch) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch && (!active || active[b])) ok[b] = fail[b] ? 0 : 1;
+}
+__global__ void clear_fail_kernel(int* fail, const int* active, int batch) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch && (!active || active[b])) fail[b] = 0;
+}
+__global__ void copy_masked_kernel(const double* src, double* dst, int len, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) dst[(size_t)b * len + i] = src[(size_t)b * len + i];
+}
+__global__ void extract_diag_kernel(const double* Pf, long long sP, int ld, int n, double* out) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[(size_t)b * n + i] = Pf[(size_t)b * sP + (size_t)i * ld + i];
+}
+
+template <class Kern>
+static void set_smem(Kern k, size_t bytes) {
+    B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
+    batch = D->batch; n = D->n; p = D->p; m = D->m; stream = st;
+    K.alloc((size_t)batch * D->ld * n); K.zero(st);
+    zinv.alloc((size_t)batch * m); delta.alloc(batch); fail.alloc(batch); fail.zero(st);
+    set_smem(gemm_nt_tile_kernel<EPI_ASSEMBLE, true>, GEMM_SMEM);
+    set_smem(gemm_nt_tile_kernel<EPI_ASSEMBLE, false>, GEMM_SMEM);
+    set_smem(gemm_nt_tile_kernel<EPI_SUB, false>, GEMM_SMEM);
+    set_smem(gemm_nt_tile_kernel<EPI_STORE, false>, GEMM_SMEM);
+    set_smem(potf2_kernel, POTF2_SMEM);
+    set_smem(trsm_kernel, TRSM_SMEM);
+    set_smem(trsv_kernel, (size_t)(n + 32) * sizeof(double) > 48 * 1024 ? (size_t)(n + 32) * sizeof(double) : 48 * 1024);
+    if (p > 0) { AtA.alloc((size_t)batch * D->ld * n); AtA.zero(st); compute_AtA(); }
+}
+
+void DenseBatchedKKT::copy_from(const DenseBatchedKKT& o) {
+    auto cp = [&](DevBuf<double>& d, const DevBuf<double>& s) { if (s.n) B200_CUDA(cudaMemcpyAsync(d.get(), s.get(), s.n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); };
+    cp(K, o.K); cp(AtA, o.AtA); cp(zinv, o.zinv); cp(delta, o.delta);
+    B200_CUDA(cudaMemcpyAsync(fail.get(), o.fail.get(), sizeof(int) * batch, cudaMemcpyDeviceToDevice, stream));
+}
+
+void DenseBatchedKKT::compute_AtA() {   // dense/kkt.hpp:53,68
+    if (p == 0 || n == 0) return;
+    GemmArgs g{};
+    g.A = D->AT.get(); g.strideA = D->sA(); g.lda = D->ld;
+    g.B = g.A; g.strideB = g.strideA; g.ldb = g.lda;
+    g.C = AtA.get(); g.strideC = D->sP(); g.ldc = D->ld;
+    g.n = n; g.rows_valid = D->ld; g.K = p; g.nt = ceil_div(n, TILE); g.tj_fixed = -1; g.tiles = g.nt * (g.nt + 1) / 2;
+    B200_LAUNCH((gemm_nt_tile_kernel<EPI_STORE, false>), (unsigned)(g.tiles * batch), GEMM_THREADS, GEMM_SMEM, stream, g);
+}
+
+void DenseBatchedKKT::update_data(int options) {   // dense/kkt.hpp:62-71
+    if (options & 2) compute_AtA();
+}
+
+void DenseBatchedKKT::assemble(const double* x_reg, const int* active) {   // dense/kkt.hpp:140-160
+    if (n == 0) return;
+    GemmArgs g{};
+    g.A = D->GT.get(); g.strideA = D->sG(); g.lda = D->ld;
+    g.B = g.A; g.strideB = g.strideA; g.ldb = g.lda;
+    g.w = zinv.get(); g.stridew = m;
+    g.C = K.get(); g.strideC = D->sP(); g.ldc = D->ld;
+    g.n = n; g.rows_valid = D->ld; g.K = m; g.nt = ceil_div(n, TILE); g.tj_fixed = -1; g.tiles = g.nt * (g.nt + 1) / 2;
+    g.Pf = D->Pf.get(); g.strideP = D->sP();
+    g.AtA = p > 0 ? AtA.get() : nullptr; g.strideAtA = D->sP();
+    g.xreg = x_reg; g.stridex = n; g.delta = delta.get(); g.active = active; g.fail = nullptr;
+    if (m > 0) B200_LAUNCH((gemm_nt_tile_kernel<EPI_ASSEMBLE, true>), (unsigned)(g.tiles * batch), GEMM_THREADS, GEMM_SMEM, stream, g);
+    else { g.A = D->Pf.get(); g.B = g.A; g.K = 0; g.w = nullptr;
+           B200_LAUNCH((gemm_nt_tile_kernel<EPI_ASSEMBLE, false>), (unsigned)(g.tiles * batch), GEMM_THREADS, GEMM_SMEM, stream, g); }
+}
+
+void DenseBatchedKKT::cholesky(const int* active) {   // Eigen::LLT<Lower>::compute -- left-looking by 128-column blocks
+    if (n == 0) return;
+    const int nt = ceil_div(n, TILE);
+    B200_LAUNCH(clear_fail_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, batch);
+    for (int jb = 0; jb < nt; jb++) {
+        const int j0 = jb * TILE;
+        if (jb > 0) {
+            GemmArgs g{};
+            g.A = K.get(); g.strideA = D->sP(); g.lda = D->ld;
+            g.B = g.A; g.strideB = g.strideA; g.ldb = g.lda;
+            g.C = K.get(); g.strideC = D->sP(); g.ldc = D->ld;
+            g.n = n; g.rows_valid = D->ld; g.K = j0; g.nt = nt; g.tj_fixed = jb; g.tiles = nt - jb;
+            g.active = active; g.fail = fail.get();
+            B200_LAUNCH((gemm_nt_tile_kernel<EPI_SUB, false>), (unsigned)(g.tiles * batch), GEMM_THREADS, GEMM_SMEM, stream, g);
+        }
+        B200_LAUNCH(potf2_kernel, batch, POTF2_THREADS, POTF2_SMEM, stream, K.get(), D->sP(), D->ld, n, j0, fail.get(), active);
+        const int rows_below = n - j0 - TILE;
+        if (rows_below > 0) {
+            const int rt = ceil_div(rows_below, TRSM_THREADS);
+            B200_LAUNCH(trsm_kernel, (unsigned)(rt * batch), TRSM_THREADS, TRSM_SMEM, stream, K.get(), D->sP(), D->ld, n, j0, rt, fail.get(), active);
+        }
+    }
+}
+
+void DenseBatchedKKT::factor(const double* delta_in, const double* x_reg, const double* z_reg, const int* active, int* ok) {
+    const size_t nz = (size_t)batch * m;
+    const size_t tot = std::max(nz, (size_t)batch);
+    B200_LAUNCH(inv_and_copy_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, z_reg, zinv.get(), nz, delta_in, delta.get(), batch);
+    assemble(x_reg, active);
+    cholesky(active);
+    B200_LAUNCH(fail_to_ok_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, ok, batch);
+}
+
+static GemvArgs gemv_args(const double* M, long long sM, int ld, int rows, int cols, const double* x, long long sx, double* z, long long sz, double alpha, const int* active) {
+    GemvArgs a{};
+    a.M = M; a.strideM = sM; a.ld = ld; a.rows = rows; a.cols = cols; a.x = x; a.stridex = sx; a.z = z; a.stridez = sz; a.alpha = alpha; a.active = active;
+    return a;
+}
+
+void DenseBatchedKKT::solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) {
+    // dense/kkt.hpp:86-105
+    if (n == 0) return;
+    dim3 gn(ceil_div(n, 256), batch);
+    B200_LAUNCH(copy_masked_kernel, gn, 256, 0, stream, rx, lx, n, active);
+    if (m > 0) {
+        GemvArgs a = gemv_args(D->GT.get(), D->sG(), D->ld, n, m, rz, m, lx, n, 1.0, active);
+        a.s = zinv.get(); a.strides = m; a.accumulate = 1;
+        B200_LAUNCH(gemv_n_kernel, gn, 256, 0, stream, a);
+    }
+    if (p > 0) {
+        GemvArgs a = gemv_args(D->AT.get(), D->sA(), D->ld, n, p, ry, p, lx, n, 1.0, active);
+        a.alpha_v = delta.get(); a.alpha_v_inverse = 1; a.accumulate = 1;
+        B200_LAUNCH(gemv_n_kernel, gn, 256, 0, stream, a);
+    }
+    B200_LAUNCH(trsv_kernel, batch, TRSV_THREADS, (size_t)(n + 32) * sizeof(double), stream, K.get(), D->sP(), D->ld, n, lx, (long long)n, active);
+    if (p > 0) {
+        GemvArgs a = gemv_args(D->AT.get(), D->sA(), D->ld, n, p, lx, n, ly, p, 1.0, active);
+        a.alpha_v = delta.get(); a.alpha_v_inverse = 1; a.sub = ry; a.stridesub = p; a.alpha2 = 1.0;
+        dim3 g(ceil_div(p, 8), batch);
+        B200_LAUNCH(gemv_t_kernel, g, 256, 0, stream, a);
+    }
+    if (m > 0) {
+        GemvArgs a = gemv_args(D->GT.get(), D->sG(), D->ld, n, m, lx, n, lz, m, 1.0, active);
+        a.sub = rz; a.stridesub = m; a.alpha2 = 1.0; a.s = zinv.get(); a.strides = m;
+        dim3 g(ceil_div(m, 8), batch);
+        B200_LAUNCH(gemv_t_kernel, g, 256, 0, stream, a);
+    }
+}
+
+void DenseBatchedKKT::eval_P_x(double alpha, const double* x, double* z, const int* active) {   // dense/kkt.hpp:108-114
+    if (n == 0) return;
+    dim3 gn(ceil_div(n, 256), batch);
+    GemvArgs a = gemv_args(D->Pf.get(), D->sP(), D->ld, n, n, x, n, z, n, alpha, active);
+    B200_LAUNCH(gemv_n_kernel, gn, 256, 0, stream, a);
+}
+void DenseBatchedKKT::eval_A(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) {   // :117-123
+    if (p > 0) {
+        GemvArgs a = gemv_args(D->AT.get(), D->sA(), D->ld, n, p, xn, n, zn, p, an, active);
+        dim3 g(ceil_div(p, 8), batch);
+        B200_LAUNCH(gemv_t_kernel, g, 256, 0, stream, a);
+    }
+    if (n > 0) {
+        GemvArgs a = gemv_args(D->AT.get(), D->sA(), D->ld, n, p, xt, p, zt, n, at, active);
+        dim3 gn(ceil_div(n, 256), batch);
+        B200_LAUNCH(gemv_n_kernel, gn, 256, 0, stream, a);
+    }
+}
+void DenseBatchedKKT::eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) {   // :126-132
+    if (m > 0) {
+        GemvArgs a = gemv_args(D->GT.get(), D->sG(), D->ld, n, m, xn, n, zn, m, an, active);
+        dim3 g(ceil_div(m, 8), batch);
+        B200_LAUNCH(gemv_t_kernel, g, 256, 0, stream, a);
+    }
+    if (n > 0) {
+        GemvArgs a = gemv_args(D->GT.get(), D->sG(), D->ld, n, m, xt, m, zt, n, at, active);
+        dim3 gn(ceil_div(n, 256), batch);
+        B200_LAUNCH(gemv_n_kernel, gn, 256, 0, stream, a);
+    }
+}
+void DenseBatchedKKT::extract_P_diag(double* P_diag) {
+    if (n == 0) return;
+    dim3 gn(ceil_div(n, 256), batch);
+    B200_LAUNCH(extract_diag_kernel, gn, 256, 0, stream, D->Pf.get(), D->sP(), D->ld, n, P_diag);
+}
+void DenseBatchedKKT::print_info() const {
+    printf("b200 dense backend: batch = %d, n = %d, p = %d, m = %d, tile = %d, DMMA m8n8k4 fp64\n", batch, n, p, m, TILE);
+}
+// algorithmic work per call and instance
+double DenseBatchedKKT::factor_flops() const { return (double)n * n * m + (double)n * n * n / 3.0; }
+double DenseBatchedKKT::factor_bytes() const { return 8.0 * ((double)n * m + 0.5 * n * n * (2 + (p > 0 ? 1 : 0))) + 8.0 * (n + m); }
+double DenseBatchedKKT::solve_flops() const { return 2.0 * n * n + 4.0 * n * m + 4.0 * n * p; }
+double DenseBatchedKKT::solve_bytes() const { return 8.0 * ((double)n * n + 2.0 * n * m + 2.0 * n * p); }
+
+}  // namespace b200

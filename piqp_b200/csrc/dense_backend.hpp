@@ -1,0 +1,71 @@
+// piqp_b200/csrc/dense_backend.hpp -- batched dense problem data + dense KKT backend (host-side classes).
+#pragma once
+#include "kkt_backend.hpp"
+
+namespace b200 {
+
+// Device twin of dense::Data's matrix members (include/piqp/dense/data.hpp:23-32) for a batch.
+//   Pf : [batch][ld * n]  FULL symmetric P (both triangles; the reference keeps only P_utri -- the lower
+//        mirror lets the KKT assembly epilogue and the row-norm sweeps read coalesced columns)
+//   AT : [batch][ld * p]  (n x p column-major == A row-major)
+//   GT : [batch][ld * m]
+// ld = round_up(n, 8); padding rows are kept at zero.
+struct DenseData {
+    int batch = 0, n = 0, p = 0, m = 0, ld = 0;
+    DevBuf<double> Pf, AT, GT;
+    long long sP() const { return (long long)ld * n; }
+    long long sA() const { return (long long)ld * p; }
+    long long sG() const { return (long long)ld * m; }
+    void alloc(int batch_, int n_, int p_, int m_);
+};
+
+// element (i, j) of source instance b is src[b*sb + i*rs + j*cs]
+void dense_pack_sym_upper(const double* src, long long sb, long long rs, long long cs, DenseData& D, cudaStream_t st);  // -> Pf
+void dense_pack_cols(const double* src, long long sb, int rows, int cols, int ld_src, double* dst, long long sdst, int ld, int batch, cudaStream_t st);
+void dense_zero_G_rows(DenseData& D, const int* row_mask /*[batch][m], 1 = zero it*/, cudaStream_t st);
+
+// Ruiz equilibration state for a batch (dense/preconditioner.hpp:26-437)
+struct RuizState {
+    int batch = 0, n = 0, p = 0, m = 0;
+    DevBuf<double> delta, delta_b, delta_inv, delta_b_inv, c, c_inv;   // [batch][n+p+m], [batch][n], ..., [batch]
+    DevBuf<double> it, itb;                                            // per-sweep scalings
+    DevBuf<int> done;                                                  // [batch] converged flag
+    void alloc(int batch_, int n_, int p_, int m_);
+};
+struct BoundVectors;  // ip_solver.hpp
+void dense_ruiz_scale(DenseData& D, RuizState& R, double* c, double* b, double* h_l, double* h_u, double* x_l, double* x_u,
+                      double* x_b_scaling, bool reuse_prev, bool scale_cost, int max_iter, cudaStream_t st);
+void dense_ruiz_unscale(DenseData& D, RuizState& R, double* c, double* b, double* h_l, double* h_u, double* x_l, double* x_u,
+                        double* x_b_scaling, cudaStream_t st);
+
+class DenseBatchedKKT : public BatchedKKT {
+public:
+    DenseBatchedKKT(DenseData* data, cudaStream_t st);
+    void update_data(int options) override;
+    void factor(const double* delta, const double* x_reg, const double* z_reg, const int* active, int* ok) override;
+    void solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) override;
+    void eval_P_x(double alpha, const double* x, double* z, const int* active) override;
+    void eval_A(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) override;
+    void eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) override;
+    void extract_P_diag(double* P_diag) override;
+    void print_info() const override;
+    double factor_flops() const override;
+    double factor_bytes() const override;
+    double solve_flops() const override;
+    double solve_bytes() const override;
+
+    // pieces of factor(), exposed for tests / diagnostics
+    void assemble(const double* x_reg, const int* active);     // dense::KKT::update_kkt
+    void cholesky(const int* active);                          // Eigen::LLT::compute
+    void copy_from(const DenseBatchedKKT& o);                  // clone()
+    DenseData* D;
+    DevBuf<double> K;        // [batch][ld*n] assembled KKT (lower), overwritten by its Cholesky factor
+    DevBuf<double> AtA;      // [batch][ld*n] lower, only if p > 0
+    DevBuf<double> zinv;     // [batch][m]
+    DevBuf<double> delta;    // [batch]
+    DevBuf<int> fail;        // [batch] 0 = ok, else failing column + 1
+private:
+    void compute_AtA();
+};
+
+}  // namespace b200

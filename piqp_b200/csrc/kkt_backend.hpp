@@ -1,0 +1,39 @@
+// piqp_b200/csrc/kkt_backend.hpp -- device-side twin of piqp::KKTSolverBase for a BATCH of instances.
+//
+// The reference's plugin interface (include/piqp/kkt_solver_base.hpp:21-44) has seven virtuals that act on
+// one QP.  Here the same seven operations act on `batch` independent QPs of identical shape whose vectors
+// live in HBM, instance-major ([batch][len], no padding).  Every call takes an optional per-instance
+// `active` mask so the lock-step interior-point driver can retire converged instances.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct BatchedKKT {
+    int batch = 0, n = 0, p = 0, m = 0;
+    cudaStream_t stream = 0;
+    virtual ~BatchedKKT() = default;
+
+    // KKTSolverBase::update_data(data, options): the owner has already rewritten the device problem data
+    virtual void update_data(int options) = 0;
+    // KKTSolverBase::update_scalings_and_factor: delta[batch], x_reg[batch][n], z_reg[batch][m];
+    // ok[b] <- 1 / 0 for active instances
+    virtual void factor(const double* delta, const double* x_reg, const double* z_reg, const int* active, int* ok) = 0;
+    // KKTSolverBase::solve
+    virtual void solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) = 0;
+    // z = alpha P x
+    virtual void eval_P_x(double alpha, const double* x, double* z, const int* active) = 0;
+    // zn = an * A xn ; zt = at * A^T xt
+    virtual void eval_A(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) = 0;
+    virtual void eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) = 0;
+    // diag(P) for KKTSystem's static regularisation (kkt_system.hpp:198,430-453): P_diag[batch][n]
+    virtual void extract_P_diag(double* P_diag) = 0;
+    virtual void print_info() const {}
+    // algorithmic work per call and instance, for GFLOP/s and roofline reporting
+    virtual double factor_flops() const = 0;
+    virtual double factor_bytes() const = 0;
+    virtual double solve_flops() const = 0;
+    virtual double solve_bytes() const = 0;
+};
+
+}  // namespace b200
