@@ -172,6 +172,10 @@ typedef struct {
     double solve_ms;            /* device time in the KKT-solve bucket                             */
     double total_ms;            /* device time of the whole solve                                  */
     unsigned long long kernel_launches;
+    /* per-kernel-class device times of the last solve (only when profiling was enabled with
+     * b200qp_set_profiling): KKT assembly contraction, Cholesky, backend solve */
+    double assemble_ms, cholesky_ms, backend_solve_ms;
+    long long assemble_launches, cholesky_calls, backend_solve_launch_groups;
 } b200qp_stats;
 
 typedef struct b200qp_handle b200qp_handle;
@@ -213,6 +217,8 @@ int b200qp_get_stats(b200qp_handle* h, b200qp_stats* stats);
 /* per-iteration trace of instance `b`: rows of (rho, delta, mu, primal_step, dual_step, primal_res, dual_res,
  * primal_obj, dual_obj, duality_gap); returns number of rows (needs settings.verbose >= 2 at setup). */
 int b200qp_get_trace(b200qp_handle* h, int b, double* rows, int max_rows);
+/* enable / disable CUDA-event timing of the backend's kernel classes (adds two event records per call) */
+int b200qp_set_profiling(b200qp_handle* h, int enable);
 void b200qp_cleanup(b200qp_handle* h);
 
 /* Bench hooks: run `reps` factor calls (assemble + factorise) and `nsolve` backend solves per factor on the

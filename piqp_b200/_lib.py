@@ -55,6 +55,8 @@ class Stats(C.Structure):
         ("ip_iterations", C.c_longlong), ("lockstep_iterations", C.c_int),
         ("factor_ms", C.c_double), ("solve_ms", C.c_double), ("total_ms", C.c_double),
         ("kernel_launches", C.c_ulonglong),
+        ("assemble_ms", C.c_double), ("cholesky_ms", C.c_double), ("backend_solve_ms", C.c_double),
+        ("assemble_launches", C.c_longlong), ("cholesky_calls", C.c_longlong), ("backend_solve_launch_groups", C.c_longlong),
     ]
 
 
@@ -66,7 +68,7 @@ SYMBOLS = [
     "b200kkt_clone", "b200kkt_print_info", "b200kkt_destroy", "b200kkt_dense_get_kkt",
     "b200qp_set_default_settings_dense", "b200qp_set_default_settings_sparse", "b200qp_setup_dense",
     "b200qp_update_dense", "b200qp_update_settings", "b200qp_solve", "b200qp_get_result", "b200qp_get_info",
-    "b200qp_get_stats", "b200qp_get_trace", "b200qp_cleanup", "b200qp_bench_factor_solve",
+    "b200qp_get_stats", "b200qp_get_trace", "b200qp_set_profiling", "b200qp_cleanup", "b200qp_bench_factor_solve",
 ]
 
 

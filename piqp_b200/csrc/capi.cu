@@ -410,6 +410,7 @@ int b200qp_solve(b200qp_handle* h) {
     if (!h) return fail(B200_E_INVALID, "null handle");
     B200_TRY(
         B200_CUDA(cudaSetDevice(h->device));
+        h->dense->reset_profile();
         h->ip->solve();
         h->solved = true;
     )
@@ -445,7 +446,20 @@ int b200qp_get_info(b200qp_handle* h, b200qp_info* infos) {
 }
 int b200qp_get_stats(b200qp_handle* h, b200qp_stats* stats) {
     if (!h || !stats) return fail(B200_E_INVALID, "null argument");
-    B200_TRY( h->ip->infos(); *stats = h->ip->stats(); )
+    B200_TRY(
+        h->ip->infos(); *stats = h->ip->stats();
+        BatchedKKT* be = h->dense.get();
+        be->collect();
+        stats->assemble_ms = be->prof_ms[BatchedKKT::T_ASSEMBLE]; stats->assemble_launches = be->prof_calls[BatchedKKT::T_ASSEMBLE];
+        stats->cholesky_ms = be->prof_ms[BatchedKKT::T_FACTOR]; stats->cholesky_calls = be->prof_calls[BatchedKKT::T_FACTOR];
+        stats->backend_solve_ms = be->prof_ms[BatchedKKT::T_SOLVE]; stats->backend_solve_launch_groups = be->prof_calls[BatchedKKT::T_SOLVE];
+    )
+    return B200_OK;
+}
+int b200qp_set_profiling(b200qp_handle* h, int enable) {
+    if (!h) return fail(B200_E_INVALID, "null handle");
+    h->dense->collect();
+    h->dense->profile = enable != 0;
     return B200_OK;
 }
 int b200qp_get_trace(b200qp_handle* h, int b, double* rows, int max_rows) {

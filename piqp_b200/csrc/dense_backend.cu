@@ -6,6 +6,31 @@ namespace b200 {
 
 unsigned long long g_launches = 0;
 
+void BatchedKKT::tic(int kind) {
+    if (!profile) return;
+    cudaEvent_t e;
+    if (free_events_.empty()) B200_CUDA(cudaEventCreate(&e)); else { e = free_events_.back(); free_events_.pop_back(); }
+    B200_CUDA(cudaEventRecord(e, stream));
+    open_[kind] = e;
+}
+void BatchedKKT::toc(int kind) {
+    if (!profile || !open_[kind]) return;
+    cudaEvent_t e;
+    if (free_events_.empty()) B200_CUDA(cudaEventCreate(&e)); else { e = free_events_.back(); free_events_.pop_back(); }
+    B200_CUDA(cudaEventRecord(e, stream));
+    spans_.push_back({open_[kind], e, kind});
+    open_[kind] = nullptr;
+}
+void BatchedKKT::collect() {
+    for (auto& s : spans_) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { prof_ms[s.kind] += ms; prof_calls[s.kind]++; }
+        free_events_.push_back(s.a); free_events_.push_back(s.b);
+    }
+    spans_.clear();
+}
+void BatchedKKT::reset_profile() { collect(); for (int i = 0; i < T_COUNT; i++) { prof_ms[i] = 0; prof_calls[i] = 0; } }
+
 // =====================================================================================================
 // data packing
 // =====================================================================================================
@@ -374,8 +399,12 @@ void DenseBatchedKKT::factor(const double* delta_in, const double* x_reg, const 
     const size_t nz = (size_t)batch * m;
     const size_t tot = std::max(nz, (size_t)batch);
     B200_LAUNCH(inv_and_copy_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, z_reg, zinv.get(), nz, delta_in, delta.get(), batch);
+    tic(T_ASSEMBLE);
     assemble(x_reg, active);
+    toc(T_ASSEMBLE);
+    tic(T_FACTOR);
     cholesky(active);
+    toc(T_FACTOR);
     B200_LAUNCH(fail_to_ok_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, ok, batch);
 }
 
@@ -388,6 +417,7 @@ static GemvArgs gemv_args(const double* M, long long sM, int ld, int rows, int c
 void DenseBatchedKKT::solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) {
     // dense/kkt.hpp:86-105
     if (n == 0) return;
+    tic(T_SOLVE);
     dim3 gn(ceil_div(n, 256), batch);
     B200_LAUNCH(copy_masked_kernel, gn, 256, 0, stream, rx, lx, n, active);
     if (m > 0) {
@@ -413,6 +443,7 @@ void DenseBatchedKKT::solve(const double* rx, const double* ry, const double* rz
         dim3 g(ceil_div(m, 8), batch);
         B200_LAUNCH(gemv_t_kernel, g, 256, 0, stream, a);
     }
+    toc(T_SOLVE);
 }
 
 void DenseBatchedKKT::eval_P_x(double alpha, const double* x, double* z, const int* active) {   // dense/kkt.hpp:108-114

@@ -5,6 +5,7 @@
 // live in HBM, instance-major ([batch][len], no padding).  Every call takes an optional per-instance
 // `active` mask so the lock-step interior-point driver can retire converged instances.
 #pragma once
+#include <vector>
 #include "common.cuh"
 
 namespace b200 {
@@ -34,6 +35,21 @@ struct BatchedKKT {
     virtual double factor_bytes() const = 0;
     virtual double solve_flops() const = 0;
     virtual double solve_bytes() const = 0;
+
+    // ---- optional per-kernel-class device timers (CUDA events on `stream`), used by bench.py's roofline block
+    enum { T_ASSEMBLE = 0, T_FACTOR = 1, T_SOLVE = 2, T_COUNT = 3 };
+    bool profile = false;
+    double prof_ms[T_COUNT] = {0, 0, 0};
+    long long prof_calls[T_COUNT] = {0, 0, 0};
+    void tic(int kind);
+    void toc(int kind);
+    void collect();      // after a stream sync: fold finished event pairs into prof_ms / prof_calls
+    void reset_profile();
+private:
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans_;
+    std::vector<cudaEvent_t> free_events_;
+    cudaEvent_t open_[T_COUNT] = {nullptr, nullptr, nullptr};
 };
 
 }  // namespace b200

@@ -126,6 +126,9 @@ class DenseSolverBatched:
         """copy x into a CUDA torch tensor (batch, n) without leaving the device"""
         _lib.check(self._L.b200qp_get_result(self._h, C.cast(x_out.data_ptr(), dp), *([None] * 9), 1), "b200qp_get_result")
 
+    def set_profiling(self, enable=True):
+        _lib.check(self._L.b200qp_set_profiling(self._h, int(enable)), "b200qp_set_profiling")
+
     def trace(self, b=0):
         rows = np.zeros((self.settings.max_iter + 1, 10))
         k = self._L.b200qp_get_trace(self._h, b, rows.ctypes.data_as(dp), rows.shape[0])

@@ -93,3 +93,42 @@ def sparse_strongly_convex_qp(dim, n_eq, n_ineq, sparsity_factor, bounds_perc=0.
     b = A @ x_sol
     h_l, h_u, x_l, x_u = _bounds(rng, x_sol, G @ x_sol, n_ineq, dim, bounds_perc)
     return dict(P=P, c=c, A=A, b=b, G=G, h_l=h_l, h_u=h_u, x_l=x_l, x_u=x_u, x_sol=x_sol)
+
+
+def dense_batch_torch(batch, n, p, m, seed0=42, device="cuda", bounds_perc=0.5, strong_convexity_factor=1e-2):
+    """Batched, device-side version of dense_strongly_convex_qp (same distributions, torch's Philox stream):
+    instance b is drawn from a generator seeded with seed0 + b.  Returns a dict of float64 torch tensors
+    (P [B,n,n] upper triangular, c, A, b, G, h_l, h_u, x_l, x_u) resident on `device`."""
+    import torch
+    dd = dict(dtype=torch.float64, device=device)
+    out = {k: [] for k in ("P", "c", "A", "b", "G", "h_l", "h_u", "x_l", "x_u")}
+    inf = float("inf")
+    for i in range(batch):
+        g = torch.Generator(device=device)
+        g.manual_seed(seed0 + i)
+        rn = lambda *s: torch.randn(*s, generator=g, **dd)
+        ru = lambda *s: torch.rand(*s, generator=g, **dd)
+        P = torch.triu(rn(n, n), 1)
+        lam_min = torch.linalg.eigvalsh(P + P.T).min()
+        P = P + torch.eye(n, **dd) * (strong_convexity_factor + lam_min.abs())
+        A = rn(p, n); G = rn(m, n); x_sol = rn(n); c = rn(n)
+        b = A @ x_sol
+        delta_u = torch.where(ru(m) < 0.3, ru(m), torch.zeros(m, **dd))
+        delta_l = torch.where(ru(m) < 0.3, ru(m), torch.zeros(m, **dd))
+        Gx = G @ x_sol
+        h_l = Gx - delta_l; h_u = Gx + delta_u
+        r = ru(m)
+        h_l = torch.where(r < 0.33, torch.full_like(h_l, -inf), h_l)
+        h_u = torch.where((r >= 0.33) & (r < 0.66), torch.full_like(h_u, inf), h_u)
+        r = ru(n); act = ru(n) < 0.5; shift = ru(n); side = ru(n) < 0.5
+        lo = r < bounds_perc / 3
+        up = (r >= bounds_perc / 3) & (r < bounds_perc * 2 / 3)
+        both = (r >= bounds_perc * 2 / 3) & (r < bounds_perc)
+        x_l = torch.full((n,), -inf, **dd); x_u = torch.full((n,), inf, **dd)
+        x_l = torch.where(lo, x_sol - torch.where(act, shift, torch.zeros_like(shift)), x_l)
+        x_u = torch.where(up, x_sol + torch.where(act, shift, torch.zeros_like(shift)), x_u)
+        x_l = torch.where(both, x_sol - torch.where(side, shift, torch.zeros_like(shift)), x_l)
+        x_u = torch.where(both, x_sol + torch.where(~side, shift, torch.zeros_like(shift)), x_u)
+        for k, v in (("P", P), ("c", c), ("A", A), ("b", b), ("G", G), ("h_l", h_l), ("h_u", h_u), ("x_l", x_l), ("x_u", x_u)):
+            out[k].append(v)
+    return {k: torch.stack(v).contiguous() for k, v in out.items()}
