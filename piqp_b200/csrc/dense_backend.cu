@@ -329,8 +329,9 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
     set_smem(gemm_nt_tile_kernel<EPI_ASSEMBLE, false>, GEMM_SMEM);
     set_smem(gemm_nt_tile_kernel<EPI_SUB, false>, GEMM_SMEM);
     set_smem(gemm_nt_tile_kernel<EPI_STORE, false>, GEMM_SMEM);
-    set_smem(potf2_kernel, POTF2_SMEM);
-    set_smem(trsm_kernel, TRSM_SMEM);
+    set_smem(chol_diag_kernel, CHOL_DIAG_SMEM);
+    set_smem(chol_panel_kernel, CHOL_PANEL_SMEM);
+    invbuf.alloc((size_t)batch * 4 * LB_SZ); invbuf.zero(st);
     set_smem(trsv_kernel, (size_t)(n + 32) * sizeof(double) > 48 * 1024 ? (size_t)(n + 32) * sizeof(double) : 48 * 1024);
     if (p > 0) { AtA.alloc((size_t)batch * D->ld * n); AtA.zero(st); compute_AtA(); }
 }
@@ -371,27 +372,17 @@ void DenseBatchedKKT::assemble(const double* x_reg, const int* active) {   // de
            B200_LAUNCH((gemm_nt_tile_kernel<EPI_ASSEMBLE, false>), (unsigned)(g.tiles * batch), GEMM_THREADS, GEMM_SMEM, stream, g); }
 }
 
-void DenseBatchedKKT::cholesky(const int* active) {   // Eigen::LLT<Lower>::compute -- left-looking by 128-column blocks
+void DenseBatchedKKT::cholesky(const int* active) {   // Eigen::LLT<Lower>::compute -- see dense_chol.cuh
     if (n == 0) return;
     const int nt = ceil_div(n, TILE);
     B200_LAUNCH(clear_fail_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, batch);
     for (int jb = 0; jb < nt; jb++) {
         const int j0 = jb * TILE;
-        if (jb > 0) {
-            GemmArgs g{};
-            g.A = K.get(); g.strideA = D->sP(); g.lda = D->ld;
-            g.B = g.A; g.strideB = g.strideA; g.ldb = g.lda;
-            g.C = K.get(); g.strideC = D->sP(); g.ldc = D->ld;
-            g.n = n; g.rows_valid = D->ld; g.K = j0; g.nt = nt; g.tj_fixed = jb; g.tiles = nt - jb;
-            g.active = active; g.fail = fail.get();
-            B200_LAUNCH((gemm_nt_tile_kernel<EPI_SUB, false>), (unsigned)(g.tiles * batch), GEMM_THREADS, GEMM_SMEM, stream, g);
-        }
-        B200_LAUNCH(potf2_kernel, batch, POTF2_THREADS, POTF2_SMEM, stream, K.get(), D->sP(), D->ld, n, j0, fail.get(), active);
-        const int rows_below = n - j0 - TILE;
-        if (rows_below > 0) {
-            const int rt = ceil_div(rows_below, TRSM_THREADS);
-            B200_LAUNCH(trsm_kernel, (unsigned)(rt * batch), TRSM_THREADS, TRSM_SMEM, stream, K.get(), D->sP(), D->ld, n, j0, rt, fail.get(), active);
-        }
+        B200_LAUNCH(chol_diag_kernel, batch, CHOL_THREADS, CHOL_DIAG_SMEM, stream, K.get(), D->sP(), D->ld, n, j0, invbuf.get(), fail.get(), active);
+        const int rt = nt - jb - 1;
+        if (rt > 0)
+            B200_LAUNCH(chol_panel_kernel, (unsigned)(rt * batch), CHOL_THREADS, CHOL_PANEL_SMEM, stream, K.get(), D->sP(), D->ld, n, jb, rt,
+                        invbuf.get(), fail.get(), active);
     }
 }
 

@@ -64,6 +64,7 @@ public:
     DevBuf<double> zinv;     // [batch][m]
     DevBuf<double> delta;    // [batch]
     DevBuf<int> fail;        // [batch] 0 = ok, else failing column + 1
+    DevBuf<double> invbuf;   // [batch][4][32 x 36] inverses of the 32 x 32 diagonal blocks of the current diagonal tile
 private:
     void compute_AtA();
 };

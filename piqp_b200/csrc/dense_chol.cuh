@@ -1,0 +1,282 @@
+// piqp_b200/csrc/dense_chol.cuh -- batched blocked Cholesky (replaces Eigen::LLT::compute, dense/kkt.hpp:82).
+//
+// Left-looking over 128-column block columns; two kernels per block column jb:
+//   chol_diag_kernel  : one CTA per instance.  Diagonal tile -> shared memory, blocked (32) Cholesky in place:
+//                       DMMA for the inter-block updates and the below-diagonal solves, one warp for the 32 x 32
+//                       pivot blocks, and the inverses of the four 32 x 32 diagonal blocks of L11 as a by-product.
+//   chol_panel_kernel : one CTA per (instance, row tile below).  DMMA mainloop for the left-looking update
+//                       T = A - sum_k L(ti,k) L(jb,k)^T, then the triangular solve X L11^T = T as a blocked forward
+//                       substitution on 16-row strips (one warp each, all DMMA: off-diagonal blocks of L11 and the
+//                       inverted diagonal blocks), then the rank-128 update of this row tile's OWN diagonal tile
+//                       (right-looking look-ahead), so the diag kernel has no mainloop.
+// All fp64; pivots <= 0 (or NaN) report failure like Eigen's LLT (info() != Success).
+// (textually included from dense_kernels.cuh inside namespace b200 and #ifdef __CUDACC__)
+
+constexpr int CB = 32;                 // inner block
+constexpr int LB_LD = CB + 4;          // leading dim of a 32 x 32 block in smem: Bs[k * LB_LD + n]
+constexpr int LB_SZ = CB * LB_LD;      // doubles per block
+constexpr size_t CHOL_DIAG_SMEM = TILE_SMEM + 4 * LB_SZ * sizeof(double);
+constexpr size_t CHOL_PANEL_SMEM = TILE_SMEM + 10 * LB_SZ * sizeof(double);
+constexpr int CHOL_THREADS = 256;
+
+// acc(16 x 32) += sgn * A(16 x K) * B(K x 32); As[k * lda + row], Bs[k * ldb + n]; K multiple of 4
+__device__ __forceinline__ void warp_mma_16x32(double (&acc)[2][4][2], const double* As, int lda, const double* Bs, int ldb, int K, bool negate) {
+    const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+#pragma unroll 4
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        double a[2], bb[4];
+#pragma unroll
+        for (int i = 0; i < 2; i++) { a[i] = As[(k0 + tq) * lda + i * 8 + gq]; if (negate) a[i] = -a[i]; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) bb[j] = Bs[(k0 + tq) * ldb + j * 8 + gq];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+    }
+}
+// 16 x 32 block in C-fragment layout <-> Ts (element (row, col) at Ts[col * TS_LD + row])
+__device__ __forceinline__ void cfrag_load(double (&acc)[2][4][2], const double* Ts) {
+    const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) acc[i][j][e] = Ts[(j * 8 + tq * 2 + e) * TS_LD + i * 8 + gq];
+}
+__device__ __forceinline__ void cfrag_store(const double (&acc)[2][4][2], double* Ts) {
+    const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) Ts[(j * 8 + tq * 2 + e) * TS_LD + i * 8 + gq] = acc[i][j][e];
+}
+__device__ __forceinline__ void cfrag_zero(double (&acc)[2][4][2]) {
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+}
+
+// One warp: Cholesky of the 32 x 32 block T (T[c * TS_LD + r], lower) in place and inv <- L^{-1} (inv[k * LB_LD + n] = Linv(n,k)).
+// Returns 0 or (failing column + 1).
+__device__ __forceinline__ int warp_potf2_32(double* T, double* inv) {
+    const int lane = threadIdx.x & 31;
+    double a[CB];
+#pragma unroll
+    for (int c = 0; c < CB; c++) a[c] = (c <= lane) ? T[c * TS_LD + lane] : 0.0;
+    int failed = 0;
+#pragma unroll
+    for (int k = 0; k < CB; k++) {
+        double dk = __shfl_sync(0xffffffffu, a[k], k);
+        if (!(dk > 0.0)) { if (!failed) failed = k + 1; dk = 1.0; }
+        const double lkk = sqrt(dk);
+        const double rinv = 1.0 / lkk;
+        const double lrk = a[k] * rinv;
+        a[k] = (lane == k) ? lkk : lrk;
+#pragma unroll
+        for (int j = k + 1; j < CB; j++) {
+            const double ljk = __shfl_sync(0xffffffffu, lrk, j);
+            if (lane >= j) a[j] -= lrk * ljk;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CB; c++) if (c <= lane) T[c * TS_LD + lane] = a[c];
+    __syncwarp();
+    // inverse, column `lane` of L^{-1}: x_i = ((i == lane) - sum_{k<i} l_ik x_k) / l_ii   (x_k = 0 for k < lane)
+    double x[CB];
+#pragma unroll
+    for (int i = 0; i < CB; i++) {
+        double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; k++) s -= T[k * TS_LD + i] * x[k];
+        x[i] = s / T[i * TS_LD + i];
+    }
+#pragma unroll
+    for (int i = 0; i < CB; i++) inv[lane * LB_LD + i] = x[i];
+    return failed;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CHOL_THREADS, 1)
+chol_diag_kernel(double* Kmat, long long strideK, int ld, int n, int j0, double* invbuf, int* fail, const int* active) {
+    extern __shared__ __align__(16) double smem[];
+    double* Ts = smem;
+    double* inv = smem + TILE * TS_LD;          // 4 blocks
+    __shared__ int s_fail;
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    if (fail[b]) return;
+    double* K = Kmat + (size_t)b * strideK;
+    const int nb = min(TILE, n - j0);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) s_fail = 0;
+    // lower triangle of the tile; identity on the padding so that partial tiles factor trivially there
+    for (int c = warp; c < TILE; c += CHOL_THREADS / 32)
+        for (int r = tid & 31; r < TILE; r += 32) {
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < nb && c < nb) v = (r >= c) ? K[(size_t)(j0 + c) * ld + j0 + r] : 0.0;
+            Ts[c * TS_LD + r] = v;
+        }
+    for (int i = tid; i < 4 * LB_SZ; i += CHOL_THREADS) inv[i] = 0.0;
+    __syncthreads();
+    const int nblk = (nb + CB - 1) / CB;
+    const int row0 = warp * 16;                 // this warp's 16-row strip
+    for (int s = 0; s < nblk; s++) {
+        // (1) left-looking update of block column s with block columns < s, rows >= 32 s
+        if (s > 0 && row0 >= CB * s) {
+            double acc[2][4][2];
+            cfrag_load(acc, Ts + (CB * s) * TS_LD + row0);
+            for (int k = 0; k < s; k++)
+                warp_mma_16x32(acc, Ts + (CB * k) * TS_LD + row0, TS_LD, Ts + (CB * k) * TS_LD + CB * s, TS_LD, CB, true);
+            __syncwarp();
+            cfrag_store(acc, Ts + (CB * s) * TS_LD + row0);
+        }
+        __syncthreads();
+        // (2) pivot block + its inverse
+        if (warp == 0) {
+            const int f = warp_potf2_32(Ts + (CB * s) * TS_LD + CB * s, inv + s * LB_SZ);
+            if (f && (tid == 0)) s_fail = j0 + CB * s + f;
+        }
+        __syncthreads();
+        if (s_fail) break;
+        // (3) rows below: X = T * L_ss^{-T}
+        if (row0 >= CB * (s + 1)) {
+            double acc[2][4][2];
+            cfrag_zero(acc);
+            warp_mma_16x32(acc, Ts + (CB * s) * TS_LD + row0, TS_LD, inv + s * LB_SZ, LB_LD, CB, false);
+            __syncwarp();
+            cfrag_store(acc, Ts + (CB * s) * TS_LD + row0);
+        }
+        __syncthreads();
+    }
+    if (s_fail) { if (tid == 0) fail[b] = s_fail; return; }
+    for (int c = warp; c < nb; c += CHOL_THREADS / 32)
+        for (int r = c + (tid & 31); r < nb; r += 32) K[(size_t)(j0 + c) * ld + j0 + r] = Ts[c * TS_LD + r];
+    double* ib = invbuf + (size_t)b * 4 * LB_SZ;
+    for (int i = tid; i < 4 * LB_SZ; i += CHOL_THREADS) ib[i] = inv[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CHOL_THREADS, 1)
+chol_panel_kernel(double* Kmat, long long strideK, int ld, int n, int jb, int row_tiles, const double* invbuf, const int* fail, const int* active) {
+    extern __shared__ __align__(16) double smem[];
+    double* Ts = smem;                          // the tile being solved: Ts[col * TS_LD + row]
+    double* Lb = smem + TILE * TS_LD;           // 6 off-diagonal 32 x 32 blocks of L11, then 4 inverse diagonal blocks
+    double* inv = Lb + 6 * LB_SZ;
+    const int b = blockIdx.x / row_tiles, t = blockIdx.x % row_tiles;
+    if (active && !active[b]) return;
+    if (fail[b]) return;
+    double* K = Kmat + (size_t)b * strideK;
+    const int j0 = jb * TILE, ti = jb + 1 + t, rows0 = ti * TILE;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    // ---- left-looking update: acc = sum_{k < j0} L(ti,k) L(jb,k)^T
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    if (j0 > 0) {
+        gemm_mainloop<false>(acc, smem, K, ld, rows0, K, ld, j0, ld, j0, nullptr, false);
+        __syncthreads();
+    }
+    acc_to_smem(acc, Ts, -1.0);
+    __syncthreads();
+    // ---- T = A - acc (coalesced), and the blocks of L11 / inverse diagonal blocks
+    {
+        const int r = (tid & 63) * 2;
+        const bool rok = rows0 + r + 1 < ld + 0;
+#pragma unroll 4
+        for (int it = 0; it < TILE / 4; it++) {
+            const int c = it * 4 + (tid >> 6);
+            double2 a = make_double2(0.0, 0.0);
+            if (rok) a = *reinterpret_cast<const double2*>(K + (size_t)(j0 + c) * ld + rows0 + r);
+            double2* p = reinterpret_cast<double2*>(Ts + c * TS_LD + r);
+            double2 v = *p; v.x += a.x; v.y += a.y; *p = v;
+        }
+        // Lb(s,k)[kk * LB_LD + nn] = L11(32 s + nn, 32 k + kk), k < s
+        for (int e = tid; e < 6 * CB * CB; e += CHOL_THREADS) {
+            const int blk = e / (CB * CB), kk = (e / CB) % CB, nn = e % CB;
+            int s = 1, k = blk;
+            while (k >= s) { k -= s; s++; }
+            Lb[blk * LB_SZ + kk * LB_LD + nn] = K[(size_t)(j0 + CB * k + kk) * ld + j0 + CB * s + nn];
+        }
+        const double* ib = invbuf + (size_t)b * 4 * LB_SZ;
+        for (int i = tid; i < 4 * LB_SZ; i += CHOL_THREADS) inv[i] = ib[i];
+    }
+    __syncthreads();
+    // ---- X * L11^T = T on this warp's 16-row strip, blocked forward substitution (no block-level barriers)
+    {
+        const int row0 = warp * 16;
+        for (int s = 0; s < 4; s++) {
+            double c2[2][4][2];
+            if (s > 0) {
+                cfrag_load(c2, Ts + (CB * s) * TS_LD + row0);
+                for (int k = 0; k < s; k++)
+                    warp_mma_16x32(c2, Ts + (CB * k) * TS_LD + row0, TS_LD, Lb + (s * (s - 1) / 2 + k) * LB_SZ, LB_LD, CB, true);
+                __syncwarp();
+                cfrag_store(c2, Ts + (CB * s) * TS_LD + row0);
+                __syncwarp();
+            }
+            cfrag_zero(c2);
+            warp_mma_16x32(c2, Ts + (CB * s) * TS_LD + row0, TS_LD, inv + s * LB_SZ, LB_LD, CB, false);
+            __syncwarp();
+            cfrag_store(c2, Ts + (CB * s) * TS_LD + row0);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // ---- store L21 tile
+    {
+        const int r = (tid & 63) * 2;
+#pragma unroll 4
+        for (int it = 0; it < TILE / 4; it++) {
+            const int c = it * 4 + (tid >> 6);
+            const double2 v = *reinterpret_cast<const double2*>(Ts + c * TS_LD + r);
+            double* dst = K + (size_t)(j0 + c) * ld + rows0 + r;
+            if (rows0 + r + 1 < n) *reinterpret_cast<double2*>(dst) = v;
+            else if (rows0 + r < n) dst[0] = v.x;
+        }
+    }
+    // ---- look-ahead: this row tile's own diagonal tile (ti,ti) gets its rank-128 contribution of block column jb now
+    //      (D -= X X^T, lower part), so chol_diag_kernel never needs a mainloop and the work is spread over all panel CTAs
+    {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        const int lane = tid & 31, wm = warp >> 2, wn = warp & 3, gq = lane >> 2, tq = lane & 3;
+#pragma unroll 2
+        for (int k0 = 0; k0 < TILE; k0 += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) af[i] = Ts[(k0 + tq) * TS_LD + wm * 64 + i * 8 + gq];
+#pragma unroll
+            for (int j = 0; j < 4; j++) bf[j] = Ts[(k0 + tq) * TS_LD + wn * 32 + j * 8 + gq];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncthreads();
+        acc_to_smem(acc, Ts, 1.0);
+        __syncthreads();
+        const int r = (tid & 63) * 2;
+        const int d0 = rows0;                     // the next diagonal tile starts at row/col rows0
+#pragma unroll 4
+        for (int it = 0; it < TILE / 4; it++) {
+            const int c = it * 4 + (tid >> 6);
+            const int gr = d0 + r, gc = d0 + c;
+            if (gc >= n || gr + 1 < gc || gr >= n) continue;
+            const double2 u = *reinterpret_cast<const double2*>(Ts + c * TS_LD + r);
+            double* dst = K + (size_t)gc * ld + gr;
+            if (gr >= gc && gr + 1 < n) { double2 v = *reinterpret_cast<double2*>(dst); v.x -= u.x; v.y -= u.y; *reinterpret_cast<double2*>(dst) = v; }
+            else { if (gr >= gc && gr < n) dst[0] -= u.x; if (gr + 1 >= gc && gr + 1 < n) dst[1] -= u.y; }
+        }
+    }
+}
+

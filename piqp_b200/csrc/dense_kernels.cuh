@@ -24,7 +24,10 @@ constexpr int KB = 16;          // k-depth of one pipeline stage
 constexpr int STAGES = 3;
 constexpr int LDS_T = TILE + 4; // padded smem row (doubles): conflict-free DMMA fragment loads
 constexpr int GEMM_THREADS = 256;
-constexpr size_t GEMM_SMEM = (size_t)STAGES * 2 * KB * LDS_T * sizeof(double);
+constexpr size_t GEMM_STAGE_SMEM = (size_t)STAGES * 2 * KB * LDS_T * sizeof(double);
+constexpr int TS_LD = TILE + 4; // leading dimension of a full 128 x 128 tile staged in smem: Ts[col * TS_LD + row]
+constexpr size_t TILE_SMEM = (size_t)TILE * TS_LD * sizeof(double);
+constexpr size_t GEMM_SMEM = TILE_SMEM > GEMM_STAGE_SMEM ? TILE_SMEM : GEMM_STAGE_SMEM;
 
 enum Epilogue { EPI_STORE = 0, EPI_SUB = 1, EPI_ASSEMBLE = 2 };
 
@@ -78,6 +81,72 @@ __device__ __forceinline__ void load_panel(double* sm, const double* M, int ld, 
     }
 }
 
+// acc(i,j) += sum_{k<K} A[(rowA0+i) + k*lda] * w[k] * B[(rowB0+j) + k*ldb] for the 128 x 128 tile; warp grid 2 (M) x 4 (N),
+// warp tile 64 x 32, lane holds C(row = gq, cols 2*tq, 2*tq+1) of each 8x8 fragment.  Ends with all cp.async drained.
+template <bool HAS_W>
+__device__ __forceinline__ void gemm_mainloop(double (&acc)[8][4][2], double* smem, const double* A, int lda, int rowA0,
+                                              const double* B, int ldb, int rowB0, int rows_valid, int K, const double* w, bool diag) {
+    double* As = smem;                              // [STAGES][KB][LDS_T]
+    double* Bs = smem + STAGES * KB * LDS_T;        // [STAGES][KB][LDS_T]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int nkb = (K + KB - 1) / KB;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nkb) {
+            load_panel(As + s * KB * LDS_T, A, lda, rowA0, rows_valid, s * KB, K);
+            if (!diag) load_panel(Bs + s * KB * LDS_T, B, ldb, rowB0, rows_valid, s * KB, K);
+        }
+        cp_async_commit();
+    }
+    for (int kb = 0; kb < nkb; kb++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nx = kb + STAGES - 1;
+            if (nx < nkb) {
+                const int s = nx % STAGES;
+                load_panel(As + s * KB * LDS_T, A, lda, rowA0, rows_valid, nx * KB, K);
+                if (!diag) load_panel(Bs + s * KB * LDS_T, B, ldb, rowB0, rows_valid, nx * KB, K);
+            }
+            cp_async_commit();
+        }
+        const int s = kb % STAGES;
+        const double* as = As + s * KB * LDS_T;
+        const double* bs = diag ? as : (Bs + s * KB * LDS_T);
+#pragma unroll
+        for (int kk = 0; kk < KB / 4; kk++) {
+            double af[8], bf[4];
+            const int krow = kk * 4 + tq;
+#pragma unroll
+            for (int i = 0; i < 8; i++) af[i] = as[krow * LDS_T + wm * 64 + i * 8 + gq];
+            double wk = 1.0;
+            if (HAS_W) { const int gk = kb * KB + krow; wk = gk < K ? w[gk] : 0.0; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) { bf[j] = bs[krow * LDS_T + wn * 32 + j * 8 + gq]; if (HAS_W) bf[j] *= wk; }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// stage the accumulators of the 2x4 warp grid into a full tile in smem: Cs[col * TS_LD + row] = sign * acc
+__device__ __forceinline__ void acc_to_smem(const double (&acc)[8][4][2], double* Cs, double sign) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp >> 2, wn = warp & 3, gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+                Cs[(wn * 32 + j * 8 + tq * 2 + e) * TS_LD + wm * 64 + i * 8 + gq] = sign * acc[i][j][e];
+}
+
 template <int EPI, bool HAS_W>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_tile_kernel(GemmArgs g) {
     extern __shared__ __align__(16) double smem[];
@@ -94,181 +163,63 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_tile_kernel(GemmArgs 
     const double* w = HAS_W ? g.w + (size_t)b * g.stridew : nullptr;
     const int rowA0 = ti * TILE, rowB0 = tj * TILE;
 
-    double* As = smem;                              // [STAGES][KB][LDS_T]
-    double* Bs = smem + STAGES * KB * LDS_T;        // [STAGES][KB][LDS_T]
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wm = warp >> 2, wn = warp & 3;        // 2 x 4 warps; warp tile 64 (M) x 32 (N)
-    const int gq = lane >> 2, tq = lane & 3;        // DMMA groupID / threadID_in_group
-
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    gemm_mainloop<HAS_W>(acc, smem, A, g.lda, rowA0, B, g.ldb, rowB0, g.rows_valid, g.K, w, diag);
 
-    const int nkb = (g.K + KB - 1) / KB;
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < nkb) {
-            load_panel(As + s * KB * LDS_T, A, g.lda, rowA0, g.rows_valid, s * KB, g.K);
-            if (!diag) load_panel(Bs + s * KB * LDS_T, B, g.ldb, rowB0, g.rows_valid, s * KB, g.K);
-        }
-        cp_async_commit();
-    }
-    for (int kb = 0; kb < nkb; kb++) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            const int nx = kb + STAGES - 1;
-            if (nx < nkb) {
-                const int s = nx % STAGES;
-                load_panel(As + s * KB * LDS_T, A, g.lda, rowA0, g.rows_valid, nx * KB, g.K);
-                if (!diag) load_panel(Bs + s * KB * LDS_T, B, g.ldb, rowB0, g.rows_valid, nx * KB, g.K);
-            }
-            cp_async_commit();
-        }
-        const int s = kb % STAGES;
-        const double* as = As + s * KB * LDS_T;
-        const double* bs = diag ? as : (Bs + s * KB * LDS_T);
-#pragma unroll
-        for (int kk = 0; kk < KB / 4; kk++) {
-            double af[8], bf[4];
-            const int krow = kk * 4 + tq;
-#pragma unroll
-            for (int i = 0; i < 8; i++) af[i] = as[krow * LDS_T + wm * 64 + i * 8 + gq];
-            double wk = 1.0;
-            if (HAS_W) { const int gk = kb * KB + krow; wk = gk < g.K ? w[gk] : 0.0; }
-#pragma unroll
-            for (int j = 0; j < 4; j++) { bf[j] = bs[krow * LDS_T + wn * 32 + j * 8 + gq]; if (HAS_W) bf[j] *= wk; }
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
-    }
-    cp_async_wait<0>();
-
-    // ---- epilogue: lane holds C(row = gq, cols = 2*tq, 2*tq+1) of every 8x8 fragment
-    double* C = g.C + (size_t)b * g.strideC;
+    // ---- epilogue through shared memory: coalesced 16-byte global accesses, loads batched ahead of the stores
+    __syncthreads();
+    acc_to_smem(acc, smem, 1.0);
+    __syncthreads();
+    double* __restrict__ C = g.C + (size_t)b * g.strideC;
     const double dinv = (EPI == EPI_ASSEMBLE) ? 1.0 / g.delta[b] : 0.0;
-    const double* Pf = (EPI == EPI_ASSEMBLE) ? g.Pf + (size_t)b * g.strideP : nullptr;
-    const double* AtA = (EPI == EPI_ASSEMBLE && g.AtA) ? g.AtA + (size_t)b * g.strideAtA : nullptr;
-    const double* xr = (EPI == EPI_ASSEMBLE) ? g.xreg + (size_t)b * g.stridex : nullptr;
+    const double* __restrict__ Pf = (EPI == EPI_ASSEMBLE) ? g.Pf + (size_t)b * g.strideP : nullptr;
+    const double* __restrict__ AtA = (EPI == EPI_ASSEMBLE && g.AtA) ? g.AtA + (size_t)b * g.strideAtA : nullptr;
+    const double* __restrict__ xr = (EPI == EPI_ASSEMBLE) ? g.xreg + (size_t)b * g.stridex : nullptr;
+    const int r = rowA0 + (threadIdx.x & 63) * 2;
+    constexpr int U = 4;
+#pragma unroll 1
+    for (int it0 = 0; it0 < TILE / 4; it0 += U) {
+        double2 base[U], extra[U];
+        bool ok[U];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int r = rowA0 + wm * 64 + i * 8 + gq;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int c = rowB0 + wn * 32 + j * 8 + tq * 2 + e;
-                if (r < g.n && c < g.n && r >= c) {
-                    const size_t idx = (size_t)c * g.ldc + r;
-                    double v = acc[i][j][e];
-                    if (EPI == EPI_SUB) v = C[idx] - v;
-                    if (EPI == EPI_ASSEMBLE) {
-                        double base = Pf[idx];
-                        if (r == c) base += xr[r];
-                        if (AtA) base += dinv * AtA[idx];
-                        v = base + v;
-                    }
-                    C[idx] = v;
-                }
+        for (int u = 0; u < U; u++) {
+            const int cl = (it0 + u) * 4 + (threadIdx.x >> 6);
+            const int c = rowB0 + cl;
+            ok[u] = (r + 1 < g.rows_valid + 0) && (c < g.n) && (r < g.n) && (r + 1 >= c);
+            base[u] = make_double2(0.0, 0.0); extra[u] = make_double2(0.0, 0.0);
+            if (ok[u]) {
+                const size_t idx = (size_t)c * g.ldc + r;
+                if (EPI == EPI_SUB) base[u] = *reinterpret_cast<const double2*>(C + idx);
+                if (EPI == EPI_ASSEMBLE) { base[u] = *reinterpret_cast<const double2*>(Pf + idx); if (AtA) extra[u] = *reinterpret_cast<const double2*>(AtA + idx); }
             }
         }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!ok[u]) continue;
+            const int cl = (it0 + u) * 4 + (threadIdx.x >> 6);
+            const int c = rowB0 + cl;
+            const double2 a = *reinterpret_cast<const double2*>(smem + cl * TS_LD + (threadIdx.x & 63) * 2);
+            double v0 = a.x, v1 = a.y;
+            if (EPI == EPI_SUB) { v0 = base[u].x - v0; v1 = base[u].y - v1; }
+            if (EPI == EPI_ASSEMBLE) {
+                double b0 = base[u].x, b1 = base[u].y;
+                if (r == c) b0 += xr[r];
+                if (r + 1 == c) b1 += xr[r + 1];
+                if (AtA) { b0 += dinv * extra[u].x; b1 += dinv * extra[u].y; }
+                v0 = b0 + v0; v1 = b1 + v1;
+            }
+            const size_t idx = (size_t)c * g.ldc + r;
+            if (r >= c && r + 1 < g.n) *reinterpret_cast<double2*>(C + idx) = make_double2(v0, v1);
+            else { if (r >= c && r < g.n) C[idx] = v0; if (r + 1 >= c && r + 1 < g.n) C[idx + 1] = v1; }
+        }
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// potf2: Cholesky of one diagonal tile (<= 128 x 128) per CTA, in shared memory.
-//   fail[b] = failing column + 1 (global column index) if a pivot is <= 0 (Eigen LLT: NumericalIssue).
-// ---------------------------------------------------------------------------------------------------
-constexpr int POTF2_THREADS = 256;
-constexpr int POTF2_LD = TILE + 1;
-constexpr size_t POTF2_SMEM = (size_t)TILE * POTF2_LD * sizeof(double);
-
-__global__ void __launch_bounds__(POTF2_THREADS, 1)
-potf2_kernel(double* Kmat, long long strideK, int ld, int n, int j0, int* fail, const int* active) {
-    extern __shared__ __align__(16) double S[];   // S[i + j*POTF2_LD]
-    const int b = blockIdx.x;
-    if (active && !active[b]) return;
-    if (fail[b]) return;
-    double* K = Kmat + (size_t)b * strideK;
-    const int nb = min(TILE, n - j0);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = POTF2_THREADS / 32;
-    for (int j = warp; j < nb; j += nwarps)
-        for (int i = j + lane; i < nb; i += 32) S[i + j * POTF2_LD] = K[(size_t)(j0 + j) * ld + j0 + i];
-    __shared__ int s_fail;
-    __shared__ double s_rinv[TILE];
-    if (tid == 0) s_fail = 0;
-    // Right-looking, one barrier per column.  Column k is never rewritten once step k starts, so it stays
-    // "unscaled" in smem (S[i,k] = l_ik * l_kk) and is scaled by 1/l_kk on the fly and at write-out.
-    for (int k = 0; k < nb; k++) {
-        __syncthreads();
-        const double d = S[k + k * POTF2_LD];
-        if (!(d > 0.0)) {   // uniform branch; also catches NaN
-            if (tid == 0) s_fail = j0 + k + 1;
-            break;
-        }
-        const double rinv = 1.0 / sqrt(d);
-        if (tid == 0) s_rinv[k] = rinv;
-        for (int j = k + 1 + warp; j < nb; j += nwarps) {
-            const double ljk = S[j + k * POTF2_LD] * rinv;
-            for (int i = j + lane; i < nb; i += 32) S[i + j * POTF2_LD] -= (S[i + k * POTF2_LD] * rinv) * ljk;
-        }
-    }
-    __syncthreads();
-    if (s_fail) { if (tid == 0) fail[b] = s_fail; return; }
-    for (int j = warp; j < nb; j += nwarps)
-        for (int i = j + lane; i < nb; i += 32) {
-            const double v = S[i + j * POTF2_LD];
-            K[(size_t)(j0 + j) * ld + j0 + i] = (i == j) ? sqrt(v) : v * s_rinv[j];
-        }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// trsm: rows below the diagonal tile, X * L11^T = A21, one thread per row, L11 (row-major) in smem.
-// ---------------------------------------------------------------------------------------------------
-constexpr int TRSM_THREADS = 128;
-constexpr int TRSM_LD = TILE + 2;  // row-major L11 in smem: Ls[j*TRSM_LD + k] = L11(j,k)
-constexpr size_t TRSM_SMEM = (size_t)TILE * TRSM_LD * sizeof(double);
-
-__global__ void __launch_bounds__(TRSM_THREADS)
-trsm_kernel(double* Kmat, long long strideK, int ld, int n, int j0, int row_tiles, const int* fail, const int* active) {
-    extern __shared__ __align__(16) double Ls[];
-    const int b = blockIdx.x / row_tiles, rt = blockIdx.x % row_tiles;
-    if (active && !active[b]) return;
-    if (fail[b]) return;
-    double* K = Kmat + (size_t)b * strideK;
-    const int nb = TILE;   // rows below the diagonal tile exist only when the tile is full
-    const int tid = threadIdx.x;
-    for (int k = 0; k < nb; k++)
-        for (int j = k + tid; j < nb; j += TRSM_THREADS) Ls[j * TRSM_LD + k] = K[(size_t)(j0 + k) * ld + j0 + j];
-    __syncthreads();
-    const int row = j0 + TILE + rt * TRSM_THREADS + tid;
-    if (row >= n) return;
-    double* Xr = K + row;   // element (row, j0 + c) at Xr[(j0 + c) * ld]
-    for (int c0 = 0; c0 < nb; c0 += 32) {
-        double acc[32];
-#pragma unroll
-        for (int jj = 0; jj < 32; jj++) acc[jj] = Xr[(size_t)(j0 + c0 + jj) * ld];
-        for (int k = 0; k < c0; k++) {
-            const double xk = Xr[(size_t)(j0 + k) * ld];
-#pragma unroll
-            for (int jj = 0; jj < 32; jj++) acc[jj] -= xk * Ls[(c0 + jj) * TRSM_LD + k];
-        }
-#pragma unroll
-        for (int jj = 0; jj < 32; jj++) {
-            const double x = acc[jj] / Ls[(c0 + jj) * TRSM_LD + c0 + jj];
-            acc[jj] = x;
-#pragma unroll
-            for (int j2 = jj + 1; j2 < 32; j2++) acc[j2] -= x * Ls[(c0 + j2) * TRSM_LD + c0 + jj];
-        }
-#pragma unroll
-        for (int jj = 0; jj < 32; jj++) Xr[(size_t)(j0 + c0 + jj) * ld] = acc[jj];
-    }
-}
+#include "dense_chol.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // trsv: x <- L^{-T} L^{-1} x for one instance per CTA (x in shared memory).
