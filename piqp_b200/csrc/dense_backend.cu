@@ -331,14 +331,15 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
     set_smem(gemm_nt_tile_kernel<EPI_STORE, false>, GEMM_SMEM);
     set_smem(chol_diag_kernel, CHOL_DIAG_SMEM);
     set_smem(chol_panel_kernel, CHOL_PANEL_SMEM);
-    invbuf.alloc((size_t)batch * 4 * LB_SZ); invbuf.zero(st);
+    Linv_stride = (long long)ceil_div(std::max(n, 1), TILE) * 4 * LB_SZ;
+    Linv.alloc((size_t)batch * Linv_stride); Linv.zero(st);
     set_smem(trsv_kernel, (size_t)(n + 32) * sizeof(double) > 48 * 1024 ? (size_t)(n + 32) * sizeof(double) : 48 * 1024);
     if (p > 0) { AtA.alloc((size_t)batch * D->ld * n); AtA.zero(st); compute_AtA(); }
 }
 
 void DenseBatchedKKT::copy_from(const DenseBatchedKKT& o) {
     auto cp = [&](DevBuf<double>& d, const DevBuf<double>& s) { if (s.n) B200_CUDA(cudaMemcpyAsync(d.get(), s.get(), s.n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); };
-    cp(K, o.K); cp(AtA, o.AtA); cp(zinv, o.zinv); cp(delta, o.delta);
+    cp(K, o.K); cp(AtA, o.AtA); cp(zinv, o.zinv); cp(delta, o.delta); cp(Linv, o.Linv);
     B200_CUDA(cudaMemcpyAsync(fail.get(), o.fail.get(), sizeof(int) * batch, cudaMemcpyDeviceToDevice, stream));
 }
 
@@ -378,11 +379,11 @@ void DenseBatchedKKT::cholesky(const int* active) {   // Eigen::LLT<Lower>::comp
     B200_LAUNCH(clear_fail_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, batch);
     for (int jb = 0; jb < nt; jb++) {
         const int j0 = jb * TILE;
-        B200_LAUNCH(chol_diag_kernel, batch, CHOL_THREADS, CHOL_DIAG_SMEM, stream, K.get(), D->sP(), D->ld, n, j0, invbuf.get(), fail.get(), active);
+        B200_LAUNCH(chol_diag_kernel, batch, CHOL_THREADS, CHOL_DIAG_SMEM, stream, K.get(), D->sP(), D->ld, n, j0, Linv.get(), Linv_stride, fail.get(), active);
         const int rt = nt - jb - 1;
         if (rt > 0)
             B200_LAUNCH(chol_panel_kernel, (unsigned)(rt * batch), CHOL_THREADS, CHOL_PANEL_SMEM, stream, K.get(), D->sP(), D->ld, n, jb, rt,
-                        invbuf.get(), fail.get(), active);
+                        Linv.get(), Linv_stride, fail.get(), active);
     }
 }
 
@@ -421,7 +422,7 @@ void DenseBatchedKKT::solve(const double* rx, const double* ry, const double* rz
         a.alpha_v = delta.get(); a.alpha_v_inverse = 1; a.accumulate = 1;
         B200_LAUNCH(gemv_n_kernel, gn, 256, 0, stream, a);
     }
-    B200_LAUNCH(trsv_kernel, batch, TRSV_THREADS, (size_t)(n + 32) * sizeof(double), stream, K.get(), D->sP(), D->ld, n, lx, (long long)n, active);
+    B200_LAUNCH(trsv_kernel, batch, TRSV_THREADS, (size_t)(n + 32) * sizeof(double), stream, K.get(), D->sP(), D->ld, n, Linv.get(), Linv_stride, lx, (long long)n, active);
     if (p > 0) {
         GemvArgs a = gemv_args(D->AT.get(), D->sA(), D->ld, n, p, lx, n, ly, p, 1.0, active);
         a.alpha_v = delta.get(); a.alpha_v_inverse = 1; a.sub = ry; a.stridesub = p; a.alpha2 = 1.0;

@@ -64,7 +64,8 @@ public:
     DevBuf<double> zinv;     // [batch][m]
     DevBuf<double> delta;    // [batch]
     DevBuf<int> fail;        // [batch] 0 = ok, else failing column + 1
-    DevBuf<double> invbuf;   // [batch][4][32 x 36] inverses of the 32 x 32 diagonal blocks of the current diagonal tile
+    DevBuf<double> Linv;     // [batch][n/32 (padded to whole tiles)][32 x 36] inverses of the 32 x 32 diagonal blocks of L
+    long long Linv_stride = 0;
 private:
     void compute_AtA();
 };

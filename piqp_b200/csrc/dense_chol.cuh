@@ -63,20 +63,22 @@ __device__ __forceinline__ void cfrag_zero(double (&acc)[2][4][2]) {
 
 // One warp: Cholesky of the 32 x 32 block T (T[c * TS_LD + r], lower) in place and inv <- L^{-1} (inv[k * LB_LD + n] = Linv(n,k)).
 // Returns 0 or (failing column + 1).
-__device__ __forceinline__ int warp_potf2_32(double* T, double* inv) {
+__device__ __noinline__ int warp_potf2_32(double* T, double* inv) {
     const int lane = threadIdx.x & 31;
     double a[CB];
 #pragma unroll
     for (int c = 0; c < CB; c++) a[c] = (c <= lane) ? T[c * TS_LD + lane] : 0.0;
     int failed = 0;
+    double my_rinv = 1.0;           // lane k keeps 1 / l_kk
 #pragma unroll
     for (int k = 0; k < CB; k++) {
         double dk = __shfl_sync(0xffffffffu, a[k], k);
         if (!(dk > 0.0)) { if (!failed) failed = k + 1; dk = 1.0; }
-        const double lkk = sqrt(dk);
-        const double rinv = 1.0 / lkk;
+        const double rinv = rsqrt(dk);
+        const double lkk = dk * rinv;
         const double lrk = a[k] * rinv;
         a[k] = (lane == k) ? lkk : lrk;
+        if (lane == k) my_rinv = rinv;
 #pragma unroll
         for (int j = k + 1; j < CB; j++) {
             const double ljk = __shfl_sync(0xffffffffu, lrk, j);
@@ -93,7 +95,7 @@ __device__ __forceinline__ int warp_potf2_32(double* T, double* inv) {
         double s = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
         for (int k = 0; k < i; k++) s -= T[k * TS_LD + i] * x[k];
-        x[i] = s / T[i * TS_LD + i];
+        x[i] = s * __shfl_sync(0xffffffffu, my_rinv, i);
     }
 #pragma unroll
     for (int i = 0; i < CB; i++) inv[lane * LB_LD + i] = x[i];
@@ -102,7 +104,7 @@ __device__ __forceinline__ int warp_potf2_32(double* T, double* inv) {
 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
-chol_diag_kernel(double* Kmat, long long strideK, int ld, int n, int j0, double* invbuf, int* fail, const int* active) {
+chol_diag_kernel(double* Kmat, long long strideK, int ld, int n, int j0, double* Linv, long long strideLinv, int* fail, const int* active) {
     extern __shared__ __align__(16) double smem[];
     double* Ts = smem;
     double* inv = smem + TILE * TS_LD;          // 4 blocks
@@ -156,13 +158,13 @@ chol_diag_kernel(double* Kmat, long long strideK, int ld, int n, int j0, double*
     if (s_fail) { if (tid == 0) fail[b] = s_fail; return; }
     for (int c = warp; c < nb; c += CHOL_THREADS / 32)
         for (int r = c + (tid & 31); r < nb; r += 32) K[(size_t)(j0 + c) * ld + j0 + r] = Ts[c * TS_LD + r];
-    double* ib = invbuf + (size_t)b * 4 * LB_SZ;
+    double* ib = Linv + (size_t)b * strideLinv + (size_t)(j0 / CB) * LB_SZ;   // blocks j0/32 .. j0/32 + 3 (allocation is padded to whole tiles)
     for (int i = tid; i < 4 * LB_SZ; i += CHOL_THREADS) ib[i] = inv[i];
 }
 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
-chol_panel_kernel(double* Kmat, long long strideK, int ld, int n, int jb, int row_tiles, const double* invbuf, const int* fail, const int* active) {
+chol_panel_kernel(double* Kmat, long long strideK, int ld, int n, int jb, int row_tiles, const double* Linv, long long strideLinv, const int* fail, const int* active) {
     extern __shared__ __align__(16) double smem[];
     double* Ts = smem;                          // the tile being solved: Ts[col * TS_LD + row]
     double* Lb = smem + TILE * TS_LD;           // 6 off-diagonal 32 x 32 blocks of L11, then 4 inverse diagonal blocks
@@ -173,6 +175,20 @@ chol_panel_kernel(double* Kmat, long long strideK, int ld, int n, int jb, int ro
     double* K = Kmat + (size_t)b * strideK;
     const int j0 = jb * TILE, ti = jb + 1 + t, rows0 = ti * TILE;
     const int tid = threadIdx.x, warp = tid >> 5;
+
+    // ---- prefetch the blocks of L11 (Lb(s,k)[kk * LB_LD + nn] = L11(32 s + nn, 32 k + kk), k < s) and the inverse
+    //      diagonal blocks with cp.async into the smem region behind the mainloop stages; they land during the mainloop
+    for (int e = tid; e < 6 * CB * (CB / 2); e += CHOL_THREADS) {
+        const int blk = e / (CB * CB / 2), kk = (e / (CB / 2)) % CB, n2 = (e % (CB / 2)) * 2;
+        int s = 1, k = blk;
+        while (k >= s) { k -= s; s++; }
+        cp_async16(Lb + blk * LB_SZ + kk * LB_LD + n2, K + (size_t)(j0 + CB * k + kk) * ld + j0 + CB * s + n2, 16);
+    }
+    {
+        const double* ib = Linv + (size_t)b * strideLinv + (size_t)(j0 / CB) * LB_SZ;
+        for (int i = tid; i < 4 * LB_SZ / 2; i += CHOL_THREADS) cp_async16(inv + 2 * i, ib + 2 * i, 16);
+    }
+    cp_async_commit();
 
     // ---- left-looking update: acc = sum_{k < j0} L(ti,k) L(jb,k)^T
     double acc[8][4][2];
@@ -185,28 +201,25 @@ chol_panel_kernel(double* Kmat, long long strideK, int ld, int n, int jb, int ro
         __syncthreads();
     }
     acc_to_smem(acc, Ts, -1.0);
+    cp_async_wait<0>();
     __syncthreads();
-    // ---- T = A - acc (coalesced), and the blocks of L11 / inverse diagonal blocks
+    // ---- T = A - acc: all 32 16-byte loads of this thread are in flight before the first use
     {
         const int r = (tid & 63) * 2;
         const bool rok = rows0 + r + 1 < ld + 0;
-#pragma unroll 4
+        double2 a[TILE / 4];
+#pragma unroll
         for (int it = 0; it < TILE / 4; it++) {
             const int c = it * 4 + (tid >> 6);
-            double2 a = make_double2(0.0, 0.0);
-            if (rok) a = *reinterpret_cast<const double2*>(K + (size_t)(j0 + c) * ld + rows0 + r);
+            a[it] = make_double2(0.0, 0.0);
+            if (rok) a[it] = *reinterpret_cast<const double2*>(K + (size_t)(j0 + c) * ld + rows0 + r);
+        }
+#pragma unroll
+        for (int it = 0; it < TILE / 4; it++) {
+            const int c = it * 4 + (tid >> 6);
             double2* p = reinterpret_cast<double2*>(Ts + c * TS_LD + r);
-            double2 v = *p; v.x += a.x; v.y += a.y; *p = v;
+            double2 v = *p; v.x += a[it].x; v.y += a[it].y; *p = v;
         }
-        // Lb(s,k)[kk * LB_LD + nn] = L11(32 s + nn, 32 k + kk), k < s
-        for (int e = tid; e < 6 * CB * CB; e += CHOL_THREADS) {
-            const int blk = e / (CB * CB), kk = (e / CB) % CB, nn = e % CB;
-            int s = 1, k = blk;
-            while (k >= s) { k -= s; s++; }
-            Lb[blk * LB_SZ + kk * LB_LD + nn] = K[(size_t)(j0 + CB * k + kk) * ld + j0 + CB * s + nn];
-        }
-        const double* ib = invbuf + (size_t)b * 4 * LB_SZ;
-        for (int i = tid; i < 4 * LB_SZ; i += CHOL_THREADS) inv[i] = ib[i];
     }
     __syncthreads();
     // ---- X * L11^T = T on this warp's 16-row strip, blocked forward substitution (no block-level barriers)
@@ -266,16 +279,24 @@ chol_panel_kernel(double* Kmat, long long strideK, int ld, int n, int jb, int ro
         acc_to_smem(acc, Ts, 1.0);
         __syncthreads();
         const int r = (tid & 63) * 2;
-        const int d0 = rows0;                     // the next diagonal tile starts at row/col rows0
-#pragma unroll 4
+        const int d0 = rows0;                     // this row tile's diagonal tile starts at row/col rows0
+        double2 old[TILE / 4];
+#pragma unroll
+        for (int it = 0; it < TILE / 4; it++) {
+            const int c = it * 4 + (tid >> 6);
+            const int gr = d0 + r, gc = d0 + c;
+            old[it] = make_double2(0.0, 0.0);
+            if (gc < n && gr + 1 >= gc && gr + 1 < ld) old[it] = *reinterpret_cast<const double2*>(K + (size_t)gc * ld + gr);
+        }
+#pragma unroll
         for (int it = 0; it < TILE / 4; it++) {
             const int c = it * 4 + (tid >> 6);
             const int gr = d0 + r, gc = d0 + c;
             if (gc >= n || gr + 1 < gc || gr >= n) continue;
             const double2 u = *reinterpret_cast<const double2*>(Ts + c * TS_LD + r);
             double* dst = K + (size_t)gc * ld + gr;
-            if (gr >= gc && gr + 1 < n) { double2 v = *reinterpret_cast<double2*>(dst); v.x -= u.x; v.y -= u.y; *reinterpret_cast<double2*>(dst) = v; }
-            else { if (gr >= gc && gr < n) dst[0] -= u.x; if (gr + 1 >= gc && gr + 1 < n) dst[1] -= u.y; }
+            if (gr >= gc && gr + 1 < n) *reinterpret_cast<double2*>(dst) = make_double2(old[it].x - u.x, old[it].y - u.y);
+            else { if (gr >= gc && gr < n) dst[0] = old[it].x - u.x; if (gr + 1 >= gc && gr + 1 < n) dst[1] = old[it].y - u.y; }
         }
     }
 }

@@ -100,6 +100,14 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[8][4][2], double* sm
         }
         cp_async_commit();
     }
+    // per-lane scale factors w[k] for the k rows this lane touches (k = kb*KB + kk*4 + tq), fetched one k-block ahead
+    double wcur[KB / 4], wnext[KB / 4];
+#pragma unroll
+    for (int kk = 0; kk < KB / 4; kk++) { wcur[kk] = 1.0; wnext[kk] = 1.0; }
+    if (HAS_W) {
+#pragma unroll
+        for (int kk = 0; kk < KB / 4; kk++) { const int gk = kk * 4 + tq; wcur[kk] = gk < K ? w[gk] : 0.0; }
+    }
     for (int kb = 0; kb < nkb; kb++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -112,6 +120,10 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[8][4][2], double* sm
             }
             cp_async_commit();
         }
+        if (HAS_W) {
+#pragma unroll
+            for (int kk = 0; kk < KB / 4; kk++) { const int gk = (kb + 1) * KB + kk * 4 + tq; wnext[kk] = gk < K ? w[gk] : 0.0; }
+        }
         const int s = kb % STAGES;
         const double* as = As + s * KB * LDS_T;
         const double* bs = diag ? as : (Bs + s * KB * LDS_T);
@@ -121,14 +133,16 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[8][4][2], double* sm
             const int krow = kk * 4 + tq;
 #pragma unroll
             for (int i = 0; i < 8; i++) af[i] = as[krow * LDS_T + wm * 64 + i * 8 + gq];
-            double wk = 1.0;
-            if (HAS_W) { const int gk = kb * KB + krow; wk = gk < K ? w[gk] : 0.0; }
 #pragma unroll
-            for (int j = 0; j < 4; j++) { bf[j] = bs[krow * LDS_T + wn * 32 + j * 8 + gq]; if (HAS_W) bf[j] *= wk; }
+            for (int j = 0; j < 4; j++) { bf[j] = bs[krow * LDS_T + wn * 32 + j * 8 + gq]; if (HAS_W) bf[j] *= wcur[kk]; }
 #pragma unroll
             for (int i = 0; i < 8; i++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        if (HAS_W) {
+#pragma unroll
+            for (int kk = 0; kk < KB / 4; kk++) wcur[kk] = wnext[kk];
         }
     }
     cp_async_wait<0>();
@@ -227,29 +241,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_tile_kernel(GemmArgs 
 // ---------------------------------------------------------------------------------------------------
 constexpr int TRSV_THREADS = 512;
 
+// x <- L^{-T} L^{-1} x, one instance per CTA, x in shared memory.  The 32 x 32 diagonal blocks are applied through
+// their inverses (by-product of chol_diag_kernel, Linv[blk][k * LB_LD + n] = inv(L_blk)(n, k)), so the serial part of
+// each block step is one 32 x 32 mat-vec by warp 0 instead of 32 dependent divisions.
 __global__ void __launch_bounds__(TRSV_THREADS, 2)
-trsv_kernel(const double* Lmat, long long strideL, int ld, int n, double* X, long long strideX, const int* active) {
+trsv_kernel(const double* Lmat, long long strideL, int ld, int n, const double* Linv, long long strideLinv,
+            double* X, long long strideX, const int* active) {
     extern __shared__ __align__(16) double xs[];   // n doubles + 32 scratch
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     const double* L = Lmat + (size_t)b * strideL;
+    const double* Li = Linv + (size_t)b * strideLinv;
     double* x = X + (size_t)b * strideX;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TRSV_THREADS / 32;
     for (int i = tid; i < n; i += TRSV_THREADS) xs[i] = x[i];
     __syncthreads();
-    // ---- forward: L y = x
+    // ---- forward: L y = x (right-looking, coalesced column reads)
     for (int j0 = 0; j0 < n; j0 += 32) {
         const int nb = min(32, n - j0);
         if (warp == 0) {
-            double xi = lane < nb ? xs[j0 + lane] : 0.0;
-            for (int c = 0; c < nb; c++) {
-                const double lcc = L[(size_t)(j0 + c) * ld + j0 + c];
-                const double lic = (lane > c && lane < nb) ? L[(size_t)(j0 + c) * ld + j0 + lane] : 0.0;
-                double xc = __shfl_sync(0xffffffffu, xi, c) / lcc;
-                if (lane == c) xi = xc;
-                xi -= lic * xc;
+            const double* ib = Li + (size_t)(j0 / 32) * LB_SZ;
+            const double v = lane < nb ? xs[j0 + lane] : 0.0;
+            double y = 0.0;
+#pragma unroll
+            for (int k8 = 0; k8 < 32; k8 += 8) {
+                double col[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) col[k] = ib[(k8 + k) * LB_LD + lane];      // inv(lane, k), coalesced
+#pragma unroll
+                for (int k = 0; k < 8; k++) y += col[k] * __shfl_sync(0xffffffffu, v, k8 + k);
             }
-            if (lane < nb) xs[j0 + lane] = xi;
+            if (lane < nb) xs[j0 + lane] = y;
         }
         __syncthreads();
         for (int i = j0 + nb + tid; i < n; i += TRSV_THREADS) {
@@ -260,12 +282,11 @@ trsv_kernel(const double* Lmat, long long strideL, int ld, int n, double* X, lon
         }
         __syncthreads();
     }
-    // ---- backward: L^T x = y ; block of 32 columns at a time, dots over the rows below the block
+    // ---- backward: L^T x = y (left-looking: column dots over the rows below the block, then inv^T mat-vec)
     double* red = xs + n;   // 32 doubles
     for (int j1 = n; j1 > 0; j1 -= 32) {
-        const int j0 = max(0, j1 - 32);
+        const int j0 = (j1 - 1) / 32 * 32;       // blocks are aligned at multiples of 32
         const int nb = j1 - j0;
-        // each warp accumulates dots for columns c = warp, warp + nwarps, ... of the block
         for (int c = warp; c < nb; c += nwarps) {
             const double* col = L + (size_t)(j0 + c) * ld;
             double s = 0.0;
@@ -275,18 +296,21 @@ trsv_kernel(const double* Lmat, long long strideL, int ld, int n, double* X, lon
         }
         __syncthreads();
         if (warp == 0) {
-            double xi = lane < nb ? xs[j0 + lane] - red[lane] : 0.0;
-            for (int c = nb - 1; c >= 0; c--) {
-                // x_c = (xi_c) / l_cc ; then rows < c in the block: xi_r -= L(j0+c, j0+r) * x_c
-                const double lcc = L[(size_t)(j0 + c) * ld + j0 + c];
-                const double lcr = (lane < c) ? L[(size_t)(j0 + lane) * ld + j0 + c] : 0.0;
-                double xc = __shfl_sync(0xffffffffu, xi, c) / lcc;
-                if (lane == c) xi = xc;
-                xi -= lcr * xc;
+            const double* ib = Li + (size_t)(j0 / 32) * LB_SZ;
+            const double v = lane < nb ? xs[j0 + lane] - red[lane] : 0.0;
+            double y = 0.0;
+#pragma unroll
+            for (int k8 = 0; k8 < 32; k8 += 8) {
+                double row[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) row[k] = ib[lane * LB_LD + k8 + k];      // inv(k, lane)
+#pragma unroll
+                for (int k = 0; k < 8; k++) y += row[k] * __shfl_sync(0xffffffffu, v, k8 + k);   // sum_k inv(k, lane) v_k
             }
-            if (lane < nb) xs[j0 + lane] = xi;
+            if (lane < nb) xs[j0 + lane] = y;
         }
         __syncthreads();
+        j1 = j0 + 32;   // loop decrement brings it to j0
     }
     for (int i = tid; i < n; i += TRSV_THREADS) x[i] = xs[i];
 }
