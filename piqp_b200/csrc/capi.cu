@@ -2,6 +2,8 @@
 #include "../../include/piqp_b200.h"
 #include "dense_backend.hpp"
 #include "ip_solver.hpp"
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -352,6 +354,9 @@ int b200qp_setup_dense(b200qp_handle** out, int batch, int n, int p, int m, cons
         B200_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         cudaEvent_t e0, e1;
         B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
+        const bool verbose_timing = getenv("B200_TIMING") != nullptr;
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double t_0 = now();
         h->dd.alloc(batch, n, p, m);
         B200_CUDA(cudaDeviceSynchronize());
         B200_CUDA(cudaEventRecord(e0, h->stream));
@@ -360,8 +365,14 @@ int b200qp_setup_dense(b200qp_handle** out, int batch, int n, int p, int m, cons
         h->zero_rows.alloc(std::max<size_t>((size_t)batch * m, 1)); h->zero_rows.zero(h->stream);
         IpDev& d = h->ip->dev();
         fill_d(d.xbs, (size_t)batch * n, 1.0, h->stream);
+        if (verbose_timing) { B200_CUDA(cudaStreamSynchronize(h->stream)); }
+        double t_1 = now();
         load_problem(h.get(), true, P, c, A, b, G, h_l, h_u, x_l, x_u, on_device);
+        double t_2 = now();
         scale_problem(h.get(), false);
+        if (verbose_timing) { B200_CUDA(cudaStreamSynchronize(h->stream)); }
+        double t_3 = now();
+        if (verbose_timing) fprintf(stderr, "[b200 setup] alloc %.1f ms, load(H2D+pack) %.1f ms, ruiz %.1f ms\n", t_1 - t_0, t_2 - t_1, t_3 - t_2);
         // hand the preconditioner to the IP driver (device pointers stay owned by RuizState)
         d.pd = h->ruiz.delta.get(); d.pd_inv = h->ruiz.delta_inv.get(); d.pdb = h->ruiz.delta_b.get(); d.pdb_inv = h->ruiz.delta_b_inv.get();
         d.pc = h->ruiz.c.get(); d.pc_inv = h->ruiz.c_inv.get();
