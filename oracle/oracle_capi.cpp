@@ -254,6 +254,27 @@ int orc_dense_get_kkt(void* h, double* kkt, double* L) {
     return 0;
 }
 
+// multistage backend: detected block structure as (start, diag, off) triples; returns the number of blocks (incl. arrow)
+int orc_multistage_blocks(void* h, int* out, int cap) {
+    auto* H = static_cast<Handle*>(h);
+    auto* be = dynamic_cast<MultistageKKT*>(H->ip.kkt.be.get());
+    if (!be) return -1;
+    int k = 0;
+    for (const auto& b : be->bi) { if (3 * k + 2 < cap) { out[3 * k] = b.start; out[3 * k + 1] = b.diag; out[3 * k + 2] = b.off; } k++; }
+    return k;
+}
+double orc_multistage_factor_flops(void* h) {
+    auto* be = dynamic_cast<MultistageKKT*>(static_cast<Handle*>(h)->ip.kkt.be.get());
+    return be ? be->factor_flops() : -1.0;
+}
+// sparse_ldlt backend: nnz(L) and the flop count of the numeric factorisation
+double orc_sparse_ldlt_stats(void* h, double* nnzL) {
+    auto* be = dynamic_cast<SparseKKTFull*>(static_cast<Handle*>(h)->ip.kkt.be.get());
+    if (!be) return -1.0;
+    if (nnzL) *nnzL = (double)be->ldlt.Lp.back();
+    return be->ldlt.flops();
+}
+
 void orc_destroy(void* h) { delete static_cast<Handle*>(h); }
 
 // raw dense factorisations (unit tests against scipy; reference tests/src/dense/ldlt_test.cpp:22-77)

@@ -148,7 +148,7 @@ struct SparseKKTFull : KKTBackend {
     void eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt) override;
 };
 
-std::unique_ptr<KKTBackend> make_multistage_backend(const SparseMatrices& S);  // oracle_multistage.hpp
+inline std::unique_ptr<KKTBackend> make_multistage_backend(const SparseMatrices& S);  // oracle_multistage.hpp
 
 struct SparseMatrices : QPMatrices {
     int n = 0, p = 0, m = 0;

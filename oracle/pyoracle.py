@@ -105,6 +105,9 @@ def lib(native=False):
     L.orc_dense_setup.restype = C.c_void_p
     L.orc_sparse_setup.restype = C.c_void_p
     L.orc_dense_time_factor_solve.restype = C.c_double
+    L.orc_multistage_factor_flops.restype = C.c_double
+    L.orc_sparse_ldlt_stats.restype = C.c_double
+    L.orc_multistage_blocks.restype = C.c_int
     for f in ("orc_solve", "orc_dense_update", "orc_sparse_update", "orc_get_trace", "orc_kktsystem_roundtrip",
               "orc_backend_factor", "orc_dense_get_kkt", "orc_chol", "orc_ldlt", "orc_settings_size", "orc_info_size"):
         getattr(L, f).restype = C.c_int
@@ -341,6 +344,16 @@ class SparseSolver(_Base):
                                            _ip(GTp), _ip(GTi), _dp(GTx), _dp(v[2]), _dp(v[3]), _dp(v[4]), _dp(v[5]),
                                            C.byref(self.settings), int(self.identity),
                                            C.byref(self.vt) if self.vt is not None else None, _ip(perm))
+
+    def multistage_blocks(self):
+        buf = (C.c_int * 30000)()
+        k = self._L.orc_multistage_blocks(C.c_void_p(self._h), buf, 30000)
+        return [(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]) for i in range(max(k, 0))]
+
+    def ldlt_stats(self):
+        nn = C.c_double()
+        fl = self._L.orc_sparse_ldlt_stats(C.c_void_p(self._h), C.byref(nn))
+        return nn.value, fl
 
     def update(self, P=None, c=None, A=None, b=None, G=None, h_l=None, h_u=None, x_l=None, x_u=None):
         import scipy.sparse as sp

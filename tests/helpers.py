@@ -71,3 +71,23 @@ def kkt_residuals(q, r):
     xu = q["x_u"] if q.get("x_u") is not None else np.full(len(x), INF)
     res.append(max(0.0, (xl - x).max(), (x - xu).max()))
     return max(res)
+
+
+def load_scenario_mpc():
+    """tests/golden/scenario_mpc_small.npz (+ golden JSON): the QP of the reference's documentation notebook."""
+    import json
+    import os
+    import scipy.sparse as sp
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    d = np.load(os.path.join(here, "scenario_mpc_small.npz"))
+    g = json.load(open(os.path.join(here, "scenario_mpc_small_golden.json")))
+    n, p = int(d["n"]), int(d["p"])
+    P = sp.csc_matrix((d["P_data"], d["P_indices"], d["P_indptr"]), shape=(n, n))
+    A = sp.csc_matrix((d["A_data"], d["A_indices"], d["A_indptr"]), shape=(p, n))
+    return dict(P=P, c=d["c"], A=A, b=d["b"], G=None, h_l=None, h_u=None, x_l=d["x_l"], x_u=d["x_u"]), g
+
+
+def trace_as_printed(t):
+    """oracle/b200 trace rows (rho, delta, mu, p_step, d_step, prim_res, dual_res, prim_obj, dual_obj, gap) ->
+    the column order the reference prints (prim_obj dual_obj gap prim_res dual_res rho delta mu p_step d_step)"""
+    return np.column_stack([t[:, 7], t[:, 8], t[:, 9], t[:, 5], t[:, 6], t[:, 0], t[:, 1], t[:, 2], t[:, 3], t[:, 4]])
