@@ -1,0 +1,62 @@
+"""CPU-only, build-container-only: the oracle on the reference's own structured .mat fixtures
+(/root/reference/tests/data/*.mat, used by tests/src/sparse/multistage_kkt_test.cpp:172-211).  Skipped where the
+reference tree is not mounted (the GPU box)."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+DATA = "/root/reference/tests/data"
+pytestmark = pytest.mark.skipif(not os.path.isdir(DATA), reason="reference fixtures not mounted")
+
+NAMES = ["small_sparse_dual_inf", "small_dense", "scenario_mpc_small", "scenario_mpc", "chain_mass_sqp", "robot_arm_sqp",
+         "robot_arm_sqp_constr_perm", "robot_arm_sqp_no_global"]
+
+
+def load(name):
+    import scipy.io
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d = scipy.io.loadmat(os.path.join(DATA, name + ".mat"))
+    g = lambda k: np.asarray(d[k], dtype=float).ravel()
+    P, A, G = sp.csc_matrix(d["P"]), sp.csc_matrix(d["A"]), sp.csc_matrix(d["G"])
+    return (P, g("c"), A if A.shape[0] else None, g("b") if A.shape[0] else None, G if G.shape[0] else None,
+            g("h_l") if G.shape[0] else None, g("h_u") if G.shape[0] else None, g("x_l"), g("x_u"))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_multistage_equals_sparse_ldlt(oracle, name):
+    """multistage_kkt_test.cpp:24-98 (`test_solve_multiply`): both backends, same rho/delta/scalings -> same solve and
+    mat-vec results to 1e-8, on every structured fixture"""
+    q = load(name)
+    sol = {}
+    for bk in ("sparse_ldlt", "sparse_multistage"):
+        s = oracle.SparseSolver(oracle.default_settings(kkt_solver=bk)); s.setup(*q)
+        n, p, m = s.dims[:3]
+        rng = np.random.default_rng(0)
+        assert s.backend_factor(1.2, np.full(n, 0.9), np.full(m, 2.2)) == 1
+        x, y, z = rng.standard_normal(n), rng.standard_normal(p), rng.standard_normal(m)
+        sol[bk] = list(s.backend_solve(x, y, z)) + [s.backend_eval_P_x(1.0, x)] + list(s.backend_eval_A(1.0, 1.0, x, y)) + list(s.backend_eval_G(1.0, 1.0, x, z))
+    for a, b in zip(sol["sparse_ldlt"], sol["sparse_multistage"]):
+        if len(a):
+            assert np.abs(a - b).max() <= 1e-8 * max(1.0, np.abs(a).max())
+
+
+@pytest.mark.parametrize("name,status,iters", [("small_sparse_dual_inf", -3, 13), ("small_dense", 1, 7), ("scenario_mpc_small", 1, 8),
+                                               ("scenario_mpc", 1, 13), ("chain_mass_sqp", 1, 9)])
+def test_full_solves_agree_between_backends(oracle, name, status, iters):
+    q = load(name)
+    for bk in ("sparse_ldlt", "sparse_multistage"):
+        s = oracle.SparseSolver(oracle.default_settings(kkt_solver=bk)); s.setup(*q)
+        assert s.solve() == status
+        assert s.info().iter == iters
+
+
+def test_sqp_benchmark_settings(oracle):
+    """benchmarks/src/sqp_benchmarks.cpp:16-118: the robot-arm QP is solved with reg_lower_limit = reg_finetune_lower_limit = 1e-8"""
+    q = load("robot_arm_sqp")
+    for bk in ("sparse_ldlt", "sparse_multistage"):
+        s = oracle.SparseSolver(oracle.default_settings(kkt_solver=bk, reg_lower_limit=1e-8, reg_finetune_lower_limit=1e-8)); s.setup(*q)
+        assert s.solve() == 1
