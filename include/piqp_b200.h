@@ -200,6 +200,24 @@ int b200qp_update_dense(b200qp_handle* h, const double* P, const double* c, cons
                         const double* G, const double* h_l, const double* h_u,
                         const double* x_l, const double* x_u, int on_device);
 
+/* Batched twin of piqp_setup_sparse (piqp.h:28, piqp_data_sparse piqp_typedef.h:56-68): all instances share the CSC
+ * patterns of P (n x n, upper triangle used), A (p x n) and G (m x n) -- int32 column pointers / row indices on the host --
+ * and differ in the value arrays Px[batch][nnz(P)], Ax[batch][nnz(A)], Gx[batch][nnz(G)] and in the vectors.
+ * settings->kkt_solver selects the backend: 5 = sparse_multistage (block-tridiagonal-arrow Cholesky; built),
+ * 1..4 = sparse_ldlt variants (next round).                                                                        */
+int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
+                        const int* Pp, const int* Pi, const double* Px, const double* c,
+                        const int* Ap, const int* Ai, const double* Ax, const double* b,
+                        const int* Gp, const int* Gi, const double* Gx, const double* h_l, const double* h_u,
+                        const double* x_l, const double* x_u, const b200qp_settings* settings, int device, int on_device);
+/* Batched twin of piqp_update_sparse (piqp.h:36): same patterns, new values; NULL = keep. */
+int b200qp_update_sparse(b200qp_handle* h, const double* Px, const double* c, const double* Ax, const double* b, const double* Gx,
+                         const double* h_l, const double* h_u, const double* x_l, const double* x_u, int on_device);
+/* detected multistage structure as (start, diag_size, off_diag_size) triples, last = arrow block
+ * (what MultistageKKT::print_info prints, multistage_kkt.hpp:385-392); returns the number of blocks */
+int b200qp_multistage_blocks(b200qp_handle* h, int* out, int cap);
+int b200kkt_multistage_blocks(b200kkt_handle* h, int* out, int cap);
+
 /* piqp_update_settings (piqp.h:30) */
 int b200qp_update_settings(b200qp_handle* h, const b200qp_settings* settings);
 

@@ -27,6 +27,10 @@ struct OrcBackendVTable {
     int (*eval_A)(void* h, double an, double at, const double* xn, const double* xt, double* zn, double* zt);
     int (*eval_G)(void* h, double an, double at, const double* xn, const double* xt, double* zn, double* zt);
     void (*destroy)(void* h);
+    int (*create_multistage)(void** out, int n, int p, int m,
+                             const int* Pp, const int* Pi, const double* Px,
+                             const int* ATp, const int* ATi, const double* ATx,
+                             const int* GTp, const int* GTi, const double* GTx, int device);
 };
 
 }  // extern "C"
@@ -52,7 +56,10 @@ struct ForeignSparse : KKTBackend {
     const OrcBackendVTable* vt; void* h; const SparseMatrices& S;
     ForeignSparse(const OrcBackendVTable* v, const SparseMatrices& S_) : vt(v), S(S_) {
         h = nullptr;
-        vt->create_sparse(&h, S.n, S.p, S.m, S.P.p.data(), S.P.i.data(), S.P.x.data(), S.AT.p.data(), S.AT.i.data(), S.AT.x.data(),
+        if (S.kkt_solver_hint == 5 && vt->create_multistage)
+            vt->create_multistage(&h, S.n, S.p, S.m, S.P.p.data(), S.P.i.data(), S.P.x.data(), S.AT.p.data(), S.AT.i.data(), S.AT.x.data(),
+                                  S.GT.p.data(), S.GT.i.data(), S.GT.x.data(), 0);
+        else vt->create_sparse(&h, S.n, S.p, S.m, S.P.p.data(), S.P.i.data(), S.P.x.data(), S.AT.p.data(), S.AT.i.data(), S.AT.x.data(),
                           S.GT.p.data(), S.GT.i.data(), S.GT.x.data(), 0, S.user_perm.empty() ? nullptr : S.user_perm.data(), 0);
     }
     ~ForeignSparse() override { if (h) vt->destroy(h); }
@@ -156,6 +163,7 @@ void* orc_sparse_setup(int n, int p, int m,
     M->AT = Csc::from(n, p, ATp, ATi, ATx);
     M->GT = Csc::from(n, m, GTp, GTi, GTx);
     if (kkt_perm) M->user_perm.assign(kkt_perm, kkt_perm + n + p + m);
+    M->kkt_solver_hint = H->ip.st.kkt_solver;
     if (ext) { H->vt = *ext; M->backend_factory = make_foreign_sparse; M->backend_factory_arg = &H->vt; }
     H->ip.pre.identity = identity_precond != 0;
     H->ip.d.resize(n, p, m);
@@ -211,6 +219,22 @@ void orc_dense_get_scaled(void* h, double* P, double* AT, double* GT) {
     if (P) std::copy(M->P.begin(), M->P.end(), P);
     if (AT) std::copy(M->AT.begin(), M->AT.end(), AT);
     if (GT) std::copy(M->GT.begin(), M->GT.end(), GT);
+}
+// scaled sparse data as the backend sees it: values of P_utri / AT / GT in CSC order (patterns: orc_sparse_get_pattern)
+void orc_sparse_get_scaled(void* h, double* Px, double* ATx, double* GTx) {
+    auto* H = static_cast<Handle*>(h); auto* M = static_cast<SparseMatrices*>(H->ip.M.get());
+    if (Px) std::copy(M->P.x.begin(), M->P.x.end(), Px);
+    if (ATx) std::copy(M->AT.x.begin(), M->AT.x.end(), ATx);
+    if (GTx) std::copy(M->GT.x.begin(), M->GT.x.end(), GTx);
+}
+void orc_sparse_get_nnz(void* h, int* out) {
+    auto* H = static_cast<Handle*>(h); auto* M = static_cast<SparseMatrices*>(H->ip.M.get());
+    out[0] = M->P.nnz(); out[1] = M->AT.nnz(); out[2] = M->GT.nnz();
+}
+void orc_sparse_get_pattern(void* h, int which, int* colptr, int* rowidx) {
+    auto* H = static_cast<Handle*>(h); auto* M = static_cast<SparseMatrices*>(H->ip.M.get());
+    const Csc& A = which == 0 ? M->P : (which == 1 ? M->AT : M->GT);
+    std::copy(A.p.begin(), A.p.end(), colptr); std::copy(A.i.begin(), A.i.end(), rowidx);
 }
 void orc_get_scaled_vectors(void* h, double* c, double* b, double* h_l, double* h_u, double* x_l, double* x_u, double* x_b_scaling,
                             double* delta, double* delta_b, double* c_scale) {

@@ -154,6 +154,7 @@ struct SparseMatrices : QPMatrices {
     int n = 0, p = 0, m = 0;
     Csc P, AT, GT;  // P: upper triangle CSC; AT: n x p; GT: n x m
     IVec user_perm; // optional KKT ordering supplied by the caller (size n+p+m)
+    int kkt_solver_hint = 1;   // Settings::kkt_solver at setup (lets a foreign backend factory pick its constructor)
     std::unique_ptr<KKTBackend> (*backend_factory)(const SparseMatrices&, void*) = nullptr;
     void* backend_factory_arg = nullptr;
 

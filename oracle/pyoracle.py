@@ -66,7 +66,7 @@ class BackendVTable(C.Structure):
     """Function-pointer table with the shape of the product's C-ABI (include/piqp_b200.h)."""
     _fields_ = [(name, C.c_void_p) for name in
                 ("create_dense", "create_sparse", "update_data", "factor", "solve",
-                 "eval_P_x", "eval_A", "eval_G", "destroy")]
+                 "eval_P_x", "eval_A", "eval_G", "destroy", "create_multistage")]
 
 
 STATUS = {1: "solved", -1: "max_iter_reached", -2: "primal_infeasible", -3: "dual_infeasible",
@@ -344,6 +344,21 @@ class SparseSolver(_Base):
                                            _ip(GTp), _ip(GTi), _dp(GTx), _dp(v[2]), _dp(v[3]), _dp(v[4]), _dp(v[5]),
                                            C.byref(self.settings), int(self.identity),
                                            C.byref(self.vt) if self.vt is not None else None, _ip(perm))
+
+    def scaled_matrices(self):
+        """(P_utri, AT, GT) as scipy CSC matrices with the Ruiz-scaled values the backend works on"""
+        import scipy.sparse as sp
+        n, p, m = self.dims[:3]
+        nnz = (C.c_int * 3)()
+        self._L.orc_sparse_get_nnz(C.c_void_p(self._h), nnz)
+        vals = [np.zeros(nnz[k]) for k in range(3)]
+        self._L.orc_sparse_get_scaled(C.c_void_p(self._h), _dp(vals[0]), _dp(vals[1]), _dp(vals[2]))
+        out = []
+        for k, (r, c_) in enumerate(((n, n), (n, p), (n, m))):
+            cp = np.zeros(c_ + 1, dtype=np.int32); ri = np.zeros(max(nnz[k], 1), dtype=np.int32)
+            self._L.orc_sparse_get_pattern(C.c_void_p(self._h), k, _ip(cp), _ip(ri))
+            out.append(sp.csc_matrix((vals[k], ri[:nnz[k]], cp), shape=(r, c_)))
+        return out
 
     def multistage_blocks(self):
         buf = (C.c_int * 30000)()

@@ -112,6 +112,48 @@ class DenseKKT(KKTSolverBase):
         return Lf if factor else K
 
 
+def _csc_arrays(M, upper=False):
+    import scipy.sparse as sp
+    M = sp.csc_matrix(M)
+    if upper:
+        M = sp.triu(M, format="csc")
+    M.sort_indices()
+    return (np.ascontiguousarray(M.indptr, dtype=np.int32), np.ascontiguousarray(M.indices, dtype=np.int32),
+            np.ascontiguousarray(M.data, dtype=np.float64))
+
+
+class MultistageKKT(KKTSolverBase):
+    """Twin of piqp::sparse::MultistageKKT<T, I> (include/piqp/sparse/multistage_kkt.hpp:41-1816).
+
+    P_utri: (n, n) sparse, upper triangle; AT: (n, p) sparse; GT: (n, m) sparse -- the members of sparse::Data.
+    """
+
+    def __init__(self, P_utri, AT=None, GT=None, device=0):
+        import scipy.sparse as sp
+        super().__init__()
+        self.n = P_utri.shape[0]
+        AT = sp.csc_matrix((self.n, 0)) if AT is None else AT
+        GT = sp.csc_matrix((self.n, 0)) if GT is None else GT
+        self.p, self.m = AT.shape[1], GT.shape[1]
+        self._P = _csc_arrays(P_utri, upper=True); self._A = _csc_arrays(AT); self._G = _csc_arrays(GT)
+        ipp = lambda a: a.ctypes.data_as(ip)
+        _lib.check(self._L.b200kkt_multistage_create(C.byref(self._h), self.n, self.p, self.m, ipp(self._P[0]), ipp(self._P[1]), _p(self._P[2]),
+                                                     ipp(self._A[0]), ipp(self._A[1]), _p(self._A[2]), ipp(self._G[0]), ipp(self._G[1]), _p(self._G[2]), device),
+                   "b200kkt_multistage_create")
+
+    def update_data(self, options, P_utri=None, AT=None, GT=None):
+        P = None if P_utri is None else _csc_arrays(P_utri, upper=True)[2]
+        A = None if AT is None else _csc_arrays(AT)[2]
+        G = None if GT is None else _csc_arrays(GT)[2]
+        _lib.check(self._L.b200kkt_update_data(self._h, int(options), None if P is None else _p(P), None if A is None else _p(A),
+                                               None if G is None else _p(G)), "b200kkt_update_data")
+
+    def block_info(self):
+        buf = (C.c_int * 30000)()
+        k = _lib.check(self._L.b200kkt_multistage_blocks(self._h, buf, 30000), "b200kkt_multistage_blocks")
+        return [(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]) for i in range(k)]
+
+
 def c_abi_vtable():
     """Function-pointer table of the C-ABI in the layout oracle/oracle_capi.cpp::OrcBackendVTable expects
     (used by tests to put the CUDA backend behind the oracle's KKTSystem + IP loop)."""
@@ -125,4 +167,5 @@ def c_abi_vtable():
         "update_data": addr("b200kkt_update_data"), "factor": addr("b200kkt_factor"), "solve": addr("b200kkt_solve"),
         "eval_P_x": addr("b200kkt_eval_P_x"), "eval_A": addr("b200kkt_eval_A_xn_and_AT_xt"),
         "eval_G": addr("b200kkt_eval_G_xn_and_GT_xt"), "destroy": addr("b200kkt_destroy"),
+        "create_multistage": addr("b200kkt_multistage_create"),
     }

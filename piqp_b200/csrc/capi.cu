@@ -2,6 +2,8 @@
 #include "../../include/piqp_b200.h"
 #include "dense_backend.hpp"
 #include "ip_solver.hpp"
+#include "multistage_backend.hpp"
+#include "sparse_data.hpp"
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +29,8 @@ struct b200kkt_handle {
     cudaStream_t stream = nullptr;
     DenseData dd;
     std::unique_ptr<DenseBatchedKKT> dense;
+    SparseData sd;
+    std::unique_ptr<MultistageBatchedKKT> ms;
     BatchedKKT* be = nullptr;
     // staging
     DevBuf<double> stage_mat;   // raw matrix upload
@@ -99,17 +103,45 @@ int b200kkt_sparse_create(b200kkt_handle** out, int, int, int, const int*, const
     if (out) *out = nullptr;
     return fail(B200_E_UNSUPPORTED, "b200kkt_sparse_create: sparse backend not built yet");
 }
-int b200kkt_multistage_create(b200kkt_handle** out, int, int, int, const int*, const int*, const double*, const int*, const int*, const double*,
-                              const int*, const int*, const double*, int) {
-    if (out) *out = nullptr;
-    return fail(B200_E_UNSUPPORTED, "b200kkt_multistage_create: multistage backend not built yet");
+int b200kkt_multistage_create(b200kkt_handle** out, int n, int p, int m, const int* Pp, const int* Pi, const double* Px,
+                              const int* ATp, const int* ATi, const double* ATx, const int* GTp, const int* GTi, const double* GTx, int device) {
+    if (!out || n <= 0 || p < 0 || m < 0 || !Pp || (p > 0 && !ATp) || (m > 0 && !GTp)) return fail(B200_E_INVALID, "b200kkt_multistage_create: bad arguments");
+    B200_TRY(
+        B200_CUDA(cudaSetDevice(device));
+        auto h = std::make_unique<b200kkt_handle>();
+        h->kind = 1; h->device = device; h->n = n; h->p = p; h->m = m;
+        B200_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        SparseData& S = h->sd;
+        S.n = n; S.p = p; S.m = m;
+        S.P.build(n, n, Pp, Pi);
+        S.AT.build(n, p, ATp, ATi);
+        S.GT.build(n, m, GTp, GTi);
+        S.alloc_values(1);
+        if (S.P.nnz) B200_CUDA(cudaMemcpy(S.Px.get(), Px, sizeof(double) * S.P.nnz, cudaMemcpyHostToDevice));
+        if (S.AT.nnz) B200_CUDA(cudaMemcpy(S.ATx.get(), ATx, sizeof(double) * S.AT.nnz, cudaMemcpyHostToDevice));
+        if (S.GT.nnz) B200_CUDA(cudaMemcpy(S.GTx.get(), GTx, sizeof(double) * S.GT.nnz, cudaMemcpyHostToDevice));
+        for (int i = 0; i < 4; i++) { h->vx[i].alloc(std::max(n, 1)); h->vy[i].alloc(std::max(p, 1)); h->vz[i].alloc(std::max(m, 1)); }
+        h->delta.alloc(1); h->ok.alloc(1);
+        B200_CUDA(cudaDeviceSynchronize());
+        h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream);
+        h->be = h->ms.get();
+        B200_CUDA(cudaStreamSynchronize(h->stream));
+        *out = h.release();
+    )
+    return B200_OK;
 }
 
 int b200kkt_update_data(b200kkt_handle* h, int options, const double* P, const double* AT, const double* GT) {
     if (!h) return fail(B200_E_INVALID, "null handle");
     B200_TRY(
         B200_CUDA(cudaSetDevice(h->device));
-        dense_single_upload(h, options, P, AT, GT);
+        if (h->kind == 0) dense_single_upload(h, options, P, AT, GT);
+        else {
+            SparseData& S = h->sd;
+            if ((options & B200_KKT_UPDATE_P) && S.P.nnz) B200_CUDA(cudaMemcpyAsync(S.Px.get(), P, sizeof(double) * S.P.nnz, cudaMemcpyHostToDevice, h->stream));
+            if ((options & B200_KKT_UPDATE_A) && S.AT.nnz) B200_CUDA(cudaMemcpyAsync(S.ATx.get(), AT, sizeof(double) * S.AT.nnz, cudaMemcpyHostToDevice, h->stream));
+            if ((options & B200_KKT_UPDATE_G) && S.GT.nnz) B200_CUDA(cudaMemcpyAsync(S.GTx.get(), GT, sizeof(double) * S.GT.nnz, cudaMemcpyHostToDevice, h->stream));
+        }
         h->be->update_data(options);
         B200_CUDA(cudaStreamSynchronize(h->stream));
     )
@@ -182,8 +214,25 @@ b200kkt_handle* b200kkt_clone(const b200kkt_handle* src) {
     try {
         B200_CUDA(cudaSetDevice(src->device));
         auto h = std::make_unique<b200kkt_handle>();
-        h->device = src->device; h->n = src->n; h->p = src->p; h->m = src->m;
+        h->device = src->device; h->n = src->n; h->p = src->p; h->m = src->m; h->kind = src->kind;
         B200_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        if (src->kind != 0) {
+            const SparseData& O = src->sd; SparseData& S = h->sd;
+            S.n = O.n; S.p = O.p; S.m = O.m;
+            S.P.build(O.P.rows, O.P.cols, O.P.p.data(), O.P.i.data()); S.AT.build(O.AT.rows, O.AT.cols, O.AT.p.data(), O.AT.i.data());
+            S.GT.build(O.GT.rows, O.GT.cols, O.GT.p.data(), O.GT.i.data());
+            S.alloc_values(1);
+            auto cpv = [&](DevBuf<double>& d, const DevBuf<double>& s) { if (s.n) B200_CUDA(cudaMemcpy(d.get(), s.get(), s.n * sizeof(double), cudaMemcpyDeviceToDevice)); };
+            cpv(S.Px, O.Px); cpv(S.ATx, O.ATx); cpv(S.GTx, O.GTx);
+            for (int i = 0; i < 4; i++) { h->vx[i].alloc(std::max(h->n, 1)); h->vy[i].alloc(std::max(h->p, 1)); h->vz[i].alloc(std::max(h->m, 1)); }
+            h->delta.alloc(1); h->ok.alloc(1);
+            B200_CUDA(cudaDeviceSynchronize());
+            h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream);
+            h->ms->copy_from(*src->ms);
+            h->be = h->ms.get();
+            B200_CUDA(cudaStreamSynchronize(h->stream));
+            return h.release();
+        }
         h->dd.alloc(1, h->n, h->p, h->m);
         B200_CUDA(cudaDeviceSynchronize());
         auto cp = [&](DevBuf<double>& d, const DevBuf<double>& s) { if (s.n) B200_CUDA(cudaMemcpyAsync(d.get(), s.get(), s.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream)); };
@@ -231,14 +280,21 @@ struct b200qp_handle {
     int device = 0, batch = 0, n = 0, p = 0, m = 0;
     cudaStream_t stream = nullptr;
     b200qp_settings st{};
+    int kind = 0;   // 0 dense, 1 sparse pattern + multistage backend
     DenseData dd;
+    SparseData sd;
+    std::vector<int> A_map, G_map, P_map;    // internal value index -> index in the caller's CSC value arrays
+    DevBuf<int> d_A_map, d_G_map, d_P_map;
+    int nnzP_in = 0, nnzA_in = 0, nnzG_in = 0;
     RuizState ruiz;
     std::unique_ptr<DenseBatchedKKT> dense;
+    std::unique_ptr<MultistageBatchedKKT> ms;
+    BatchedKKT* be = nullptr;
     std::unique_ptr<BatchedIPSolver> ip;
     DevBuf<int> zero_rows;
     bool solved = false;
     double setup_ms = 0, update_ms = 0;
-    ~b200qp_handle() { ip.reset(); dense.reset(); if (stream) cudaStreamDestroy(stream); }
+    ~b200qp_handle() { ip.reset(); dense.reset(); ms.reset(); if (stream) cudaStreamDestroy(stream); }
 };
 
 namespace {
@@ -377,7 +433,8 @@ int b200qp_setup_dense(b200qp_handle** out, int batch, int n, int p, int m, cons
         d.pd = h->ruiz.delta.get(); d.pd_inv = h->ruiz.delta_inv.get(); d.pdb = h->ruiz.delta_b.get(); d.pdb_inv = h->ruiz.delta_b_inv.get();
         d.pc = h->ruiz.c.get(); d.pc_inv = h->ruiz.c_inv.get();
         h->dense = std::make_unique<DenseBatchedKKT>(&h->dd, h->stream);
-        h->ip->finish_setup(h->dense.get());
+        h->be = h->dense.get();
+        h->ip->finish_setup(h->be);
         B200_CUDA(cudaEventRecord(e1, h->stream));
         B200_CUDA(cudaEventSynchronize(e1));
         float ms = 0; B200_CUDA(cudaEventElapsedTime(&ms, e0, e1)); h->setup_ms = ms;
@@ -390,6 +447,7 @@ int b200qp_setup_dense(b200qp_handle** out, int batch, int n, int p, int m, cons
 int b200qp_update_dense(b200qp_handle* h, const double* P, const double* c, const double* A, const double* b, const double* G,
                         const double* h_l, const double* h_u, const double* x_l, const double* x_u, int on_device) {
     if (!h) return fail(B200_E_INVALID, "null handle");
+    if (h->kind != 0) return fail(B200_E_INVALID, "b200qp_update_dense on a sparse handle");
     B200_TRY(
         B200_CUDA(cudaSetDevice(h->device));
         IpDev& d = h->ip->dev();
@@ -411,6 +469,147 @@ int b200qp_update_dense(b200qp_handle* h, const double* P, const double* c, cons
     return B200_OK;
 }
 
+namespace {
+__global__ void k_gather_vals(const double* src, long long src_stride, const int* map, int nnz, double* dst) {
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nnz) dst[(size_t)b * nnz + q] = src[(size_t)b * src_stride + map[q]];
+}
+// CSC of M (rows x cols) -> CSC of M^T with the map "entry of M^T -> entry of M"
+void transpose_pattern(int rows, int cols, const int* cp, const int* ri, std::vector<int>& tp, std::vector<int>& ti, std::vector<int>& map) {
+    const int nnz = cp ? cp[cols] : 0;
+    tp.assign(rows + 1, 0); ti.assign(nnz, 0); map.assign(nnz, 0);
+    for (int q = 0; q < nnz; q++) tp[ri[q] + 1]++;
+    for (int r = 0; r < rows; r++) tp[r + 1] += tp[r];
+    std::vector<int> w(tp.begin(), tp.end() - 1);
+    for (int j = 0; j < cols; j++) for (int q = cp[j]; q < cp[j + 1]; q++) { const int t = w[ri[q]]++; ti[t] = j; map[t] = q; }
+}
+void gather_values(b200qp_handle* h, const double* src, int nnz_in, const DevBuf<int>& map, int nnz, double* dst, int on_device) {
+    if (!src || nnz == 0) return;
+    Staged s;
+    const double* dsrc = s.get(src, (size_t)h->batch * nnz_in, on_device, h->stream);
+    dim3 g(ceil_div(nnz, 256), h->batch);
+    B200_LAUNCH(k_gather_vals, g, 256, 0, h->stream, dsrc, (long long)nnz_in, map.get(), nnz, dst);
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+}
+void load_vectors_and_bounds(b200qp_handle* h, bool first, const double* c, const double* b, const double* h_l, const double* h_u,
+                             const double* x_l, const double* x_u, int on_device) {
+    const int B = h->batch, n = h->n, p = h->p, m = h->m;
+    cudaStream_t st = h->stream;
+    IpDev& d = h->ip->dev();
+    copy_vec(d.c, c, (size_t)B * n, on_device, st);
+    copy_vec(d.b, b, (size_t)B * p, on_device, st);
+    Staged s1, s2, s3, s4;
+    const double* dhl = s1.get(h_l, (size_t)B * m, on_device, st);
+    const double* dhu = s2.get(h_u, (size_t)B * m, on_device, st);
+    const double* dxl = s3.get(x_l, (size_t)B * n, on_device, st);
+    const double* dxu = s4.get(x_u, (size_t)B * n, on_device, st);
+    const int set_hl = first || h_l, set_hu = first || h_u, set_xl = first || x_l, set_xu = first || x_u;
+    const int len = std::max(1, std::max(n, m));
+    dim3 grid(ceil_div(len, 256), B);
+    B200_LAUNCH(k_setup_bounds, grid, 256, 0, st, d, dhl, dhu, dxl, dxu, set_hl, set_hu, set_xl, set_xu, h->zero_rows.get());
+    if (m > 0 && (set_hl || set_hu)) sparse_zero_G_rows(h->sd, h->zero_rows.get(), st);
+    B200_CUDA(cudaStreamSynchronize(st));
+}
+}  // namespace
+
+int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
+                        const int* Pp, const int* Pi, const double* Px, const double* c,
+                        const int* Ap, const int* Ai, const double* Ax, const double* b,
+                        const int* Gp, const int* Gi, const double* Gx, const double* h_l, const double* h_u,
+                        const double* x_l, const double* x_u, const b200qp_settings* settings, int device, int on_device) {
+    if (!out || batch <= 0 || n <= 0 || p < 0 || m < 0 || !Pp || !c) return fail(B200_E_INVALID, "b200qp_setup_sparse: bad arguments");
+    if ((p > 0 && (!Ap || !b)) || (m > 0 && (!Gp || (!h_l && !h_u)))) return fail(B200_E_INVALID, "b200qp_setup_sparse: missing constraint data");
+    B200_TRY(
+        B200_CUDA(cudaSetDevice(device));
+        auto h = std::make_unique<b200qp_handle>();
+        h->kind = 1; h->device = device; h->batch = batch; h->n = n; h->p = p; h->m = m;
+        if (settings) h->st = *settings; else b200qp_set_default_settings_sparse(&h->st);
+        if (h->st.kkt_solver != 5) throw std::runtime_error("b200qp_setup_sparse: only kkt_solver = sparse_multistage (5) is built in this round");
+        B200_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        cudaEvent_t e0, e1;
+        B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
+        // patterns: P -> upper triangle (solver.hpp:182), A / G -> transposes (solver.hpp:183-184)
+        std::vector<int> up, ui;
+        up.assign(n + 1, 0);
+        for (int j = 0; j < n; j++) { for (int q = Pp[j]; q < Pp[j + 1]; q++) if (Pi[q] <= j) { ui.push_back(Pi[q]); h->P_map.push_back(q); } up[j + 1] = (int)ui.size(); }
+        h->nnzP_in = Pp[n]; h->nnzA_in = p > 0 ? Ap[n] : 0; h->nnzG_in = m > 0 ? Gp[n] : 0;
+        SparseData& S = h->sd;
+        S.n = n; S.p = p; S.m = m;
+        S.P.build(n, n, up.data(), ui.data());
+        std::vector<int> tp, ti;
+        transpose_pattern(p, n, p > 0 ? Ap : nullptr, Ai, tp, ti, h->A_map);
+        if (p == 0) tp.assign(1, 0);
+        S.AT.build(n, p, tp.data(), ti.data());
+        transpose_pattern(m, n, m > 0 ? Gp : nullptr, Gi, tp, ti, h->G_map);
+        if (m == 0) tp.assign(1, 0);
+        S.GT.build(n, m, tp.data(), ti.data());
+        S.alloc_values(batch);
+        auto upm = [](DevBuf<int>& d, const std::vector<int>& v) { d.alloc(std::max<size_t>(v.size(), 1)); if (!v.empty()) B200_CUDA(cudaMemcpy(d.get(), v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice)); };
+        upm(h->d_P_map, h->P_map); upm(h->d_A_map, h->A_map); upm(h->d_G_map, h->G_map);
+        B200_CUDA(cudaDeviceSynchronize());
+        B200_CUDA(cudaEventRecord(e0, h->stream));
+        h->ip = std::make_unique<BatchedIPSolver>(batch, n, p, m, h->st, h->stream);
+        h->ruiz.alloc(batch, n, p, m);
+        h->zero_rows.alloc(std::max<size_t>((size_t)batch * m, 1)); h->zero_rows.zero(h->stream);
+        IpDev& d = h->ip->dev();
+        fill_d(d.xbs, (size_t)batch * n, 1.0, h->stream);
+        gather_values(h.get(), Px, h->nnzP_in, h->d_P_map, S.P.nnz, S.Px.get(), on_device);
+        gather_values(h.get(), Ax, h->nnzA_in, h->d_A_map, S.AT.nnz, S.ATx.get(), on_device);
+        gather_values(h.get(), Gx, h->nnzG_in, h->d_G_map, S.GT.nnz, S.GTx.get(), on_device);
+        load_vectors_and_bounds(h.get(), true, c, b, h_l, h_u, x_l, x_u, on_device);
+        sparse_ruiz_scale(S, h->ruiz, d.c, d.b, d.h_l, d.h_u, d.x_l, d.x_u, d.xbs, false, h->st.preconditioner_scale_cost != 0, h->st.preconditioner_iter, h->stream);
+        d.pd = h->ruiz.delta.get(); d.pd_inv = h->ruiz.delta_inv.get(); d.pdb = h->ruiz.delta_b.get(); d.pdb_inv = h->ruiz.delta_b_inv.get();
+        d.pc = h->ruiz.c.get(); d.pc_inv = h->ruiz.c_inv.get();
+        h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream);
+        h->be = h->ms.get();
+        h->ip->finish_setup(h->be);
+        B200_CUDA(cudaEventRecord(e1, h->stream));
+        B200_CUDA(cudaEventSynchronize(e1));
+        float ms_ = 0; B200_CUDA(cudaEventElapsedTime(&ms_, e0, e1)); h->setup_ms = ms_;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        *out = h.release();
+    )
+    return B200_OK;
+}
+
+int b200qp_update_sparse(b200qp_handle* h, const double* Px, const double* c, const double* Ax, const double* b, const double* Gx,
+                         const double* h_l, const double* h_u, const double* x_l, const double* x_u, int on_device) {
+    if (!h) return fail(B200_E_INVALID, "null handle");
+    if (h->kind != 1) return fail(B200_E_INVALID, "b200qp_update_sparse on a dense handle");
+    B200_TRY(
+        B200_CUDA(cudaSetDevice(h->device));
+        IpDev& d = h->ip->dev();
+        SparseData& S = h->sd;
+        sparse_ruiz_unscale(S, h->ruiz, d.c, d.b, d.h_l, d.h_u, d.x_l, d.x_u, d.xbs, h->stream);
+        int options = 0;
+        if (Px) { options |= B200_KKT_UPDATE_P; gather_values(h, Px, h->nnzP_in, h->d_P_map, S.P.nnz, S.Px.get(), on_device); }
+        if (Ax) { options |= B200_KKT_UPDATE_A; gather_values(h, Ax, h->nnzA_in, h->d_A_map, S.AT.nnz, S.ATx.get(), on_device); }
+        if (Gx) { options |= B200_KKT_UPDATE_G; gather_values(h, Gx, h->nnzG_in, h->d_G_map, S.GT.nnz, S.GTx.get(), on_device); }
+        load_vectors_and_bounds(h, false, c, b, h_l, h_u, x_l, x_u, on_device);
+        bool reuse = h->st.preconditioner_reuse_on_update != 0;
+        if (options == 0) reuse = true;
+        sparse_ruiz_scale(S, h->ruiz, d.c, d.b, d.h_l, d.h_u, d.x_l, d.x_u, d.xbs, reuse, h->st.preconditioner_scale_cost != 0, h->st.preconditioner_iter, h->stream);
+        h->be->update_data(options);
+        h->ip->finish_setup(h->be);
+        B200_CUDA(cudaStreamSynchronize(h->stream));
+    )
+    return B200_OK;
+}
+
+int b200qp_multistage_blocks(b200qp_handle* h, int* out, int cap) {
+    if (!h || !h->ms) return fail(B200_E_INVALID, "not a multistage handle");
+    int k = 0;
+    for (const auto& bl : h->ms->S.bi) { if (3 * k + 2 < cap) { out[3 * k] = bl.start; out[3 * k + 1] = bl.diag; out[3 * k + 2] = bl.off; } k++; }
+    return k;
+}
+int b200kkt_multistage_blocks(b200kkt_handle* h, int* out, int cap) {
+    if (!h || !h->ms) return fail(B200_E_INVALID, "not a multistage handle");
+    int k = 0;
+    for (const auto& bl : h->ms->S.bi) { if (3 * k + 2 < cap) { out[3 * k] = bl.start; out[3 * k + 1] = bl.diag; out[3 * k + 2] = bl.off; } k++; }
+    return k;
+}
+
 int b200qp_update_settings(b200qp_handle* h, const b200qp_settings* s) {
     if (!h || !s) return fail(B200_E_INVALID, "null argument");
     h->st = *s; h->ip->set_settings(*s);
@@ -421,7 +620,7 @@ int b200qp_solve(b200qp_handle* h) {
     if (!h) return fail(B200_E_INVALID, "null handle");
     B200_TRY(
         B200_CUDA(cudaSetDevice(h->device));
-        h->dense->reset_profile();
+        h->be->reset_profile();
         h->ip->solve();
         h->solved = true;
     )
@@ -459,7 +658,7 @@ int b200qp_get_stats(b200qp_handle* h, b200qp_stats* stats) {
     if (!h || !stats) return fail(B200_E_INVALID, "null argument");
     B200_TRY(
         h->ip->infos(); *stats = h->ip->stats();
-        BatchedKKT* be = h->dense.get();
+        BatchedKKT* be = h->be;
         be->collect();
         stats->assemble_ms = be->prof_ms[BatchedKKT::T_ASSEMBLE]; stats->assemble_launches = be->prof_calls[BatchedKKT::T_ASSEMBLE];
         stats->cholesky_ms = be->prof_ms[BatchedKKT::T_FACTOR]; stats->cholesky_calls = be->prof_calls[BatchedKKT::T_FACTOR];
@@ -469,8 +668,8 @@ int b200qp_get_stats(b200qp_handle* h, b200qp_stats* stats) {
 }
 int b200qp_set_profiling(b200qp_handle* h, int enable) {
     if (!h) return fail(B200_E_INVALID, "null handle");
-    h->dense->collect();
-    h->dense->profile = enable != 0;
+    h->be->collect();
+    h->be->profile = enable != 0;
     return B200_OK;
 }
 int b200qp_get_trace(b200qp_handle* h, int b, double* rows, int max_rows) {
@@ -497,9 +696,9 @@ int b200qp_bench_factor_solve(b200qp_handle* h, int reps, int nsolve, double* fa
         double tf = 0, ts = 0;
         for (int r = 0; r < reps; r++) {
             B200_CUDA(cudaEventRecord(e[0], h->stream));
-            h->dense->factor(d.delta_reg, d.x_reg, d.z_reg_ir, nullptr, d.ok);
+            h->be->factor(d.delta_reg, d.x_reg, d.z_reg_ir, nullptr, d.ok);
             B200_CUDA(cudaEventRecord(e[1], h->stream));
-            for (int s = 0; s < nsolve; s++) h->dense->solve(d.rhs_x_bar, d.r.y, d.rhs_z_bar, d.ref_x, d.ref_y, d.ref_z, nullptr);
+            for (int s = 0; s < nsolve; s++) h->be->solve(d.rhs_x_bar, d.r.y, d.rhs_z_bar, d.ref_x, d.ref_y, d.ref_z, nullptr);
             B200_CUDA(cudaEventRecord(e[2], h->stream));
             B200_CUDA(cudaEventSynchronize(e[2]));
             float a, b2;

@@ -94,7 +94,7 @@ __global__ void fill_kernel(double* p, size_t n, double v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-static void fill(double* p, size_t n, double v, cudaStream_t st) {
+void fill_async(double* p, size_t n, double v, cudaStream_t st) {
     if (n) B200_LAUNCH(fill_kernel, (unsigned)((n + 255) / 256), 256, 0, st, p, n, v);
 }
 
@@ -239,6 +239,33 @@ __global__ void ruiz_vectors_kernel(double* c, double* bvec, double* h_l, double
     }
 }
 
+void ruiz_launch_begin(RuizState& R, cudaStream_t st) {
+    const int N = R.n + R.p + R.m;
+    B200_LAUNCH(ruiz_begin_kernel, R.batch, 256, 0, st, R.it.get(), R.itb.get(), N, R.n, R.done.get(), 1e-3);
+}
+void ruiz_launch_finalize(RuizState& R, double* c, double* xbs, cudaStream_t st) {
+    const int N = R.n + R.p + R.m;
+    dim3 gridN(ceil_div(std::max(1, std::max(N, R.n)), 256), R.batch);
+    B200_LAUNCH(ruiz_finalize_kernel, gridN, 256, 0, st, R.it.get(), R.itb.get(), N, R.n, c, xbs, R.delta.get(), R.delta_b.get(), R.done.get());
+}
+void ruiz_launch_inverse(RuizState& R, cudaStream_t st) {
+    const int N = R.n + R.p + R.m;
+    dim3 gridN(ceil_div(std::max(1, std::max(N, R.n)), 256), R.batch);
+    B200_LAUNCH(ruiz_inverse_kernel, gridN, 256, 0, st, R.delta.get(), R.delta_b.get(), R.c.get(), R.delta_inv.get(), R.delta_b_inv.get(), R.c_inv.get(), N, R.n);
+}
+void ruiz_launch_vectors(RuizState& R, double* c, double* b, double* h_l, double* h_u, double* x_l, double* x_u, double* xbs,
+                         const double* d, const double* db, const double* cs, int scale_c_and_xbs, cudaStream_t st) {
+    const int N = R.n + R.p + R.m;
+    dim3 gridN(ceil_div(std::max(1, std::max(N, R.n)), 256), R.batch);
+    B200_LAUNCH(ruiz_vectors_kernel, gridN, 256, 0, st, c, b, h_l, h_u, x_l, x_u, xbs, d, db, cs, R.n, R.p, R.m, N, scale_c_and_xbs);
+}
+void ruiz_reset(RuizState& R, cudaStream_t st) {
+    const size_t N = (size_t)R.n + R.p + R.m, B = R.batch;
+    fill_async(R.c.get(), B, 1.0, st); fill_async(R.delta.get(), B * N, 1.0, st); fill_async(R.delta_b.get(), B * R.n, 1.0, st);
+    fill_async(R.it.get(), B * N, 0.0, st); fill_async(R.itb.get(), B * R.n, 0.0, st);
+    B200_CUDA(cudaMemsetAsync(R.done.get(), 0, sizeof(int) * B, st));
+}
+
 void dense_ruiz_scale(DenseData& D, RuizState& R, double* c, double* b, double* h_l, double* h_u, double* x_l, double* x_u,
                       double* xbs, bool reuse_prev, bool scale_cost, int max_iter, cudaStream_t st) {
     const int n = D.n, p = D.p, m = D.m, N = n + p + m, B = D.batch;
@@ -246,8 +273,8 @@ void dense_ruiz_scale(DenseData& D, RuizState& R, double* c, double* b, double* 
     dim3 gridN(ceil_div(maxd, 256), B);
     dim3 gridMat(ceil_div(std::max(n, 1), 128), N, B);
     if (!reuse_prev) {
-        fill(R.c.get(), B, 1.0, st); fill(R.delta.get(), (size_t)B * N, 1.0, st); fill(R.delta_b.get(), (size_t)B * n, 1.0, st);
-        fill(R.it.get(), (size_t)B * N, 0.0, st); fill(R.itb.get(), (size_t)B * n, 0.0, st);
+        fill_async(R.c.get(), B, 1.0, st); fill_async(R.delta.get(), (size_t)B * N, 1.0, st); fill_async(R.delta_b.get(), (size_t)B * n, 1.0, st);
+        fill_async(R.it.get(), (size_t)B * N, 0.0, st); fill_async(R.itb.get(), (size_t)B * n, 0.0, st);
         B200_CUDA(cudaMemsetAsync(R.done.get(), 0, sizeof(int) * B, st));
         for (int iter = 0; iter < max_iter; iter++) {
             B200_LAUNCH(ruiz_begin_kernel, B, 256, 0, st, R.it.get(), R.itb.get(), N, n, R.done.get(), 1e-3);

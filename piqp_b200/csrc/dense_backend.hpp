@@ -32,7 +32,14 @@ struct RuizState {
     DevBuf<int> done;                                                  // [batch] converged flag
     void alloc(int batch_, int n_, int p_, int m_);
 };
-struct BoundVectors;  // ip_solver.hpp
+// generic pieces of the equilibration shared by the dense and the sparse data layer
+void fill_async(double* p, size_t n, double v, cudaStream_t st);
+void ruiz_reset(RuizState& R, cudaStream_t st);
+void ruiz_launch_begin(RuizState& R, cudaStream_t st);                                   // convergence test of the sweep
+void ruiz_launch_finalize(RuizState& R, double* c, double* xbs, cudaStream_t st);        // limit, 1/sqrt, fold into delta / c / x_b_scaling
+void ruiz_launch_inverse(RuizState& R, cudaStream_t st);
+void ruiz_launch_vectors(RuizState& R, double* c, double* b, double* h_l, double* h_u, double* x_l, double* x_u, double* xbs,
+                         const double* d, const double* db, const double* cs, int scale_c_and_xbs, cudaStream_t st);
 void dense_ruiz_scale(DenseData& D, RuizState& R, double* c, double* b, double* h_l, double* h_u, double* x_l, double* x_u,
                       double* x_b_scaling, bool reuse_prev, bool scale_cost, int max_iter, cudaStream_t st);
 void dense_ruiz_unscale(DenseData& D, RuizState& R, double* c, double* b, double* h_l, double* h_u, double* x_l, double* x_u,

@@ -1,0 +1,499 @@
+// piqp_b200/csrc/multistage_backend.cu -- see multistage_backend.hpp
+#include "multistage_backend.hpp"
+#include <algorithm>
+#include <cstdio>
+#include <stdexcept>
+
+namespace b200 {
+
+// =====================================================================================================
+// host: structure detection (multistage_kkt.hpp:420-597) and index maps
+// =====================================================================================================
+namespace {
+typedef unsigned long long u64;
+inline u64 fl_gemm(u64 m, u64 n, u64 k) { return 2 * m * n * k; }   // :397-418
+inline u64 fl_trsm(u64 m, u64 n) { return m * m * n; }
+inline u64 fl_syrk(u64 n, u64 k) { return n * n * k; }
+inline u64 fl_potrf(u64 n) { return n * n * n / 3; }
+}  // namespace
+
+bool MsStructure::detect(const Pattern& P, const Pattern& AT, const Pattern& GT) {
+    n = P.rows;
+    // structural upper pattern of C = P + I + A^T A + G^T G, row by row (sorted, unique)
+    std::vector<std::vector<int>> up(n);
+    for (int j = 0; j < n; j++) for (int q = P.p[j]; q < P.p[j + 1]; q++) if (P.i[q] <= j) up[P.i[q]].push_back(j);
+    for (int i = 0; i < n; i++) up[i].push_back(i);
+    for (const Pattern* M : {&AT, &GT})
+        for (int r = 0; r < M->cols; r++)
+            for (int a = M->p[r]; a < M->p[r + 1]; a++)
+                for (int b = a; b < M->p[r + 1]; b++) { const int lo = std::min(M->i[a], M->i[b]), hi = std::max(M->i[a], M->i[b]); up[lo].push_back(hi); }
+    for (auto& v : up) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+
+    struct St { int prev_diag = 0, start = 0, diag = 0, off = 0, arrow = 0; } cur;
+    u64 f_tri = 0, f_a_nosyrk = 0, f_a_syrk = 0;
+    auto advance = [&](int row, St s) {
+        if (row >= n) return s;
+        for (int col : up[row]) {
+            if (!(col >= s.start && col + s.arrow < n)) continue;
+            const int size_now = s.diag + s.off;
+            const int size_new = std::max(col - s.start + 1, size_now);
+            const int diag_cap = row - s.start + 1;
+            const int diag_new = std::max(std::max(s.diag, (size_new + 1) / 2), diag_cap);
+            const int off_new = size_new - diag_new;
+            const int arrow_new = std::min(std::max(s.arrow, n - col), n - s.start - s.diag - s.off);
+            const u64 tri_new = f_tri + fl_syrk((u64)diag_new, (u64)s.prev_diag) + fl_potrf((u64)diag_new) + fl_trsm((u64)diag_new, (u64)off_new);
+            const u64 aw = (u64)((s.arrow + 3) / 4) * 4, awn = (u64)((arrow_new + 3) / 4) * 4;   // kernels work on multiples of 4
+            const u64 arrow_now = aw * f_a_nosyrk + aw * aw * f_a_syrk + fl_potrf(aw);
+            const u64 arrow_then = awn * f_a_nosyrk + awn * awn * f_a_syrk + fl_gemm(awn, (u64)s.prev_diag, (u64)diag_new) +
+                                   fl_trsm((u64)diag_new, awn) + fl_syrk(awn, (u64)diag_new) + fl_potrf(awn);
+            if (tri_new - f_tri <= arrow_then - arrow_now) { s.diag = diag_new; s.off = off_new; }
+            else s.arrow = arrow_new;
+        }
+        return s;
+    };
+    bi.clear();
+    for (int i = 0; i < n; i++) {
+        cur = advance(i, cur);
+        if (i + 1 < cur.start + cur.diag) continue;
+        const bool ratio_ok = cur.diag >= 2 * cur.off;
+        const bool at_end = i + 1 >= n - cur.arrow;
+        bool grows = false;
+        if (!ratio_ok && !at_end) { St nx = advance(i + 1, cur); grows = nx.diag + nx.off > cur.diag + cur.off; }
+        if (ratio_ok || at_end || grows) {
+            bi.push_back({cur.start, cur.diag, cur.off});
+            f_tri += fl_syrk((u64)cur.diag, (u64)(cur.prev_diag + 1)) + fl_potrf((u64)cur.diag) + fl_trsm((u64)cur.diag, (u64)cur.off);
+            f_a_nosyrk += fl_gemm(1, (u64)cur.prev_diag, (u64)cur.diag) + fl_trsm((u64)cur.diag, 1);
+            f_a_syrk += fl_syrk(1, (u64)cur.diag);
+            cur.start += cur.diag; cur.prev_diag = cur.diag; cur.diag = cur.off; cur.off = 0;
+        }
+        if (at_end && cur.diag > 0) {
+            bi.push_back({cur.start, cur.diag, cur.off});
+            cur.start += cur.diag; cur.prev_diag = cur.diag; cur.diag = cur.off; cur.off = 0;
+        }
+        if (at_end) break;
+    }
+    for (size_t i = 0; i + 1 < bi.size(); i++)   // merge blocks that were split in two (:569-579)
+        if (bi[i].off == bi[i + 1].diag && bi[i + 1].off == 0) { bi[i].diag += bi[i].off; bi[i].off = 0; bi.erase(bi.begin() + (long)i + 1); }
+    bi.push_back({cur.start, cur.arrow, 0});
+    N = (int)bi.size(); w = bi.back().diag;
+    if (N < 2) { error = "multistage: degenerate block structure"; return false; }
+
+    // storage layout
+    offD.assign(N, 0); offB.assign(N, 0); offE.assign(N, 0); offI.assign(N, 0);
+    total = 0; total_inv = 0; dmax = 1; omax = 1;
+    for (int i = 0; i < N; i++) {
+        const int d = bi[i].diag, o = (i + 2 < N) ? bi[i].off : 0;
+        offD[i] = total; total += d * d;
+        offB[i] = total; total += o * d;
+        offE[i] = total; total += (i + 1 < N) ? w * d : 0;
+        offI[i] = total_inv; total_inv += d * d;
+        dmax = std::max(dmax, d); omax = std::max(omax, o);
+    }
+    blk_of.assign(n, 0);
+    for (int b = 0; b < N; b++) for (int k = 0; k < bi[b].diag; k++) blk_of[bi[b].start + k] = b;
+
+    // maps
+    P_slot.assign(P.nnz, -1);
+    for (int j = 0; j < n; j++) for (int q = P.p[j]; q < P.p[j + 1]; q++) {
+        if (P.i[q] > j) continue;
+        const int s = slot(j, P.i[q]);
+        if (s < 0) { error = "multistage: an entry of P lies outside the detected block structure"; return false; }
+        P_slot[q] = s;
+    }
+    diag_slot.assign(n, 0);
+    for (int i = 0; i < n; i++) diag_slot[i] = slot(i, i);
+    auto build = [&](const Pattern& M, std::vector<int>& ptr, std::vector<int>& qa, std::vector<int>& qb, std::vector<int>* row) {
+        std::vector<int> cnt(total + 1, 0);
+        for (int r = 0; r < M.cols; r++) for (int a = M.p[r]; a < M.p[r + 1]; a++) for (int b = M.p[r]; b < M.p[r + 1]; b++) {
+            if (M.i[a] < M.i[b]) continue;
+            const int s = slot(M.i[a], M.i[b]);
+            if (s < 0) return false;
+            cnt[s + 1]++;
+        }
+        ptr.assign(total + 1, 0);
+        for (int s = 0; s < total; s++) ptr[s + 1] = ptr[s] + cnt[s + 1];
+        qa.assign(ptr[total], 0); qb.assign(ptr[total], 0);
+        if (row) row->assign(ptr[total], 0);
+        std::vector<int> wpos(ptr.begin(), ptr.end() - 1);
+        for (int r = 0; r < M.cols; r++) for (int a = M.p[r]; a < M.p[r + 1]; a++) for (int b = M.p[r]; b < M.p[r + 1]; b++) {
+            if (M.i[a] < M.i[b]) continue;
+            const int s = slot(M.i[a], M.i[b]);
+            const int t = wpos[s]++;
+            qa[t] = a; qb[t] = b;
+            if (row) (*row)[t] = r;
+        }
+        return true;
+    };
+    if (!build(AT, a_ptr, a_qa, a_qb, nullptr)) { error = "multistage: a row of A couples variables outside the detected block structure"; return false; }
+    if (!build(GT, g_ptr, g_qa, g_qb, &g_row)) { error = "multistage: a row of G couples variables outside the detected block structure"; return false; }
+    return true;
+}
+
+int MsStructure::slot(int i, int j) const {
+    const int bj = blk_of[j], bI = blk_of[i];
+    if (bI == bj) return offD[bj] + (i - bi[bj].start) + (j - bi[bj].start) * bi[bj].diag;
+    if (w > 0 && i >= n - w) return offE[bj] + (i - (n - w)) + (j - bi[bj].start) * w;
+    if (bI == bj + 1 && bj + 2 < N && i - bi[bI].start < bi[bj].off) return offB[bj] + (i - bi[bI].start) + (j - bi[bj].start) * bi[bj].off;
+    return -1;
+}
+double MsStructure::factor_flops() const {   // the BLAS calls factor_kkt issues, with the reference's cost model
+    double f = 0;
+    for (int i = 0; i + 1 < N; i++) {
+        const double d = bi[i].diag, o = (i + 2 < N) ? bi[i].off : 0, po = i > 0 ? bi[i - 1].off : 0, pd = i > 0 ? bi[i - 1].diag : 0, W = w;
+        f += po * po * pd + d * d * d / 3 + d * d * o + 2 * W * po * pd + d * d * W + W * W * d;
+    }
+    return f + (double)w * w * w / 3;
+}
+double MsStructure::factor_bytes() const { return 8.0 * 3.0 * total; }   // P/AtA blocks read, kkt_fac written and read once
+double MsStructure::solve_flops() const {
+    double f = 2.0 * w * w;
+    for (int i = 0; i + 1 < N; i++) { const double d = bi[i].diag, o = (i + 2 < N) ? bi[i].off : 0; f += 2 * (d * d + 2 * o * d + 2 * w * d); }
+    return f;
+}
+double MsStructure::solve_bytes() const {
+    double by = 0;
+    for (int i = 0; i + 1 < N; i++) { const double d = bi[i].diag, o = (i + 2 < N) ? bi[i].off : 0; by += 8.0 * 2 * (d * d / 2 + o * d + w * d); }
+    return by + 8.0 * 5 * n;
+}
+
+// =====================================================================================================
+// device kernels
+// =====================================================================================================
+struct MsDev {
+    const int *start, *diag, *off, *offD, *offB, *offE, *offI;
+    int N, w, n, total, total_inv, dmax, omax;
+};
+
+// out[slot] = sum_list (w[row] *) vals[qa] * vals[qb]
+__global__ void ms_accumulate_kernel(const int* ptr, const int* qa, const int* qb, const int* row, int total, int nnz, int m, const double* vals,
+                                     const double* w, double* out, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    const double* v = vals + (size_t)b * nnz;
+    const double* wb = w ? w + (size_t)b * m : nullptr;
+    double acc = 0.0;
+    for (int t = ptr[s]; t < ptr[s + 1]; t++) { double a = v[qa[t]]; if (wb) a *= wb[row[t]]; acc += a * v[qb[t]]; }
+    out[(size_t)b * total + s] = acc;
+}
+__global__ void ms_scatter_P_kernel(const int* P_slot, int nnz, int total, const double* Px, double* Pblk) {
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nnz && P_slot[q] >= 0) Pblk[(size_t)b * total + P_slot[q]] = Px[(size_t)b * nnz + q];
+}
+// kkt_fac = P + AtA / delta + GtG + diag(x_reg)   (construct_kkt_fac :1008-1219 fused with block_syrk_ln of the scaled G)
+__global__ void ms_assemble_kernel(const int* gptr, const int* gqa, const int* gqb, const int* grow, const int* diag_var, int total, int gnnz, int m, int n,
+                                   const double* Pblk, const double* AtAblk, const double* Gx, const double* zinv, const double* delta,
+                                   const double* x_reg, double* fac, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    const double* g = Gx + (size_t)b * gnnz;
+    const double* wz = zinv + (size_t)b * m;
+    double gtg = 0.0;
+    for (int t = gptr[s]; t < gptr[s + 1]; t++) gtg += (g[gqa[t]] * wz[grow[t]]) * g[gqb[t]];
+    double v = Pblk[(size_t)b * total + s];
+    v += (1.0 / delta[b]) * AtAblk[(size_t)b * total + s];
+    v += gtg;
+    const int dv = diag_var[s];
+    if (dv >= 0) v += x_reg[(size_t)b * n + dv];
+    fac[(size_t)b * total + s] = v;
+}
+
+constexpr int MS_T = 128;
+
+// in-smem Cholesky of the d x d block A (ld = d), one barrier per column; then inv <- L^{-1} (dense d x d, ld = d)
+__device__ void ms_potrf_inv(double* A, double* inv, double* rinv, int d) {
+    const int tid = threadIdx.x;
+    for (int k = 0; k < d; k++) {
+        __syncthreads();
+        const double dk = A[k + k * d];
+        const double r = rsqrt(dk);
+        if (tid == 0) rinv[k] = r;
+        const int rem = d - k - 1;
+        for (int e = tid; e < rem * rem; e += MS_T) {      // trailing lower update with the unscaled column k
+            const int c = k + 1 + e / rem, rr = k + 1 + e % rem;
+            if (rr >= c) A[rr + c * d] -= (A[rr + k * d] * r) * (A[c + k * d] * r);
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < d * d; e += MS_T) {
+        const int c = e / d, rr = e % d;
+        if (rr > c) A[e] *= rinv[c]; else if (rr == c) A[e] = A[e] * rinv[c]; else A[e] = 0.0;    // l_cc = d_cc * rsqrt(d_cc)
+    }
+    __syncthreads();
+    // inverse: thread c computes column c of L^{-1}
+    for (int c = tid; c < d; c += MS_T) {
+        for (int i = 0; i < d; i++) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = c; k < i; k++) s -= A[i + k * d] * inv[k + c * d];
+            inv[i + c * d] = (i < c) ? 0.0 : s * rinv[i];
+        }
+    }
+    __syncthreads();
+}
+// X (rows x d, ld = ldx) <- X * L^{-T} = X * inv^T : X[r, j] = sum_k X[r,k] inv[j,k]; rows processed thread-per-row via a scratch row in registers-free manner
+__device__ void ms_apply_invT(double* X, int rows, int ldx, const double* inv, int d, double* scratch) {
+    // scratch: rows x d temporary (smem)
+    for (int e = threadIdx.x; e < rows * d; e += MS_T) {
+        const int r = e % rows, j = e / rows;
+        double s = 0.0;
+        for (int k = 0; k <= j; k++) s += X[r + k * ldx] * inv[j + k * d];
+        scratch[r + j * rows] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < rows * d; e += MS_T) { const int r = e % rows, j = e / rows; X[r + j * ldx] = scratch[r + j * rows]; }
+    __syncthreads();
+}
+
+// factor_kkt (:1253-1352): one CTA per instance, the chain of stages processed in shared memory
+__global__ void __launch_bounds__(MS_T) ms_factor_kernel(MsDev s, double* fac_all, double* inv_all, const int* active) {
+    extern __shared__ __align__(16) double sm[];
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    double* fac = fac_all + (size_t)b * s.total;
+    double* Linv = inv_all + (size_t)b * s.total_inv;
+    const int dm = s.dmax, om = s.omax, w = s.w, tid = threadIdx.x;
+    double* Dc = sm;                       // dm*dm
+    double* Ic = Dc + dm * dm;             // dm*dm (inverse of the current pivot block)
+    double* Cb0 = Ic + dm * dm;            // om*dm x2
+    double* Cb1 = Cb0 + om * dm;
+    double* Fb0 = Cb1 + om * dm;           // w*dm x2
+    double* Fb1 = Fb0 + w * dm;
+    double* DN = Fb1 + w * dm;             // w*w
+    double* scr = DN + w * w;              // max(om, w) * dm
+    double* rinv = scr + (om > w ? om : w) * dm;   // max(dm, w)
+    const int N = s.N;
+    if (w > 0) for (int e = tid; e < w * w; e += MS_T) DN[e] = fac[s.offD[N - 1] + e];
+    double *Cprev = Cb1, *Ccur = Cb0, *Fprev = Fb1, *Fcur = Fb0;
+    for (int i = 0; i + 1 < N; i++) {
+        const int d = s.diag[i], o = (i + 2 < N) ? s.off[i] : 0;
+        const int po = i > 0 ? s.off[i - 1] : 0, pd = i > 0 ? s.diag[i - 1] : 0;
+        for (int e = tid; e < d * d; e += MS_T) Dc[e] = fac[s.offD[i] + e];
+        for (int e = tid; e < o * d; e += MS_T) Ccur[e] = fac[s.offB[i] + e];
+        for (int e = tid; e < w * d; e += MS_T) Fcur[e] = fac[s.offE[i] + e];
+        __syncthreads();
+        if (po > 0) {
+            // D_i(0:po,0:po) -= C_{i-1} C_{i-1}^T ; E_i(:,0:po) -= F_{i-1} C_{i-1}^T
+            for (int e = tid; e < po * po; e += MS_T) {
+                const int c = e / po, r = e % po;
+                if (r < c) continue;
+                double acc = 0.0;
+                for (int k = 0; k < pd; k++) acc += Cprev[r + k * po] * Cprev[c + k * po];
+                Dc[r + c * d] -= acc;
+            }
+            for (int e = tid; e < w * po; e += MS_T) {
+                const int c = e / w, r = e % w;
+                double acc = 0.0;
+                for (int k = 0; k < pd; k++) acc += Fprev[r + k * w] * Cprev[c + k * po];
+                Fcur[r + c * w] -= acc;
+            }
+        }
+        ms_potrf_inv(Dc, Ic, rinv, d);
+        if (o > 0) ms_apply_invT(Ccur, o, o, Ic, d, scr);
+        if (w > 0) {
+            ms_apply_invT(Fcur, w, w, Ic, d, scr);
+            for (int e = tid; e < w * w; e += MS_T) {       // D_N -= F_i F_i^T
+                const int c = e / w, r = e % w;
+                if (r < c) continue;
+                double acc = 0.0;
+                for (int k = 0; k < d; k++) acc += Fcur[r + k * w] * Fcur[c + k * w];
+                DN[e] -= acc;
+            }
+        }
+        for (int e = tid; e < d * d; e += MS_T) { fac[s.offD[i] + e] = Dc[e]; Linv[s.offI[i] + e] = Ic[e]; }
+        for (int e = tid; e < o * d; e += MS_T) fac[s.offB[i] + e] = Ccur[e];
+        for (int e = tid; e < w * d; e += MS_T) fac[s.offE[i] + e] = Fcur[e];
+        double* t = Cprev; Cprev = Ccur; Ccur = t;
+        t = Fprev; Fprev = Fcur; Fcur = t;
+        __syncthreads();
+    }
+    if (w > 0) {
+        ms_potrf_inv(DN, Dc, rinv, w);     // w <= dmax is not guaranteed: Dc/Ic are sized max(dm, w)^2 by the host
+        for (int e = tid; e < w * w; e += MS_T) { fac[s.offD[N - 1] + e] = DN[e]; Linv[s.offI[N - 1] + e] = Dc[e]; }
+    }
+}
+
+// solve_llt_in_place (:1709-1816) with the inverted pivot blocks: every stage is two small mat-vecs
+__global__ void __launch_bounds__(MS_T) ms_solve_kernel(MsDev s, const double* fac_all, const double* inv_all, double* X, const int* active) {
+    extern __shared__ __align__(16) double xs[];   // n + dmax scratch
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    const double* fac = fac_all + (size_t)b * s.total;
+    const double* Linv = inv_all + (size_t)b * s.total_inv;
+    double* x = X + (size_t)b * s.n;
+    const int tid = threadIdx.x, N = s.N, w = s.w, n = s.n;
+    double* tmp = xs + n;
+    for (int i = tid; i < n; i += MS_T) xs[i] = x[i];
+    __syncthreads();
+    // forward
+    for (int i = 0; i + 1 < N; i++) {
+        const int d = s.diag[i], st = s.start[i];
+        const int po = i > 0 ? s.off[i - 1] : 0, pd = i > 0 ? s.diag[i - 1] : 0, pst = i > 0 ? s.start[i - 1] : 0;
+        if (tid < d) {
+            double v = xs[st + tid];
+            if (tid < po) { const double* C = fac + s.offB[i - 1]; double acc = 0.0; for (int k = 0; k < pd; k++) acc += C[tid + k * po] * xs[pst + k]; v -= acc; }
+            tmp[tid] = v;
+        }
+        __syncthreads();
+        if (tid < d) { const double* I = Linv + s.offI[i]; double acc = 0.0; for (int k = 0; k <= tid; k++) acc += I[tid + k * d] * tmp[k]; xs[st + tid] = acc; }
+        __syncthreads();
+    }
+    if (w > 0) {
+        if (tid < w) {
+            double v = xs[n - w + tid];
+            for (int i = 0; i + 1 < N; i++) { const double* F = fac + s.offE[i]; const int d = s.diag[i], st = s.start[i]; double acc = 0.0; for (int k = 0; k < d; k++) acc += F[tid + k * w] * xs[st + k]; v -= acc; }
+            tmp[tid] = v;
+        }
+        __syncthreads();
+        const double* I = Linv + s.offI[N - 1];
+        double y = 0.0;
+        if (tid < w) for (int k = 0; k <= tid; k++) y += I[tid + k * w] * tmp[k];     // L_N^{-1}
+        __syncthreads();
+        if (tid < w) tmp[tid] = y;
+        __syncthreads();
+        if (tid < w) { double acc = 0.0; for (int k = tid; k < w; k++) acc += I[k + tid * w] * tmp[k]; xs[n - w + tid] = acc; }   // L_N^{-T}
+        __syncthreads();
+    }
+    // backward
+    for (int i = N - 2; i >= 0; i--) {
+        const int d = s.diag[i], st = s.start[i], o = (i + 2 < N) ? s.off[i] : 0, nst = (i + 2 < N) ? s.start[i + 1] : 0;
+        if (tid < d) {
+            double v = xs[st + tid];
+            if (o > 0) { const double* C = fac + s.offB[i]; double acc = 0.0; for (int r = 0; r < o; r++) acc += C[r + tid * o] * xs[nst + r]; v -= acc; }
+            if (w > 0) { const double* F = fac + s.offE[i]; double acc = 0.0; for (int r = 0; r < w; r++) acc += F[r + tid * w] * xs[n - w + r]; v -= acc; }
+            tmp[tid] = v;
+        }
+        __syncthreads();
+        if (tid < d) { const double* I = Linv + s.offI[i]; double acc = 0.0; for (int k = tid; k < d; k++) acc += I[k + tid * d] * tmp[k]; xs[st + tid] = acc; }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += MS_T) x[i] = xs[i];
+}
+
+__global__ void ms_inv_copy_kernel(const double* z_reg, double* zinv, size_t nz, const double* delta_in, double* delta_out, int batch) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nz) zinv[i] = 1.0 / z_reg[i];
+    if (i < (size_t)batch) delta_out[i] = delta_in[i];
+}
+__global__ void ms_set_ok_kernel(const int* active, int* ok, int batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch && (!active || active[b])) ok[b] = 1;     // the reference never reports failure (:218)
+}
+__global__ void ms_copy_masked_kernel(const double* src, double* dst, int len, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) dst[(size_t)b * len + i] = src[(size_t)b * len + i];
+}
+
+// =====================================================================================================
+// MultistageBatchedKKT
+// =====================================================================================================
+static void upload(DevBuf<int>& d, const std::vector<int>& h) {
+    d.alloc(std::max<size_t>(h.size(), 1));
+    if (!h.empty()) B200_CUDA(cudaMemcpy(d.get(), h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+}
+
+MultistageBatchedKKT::MultistageBatchedKKT(SparseData* data, cudaStream_t st) : D(data) {
+    batch = D->batch; n = D->n; p = D->p; m = D->m; stream = st;
+    if (!S.detect(D->P, D->AT, D->GT)) throw std::runtime_error(S.error);
+    if (S.dmax > MS_T || S.w > MS_T) throw std::runtime_error("multistage: block sizes above 128 are not supported by this build");
+    std::vector<int> meta;
+    for (auto f : {0, 1, 2}) for (int i = 0; i < S.N; i++) meta.push_back(f == 0 ? S.bi[i].start : f == 1 ? S.bi[i].diag : S.bi[i].off);
+    meta.insert(meta.end(), S.offD.begin(), S.offD.end()); meta.insert(meta.end(), S.offB.begin(), S.offB.end());
+    meta.insert(meta.end(), S.offE.begin(), S.offE.end()); meta.insert(meta.end(), S.offI.begin(), S.offI.end());
+    upload(d_meta, meta);
+    upload(d_P_slot, S.P_slot);
+    std::vector<int> diag_var(S.total, -1);
+    for (int i = 0; i < n; i++) diag_var[S.diag_slot[i]] = i;
+    upload(d_diag_var, diag_var);
+    upload(d_a_ptr, S.a_ptr); upload(d_a_qa, S.a_qa); upload(d_a_qb, S.a_qb);
+    upload(d_g_ptr, S.g_ptr); upload(d_g_qa, S.g_qa); upload(d_g_qb, S.g_qb); upload(d_g_row, S.g_row);
+    const size_t T = (size_t)batch * S.total;
+    Pblk.alloc(T); AtAblk.alloc(T); fac.alloc(T); Linv.alloc((size_t)batch * S.total_inv);
+    Pblk.zero(st); AtAblk.zero(st); fac.zero(st); Linv.zero(st);
+    zinv.alloc(std::max<size_t>((size_t)batch * m, 1)); delta.alloc(batch); work_z.alloc(std::max<size_t>((size_t)batch * m, 1));
+    const int dm = std::max(S.dmax, S.w), om = S.omax, w = S.w;
+    // the factor kernel's smem carve-up uses dmax := max(dmax, w) so that the arrow corner fits in Dc / Ic
+    factor_smem = sizeof(double) * ((size_t)2 * dm * dm + 2 * (size_t)om * dm + 2 * (size_t)w * dm + (size_t)w * w + (size_t)std::max(om, w) * dm + std::max(dm, w) + 8);
+    solve_smem = sizeof(double) * ((size_t)n + std::max(dm, w) + 8);
+    if (factor_smem > 227 * 1024 || solve_smem > 227 * 1024) throw std::runtime_error("multistage: blocks too large for shared memory");
+    B200_CUDA(cudaFuncSetAttribute(ms_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(factor_smem, 48 * 1024)));
+    B200_CUDA(cudaFuncSetAttribute(ms_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(solve_smem, 48 * 1024)));
+    load_P();
+    compute_AtA();
+}
+
+static MsDev make_dev(const MsStructure& S, const int* meta) {
+    MsDev d;
+    const int N = S.N;
+    d.start = meta; d.diag = meta + N; d.off = meta + 2 * N; d.offD = meta + 3 * N; d.offB = meta + 4 * N; d.offE = meta + 5 * N; d.offI = meta + 6 * N;
+    d.N = N; d.w = S.w; d.n = S.n; d.total = S.total; d.total_inv = S.total_inv; d.dmax = std::max(S.dmax, S.w); d.omax = S.omax;
+    return d;
+}
+
+void MultistageBatchedKKT::load_P() {
+    Pblk.zero(stream);
+    if (D->P.nnz) { dim3 g(ceil_div(D->P.nnz, 256), batch);
+        B200_LAUNCH(ms_scatter_P_kernel, g, 256, 0, stream, d_P_slot.get(), D->P.nnz, S.total, D->Px.get(), Pblk.get()); }
+}
+void MultistageBatchedKKT::compute_AtA() {
+    dim3 g(ceil_div(S.total, 128), batch);
+    B200_LAUNCH(ms_accumulate_kernel, g, 128, 0, stream, d_a_ptr.get(), d_a_qa.get(), d_a_qb.get(), (const int*)nullptr, S.total, D->AT.nnz, p, D->ATx.get(),
+                (const double*)nullptr, AtAblk.get(), (const int*)nullptr);
+}
+void MultistageBatchedKKT::update_data(int options) {   // :140-178
+    if (options & 1) load_P();
+    if (options & 2) compute_AtA();
+}
+void MultistageBatchedKKT::copy_from(const MultistageBatchedKKT& o) {
+    auto cp = [&](DevBuf<double>& d, const DevBuf<double>& s) { if (s.n) B200_CUDA(cudaMemcpyAsync(d.get(), s.get(), s.n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); };
+    cp(Pblk, o.Pblk); cp(AtAblk, o.AtAblk); cp(fac, o.fac); cp(Linv, o.Linv); cp(zinv, o.zinv); cp(delta, o.delta);
+}
+
+void MultistageBatchedKKT::factor(const double* delta_in, const double* x_reg, const double* z_reg, const int* active, int* ok) {   // :180-219
+    const size_t nz = (size_t)batch * m, tot = std::max(nz, (size_t)batch);
+    B200_LAUNCH(ms_inv_copy_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, z_reg, zinv.get(), nz, delta_in, delta.get(), batch);
+    tic(T_ASSEMBLE);
+    dim3 g(ceil_div(S.total, 128), batch);
+    B200_LAUNCH(ms_assemble_kernel, g, 128, 0, stream, d_g_ptr.get(), d_g_qa.get(), d_g_qb.get(), d_g_row.get(), d_diag_var.get(), S.total, D->GT.nnz, m, n,
+                Pblk.get(), AtAblk.get(), D->GTx.get(), zinv.get(), delta.get(), x_reg, fac.get(), active);
+    toc(T_ASSEMBLE);
+    tic(T_FACTOR);
+    B200_LAUNCH(ms_factor_kernel, batch, MS_T, factor_smem, stream, make_dev(S, d_meta.get()), fac.get(), Linv.get(), active);
+    toc(T_FACTOR);
+    B200_LAUNCH(ms_set_ok_kernel, ceil_div(batch, 256), 256, 0, stream, active, ok, batch);
+}
+
+void MultistageBatchedKKT::solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) {   // :221-288
+    if (n == 0) return;
+    tic(T_SOLVE);
+    dim3 gn(ceil_div(n, 256), batch);
+    B200_LAUNCH(ms_copy_masked_kernel, gn, 256, 0, stream, rx, lx, n, active);
+    if (m > 0) spmv_rows(D->GT, D->GTx.get(), 1.0, rz, m, lx, 1, zinv.get(), nullptr, 0, batch, active, stream);          // lx += GT (zinv .* rz)
+    if (p > 0) spmv_rows(D->AT, D->ATx.get(), 1.0, ry, p, lx, 1, nullptr, delta.get(), 1, batch, active, stream);         // lx += AT ry / delta
+    B200_LAUNCH(ms_solve_kernel, batch, MS_T, solve_smem, stream, make_dev(S, d_meta.get()), fac.get(), Linv.get(), lx, active);
+    if (p > 0) spmv_cols(D->AT, D->ATx.get(), 1.0, lx, n, ly, ry, 1.0, nullptr, delta.get(), 1, batch, active, stream);    // ly = (A lx - ry) / delta
+    if (m > 0) spmv_cols(D->GT, D->GTx.get(), 1.0, lx, n, lz, rz, 1.0, zinv.get(), nullptr, 0, batch, active, stream);     // lz = zinv .* (G lx - rz)
+    toc(T_SOLVE);
+}
+void MultistageBatchedKKT::eval_P_x(double alpha, const double* x, double* z, const int* active) { spmv_sym_upper(D->P, D->Px.get(), alpha, x, z, batch, active, stream); }
+void MultistageBatchedKKT::eval_A(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) {
+    if (p > 0) spmv_cols(D->AT, D->ATx.get(), an, xn, n, zn, nullptr, 0.0, nullptr, nullptr, 0, batch, active, stream);
+    spmv_rows(D->AT, D->ATx.get(), at, xt, p, zt, 0, nullptr, nullptr, 0, batch, active, stream);
+}
+void MultistageBatchedKKT::eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) {
+    if (m > 0) spmv_cols(D->GT, D->GTx.get(), an, xn, n, zn, nullptr, 0.0, nullptr, nullptr, 0, batch, active, stream);
+    spmv_rows(D->GT, D->GTx.get(), at, xt, m, zt, 0, nullptr, nullptr, 0, batch, active, stream);
+}
+void MultistageBatchedKKT::extract_P_diag(double* P_diag) { sparse_extract_diag(*D, P_diag, stream); }
+void MultistageBatchedKKT::print_info() const {   // :385-392
+    printf("block sizes:");
+    for (int i = 0; i + 1 < S.N; i++) printf(" %d,%d", S.bi[i].diag, S.bi[i].off);
+    printf("\narrow width: %d\n", S.bi[S.N - 1].diag);
+}
+
+}  // namespace b200

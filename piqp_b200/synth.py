@@ -132,3 +132,52 @@ def dense_batch_torch(batch, n, p, m, seed0=42, device="cuda", bounds_perc=0.5, 
         for k, v in (("P", P), ("c", c), ("A", A), ("b", b), ("G", G), ("h_l", h_l), ("h_u", h_u), ("x_l", x_l), ("x_u", x_u)):
             out[k].append(v)
     return {k: torch.stack(v).contiguous() for k, v in out.items()}
+
+
+def mpc_batch(batch, N=100, nx=12, nu=4, seed0=42, umax=1.0, xmax=5.0):
+    """BASELINE config 4: linear time-invariant MPC QPs in the variable order the multistage backend requires
+    (docs/_pages/multistage.md:72): z = (x_0, u_0, x_1, u_1, ..., x_{N-1}, u_{N-1}, x_N), n = N (nx + nu) + nx,
+    dynamics equalities x_{i+1} = A_d x_i + B_d u_i (p = N nx), x_0 fixed through equal box bounds, box bounds on
+    states and inputs (handled in x_reg, no G), stage cost Q = I, R = 0.1 I, terminal cost 10 I.
+    Every instance b has its own random stable (A_d, B_d) and x_0 (seed0 + b); all share the sparsity pattern.
+    Returns dict(P, A: scipy CSC patterns (values of instance 0), Ax [batch, nnz(A)], c, b, x_l, x_u [batch, *])."""
+    import scipy.sparse as sp
+    nz = nx + nu
+    n = N * nz + nx
+    p = N * nx
+    Pd = np.concatenate([np.tile(np.concatenate([np.ones(nx), 0.1 * np.ones(nu)]), N), 10.0 * np.ones(nx)])
+    P = sp.diags(Pd).tocsc()
+    rows, cols = [], []
+    for i in range(N):
+        r0 = i * nx
+        for r in range(nx):
+            for cc in range(nz):                      # [A_d B_d] on (x_i, u_i)
+                rows.append(r0 + r); cols.append(i * nz + cc)
+            rows.append(r0 + r); cols.append((i + 1) * nz + r)   # -I on x_{i+1}
+    rows = np.array(rows); cols = np.array(cols)
+    A_pat = sp.csc_matrix((np.ones(len(rows)), (rows, cols)), shape=(p, n))
+    A_pat.sort_indices()
+    # position of every (row, col) in the CSC value array
+    order = np.lexsort((rows, cols))
+    inv = np.empty_like(order); inv[order] = np.arange(len(order))
+    Ax = np.zeros((batch, A_pat.nnz)); c = np.zeros((batch, n)); b = np.zeros((batch, p))
+    x_l = np.full((batch, n), -np.inf); x_u = np.full((batch, n), np.inf)
+    for k in range(batch):
+        rng = np.random.default_rng(seed0 + k)
+        Ad = rng.standard_normal((nx, nx)); Ad *= 0.95 / max(abs(np.linalg.eigvals(Ad)))
+        Bd = rng.standard_normal((nx, nu)) / np.sqrt(nx)
+        x0 = rng.uniform(-1.0, 1.0, nx)
+        vals = np.zeros(len(rows)); t = 0
+        blk = np.hstack([Ad, Bd])
+        for i in range(N):
+            for r in range(nx):
+                vals[t:t + nz] = blk[r]; t += nz
+                vals[t] = -1.0; t += 1
+        Ax[k, inv] = vals
+        for i in range(N):
+            x_l[k, i * nz:i * nz + nx] = -xmax; x_u[k, i * nz:i * nz + nx] = xmax
+            x_l[k, i * nz + nx:(i + 1) * nz] = -umax; x_u[k, i * nz + nx:(i + 1) * nz] = umax
+        x_l[k, N * nz:] = -xmax; x_u[k, N * nz:] = xmax
+        x_l[k, :nx] = x0; x_u[k, :nx] = x0
+    A0 = sp.csc_matrix((Ax[0], A_pat.indices, A_pat.indptr), shape=(p, n))
+    return dict(P=P, A=A0, Ax=Ax, c=c, b=b, x_l=x_l, x_u=x_u, n=n, p=p)
