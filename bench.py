@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- measures the KKT factor+solve hot path (BASELINE.json metric) on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--n N --m M --p P]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload dense|multistage] [--batch B] ...
 
-One "step" = one batched interior-point solve() of `batch` dense QPs per GPU (BASELINE config 2:
-n=1024, p=0, m=512, batch=256), i.e. ~10-15 passes of the hot path (assemble + Cholesky + 2 KKT solves +
-residual mat-vecs).  `value` = algorithmic factor+solve GFLOP/s over the whole step with inputs
-resident in HBM; `e2e` = the same metric through the public C-ABI with HOST buffers (setup H2D + solve + D2H).
-Prints ONE JSON line on rank 0.
+Default workload (the one BASELINE.json's metric is quoted on, config 2): dense QPs n=1024, p=0, m=512, batch=256 per
+GPU.  One "step" = one batched interior-point solve() of the per-GPU batch, i.e. ~10-15 passes of the hot path
+(assemble + factorise + 2 KKT solves + residual mat-vecs).  `value` = algorithmic factor+solve GFLOP/s
+over the whole step with inputs resident in HBM; `e2e` = the same metric through the public C-ABI with HOST buffers
+(setup H2D + Ruiz + solve + D2H).  `--workload multistage` runs BASELINE config 4 (MPC N=100, nx=12, nu=4, 128 QPs per
+GPU) through the block-tridiagonal-arrow backend.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -28,22 +29,21 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="instances per GPU (weak scaling)")
+    ap.add_argument("--workload", default="dense", choices=["dense", "multistage"])
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (weak scaling); 0 = workload default")
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--p", type=int, default=0)
     ap.add_argument("--m", type=int, default=512)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the CPU-baseline sample (0 = one per core, max 16)")
+    ap.add_argument("--horizon", type=int, default=100)
+    ap.add_argument("--nx", type=int, default=12)
+    ap.add_argument("--nu", type=int, default=4)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
-
-
-def factor_flops(n, p, m):   # per factor call and instance
-    return float(n) * n * m + float(n) ** 3 / 3.0
-
-
-def solve_flops(n, p, m):    # per backend solve call and instance
-    return 2.0 * n * n + 4.0 * n * m + 4.0 * n * p
+    a = ap.parse_args()
+    if a.batch == 0:
+        a.batch = 256 if a.workload == "dense" else 128
+    return a
 
 
 class ClockSampler:
@@ -75,8 +75,9 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        num = lambda s: s.replace(".", "", 1).isdigit()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and num(r[1])]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and num(r[2])]
         reasons = set()
         for r in self.rows:
             if len(r) >= 9:
@@ -87,48 +88,162 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_oracle_sample(n, p, m, n_qp, threads, seed0=1042):
-    """The CPU restatement of the reference (oracle, kind "port") solving `n_qp` QPs of the same shape with one
-    solver per host thread; returns (gflops, qps, seconds, iters)."""
+# ------------------------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------------------------
+class DenseWorkload:
+    name = "dense"
+
+    def __init__(self, a):
+        self.a = a
+        self.n, self.p, self.m = a.n, a.p, a.m
+
+    def describe(self, B):
+        return "dense batched QP n=%d p=%d m=%d batch=%d per GPU (BASELINE config 2), full IP solve per step" % (self.n, self.p, self.m, B)
+
+    def work(self):   # SURVEY.md 8(d), per call and instance
+        n, p, m = float(self.n), float(self.p), float(self.m)
+        return n * n * m + n ** 3 / 3.0, 2 * n * n + 4 * n * m + 4 * n * p
+
+    def working_set_gb(self, B):
+        return B * (3 * self.n * self.n + self.n * (self.m + self.p)) * 8 / 1e9
+
+    def device_data(self, B, seed0, dev):
+        from piqp_b200.synth import dense_batch_torch
+        return dense_batch_torch(B, self.n, self.p, self.m, seed0=seed0, device=dev)
+
+    def _pick(self, d, conv):
+        g = lambda k: conv(d[k])
+        p, m = self.p, self.m
+        return (g("P"), g("c"), g("A") if p else None, g("b") if p else None, g("G") if m else None, g("h_l") if m else None,
+                g("h_u") if m else None, g("x_l"), g("x_u"))
+
+    def make_solver(self, local, data, on_host=False):
+        import piqp_b200
+        s = piqp_b200.DenseSolverBatched(device=local)
+        s.setup(*self._pick(data, (lambda t: t.numpy()) if on_host else (lambda t: t)))
+        return s
+
+    def host_data(self, data):
+        return {k: v.cpu().pin_memory() for k, v in data.items()}
+
+    def h2d_bytes(self, host):
+        keys = ["P", "c", "x_l", "x_u"] + (["A", "b"] if self.p else []) + (["G", "h_l", "h_u"] if self.m else [])
+        return sum(host[k].numel() * 8 for k in keys)
+
+    def cpu_solvers(self, n_qp, seed0, native):
+        from oracle import pyoracle
+        from piqp_b200.synth import dense_strongly_convex_qp
+        out = []
+        for i in range(n_qp):
+            q = dense_strongly_convex_qp(self.n, self.p, self.m, seed=seed0 + i)
+            s = pyoracle.DenseSolver(native=native)
+            s.setup(q["P"], q["c"], q["A"] if self.p else None, q["b"] if self.p else None, q["G"] if self.m else None,
+                    q["h_l"] if self.m else None, q["h_u"] if self.m else None, q["x_l"], q["x_u"])
+            out.append(s)
+        return out
+
+    roofline_kernel = "gemm_nt_tile_kernel<EPI_ASSEMBLE,true> (K = P + diag + G^T Z^-1 G, DMMA m8n8k4 fp64)"
+
+
+class MultistageWorkload:
+    name = "multistage"
+
+    def __init__(self, a):
+        self.a = a
+        self.N, self.nx, self.nu = a.horizon, a.nx, a.nu
+        self._work = None
+
+    def describe(self, B):
+        return ("sparse_multistage MPC horizon N=%d nx=%d nu=%d (n=%d, p=%d) batch=%d per GPU (BASELINE config 4), full IP solve per step"
+                % (self.N, self.nx, self.nu, self.N * (self.nx + self.nu) + self.nx, self.N * self.nx, B))
+
+    def work(self):
+        return self._work
+
+    def working_set_gb(self, B):
+        return B * self.N * (3 * 16 * 16 + 2 * 12 * 16) * 8 * 3 / 1e9
+
+    def device_data(self, B, seed0, dev):
+        import torch
+        from piqp_b200.synth import mpc_batch
+        d = mpc_batch(B, N=self.N, nx=self.nx, nu=self.nu, seed0=seed0)
+        self.pat = d
+        return {k: torch.from_numpy(np_).to(dev) for k, np_ in (("Ax", d["Ax"]), ("c", d["c"]), ("b", d["b"]), ("x_l", d["x_l"]), ("x_u", d["x_u"]))}
+
+    def make_solver(self, local, data, on_host=False):
+        import piqp_b200
+        s = piqp_b200.SparseSolverBatched(device=local, kkt_solver="sparse_multistage")
+        conv = (lambda t: t.numpy()) if on_host else (lambda t: t)
+        B = data["c"].shape[0]
+        s.setup(B, self.pat["P"], conv(data["c"]), self.pat["A"], conv(data["b"]), None, None, None, conv(data["x_l"]), conv(data["x_u"]), Ax=conv(data["Ax"]))
+        w = s.work()
+        self._work = (w[0], w[2])
+        self.bytes = (w[1], w[3])
+        return s
+
+    def host_data(self, data):
+        return {k: v.cpu().pin_memory() for k, v in data.items()}
+
+    def h2d_bytes(self, host):
+        return sum(v.numel() * 8 for v in host.values()) + self.pat["P"].nnz * 8 * host["c"].shape[0]
+
+    def cpu_solvers(self, n_qp, seed0, native):
+        import scipy.sparse as sp
+        from oracle import pyoracle
+        from piqp_b200.synth import mpc_batch
+        d = mpc_batch(n_qp, N=self.N, nx=self.nx, nu=self.nu, seed0=seed0)
+        out = []
+        for k in range(n_qp):
+            A = sp.csc_matrix((d["Ax"][k], d["A"].indices, d["A"].indptr), shape=d["A"].shape)
+            s = pyoracle.SparseSolver(pyoracle.default_settings(kkt_solver="sparse_multistage"), native=native)
+            s.setup(d["P"], d["c"][k], A, d["b"][k], None, None, None, d["x_l"][k], d["x_u"][k])
+            out.append(s)
+        if self._work is None:
+            import ctypes as C
+            f = out[0]._L.orc_multistage_factor_flops(C.c_void_p(out[0]._h))
+            n = d["n"]
+            self._work = (f, 2.0 * n * 16)     # solve flops only used on the reference arm when no GPU ran: coarse
+        return out
+
+    roofline_kernel = "ms_factor_kernel (block-tridiagonal Cholesky chain, one CTA per QP)"
+
+
+def cpu_oracle_sample(wl, n_qp, threads, seed0=1042):
+    """The CPU restatement of the reference (oracle, kind "port"): `n_qp` QPs of the workload's shape, one solver per host
+    thread (the reference is single-threaded per solve).  Returns (gflops, qps, seconds, iters, native)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle
-    from piqp_b200.synth import dense_strongly_convex_qp
     try:
         pyoracle.build(native=True)
         native = True
     except Exception:
         native = False
-    qs = [dense_strongly_convex_qp(n, p, m, seed=seed0 + i) for i in range(n_qp)]
-    solvers = []
-    for q in qs:
-        s = pyoracle.DenseSolver(native=native)
-        s.setup(q["P"], q["c"], q["A"] if p else None, q["b"] if p else None, q["G"] if m else None,
-                q["h_l"] if m else None, q["h_u"] if m else None, q["x_l"], q["x_u"])
-        solvers.append(s)
+    solvers = wl.cpu_solvers(n_qp, seed0, native)
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
         list(ex.map(lambda s: s.solve(), solvers))      # ctypes releases the GIL inside orc_solve
     dt = time.perf_counter() - t0
-    flops = 0.0
-    iters = []
+    ff, sf = wl.work()
+    flops, iters = 0.0, []
     for s in solvers:
         i = s.info()
-        flops += i.n_factor * factor_flops(n, p, m) + i.n_backend_solve * solve_flops(n, p, m)
+        flops += i.n_factor * ff + i.n_backend_solve * sf
         iters.append(int(i.iter))
     return flops / dt * 1e-9, n_qp / dt, dt, iters, native
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path on the host cores.  The real PIQP cannot be
-    built here (Eigen absent), so this runs the oracle port; rank 0 only."""
+def run_reference(args, wl, rank):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The real PIQP cannot be built
+    here (Eigen absent), so this times the oracle port; rank 0 only, bounded sample per step."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    threads = min(cores, 32)
-    n_qp = args.cpu_sample or threads
+    threads = min(os.cpu_count() or 1, 32)
+    n_qp = args.cpu_sample or (threads if wl.name == "dense" else 8 * threads)
     vals, qpss, secs = [], [], []
+    native = False
     for it in range(args.warmup + args.steps):
-        g, q, dt, iters, native = cpu_oracle_sample(args.n, args.p, args.m, n_qp, threads, seed0=1042 + 1000 * it)
+        g, q, dt, iters, native = cpu_oracle_sample(wl, n_qp, threads, seed0=1042 + 1000 * it)
         if it >= args.warmup:
             vals.append(g); qpss.append(q); secs.append(dt)
         if it == 0 and dt > 40:      # keep the whole run within a few minutes
@@ -138,7 +253,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "KKT factor+solve GFLOP/s fp64", "value": v, "unit": "GFLOP/s", "qps": sum(qpss) / len(qpss),
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "dense batched QP n=%d p=%d m=%d (BASELINE config 2 shape), %d QPs per step on host threads" % (args.n, args.p, args.m, n_qp)},
+        "config": {"workload": wl.describe(n_qp) + " -- CPU: %d QPs per step on %d host threads" % (n_qp, threads)},
         "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": threads, "kind": "port",
                          "sample": "%d QPs per step, one oracle solver per thread, %s build" % (n_qp, "-march=native" if native else "x86-64-v3")},
         "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -150,12 +265,13 @@ def run_reference(args, rank, world):
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = DenseWorkload(args) if args.workload == "dense" else MultistageWorkload(args)
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, wl, rank)
         return
+    import ctypes as C
     import torch
     import piqp_b200
-    from piqp_b200.synth import dense_batch_torch
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -163,21 +279,19 @@ def main():
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
-    n, p, m, B = args.n, args.p, args.m, args.batch
+    B = args.batch
 
-    # The one collective of the path: rank 0 broadcasts the problem descriptor (shape, seed base, settings vector)
-    # over NCCL/NVLink at setup; every rank then owns the contiguous shard [rank*B, (rank+1)*B) of the global batch.
-    desc = torch.tensor([n, p, m, B, 42], dtype=torch.int64, device=dev)
+    # The one collective of the path: rank 0 broadcasts the problem descriptor (batch, seed base) over NCCL/NVLink at
+    # setup; every rank then owns the contiguous shard [rank*B, (rank+1)*B) of the global batch.  No collective follows.
+    desc = torch.tensor([B, 42], dtype=torch.int64, device=dev)
     if dist:
         dist.broadcast(desc, src=0)
-    n, p, m, B, seed0 = [int(v) for v in desc.tolist()]
-    data = dense_batch_torch(B, n, p, m, seed0=seed0 + rank * B, device=dev)
+    B, seed0 = [int(v) for v in desc.tolist()]
+    data = wl.device_data(B, seed0 + rank * B, dev)
     torch.cuda.synchronize()
-
-    solver = piqp_b200.DenseSolverBatched(device=local)
-    arg = lambda k: data[k] if (k not in ("A", "b") or p) and (k not in ("G", "h_l", "h_u") or m) else None
-    solver.setup(data["P"], data["c"], arg("A"), arg("b"), arg("G"), arg("h_l"), arg("h_u"), data["x_l"], data["x_u"])
+    solver = wl.make_solver(local, data)
     solver.set_profiling(True)
+    ff, sf = wl.work()
 
     def barrier():
         torch.cuda.synchronize()
@@ -192,111 +306,121 @@ def main():
     if sampler:
         sampler.start()
     L0 = piqp_b200.lib().b200_kernel_launch_count()
-    agg = dict(factor_calls=0, backend_solves=0, factor_ms=0.0, solve_ms=0.0, total_ms=0.0, assemble_ms=0.0, assemble_launches=0,
-               cholesky_ms=0.0, backend_solve_ms=0.0, iters=0, lockstep=0)
-    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    keys = ("factor_calls", "backend_solves", "factor_ms", "solve_ms", "total_ms", "assemble_ms", "assemble_launches", "cholesky_ms", "cholesky_calls",
+            "backend_solve_ms", "ip_iterations", "lockstep_iterations")
+    agg = {k: 0 for k in keys}
     t0 = time.perf_counter()
     for _ in range(args.steps):
         infos = solver.solve()
         st = solver.stats()
-        agg["factor_calls"] += st.factor_calls; agg["backend_solves"] += st.backend_solves
-        agg["factor_ms"] += st.factor_ms; agg["solve_ms"] += st.solve_ms; agg["total_ms"] += st.total_ms
-        agg["assemble_ms"] += st.assemble_ms; agg["assemble_launches"] += st.assemble_launches
-        agg["cholesky_ms"] += st.cholesky_ms; agg["backend_solve_ms"] += st.backend_solve_ms
-        agg["iters"] += st.ip_iterations; agg["lockstep"] += st.lockstep_iterations
-    ev1.record()
+        for k in keys:
+            agg[k] += getattr(st, k)
     barrier()
     wall = time.perf_counter() - t0
-    # device time of the timed region: the library's own CUDA events on ITS stream (total_ms) -- torch events only see torch's stream
+    # device time of the timed region: the library's own CUDA events on ITS stream (total_ms); max over ranks
     dev_ms = torch.tensor([agg["total_ms"]], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
     L1 = piqp_b200.lib().b200_kernel_launch_count()
     clocks = sampler.stop() if sampler else None
     statuses = [i.status for i in infos]
-    flops_local = agg["factor_calls"] * factor_flops(n, p, m) + agg["backend_solves"] * solve_flops(n, p, m)
-    tot = torch.tensor([flops_local, float(B * args.steps), float(agg["iters"])], dtype=torch.float64, device=dev)
+    flops_local = agg["factor_calls"] * ff + agg["backend_solves"] * sf
+    tot = torch.tensor([flops_local, float(B * args.steps), float(agg["ip_iterations"])], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     step_ms = float(dev_ms.item()) / args.steps
     gflops = float(tot[0].item()) / (float(dev_ms.item()) * 1e-3) * 1e-9
     qps = float(tot[1].item()) / (float(dev_ms.item()) * 1e-3)
 
-    # ---- e2e through the public C-ABI with HOST (pinned) buffers: setup (H2D + Ruiz) + solve + D2H of x ----
+    # ---- e2e through the public C-ABI with HOST (pinned) buffers: setup (H2D + pack/gather + Ruiz) + solve + D2H of x ----
     e2e = None
     if not args.no_e2e:
-        host = {k: v.cpu().pin_memory() for k, v in data.items()}
-        hx = torch.empty((B, n), dtype=torch.float64).pin_memory()
-        harg = lambda k: host[k].numpy() if (k not in ("A", "b") or p) and (k not in ("G", "h_l", "h_u") or m) else None
-        h2d = sum(host[k].numel() * 8 for k in host if harg(k) is not None)
+        host = wl.host_data(data)
+        n_x = solver.n
+        hx = torch.empty((B, n_x), dtype=torch.float64).pin_memory()
+        h2d = wl.h2d_bytes(host)
         d2h = hx.numel() * 8
         times, fl = [], []
         for rep in range(1 + max(2, min(args.steps, 3))):
             barrier()
             t0 = time.perf_counter()
-            s2 = piqp_b200.DenseSolverBatched(device=local)
-            s2.setup(host["P"].numpy(), host["c"].numpy(), harg("A"), harg("b"), harg("G"), harg("h_l"), harg("h_u"), host["x_l"].numpy(), host["x_u"].numpy())
+            s2 = wl.make_solver(local, host, on_host=True)
             s2.solve()
-            import ctypes as C
             piqp_b200._lib.check(s2._L.b200qp_get_result(s2._h, C.cast(hx.data_ptr(), piqp_b200._lib.dp), *([None] * 9), 0), "get_result")
             dt = time.perf_counter() - t0
             st2 = s2.stats()
             if rep > 0:
-                times.append(dt); fl.append(st2.factor_calls * factor_flops(n, p, m) + st2.backend_solves * solve_flops(n, p, m))
+                times.append(dt); fl.append(st2.factor_calls * ff + st2.backend_solves * sf)
             del s2
-        tt = torch.tensor([max(times), sum(fl) / len(fl)], dtype=torch.float64, device=dev)   # conservative: slowest repetition
-        tmax = tt[:1].clone(); fsum = tt[1:].clone()
+        tmax = torch.tensor([max(times)], dtype=torch.float64, device=dev)      # conservative: slowest repetition
+        fsum = torch.tensor([sum(fl) / len(fl)], dtype=torch.float64, device=dev)
         if dist:
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(fsum, op=dist.ReduceOp.SUM)
         e2e = {"value": float(fsum.item()) / float(tmax.item()) * 1e-9, "unit": "GFLOP/s", "qps": B * world / float(tmax.item()),
                "seconds_per_step": float(tmax.item()), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "what": "b200qp_setup_dense(host pinned buffers) + b200qp_solve + b200qp_get_result(x -> host), per GPU batch"}
+               "what": "b200qp_setup_*(host pinned buffers) + b200qp_solve + b200qp_get_result(x -> host), per GPU batch"}
 
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: the KKT assembly contraction (gemm_nt_tile_kernel<EPI_ASSEMBLE>, DMMA) ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    # FP64 peak: MEASURED_PEAKS.json has only HBM and bf16 figures; calibrate the fp64 pipe with cuBLAS DGEMM here.
-    a = torch.randn(6144, 6144, dtype=torch.float64, device=dev); bmat = torch.randn(6144, 6144, dtype=torch.float64, device=dev)
-    for _ in range(2):
-        torch.matmul(a, bmat)
-    best = 1e9
-    for _ in range(4):
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); torch.matmul(a, bmat); e1.record(); torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1))
-    fp64_peak_tflops = 2 * 6144 ** 3 / (best * 1e-3) * 1e-12
-    del a, bmat
-    asm_flops_per_launch = float(n) * n * m * (agg["factor_calls"] / max(1, agg["assemble_launches"]))
-    asm_ms = agg["assemble_ms"] / max(1, agg["assemble_launches"])
-    achieved = asm_flops_per_launch / (asm_ms * 1e-3) * 1e-12 if asm_ms > 0 else 0.0
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("gemm_nt_tile_kernel_assemble_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = {"kernel": "gemm_nt_tile_kernel<EPI_ASSEMBLE,true> (K = P + diag + G^T Z^-1 G, DMMA m8n8k4 fp64)",
-                "bound": "tensor", "achieved": achieved, "peak": fp64_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp64_peak_tflops if fp64_peak_tflops else None,
-                "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json carries no fp64 figure; hbm_gbs=%s)" % peaks.get("hbm_gbs"),
-                "flops_per_launch": asm_flops_per_launch, "ms_per_launch": asm_ms, "traffic": traffic,
-                "cholesky_tflops": (agg["factor_calls"] * float(n) ** 3 / 3.0) / (agg["cholesky_ms"] * 1e-3) * 1e-12 if agg["cholesky_ms"] else None,
-                "backend_solve_gbs": (agg["backend_solves"] * 8.0 * (float(n) * n + 2.0 * n * m + 2.0 * n * p)) / (agg["backend_solve_ms"] * 1e-3) * 1e-9 if agg["backend_solve_ms"] else None,
-                "hbm_peak_gbs": peaks.get("hbm_gbs")}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    if wl.name == "dense":
+        # FP64 peak: MEASURED_PEAKS.json has only HBM and bf16 figures; calibrate the fp64 pipe with cuBLAS DGEMM here.
+        a = torch.randn(6144, 6144, dtype=torch.float64, device=dev); bmat = torch.randn(6144, 6144, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            torch.matmul(a, bmat)
+        best = 1e9
+        for _ in range(4):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, bmat); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        fp64_peak = 2 * 6144 ** 3 / (best * 1e-3) * 1e-12
+        del a, bmat
+        n, p, m = float(wl.n), float(wl.p), float(wl.m)
+        fl_launch = n * n * m * (agg["factor_calls"] / max(1, agg["assemble_launches"]))
+        ms_launch = agg["assemble_ms"] / max(1, agg["assemble_launches"])
+        achieved = fl_launch / (ms_launch * 1e-3) * 1e-12 if ms_launch > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("gemm_nt_tile_kernel_assemble_bytes_per_launch")
+        except Exception:
+            pass
+        roofline = {"kernel": wl.roofline_kernel, "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp64_peak if fp64_peak else None,
+                    "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json carries no fp64 figure; DMMA.8x8x4 probe: 37.1 TFLOP/s, profiles/dmma_probe_b200.txt)",
+                    "flops_per_launch": fl_launch, "ms_per_launch": ms_launch, "traffic": traffic,
+                    "cholesky_tflops": (agg["factor_calls"] * n ** 3 / 3.0) / (agg["cholesky_ms"] * 1e-3) * 1e-12 if agg["cholesky_ms"] else None,
+                    "backend_solve_gbs": (agg["backend_solves"] * 8.0 * (n * n + 2 * n * m + 2 * n * p)) / (agg["backend_solve_ms"] * 1e-3) * 1e-9 if agg["backend_solve_ms"] else None,
+                    "hbm_peak_gbs": hbm_peak}
+    else:
+        fb, sb = wl.bytes
+        by_launch = fb * (agg["factor_calls"] / max(1, agg["cholesky_calls"]))
+        ms_launch = agg["cholesky_ms"] / max(1, agg["cholesky_calls"])
+        achieved = by_launch / (ms_launch * 1e-3) * 1e-9 if ms_launch > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("ms_factor_kernel_bytes_per_launch")
+        except Exception:
+            pass
+        roofline = {"kernel": wl.roofline_kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "peak_source": hbm_src, "bytes_per_launch": by_launch, "ms_per_launch": ms_launch, "traffic": traffic,
+                    "note": "latency-bound chain of N dependent 16x16 block steps per QP; algorithmic bytes = blocks read + factor written and read once",
+                    "factor_gflops": (agg["factor_calls"] * ff) / (agg["cholesky_ms"] * 1e-3) * 1e-9 if agg["cholesky_ms"] else None,
+                    "backend_solve_gbs": (agg["backend_solves"] * sb) / (agg["backend_solve_ms"] * 1e-3) * 1e-9 if agg["backend_solve_ms"] else None}
 
     cpu = None
     if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        threads = min(cores, 32)
-        n_qp = args.cpu_sample or min(threads, 16)
-        g, q, dt, iters, native = cpu_oracle_sample(n, p, m, n_qp, min(threads, n_qp))
+        threads = min(os.cpu_count() or 1, 32)
+        n_qp = args.cpu_sample or (min(threads, 16) if wl.name == "dense" else 16 * threads)
+        g, q, dt, iters, native = cpu_oracle_sample(wl, n_qp, min(threads, n_qp))
         cpu = {"value": g, "unit": "GFLOP/s", "qps": q, "cores": min(threads, n_qp), "kind": "port",
                "sample": "%d QPs of the same shape (seeds 1042..), one oracle solver per thread, %.1f s, iters %s, %s build"
                          % (n_qp, dt, sorted(set(iters)), "-march=native" if native else "x86-64-v3")}
@@ -305,12 +429,12 @@ def main():
         "metric": "KKT factor+solve GFLOP/s fp64", "value": gflops, "unit": "GFLOP/s", "qps": qps,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "dense batched QP n=%d p=%d m=%d batch=%d per GPU (BASELINE config 2), full IP solve per step" % (n, p, m, B),
-                   "parallelism": "batch sharded over %d GPU(s), no collective inside the IP loop" % world,
-                   "l2": "per-step working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (B * (3 * n * n + n * m) * 8 / 1e9),
-                   "ip_iterations_per_qp": agg["iters"] / float(B * args.steps), "statuses_all_solved": all(s == 1 for s in statuses)},
-        "buckets": {"factor_gflops": agg["factor_calls"] * factor_flops(n, p, m) / (agg["factor_ms"] * 1e-3) * 1e-9 if agg["factor_ms"] else None,
-                    "solve_gflops": agg["backend_solves"] * solve_flops(n, p, m) / (agg["solve_ms"] * 1e-3) * 1e-9 if agg["solve_ms"] else None,
+        "config": {"workload": wl.describe(B),
+                   "parallelism": "batch sharded over %d GPU(s), one NCCL broadcast at setup, no collective inside the IP loop" % world,
+                   "l2": "per-step working set %.2f GB per GPU vs 126 MB L2%s" % (wl.working_set_gb(B), "" if wl.working_set_gb(B) > 0.2 else " (fits: factor blocks are L2-resident by design)"),
+                   "ip_iterations_per_qp": agg["ip_iterations"] / float(B * args.steps), "statuses_all_solved": all(s == 1 for s in statuses)},
+        "buckets": {"factor_gflops": agg["factor_calls"] * ff / (agg["factor_ms"] * 1e-3) * 1e-9 if agg["factor_ms"] else None,
+                    "solve_gflops": agg["backend_solves"] * sf / (agg["solve_ms"] * 1e-3) * 1e-9 if agg["solve_ms"] else None,
                     "factor_ms_per_step": agg["factor_ms"] / args.steps, "solve_ms_per_step": agg["solve_ms"] / args.steps,
                     "assemble_ms_per_step": agg["assemble_ms"] / args.steps, "cholesky_ms_per_step": agg["cholesky_ms"] / args.steps,
                     "backend_solve_ms_per_step": agg["backend_solve_ms"] / args.steps, "wall_s": wall},

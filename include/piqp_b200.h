@@ -235,6 +235,9 @@ int b200qp_get_stats(b200qp_handle* h, b200qp_stats* stats);
 /* per-iteration trace of instance `b`: rows of (rho, delta, mu, primal_step, dual_step, primal_res, dual_res,
  * primal_obj, dual_obj, duality_gap); returns number of rows (needs settings.verbose >= 2 at setup). */
 int b200qp_get_trace(b200qp_handle* h, int b, double* rows, int max_rows);
+/* algorithmic work of ONE backend call for ONE instance (SURVEY.md 8d formulas; for multistage the reference's own
+ * cost model, multistage_kkt.hpp:397-418): flops and bytes of update_scalings_and_factor and of the backend solve */
+int b200qp_get_work(b200qp_handle* h, double* factor_flops, double* factor_bytes, double* solve_flops, double* solve_bytes);
 /* enable / disable CUDA-event timing of the backend's kernel classes (adds two event records per call) */
 int b200qp_set_profiling(b200qp_handle* h, int enable);
 void b200qp_cleanup(b200qp_handle* h);

@@ -482,7 +482,7 @@ void transpose_pattern(int rows, int cols, const int* cp, const int* ri, std::ve
     for (int q = 0; q < nnz; q++) tp[ri[q] + 1]++;
     for (int r = 0; r < rows; r++) tp[r + 1] += tp[r];
     std::vector<int> w(tp.begin(), tp.end() - 1);
-    for (int j = 0; j < cols; j++) for (int q = cp[j]; q < cp[j + 1]; q++) { const int t = w[ri[q]]++; ti[t] = j; map[t] = q; }
+    if (cp) for (int j = 0; j < cols; j++) for (int q = cp[j]; q < cp[j + 1]; q++) { const int t = w[ri[q]]++; ti[t] = j; map[t] = q; }
 }
 void gather_values(b200qp_handle* h, const double* src, int nnz_in, const DevBuf<int>& map, int nnz, double* dst, int on_device) {
     if (!src || nnz == 0) return;
@@ -664,6 +664,14 @@ int b200qp_get_stats(b200qp_handle* h, b200qp_stats* stats) {
         stats->cholesky_ms = be->prof_ms[BatchedKKT::T_FACTOR]; stats->cholesky_calls = be->prof_calls[BatchedKKT::T_FACTOR];
         stats->backend_solve_ms = be->prof_ms[BatchedKKT::T_SOLVE]; stats->backend_solve_launch_groups = be->prof_calls[BatchedKKT::T_SOLVE];
     )
+    return B200_OK;
+}
+int b200qp_get_work(b200qp_handle* h, double* factor_flops, double* factor_bytes, double* solve_flops, double* solve_bytes) {
+    if (!h || !h->be) return fail(B200_E_INVALID, "null handle");
+    if (factor_flops) *factor_flops = h->be->factor_flops();
+    if (factor_bytes) *factor_bytes = h->be->factor_bytes();
+    if (solve_flops) *solve_flops = h->be->solve_flops();
+    if (solve_bytes) *solve_bytes = h->be->solve_bytes();
     return B200_OK;
 }
 int b200qp_set_profiling(b200qp_handle* h, int enable) {

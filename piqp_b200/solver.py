@@ -83,6 +83,12 @@ class _BatchedBase:
         r.info = self.info()
         return r
 
+    def work(self):
+        """algorithmic (factor_flops, factor_bytes, solve_flops, solve_bytes) per backend call and instance"""
+        v = [C.c_double() for _ in range(4)]
+        _lib.check(self._L.b200qp_get_work(self._h, *[C.byref(x) for x in v]), "b200qp_get_work")
+        return tuple(x.value for x in v)
+
     def set_profiling(self, enable=True):
         _lib.check(self._L.b200qp_set_profiling(self._h, int(enable)), "b200qp_set_profiling")
 
