@@ -63,12 +63,21 @@ int b200kkt_dense_create(b200kkt_handle** out, int n, int p, int m,
 
 /* replaces sparse::KKT<T,I,KKT_FULL>::KKT(const Data&) (include/piqp/sparse/kkt.hpp:51-70)
  * CSC of P_utri (upper), AT (n x p), GT (n x m).  mode = KKTMode (kkt_fwd.hpp:15-21), only 0 (FULL)
- * is implemented in this round.  perm: optional fill-reducing ordering of the n+p+m KKT (NULL = own AMD). */
+ * is implemented.  perm: optional fill-reducing ordering of the n+p+m KKT (NULL = own AMD). */
 int b200kkt_sparse_create(b200kkt_handle** out, int n, int p, int m,
                           const int* Pp, const int* Pi, const double* Px,
                           const int* ATp, const int* ATi, const double* ATx,
                           const int* GTp, const int* GTi, const double* GTx,
                           int mode, const int* perm, int device);
+/* symbolic statistics of a sparse_ldlt handle (what LDLt::factorize_symbolic computes, sparse/ldlt.hpp:42-99) and the
+ * ordering in use (ordering.hpp:59-125): perm[n+p+m], perm[new] = old.  Any pointer may be NULL.                    */
+/* host-only symbolic phase of the sparse_ldlt backend (no GPU needed): KKT pattern (kkt_full.hpp:39-170), fill-reducing
+ * ordering (ordering.hpp:59-125; perm_in != NULL uses the caller's), elimination tree / nnz(L) (ldlt.hpp:42-99) and the
+ * number of etree level sets the device factorisation is scheduled by.                                              */
+int b200_sparse_ldlt_symbolic(int n, int p, int m, const int* Pp, const int* Pi, const int* ATp, const int* ATi,
+                              const int* GTp, const int* GTi, const int* perm_in, int* perm_out,
+                              long long* nnz_kkt, long long* nnz_L, int* etree_levels, double* factor_flops);
+int b200kkt_sparse_info(b200kkt_handle* h, long long* nnz_kkt, long long* nnz_L, int* etree_levels, int* perm);
 
 /* replaces sparse::MultistageKKT<T,I>::MultistageKKT(const Data&) (include/piqp/sparse/multistage_kkt.hpp:74-133) */
 int b200kkt_multistage_create(b200kkt_handle** out, int n, int p, int m,

@@ -154,6 +154,37 @@ class MultistageKKT(KKTSolverBase):
         return [(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]) for i in range(k)]
 
 
+class SparseKKT(KKTSolverBase):
+    """Twin of piqp::sparse::KKT<T, I, KKT_FULL> (include/piqp/sparse/kkt.hpp:31-250): LDL^T of the permuted
+    quasi-definite KKT matrix.  `perm` (optional, length n+p+m, perm[new] = old) replaces the built-in ordering."""
+
+    def __init__(self, P_utri, AT=None, GT=None, perm=None, device=0):
+        import scipy.sparse as sp
+        super().__init__()
+        self.n = P_utri.shape[0]
+        AT = sp.csc_matrix((self.n, 0)) if AT is None else AT
+        GT = sp.csc_matrix((self.n, 0)) if GT is None else GT
+        self.p, self.m = AT.shape[1], GT.shape[1]
+        self._P = _csc_arrays(P_utri, upper=True); self._A = _csc_arrays(AT); self._G = _csc_arrays(GT)
+        ipp = lambda a: a.ctypes.data_as(ip)
+        pm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+        _lib.check(self._L.b200kkt_sparse_create(C.byref(self._h), self.n, self.p, self.m, ipp(self._P[0]), ipp(self._P[1]), _p(self._P[2]),
+                                                 ipp(self._A[0]), ipp(self._A[1]), _p(self._A[2]), ipp(self._G[0]), ipp(self._G[1]), _p(self._G[2]),
+                                                 0, None if pm is None else ipp(pm), device), "b200kkt_sparse_create")
+
+    update_data = None  # set below (shared with MultistageKKT)
+
+    def symbolic_info(self):
+        nk = self.n + self.p + self.m
+        a, b, lv = C.c_longlong(), C.c_longlong(), C.c_int()
+        perm = np.zeros(nk, dtype=np.int32)
+        _lib.check(self._L.b200kkt_sparse_info(self._h, C.byref(a), C.byref(b), C.byref(lv), perm.ctypes.data_as(ip)), "b200kkt_sparse_info")
+        return {"nnz_kkt": a.value, "nnz_L": b.value, "etree_levels": lv.value, "perm": perm}
+
+
+SparseKKT.update_data = MultistageKKT.update_data
+
+
 def c_abi_vtable():
     """Function-pointer table of the C-ABI in the layout oracle/oracle_capi.cpp::OrcBackendVTable expects
     (used by tests to put the CUDA backend behind the oracle's KKTSystem + IP loop)."""

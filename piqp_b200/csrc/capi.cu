@@ -3,6 +3,7 @@
 #include "dense_backend.hpp"
 #include "ip_solver.hpp"
 #include "multistage_backend.hpp"
+#include "sparse_ldlt_backend.hpp"
 #include "sparse_data.hpp"
 #include <chrono>
 #include <cstdlib>
@@ -24,13 +25,14 @@ static int fail(int code, const std::string& what) { g_err = what; return code; 
 // single-instance backend handle
 // ---------------------------------------------------------------------------------------------------
 struct b200kkt_handle {
-    int kind = 0;   // 0 dense
+    int kind = 0;   // 0 dense, 1 multistage, 2 sparse_ldlt
     int device = 0, n = 0, p = 0, m = 0;
     cudaStream_t stream = nullptr;
     DenseData dd;
     std::unique_ptr<DenseBatchedKKT> dense;
     SparseData sd;
     std::unique_ptr<MultistageBatchedKKT> ms;
+    std::unique_ptr<SparseLdltBatchedKKT> ldlt;
     BatchedKKT* be = nullptr;
     // staging
     DevBuf<double> stage_mat;   // raw matrix upload
@@ -98,18 +100,14 @@ int b200kkt_dense_create(b200kkt_handle** out, int n, int p, int m, const double
     return B200_OK;
 }
 
-int b200kkt_sparse_create(b200kkt_handle** out, int, int, int, const int*, const int*, const double*, const int*, const int*, const double*,
-                          const int*, const int*, const double*, int, const int*, int) {
-    if (out) *out = nullptr;
-    return fail(B200_E_UNSUPPORTED, "b200kkt_sparse_create: sparse backend not built yet");
-}
-int b200kkt_multistage_create(b200kkt_handle** out, int n, int p, int m, const int* Pp, const int* Pi, const double* Px,
-                              const int* ATp, const int* ATi, const double* ATx, const int* GTp, const int* GTi, const double* GTx, int device) {
-    if (!out || n <= 0 || p < 0 || m < 0 || !Pp || (p > 0 && !ATp) || (m > 0 && !GTp)) return fail(B200_E_INVALID, "b200kkt_multistage_create: bad arguments");
+namespace {
+int sparse_single_create(b200kkt_handle** out, int kind, int n, int p, int m, const int* Pp, const int* Pi, const double* Px,
+                         const int* ATp, const int* ATi, const double* ATx, const int* GTp, const int* GTi, const double* GTx, const int* perm, int device) {
+    *out = nullptr;
     B200_TRY(
         B200_CUDA(cudaSetDevice(device));
         auto h = std::make_unique<b200kkt_handle>();
-        h->kind = 1; h->device = device; h->n = n; h->p = p; h->m = m;
+        h->kind = kind; h->device = device; h->n = n; h->p = p; h->m = m;
         B200_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         SparseData& S = h->sd;
         S.n = n; S.p = p; S.m = m;
@@ -123,11 +121,55 @@ int b200kkt_multistage_create(b200kkt_handle** out, int n, int p, int m, const i
         for (int i = 0; i < 4; i++) { h->vx[i].alloc(std::max(n, 1)); h->vy[i].alloc(std::max(p, 1)); h->vz[i].alloc(std::max(m, 1)); }
         h->delta.alloc(1); h->ok.alloc(1);
         B200_CUDA(cudaDeviceSynchronize());
-        h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream);
-        h->be = h->ms.get();
+        if (kind == 1) { h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream); h->be = h->ms.get(); }
+        else { h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, perm, h->stream); h->be = h->ldlt.get(); }
         B200_CUDA(cudaStreamSynchronize(h->stream));
         *out = h.release();
     )
+    return B200_OK;
+}
+}  // namespace
+
+int b200kkt_sparse_create(b200kkt_handle** out, int n, int p, int m, const int* Pp, const int* Pi, const double* Px, const int* ATp, const int* ATi, const double* ATx,
+                          const int* GTp, const int* GTi, const double* GTx, int mode, const int* perm, int device) {
+    if (!out || n <= 0 || p < 0 || m < 0 || !Pp || (p > 0 && !ATp) || (m > 0 && !GTp)) return fail(B200_E_INVALID, "b200kkt_sparse_create: bad arguments");
+    if (mode != 0) { *out = nullptr; return fail(B200_E_UNSUPPORTED, "b200kkt_sparse_create: only KKTMode FULL (0) is implemented"); }
+    return sparse_single_create(out, 2, n, p, m, Pp, Pi, Px, ATp, ATi, ATx, GTp, GTi, GTx, perm, device);
+}
+int b200kkt_multistage_create(b200kkt_handle** out, int n, int p, int m, const int* Pp, const int* Pi, const double* Px,
+                              const int* ATp, const int* ATi, const double* ATx, const int* GTp, const int* GTi, const double* GTx, int device) {
+    if (!out || n <= 0 || p < 0 || m < 0 || !Pp || (p > 0 && !ATp) || (m > 0 && !GTp)) return fail(B200_E_INVALID, "b200kkt_multistage_create: bad arguments");
+    return sparse_single_create(out, 1, n, p, m, Pp, Pi, Px, ATp, ATi, ATx, GTp, GTi, GTx, nullptr, device);
+}
+int b200_sparse_ldlt_symbolic(int n, int p, int m, const int* Pp, const int* Pi, const int* ATp, const int* ATi, const int* GTp, const int* GTi,
+                              const int* perm_in, int* perm_out, long long* nnz_kkt, long long* nnz_L, int* levels, double* factor_flops) {
+    if (n <= 0 || p < 0 || m < 0 || !Pp || (p > 0 && !ATp) || (m > 0 && !GTp)) return fail(B200_E_INVALID, "b200_sparse_ldlt_symbolic: bad arguments");
+    B200_TRY(
+        auto host_pattern = [](Pattern& M, int rows, int cols, const int* cp, const int* ri) {
+            M.rows = rows; M.cols = cols;
+            if (cp) M.p.assign(cp, cp + cols + 1); else M.p.assign(cols + 1, 0);
+            M.nnz = M.p[cols];
+            if (M.nnz) M.i.assign(ri, ri + M.nnz);
+        };
+        Pattern P, AT, GT;
+        host_pattern(P, n, n, Pp, Pi); host_pattern(AT, n, p, ATp, ATi); host_pattern(GT, n, m, GTp, GTi);
+        LdltSymbolic S;
+        if (!S.analyse(P, AT, GT, perm_in)) throw std::runtime_error(S.error);
+        if (perm_out) std::copy(S.perm.begin(), S.perm.end(), perm_out);
+        if (nnz_kkt) *nnz_kkt = (long long)S.PKi_rows.size();
+        if (nnz_L) *nnz_L = (long long)S.nnzL();
+        if (levels) *levels = (int)S.level_ptr.size() - 1;
+        if (factor_flops) *factor_flops = S.factor_flops();
+    )
+    return B200_OK;
+}
+int b200kkt_sparse_info(b200kkt_handle* h, long long* nnz_kkt, long long* nnz_L, int* levels, int* perm) {
+    if (!h || !h->ldlt) return fail(B200_E_INVALID, "not a sparse_ldlt handle");
+    const LdltSymbolic& S = h->ldlt->S;
+    if (nnz_kkt) *nnz_kkt = (long long)S.PKi_rows.size();
+    if (nnz_L) *nnz_L = (long long)S.nnzL();
+    if (levels) *levels = (int)S.level_ptr.size() - 1;
+    if (perm) std::copy(S.perm.begin(), S.perm.end(), perm);
     return B200_OK;
 }
 
@@ -227,9 +269,15 @@ b200kkt_handle* b200kkt_clone(const b200kkt_handle* src) {
             for (int i = 0; i < 4; i++) { h->vx[i].alloc(std::max(h->n, 1)); h->vy[i].alloc(std::max(h->p, 1)); h->vz[i].alloc(std::max(h->m, 1)); }
             h->delta.alloc(1); h->ok.alloc(1);
             B200_CUDA(cudaDeviceSynchronize());
-            h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream);
-            h->ms->copy_from(*src->ms);
-            h->be = h->ms.get();
+            if (src->kind == 1) {
+                h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream);
+                h->ms->copy_from(*src->ms);
+                h->be = h->ms.get();
+            } else {
+                h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, src->ldlt->S.perm.data(), h->stream);
+                h->ldlt->copy_from(*src->ldlt);
+                h->be = h->ldlt.get();
+            }
             B200_CUDA(cudaStreamSynchronize(h->stream));
             return h.release();
         }
@@ -289,12 +337,13 @@ struct b200qp_handle {
     RuizState ruiz;
     std::unique_ptr<DenseBatchedKKT> dense;
     std::unique_ptr<MultistageBatchedKKT> ms;
+    std::unique_ptr<SparseLdltBatchedKKT> ldlt;
     BatchedKKT* be = nullptr;
     std::unique_ptr<BatchedIPSolver> ip;
     DevBuf<int> zero_rows;
     bool solved = false;
     double setup_ms = 0, update_ms = 0;
-    ~b200qp_handle() { ip.reset(); dense.reset(); ms.reset(); if (stream) cudaStreamDestroy(stream); }
+    ~b200qp_handle() { ip.reset(); dense.reset(); ms.reset(); ldlt.reset(); if (stream) cudaStreamDestroy(stream); }
 };
 
 namespace {
@@ -525,7 +574,8 @@ int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
         auto h = std::make_unique<b200qp_handle>();
         h->kind = 1; h->device = device; h->batch = batch; h->n = n; h->p = p; h->m = m;
         if (settings) h->st = *settings; else b200qp_set_default_settings_sparse(&h->st);
-        if (h->st.kkt_solver != 5) throw std::runtime_error("b200qp_setup_sparse: only kkt_solver = sparse_multistage (5) is built in this round");
+        if (h->st.kkt_solver != 5 && h->st.kkt_solver != 1)
+            throw std::runtime_error("b200qp_setup_sparse: kkt_solver must be sparse_ldlt (1) or sparse_multistage (5); the reduced KKT modes are not built");
         B200_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         cudaEvent_t e0, e1;
         B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
@@ -561,8 +611,8 @@ int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
         sparse_ruiz_scale(S, h->ruiz, d.c, d.b, d.h_l, d.h_u, d.x_l, d.x_u, d.xbs, false, h->st.preconditioner_scale_cost != 0, h->st.preconditioner_iter, h->stream);
         d.pd = h->ruiz.delta.get(); d.pd_inv = h->ruiz.delta_inv.get(); d.pdb = h->ruiz.delta_b.get(); d.pdb_inv = h->ruiz.delta_b_inv.get();
         d.pc = h->ruiz.c.get(); d.pc_inv = h->ruiz.c_inv.get();
-        h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream);
-        h->be = h->ms.get();
+        if (h->st.kkt_solver == 5) { h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream); h->be = h->ms.get(); }
+        else { h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, nullptr, h->stream); h->be = h->ldlt.get(); }
         h->ip->finish_setup(h->be);
         B200_CUDA(cudaEventRecord(e1, h->stream));
         B200_CUDA(cudaEventSynchronize(e1));

@@ -1,0 +1,409 @@
+// piqp_b200/csrc/sparse_ldlt_backend.cu -- see sparse_ldlt_backend.hpp
+#include "sparse_ldlt_backend.hpp"
+#include <algorithm>
+#include <cstdio>
+#include <set>
+#include <stdexcept>
+
+namespace b200 {
+
+// =====================================================================================================
+// host: ordering
+// =====================================================================================================
+// Minimum-degree ordering on the graph of a symmetric matrix given by its upper triangle (CSC).  Quotient graph
+// (variables + elements, element absorption) with exact external degrees; ties broken by index.  perm[k] = k-th pivot.
+std::vector<int> minimum_degree_ordering(int n, const std::vector<int>& cp, const std::vector<int>& ri) {
+    std::vector<std::vector<int>> avar(n), aelem(n), members(n);
+    for (int j = 0; j < n; j++) for (int q = cp[j]; q < cp[j + 1]; q++) { const int i = ri[q]; if (i != j) { avar[i].push_back(j); avar[j].push_back(i); } }
+    for (auto& v : avar) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+    std::vector<char> gone(n, 0), elem_alive(n, 0);
+    std::vector<int> deg(n), mark(n, -1), mark2(n, -1);
+    std::set<std::pair<int, int>> pq;
+    for (int i = 0; i < n; i++) { deg[i] = (int)avar[i].size(); pq.insert({deg[i], i}); }
+    std::vector<int> perm; perm.reserve(n);
+    std::vector<int> Lp;
+    int stamp = 0;
+    while (!pq.empty()) {
+        const int pv = pq.begin()->second;
+        pq.erase(pq.begin());
+        perm.push_back(pv);
+        // pattern of the new element
+        Lp.clear();
+        mark[pv] = pv;
+        for (int v : avar[pv]) if (!gone[v] && mark[v] != pv) { mark[v] = pv; Lp.push_back(v); }
+        for (int e : aelem[pv]) {
+            if (!elem_alive[e]) continue;
+            for (int v : members[e]) if (!gone[v] && mark[v] != pv) { mark[v] = pv; Lp.push_back(v); }
+            elem_alive[e] = 0; members[e].clear(); members[e].shrink_to_fit();
+        }
+        gone[pv] = 1;
+        avar[pv].clear(); aelem[pv].clear();
+        members[pv] = Lp; elem_alive[pv] = 1;
+        for (int i : Lp) {
+            // prune: variables now reachable through the new element, dead elements
+            auto& av = avar[i];
+            size_t w = 0;
+            for (int v : av) if (!gone[v] && mark[v] != pv) av[w++] = v;
+            av.resize(w);
+            auto& ae = aelem[i];
+            w = 0;
+            for (int e : ae) if (elem_alive[e] && e != pv) ae[w++] = e;
+            ae.resize(w);
+            ae.push_back(pv);
+            // exact external degree
+            ++stamp;
+            int d = 0;
+            mark2[i] = stamp;
+            for (int v : av) if (mark2[v] != stamp) { mark2[v] = stamp; d++; }
+            for (int e : ae) for (int v : members[e]) if (!gone[v] && mark2[v] != stamp) { mark2[v] = stamp; d++; }
+            pq.erase({deg[i], i});
+            deg[i] = d;
+            pq.insert({d, i});
+        }
+    }
+    return perm;
+}
+
+// =====================================================================================================
+// host: symbolic analysis
+// =====================================================================================================
+bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& GT, const int* user_perm) {
+    n = P.rows; p = AT.cols; m = GT.cols; nk = n + p + m;
+    // ---- KKT pattern [[P + rho I, A^T, G^T], [., -delta I, .], [., ., -Z]], upper CSC (kkt_full.hpp:39-170)
+    Kp.assign(nk + 1, 0); Ki.clear();
+    P_to_K.assign(P.nnz, -1); AT_to_K.assign(AT.nnz, -1); GT_to_K.assign(GT.nnz, -1);
+    std::vector<int> diagK(nk, -1);
+    for (int j = 0; j < n; j++) {
+        bool has_diag = false;
+        for (int q = P.p[j]; q < P.p[j + 1]; q++) {
+            if (P.i[q] > j) { error = "sparse_ldlt: P must be upper triangular"; return false; }
+            P_to_K[q] = (int)Ki.size();
+            if (P.i[q] == j) { has_diag = true; diagK[j] = (int)Ki.size(); }
+            Ki.push_back(P.i[q]);
+        }
+        if (!has_diag) { diagK[j] = (int)Ki.size(); Ki.push_back(j); }
+        Kp[j + 1] = (int)Ki.size();
+    }
+    for (int c = 0; c < p; c++) {
+        for (int q = AT.p[c]; q < AT.p[c + 1]; q++) { AT_to_K[q] = (int)Ki.size(); Ki.push_back(AT.i[q]); }
+        diagK[n + c] = (int)Ki.size(); Ki.push_back(n + c);
+        Kp[n + c + 1] = (int)Ki.size();
+    }
+    for (int c = 0; c < m; c++) {
+        for (int q = GT.p[c]; q < GT.p[c + 1]; q++) { GT_to_K[q] = (int)Ki.size(); Ki.push_back(GT.i[q]); }
+        diagK[n + p + c] = (int)Ki.size(); Ki.push_back(n + p + c);
+        Kp[n + p + c + 1] = (int)Ki.size();
+    }
+    // ---- ordering
+    if (user_perm) perm.assign(user_perm, user_perm + nk);
+    else perm = minimum_degree_ordering(nk, Kp, Ki);
+    iperm.assign(nk, -1);
+    for (int k = 0; k < nk; k++) { if (perm[k] < 0 || perm[k] >= nk || iperm[perm[k]] != -1) { error = "sparse_ldlt: invalid permutation"; return false; } iperm[perm[k]] = k; }
+    // ---- permuted upper pattern with sorted rows + value map (utils.hpp:31-128)
+    const int nnzK = (int)Ki.size();
+    std::vector<int> colcnt(nk + 1, 0), ecol(nnzK), erow(nnzK);
+    for (int j = 0; j < nk; j++) for (int q = Kp[j]; q < Kp[j + 1]; q++) {
+        const int a = iperm[Ki[q]], b = iperm[j];
+        erow[q] = std::min(a, b); ecol[q] = std::max(a, b);
+        colcnt[ecol[q] + 1]++;
+    }
+    PKp.assign(nk + 1, 0);
+    for (int j = 0; j < nk; j++) PKp[j + 1] = PKp[j] + colcnt[j + 1];
+    std::vector<std::pair<int, int>> tmp(nnzK);   // (row, K index) grouped by column
+    {
+        std::vector<int> w(PKp.begin(), PKp.end() - 1);
+        for (int q = 0; q < nnzK; q++) tmp[w[ecol[q]]++] = {erow[q], q};
+    }
+    PKi_rows.assign(nnzK, 0); K_to_PK.assign(nnzK, 0);
+    for (int j = 0; j < nk; j++) {
+        std::sort(tmp.begin() + PKp[j], tmp.begin() + PKp[j + 1]);
+        for (int t = PKp[j]; t < PKp[j + 1]; t++) { PKi_rows[t] = tmp[t].first; K_to_PK[tmp[t].second] = t; }
+    }
+    diagPK.assign(nk, -1);
+    for (int v = 0; v < nk; v++) diagPK[v] = K_to_PK[diagK[v]];
+    // ---- elimination tree and pattern of L, row by row (ldlt.hpp:42-99 + the pattern the numeric phase fills, :101-169)
+    etree.assign(nk, -1);
+    std::vector<int> flag(nk, -1), Lnz(nk, 0);
+    for (int k = 0; k < nk; k++) {
+        flag[k] = k;
+        for (int q = PKp[k]; q < PKp[k + 1]; q++)
+            for (int i = PKi_rows[q]; flag[i] != k; i = etree[i]) { if (etree[i] == -1) etree[i] = k; Lnz[i]++; flag[i] = k; }
+    }
+    Lp.assign(nk + 1, 0);
+    for (int k = 0; k < nk; k++) Lp[k + 1] = Lp[k] + Lnz[k];
+    Li.assign(Lp[nk], 0);
+    std::fill(flag.begin(), flag.end(), -1);
+    std::vector<int> fill(nk, 0);
+    Rp.assign(nk + 1, 0);
+    std::vector<std::vector<std::pair<int, int>>> rows(nk);
+    for (int k = 0; k < nk; k++) {
+        flag[k] = k;
+        for (int q = PKp[k]; q < PKp[k + 1]; q++)
+            for (int i = PKi_rows[q]; flag[i] != k; i = etree[i]) {
+                flag[i] = k;
+                const int pos = Lp[i] + fill[i]++;
+                Li[pos] = k;
+                rows[k].push_back({i, pos});
+            }
+        std::sort(rows[k].begin(), rows[k].end());
+        Rp[k + 1] = Rp[k] + (int)rows[k].size();
+    }
+    Rcol.assign(Rp[nk], 0); Rpos.assign(Rp[nk], 0);
+    for (int k = 0; k < nk; k++) for (size_t t = 0; t < rows[k].size(); t++) { Rcol[Rp[k] + t] = rows[k][t].first; Rpos[Rp[k] + t] = rows[k][t].second; }
+    // ---- scatter map of the permuted matrix into L / D
+    PK_to_L.assign(nnzK, 0);
+    for (int j = 0; j < nk; j++) for (int q = PKp[j]; q < PKp[j + 1]; q++) {
+        const int i = PKi_rows[q];
+        if (i == j) { PK_to_L[q] = -(j + 1); continue; }
+        const int* b = &Li[Lp[i]]; const int* e = &Li[Lp[i + 1]];
+        const int* it = std::lower_bound(b, e, j);
+        if (it == e || *it != j) { error = "sparse_ldlt: internal error (entry of A missing in L)"; return false; }
+        PK_to_L[q] = (int)(it - &Li[0]);
+    }
+    // ---- level sets of the elimination tree
+    level.assign(nk, 0);
+    int maxl = 0;
+    for (int j = 0; j < nk; j++) { if (etree[j] >= 0) level[etree[j]] = std::max(level[etree[j]], level[j] + 1); maxl = std::max(maxl, level[j]); }
+    level_ptr.assign(maxl + 2, 0);
+    for (int j = 0; j < nk; j++) level_ptr[level[j] + 1]++;
+    for (int l = 0; l <= maxl; l++) level_ptr[l + 1] += level_ptr[l];
+    level_cols.assign(nk, 0);
+    { std::vector<int> w(level_ptr.begin(), level_ptr.end() - 1); for (int j = 0; j < nk; j++) level_cols[w[level[j]]++] = j; }
+    return true;
+}
+double LdltSymbolic::factor_flops() const {
+    double f = 0;
+    for (int j = 0; j < nk; j++) { const double c = Lp[j + 1] - Lp[j]; f += c * c + 2 * c; }
+    return f;
+}
+
+// =====================================================================================================
+// device kernels
+// =====================================================================================================
+__global__ void ldlt_scatter_kernel(const int* map, int nnz, int nnzPK, const double* vals, double* PKx) {
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nnz) PKx[(size_t)b * nnzPK + map[q]] = vals[(size_t)b * nnz + q];
+}
+// diagonal of the KKT matrix for this iteration (kkt_full.hpp:172-210)
+__global__ void ldlt_set_diag_kernel(const int* diagPK, int n, int p, int m, int nnzPK, const double* P_diag, const double* x_reg, const double* delta,
+                                     const double* z_reg, double* PKx, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nk = n + p + m;
+    if (v >= nk) return;
+    double val;
+    if (v < n) val = P_diag[(size_t)b * n + v] + x_reg[(size_t)b * n + v];
+    else if (v < n + p) val = -delta[b];
+    else val = -z_reg[(size_t)b * m + (v - n - p)];
+    PKx[(size_t)b * nnzPK + diagPK[v]] = val;
+}
+__global__ void ldlt_zero_kernel(double* Lx, size_t nnzL, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nnzL) Lx[(size_t)b * nnzL + e] = 0.0;
+}
+__global__ void ldlt_init_kernel(const int* PK_to_L, int nnzPK, size_t nnzL, int nk, const double* PKx, double* Lx, double* Dv, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nnzPK) return;
+    const int t = PK_to_L[q];
+    const double v = PKx[(size_t)b * nnzPK + q];
+    if (t >= 0) Lx[(size_t)b * nnzL + t] = v; else Dv[(size_t)b * nk + (-t - 1)] = v;
+}
+// one warp per (column of this level, instance): left-looking update + scaling
+__global__ void ldlt_level_kernel(const int* cols, int ncols, const int* Lp, const int* Li, const int* Rp, const int* Rcol, const int* Rpos,
+                                  size_t nnzL, int nk, double* Lx_all, double* Dv_all, double* Dinv_all, int* fail, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= ncols) return;
+    const int j = cols[warp];
+    double* Lx = Lx_all + (size_t)b * nnzL;
+    double* Dv = Dv_all + (size_t)b * nk;
+    const int cj0 = Lp[j], cj1 = Lp[j + 1];
+    double d = Dv[j];
+    for (int t = Rp[j]; t < Rp[j + 1]; t++) {
+        const int k = Rcol[t], pos = Rpos[t];
+        const double ljk = Lx[pos];
+        const double w = ljk * Dv[k];
+        d -= ljk * w;
+        for (int e = pos + 1 + lane; e < Lp[k + 1]; e += 32) {
+            const int r = Li[e];
+            int lo = cj0, hi = cj1 - 1;           // r is guaranteed to be in column j's pattern
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (Li[mid] < r) lo = mid + 1; else hi = mid; }
+            Lx[lo] -= Lx[e] * w;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (d == 0.0 && fail[b] == 0) fail[b] = j + 1;      // ldlt.hpp:161
+        Dv[j] = d;
+        Dinv_all[(size_t)b * nk + j] = 1.0 / d;
+    }
+    for (int e = cj0 + lane; e < cj1; e += 32) Lx[e] /= d;
+}
+// rhs (x | y | z blocks) -> permuted work vector, and back (ordering.hpp:102-124, sparse/kkt.hpp:113-147)
+__global__ void ldlt_gather_rhs_kernel(const int* perm, int n, int p, int m, const double* rx, const double* ry, const double* rz, double* work, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nk = n + p + m;
+    if (j >= nk) return;
+    const int v = perm[j];
+    double val;
+    if (v < n) val = rx[(size_t)b * n + v]; else if (v < n + p) val = ry[(size_t)b * p + (v - n)]; else val = rz[(size_t)b * m + (v - n - p)];
+    work[(size_t)b * nk + j] = val;
+}
+__global__ void ldlt_scatter_lhs_kernel(const int* perm, int n, int p, int m, const double* work, double* lx, double* ly, double* lz, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nk = n + p + m;
+    if (j >= nk) return;
+    const int v = perm[j];
+    const double val = work[(size_t)b * nk + j];
+    if (v < n) lx[(size_t)b * n + v] = val; else if (v < n + p) ly[(size_t)b * p + (v - n)] = val; else lz[(size_t)b * m + (v - n - p)] = val;
+}
+__global__ void ldlt_fwd_level_kernel(const int* cols, int ncols, const int* Rp, const int* Rcol, const int* Rpos, size_t nnzL, int nk, const double* Lx_all,
+                                      double* work_all, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncols) return;
+    const int j = cols[t];
+    const double* Lx = Lx_all + (size_t)b * nnzL;
+    double* w = work_all + (size_t)b * nk;
+    double acc = w[j];
+    for (int q = Rp[j]; q < Rp[j + 1]; q++) acc -= Lx[Rpos[q]] * w[Rcol[q]];
+    w[j] = acc;
+}
+__global__ void ldlt_dscale_kernel(int nk, const double* Dinv, double* work, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nk) work[(size_t)b * nk + j] *= Dinv[(size_t)b * nk + j];
+}
+__global__ void ldlt_bwd_level_kernel(const int* cols, int ncols, const int* Lp, const int* Li, size_t nnzL, int nk, const double* Lx_all, double* work_all,
+                                      const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncols) return;
+    const int j = cols[t];
+    const double* Lx = Lx_all + (size_t)b * nnzL;
+    double* w = work_all + (size_t)b * nk;
+    double acc = w[j];
+    for (int e = Lp[j]; e < Lp[j + 1]; e++) acc -= Lx[e] * w[Li[e]];
+    w[j] = acc;
+}
+__global__ void ldlt_clear_fail_kernel(int* fail, const int* active, int batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch && (!active || active[b])) fail[b] = 0;
+}
+__global__ void ldlt_fail_to_ok_kernel(const int* fail, const int* active, int* ok, int batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch && (!active || active[b])) ok[b] = fail[b] ? 0 : 1;
+}
+
+// =====================================================================================================
+static void upload(DevBuf<int>& d, const std::vector<int>& h) {
+    d.alloc(std::max<size_t>(h.size(), 1));
+    if (!h.empty()) B200_CUDA(cudaMemcpy(d.get(), h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+}
+
+SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_perm, cudaStream_t st) : D(data) {
+    batch = D->batch; n = D->n; p = D->p; m = D->m; stream = st;
+    if (!S.analyse(D->P, D->AT, D->GT, user_perm)) throw std::runtime_error(S.error);
+    auto compose = [&](const std::vector<int>& toK) { std::vector<int> r(toK.size()); for (size_t q = 0; q < toK.size(); q++) r[q] = S.K_to_PK[toK[q]]; return r; };
+    upload(d_P_to_PK, compose(S.P_to_K)); upload(d_AT_to_PK, compose(S.AT_to_K)); upload(d_GT_to_PK, compose(S.GT_to_K));
+    upload(d_diagPK, S.diagPK); upload(d_PK_to_L, S.PK_to_L); upload(d_PKp, S.PKp);
+    upload(d_Lp, S.Lp); upload(d_Li, S.Li); upload(d_Rp, S.Rp); upload(d_Rcol, S.Rcol); upload(d_Rpos, S.Rpos);
+    upload(d_level_cols, S.level_cols); upload(d_perm, S.perm);
+    const size_t B = batch, nnzPK = S.PKi_rows.size(), nnzL = std::max<size_t>(S.Li.size(), 1);
+    PKx.alloc(B * nnzPK); PKx.zero(st);
+    P_diag.alloc(std::max<size_t>(B * n, 1));
+    Lx.alloc(B * nnzL); Dv.alloc(B * S.nk); Dinv.alloc(B * S.nk); work.alloc(B * S.nk); fail.alloc(B); fail.zero(st);
+    scatter_static(7);
+}
+void SparseLdltBatchedKKT::copy_from(const SparseLdltBatchedKKT& o) {
+    auto cp = [&](DevBuf<double>& d, const DevBuf<double>& s) { if (s.n) B200_CUDA(cudaMemcpyAsync(d.get(), s.get(), s.n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); };
+    cp(PKx, o.PKx); cp(P_diag, o.P_diag); cp(Lx, o.Lx); cp(Dv, o.Dv); cp(Dinv, o.Dinv);
+}
+void SparseLdltBatchedKKT::scatter_static(int options) {   // kkt_full.hpp:212-251
+    const int nnzPK = (int)S.PKi_rows.size();
+    if ((options & 1) && D->P.nnz) {
+        dim3 g(ceil_div(D->P.nnz, 256), batch);
+        B200_LAUNCH(ldlt_scatter_kernel, g, 256, 0, stream, d_P_to_PK.get(), D->P.nnz, nnzPK, D->Px.get(), PKx.get());
+        sparse_extract_diag(*D, P_diag.get(), stream);
+    }
+    if ((options & 2) && D->AT.nnz) { dim3 g(ceil_div(D->AT.nnz, 256), batch);
+        B200_LAUNCH(ldlt_scatter_kernel, g, 256, 0, stream, d_AT_to_PK.get(), D->AT.nnz, nnzPK, D->ATx.get(), PKx.get()); }
+    if ((options & 4) && D->GT.nnz) { dim3 g(ceil_div(D->GT.nnz, 256), batch);
+        B200_LAUNCH(ldlt_scatter_kernel, g, 256, 0, stream, d_GT_to_PK.get(), D->GT.nnz, nnzPK, D->GTx.get(), PKx.get()); }
+}
+void SparseLdltBatchedKKT::update_data(int options) { scatter_static(options); }
+
+void SparseLdltBatchedKKT::factor(const double* delta, const double* x_reg, const double* z_reg, const int* active, int* ok) {   // sparse/kkt.hpp:83-105
+    const int nk = S.nk, nnzPK = (int)S.PKi_rows.size();
+    const size_t nnzL = std::max<size_t>(S.Li.size(), 1);
+    tic(T_ASSEMBLE);
+    { dim3 g(ceil_div(nk, 256), batch);
+      B200_LAUNCH(ldlt_set_diag_kernel, g, 256, 0, stream, d_diagPK.get(), n, p, m, nnzPK, P_diag.get(), x_reg, delta, z_reg, PKx.get(), active); }
+    { dim3 g((unsigned)((nnzL + 255) / 256), batch); B200_LAUNCH(ldlt_zero_kernel, g, 256, 0, stream, Lx.get(), nnzL, active); }
+    { dim3 g(ceil_div(nnzPK, 256), batch);
+      B200_LAUNCH(ldlt_init_kernel, g, 256, 0, stream, d_PK_to_L.get(), nnzPK, nnzL, nk, PKx.get(), Lx.get(), Dv.get(), active); }
+    toc(T_ASSEMBLE);
+    tic(T_FACTOR);
+    B200_LAUNCH(ldlt_clear_fail_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, batch);
+    const int nlev = (int)S.level_ptr.size() - 1;
+    for (int l = 0; l < nlev; l++) {
+        const int c0 = S.level_ptr[l], nc = S.level_ptr[l + 1] - c0;
+        dim3 g(ceil_div(nc * 32, 128), batch);
+        B200_LAUNCH(ldlt_level_kernel, g, 128, 0, stream, d_level_cols.get() + c0, nc, d_Lp.get(), d_Li.get(), d_Rp.get(), d_Rcol.get(), d_Rpos.get(),
+                    nnzL, nk, Lx.get(), Dv.get(), Dinv.get(), fail.get(), active);
+    }
+    toc(T_FACTOR);
+    B200_LAUNCH(ldlt_fail_to_ok_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, ok, batch);
+}
+
+void SparseLdltBatchedKKT::solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) {   // sparse/kkt.hpp:107-147 (FULL)
+    const int nk = S.nk;
+    const size_t nnzL = std::max<size_t>(S.Li.size(), 1);
+    tic(T_SOLVE);
+    dim3 gk(ceil_div(nk, 256), batch);
+    B200_LAUNCH(ldlt_gather_rhs_kernel, gk, 256, 0, stream, d_perm.get(), n, p, m, rx, ry, rz, work.get(), active);
+    const int nlev = (int)S.level_ptr.size() - 1;
+    for (int l = 1; l < nlev; l++) {     // level 0 rows have empty row patterns
+        const int c0 = S.level_ptr[l], nc = S.level_ptr[l + 1] - c0;
+        dim3 g(ceil_div(nc, 128), batch);
+        B200_LAUNCH(ldlt_fwd_level_kernel, g, 128, 0, stream, d_level_cols.get() + c0, nc, d_Rp.get(), d_Rcol.get(), d_Rpos.get(), nnzL, nk, Lx.get(), work.get(), active);
+    }
+    B200_LAUNCH(ldlt_dscale_kernel, gk, 256, 0, stream, nk, Dinv.get(), work.get(), active);
+    for (int l = nlev - 2; l >= 0; l--) {   // the top level has empty columns
+        const int c0 = S.level_ptr[l], nc = S.level_ptr[l + 1] - c0;
+        dim3 g(ceil_div(nc, 128), batch);
+        B200_LAUNCH(ldlt_bwd_level_kernel, g, 128, 0, stream, d_level_cols.get() + c0, nc, d_Lp.get(), d_Li.get(), nnzL, nk, Lx.get(), work.get(), active);
+    }
+    B200_LAUNCH(ldlt_scatter_lhs_kernel, gk, 256, 0, stream, d_perm.get(), n, p, m, work.get(), lx, ly, lz, active);
+    toc(T_SOLVE);
+}
+void SparseLdltBatchedKKT::eval_P_x(double alpha, const double* x, double* z, const int* active) { spmv_sym_upper(D->P, D->Px.get(), alpha, x, z, batch, active, stream); }
+void SparseLdltBatchedKKT::eval_A(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) {
+    if (p > 0) spmv_cols(D->AT, D->ATx.get(), an, xn, n, zn, nullptr, 0.0, nullptr, nullptr, 0, batch, active, stream);
+    spmv_rows(D->AT, D->ATx.get(), at, xt, p, zt, 0, nullptr, nullptr, 0, batch, active, stream);
+}
+void SparseLdltBatchedKKT::eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) {
+    if (m > 0) spmv_cols(D->GT, D->GTx.get(), an, xn, n, zn, nullptr, 0.0, nullptr, nullptr, 0, batch, active, stream);
+    spmv_rows(D->GT, D->GTx.get(), at, xt, m, zt, 0, nullptr, nullptr, 0, batch, active, stream);
+}
+void SparseLdltBatchedKKT::extract_P_diag(double* out) { sparse_extract_diag(*D, out, stream); }
+void SparseLdltBatchedKKT::print_info() const {
+    printf("b200 sparse_ldlt backend: n_kkt = %d, nnz(KKT upper) = %zu, nnz(L) = %.0f, etree levels = %zu, factor flops = %.3g\n",
+           S.nk, S.PKi_rows.size(), S.nnzL(), S.level_ptr.size() - 1, S.factor_flops());
+}
+
+}  // namespace b200

@@ -1,0 +1,75 @@
+// piqp_b200/csrc/sparse_ldlt_backend.hpp -- batched general sparse KKT backend (sparse_ldlt, KKTMode FULL).
+//
+// Replaces sparse::KKT<T,I,KKT_FULL> (include/piqp/sparse/kkt.hpp:31-250) with its helpers
+//   KKTImpl<FULL>::create_kkt_matrix / update_kkt_* / update_data_impl   include/piqp/sparse/kkt_full.hpp:39-251
+//   AMDOrdering (Eigen::AMDOrdering, third party)                        include/piqp/sparse/ordering.hpp:59-125
+//   permute_sparse_symmetric_matrix                                      include/piqp/sparse/utils.hpp:31-128
+//   LDLt::factorize_symbolic / factorize_numeric / solve_inplace         include/piqp/sparse/ldlt.hpp:42-218
+// for a batch of QPs sharing one sparsity pattern.
+//
+// Host, once per pattern: KKT pattern -> fill-reducing ordering (own quotient-graph minimum degree; any valid
+// permutation yields the same solve() results to rounding) -> permuted upper pattern -> elimination tree, pattern of L,
+// etree LEVEL SETS.  Device, per iteration: the reference's up-looking row-by-row LDL^T is inherently serial, so the
+// numeric factorisation is restated as a LEFT-LOOKING column algorithm scheduled by etree levels: all columns of one
+// level are independent, one warp per (column, instance) gathers the updates of its descendants (binary search into
+// the target column's sorted row list), then scales by D_j.  Triangular solves are level-scheduled gathers (row view for
+// L, column view for L^T): deterministic, no atomics.  Zero pivots report failure like ldlt.hpp:161.
+#pragma once
+#include <string>
+#include "kkt_backend.hpp"
+#include "sparse_data.hpp"
+
+namespace b200 {
+
+struct LdltSymbolic {   // host
+    int n = 0, p = 0, m = 0, nk = 0;
+    std::vector<int> perm, iperm;                 // perm[new] = old ; iperm[old] = new   (ordering.P / P_inv)
+    // unpermuted KKT (upper CSC) and the maps of kkt_full.hpp:39-170
+    std::vector<int> Kp, Ki;
+    std::vector<int> P_to_K, AT_to_K, GT_to_K;    // value index of P_utri / AT / GT -> value index of K
+    std::vector<int> K_to_PK;                     // PKi: value index of K -> value index of the permuted upper matrix
+    std::vector<int> PKp, PKi_rows;               // permuted upper CSC pattern
+    std::vector<int> diagPK;                      // variable (unpermuted KKT index) -> value index of its diagonal in PK
+    // L (unit lower, CSC, sorted rows) and its row view
+    std::vector<int> Lp, Li, etree, level, level_ptr, level_cols;
+    std::vector<int> Rp, Rcol, Rpos;              // row j: columns k < j with L(j,k) != 0 and the position of L(j,k) in column k
+    std::vector<int> PK_to_L;                     // value index of PK -> position in L (off-diagonal) or -(j+1) for the diagonal of column j
+    std::string error;
+    bool analyse(const Pattern& P, const Pattern& AT, const Pattern& GT, const int* user_perm);
+    double nnzL() const { return Lp.empty() ? 0.0 : (double)Lp.back(); }
+    double factor_flops() const;                  // sum_j (c_j^2 + 2 c_j), SURVEY 8(d)
+};
+
+std::vector<int> minimum_degree_ordering(int n, const std::vector<int>& colptr, const std::vector<int>& rowidx);   // pattern of upper(A), A symmetric
+
+class SparseLdltBatchedKKT : public BatchedKKT {
+public:
+    SparseLdltBatchedKKT(SparseData* data, const int* user_perm, cudaStream_t st);
+    void update_data(int options) override;
+    void factor(const double* delta, const double* x_reg, const double* z_reg, const int* active, int* ok) override;
+    void solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) override;
+    void eval_P_x(double alpha, const double* x, double* z, const int* active) override;
+    void eval_A(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) override;
+    void eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) override;
+    void extract_P_diag(double* P_diag) override;
+    void print_info() const override;
+    double factor_flops() const override { return S.factor_flops(); }
+    double factor_bytes() const override { return 12.0 * S.nnzL() + 12.0 * (double)S.PKi_rows.size(); }
+    double solve_flops() const override { return 4.0 * S.nnzL() + S.nk; }
+    double solve_bytes() const override { return 2.0 * 12.0 * S.nnzL() + 5.0 * 8.0 * S.nk; }
+    void copy_from(const SparseLdltBatchedKKT& o);
+
+    SparseData* D;
+    LdltSymbolic S;
+    DevBuf<int> d_P_to_PK, d_AT_to_PK, d_GT_to_PK, d_diagPK, d_PK_to_L, d_PKp;
+    DevBuf<int> d_Lp, d_Li, d_Rp, d_Rcol, d_Rpos, d_level_cols, d_perm;
+    DevBuf<double> PKx;        // [batch][nnz(PK)] permuted KKT values (upper)
+    DevBuf<double> P_diag;     // [batch][n]
+    DevBuf<double> Lx, Dv, Dinv;   // [batch][nnz(L)], [batch][nk] x2
+    DevBuf<double> work;       // [batch][nk] permuted rhs / solution
+    DevBuf<int> fail;
+private:
+    void scatter_static(int options);
+};
+
+}  // namespace b200

@@ -126,9 +126,12 @@ class SparseSolverBatched(_BatchedBase):
         M.sort_indices()
         return (np.ascontiguousarray(M.indptr, dtype=np.int32), np.ascontiguousarray(M.indices, dtype=np.int32), np.ascontiguousarray(M.data, dtype=np.float64))
 
-    def _vals(self, M_data, override, nnz):
+    def _vals(self, M_data, override, nnz, like=None):
         if override is not None:
             return _Arg(override, (self.batch, nnz))
+        if like is not None:   # the other inputs live on a GPU: replicate the pattern's values there
+            import torch
+            return _Arg(torch.from_numpy(np.ascontiguousarray(M_data)).to(like.device).unsqueeze(0).expand(self.batch, nnz).contiguous(), (self.batch, nnz))
         return _Arg(np.broadcast_to(M_data, (self.batch, nnz)), (self.batch, nnz))
 
     def setup(self, batch, P, c, A=None, b=None, G=None, h_l=None, h_u=None, x_l=None, x_u=None, Px=None, Ax=None, Gx=None):
@@ -139,8 +142,9 @@ class SparseSolverBatched(_BatchedBase):
         B, n, p, m = self.batch, self.n, self.p, self.m
         self._P = self._csc(P); self._A = self._csc(A) if p else None; self._G = self._csc(G) if m else None
         vec = lambda v, k: _Arg(None, ()) if v is None else _Arg(np.broadcast_to(np.asarray(v, dtype=np.float64), (B, k)) if not _is_torch(v) else v, (B, k))
-        a = [self._vals(self._P[2], Px, len(self._P[2])), vec(c, n), self._vals(self._A[2], Ax, len(self._A[2])) if p else _Arg(None, ()), vec(b, p) if p else _Arg(None, ()),
-             self._vals(self._G[2], Gx, len(self._G[2])) if m else _Arg(None, ()), vec(h_l, m) if m else _Arg(None, ()), vec(h_u, m) if m else _Arg(None, ()), vec(x_l, n), vec(x_u, n)]
+        like = next((v for v in (Px, c, Ax, b, Gx, h_l, h_u, x_l, x_u) if v is not None and _is_torch(v) and v.is_cuda), None)
+        a = [self._vals(self._P[2], Px, len(self._P[2]), like), vec(c, n), self._vals(self._A[2], Ax, len(self._A[2]), like) if p else _Arg(None, ()), vec(b, p) if p else _Arg(None, ()),
+             self._vals(self._G[2], Gx, len(self._G[2]), like) if m else _Arg(None, ()), vec(h_l, m) if m else _Arg(None, ()), vec(h_u, m) if m else _Arg(None, ()), vec(x_l, n), vec(x_u, n)]
         devs = {x.on_device for x in a if x.ptr is not None}
         if len(devs) > 1:
             raise ValueError("mixing host and device inputs is not supported")

@@ -1,0 +1,75 @@
+"""Host-side symbolic phase of the sparse_ldlt backend (no GPU): ordering validity / quality and nnz(L) against the
+oracle's restatement of LDLt::factorize_symbolic (include/piqp/sparse/ldlt.hpp:42-99) under the SAME permutation."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import load_scenario_mpc, setup_args
+from piqp_b200 import _lib
+from piqp_b200.synth import mpc_batch, sparse_strongly_convex_qp
+
+
+def _symbolic(P, AT, GT, perm=None):
+    L = _lib.lib()
+    ip = C.POINTER(C.c_int)
+
+    def csc(M, upper=False):
+        M = sp.csc_matrix(M)
+        if upper:
+            M = sp.triu(M, format="csc")
+        M.sort_indices()
+        return np.ascontiguousarray(M.indptr, dtype=np.int32), np.ascontiguousarray(M.indices, dtype=np.int32)
+    n, p, m = P.shape[0], AT.shape[1], GT.shape[1]
+    Pp, Pi = csc(P, True); Ap, Ai = csc(AT); Gp, Gi = csc(GT)
+    out = np.zeros(n + p + m, dtype=np.int32)
+    nk, nl, lv, fl = C.c_longlong(), C.c_longlong(), C.c_int(), C.c_double()
+    pin = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+    rc = L.b200_sparse_ldlt_symbolic(n, p, m, Pp.ctypes.data_as(ip), Pi.ctypes.data_as(ip), Ap.ctypes.data_as(ip), Ai.ctypes.data_as(ip),
+                                     Gp.ctypes.data_as(ip), Gi.ctypes.data_as(ip), None if pin is None else pin.ctypes.data_as(ip),
+                                     out.ctypes.data_as(ip), C.byref(nk), C.byref(nl), C.byref(lv), C.byref(fl))
+    _lib.check(rc, "b200_sparse_ldlt_symbolic")
+    return {"perm": out, "nnz_kkt": nk.value, "nnz_L": nl.value, "levels": lv.value, "flops": fl.value}
+
+
+def _cases():
+    q, _ = load_scenario_mpc()
+    yield "notebook", setup_args(q)
+    d = mpc_batch(1, N=20)
+    yield "mpc", (d["P"], d["c"][0], d["A"], d["b"][0], None, None, None, d["x_l"][0], d["x_u"][0])
+    q = sparse_strongly_convex_qp(60, 20, 30, 0.1, seed=3)
+    yield "random", (q["P"], q["c"], q["A"], q["b"], q["G"], q["h_l"], q["h_u"], q["x_l"], q["x_u"])
+
+
+@pytest.mark.parametrize("name,args", list(_cases()))
+def test_symbolic_matches_oracle_under_same_permutation(oracle, name, args):
+    o = oracle.SparseSolver(oracle.default_settings(kkt_solver="sparse_ldlt")); o.setup(*args)
+    P, AT, GT = o.scaled_matrices()
+    mine = _symbolic(P, AT, GT)
+    nk = P.shape[0] + AT.shape[1] + GT.shape[1]
+    assert sorted(mine["perm"].tolist()) == list(range(nk))
+    # nnz(KKT upper) = nnz(P_utri incl. every diagonal) + nnz(A) + nnz(G) + p + m   (kkt_full.hpp:39-170)
+    Pu = sp.triu(sp.csc_matrix(P)); diag_present = int((Pu.tocoo().row == Pu.tocoo().col).sum())
+    assert mine["nnz_kkt"] == Pu.nnz + (P.shape[0] - diag_present) + AT.nnz + GT.nnz + AT.shape[1] + GT.shape[1]
+    # same permutation -> the oracle's LDLt::factorize_symbolic must count the same nnz(L) and flops
+    o2 = oracle.SparseSolver(oracle.default_settings(kkt_solver="sparse_ldlt"), kkt_perm=mine["perm"]); o2.setup(*args)
+    nnzL, flops = o2.ldlt_stats()
+    assert nnzL == mine["nnz_L"]
+    assert flops == pytest.approx(mine["flops"], rel=1e-12)
+    # ordering quality: own minimum degree is in the same class as the oracle's
+    nnzL_oracle, _ = o.ldlt_stats()
+    assert mine["nnz_L"] <= 1.3 * nnzL_oracle + 16
+    # user permutation round trip
+    rev = np.arange(nk)[::-1].copy()
+    again = _symbolic(P, AT, GT, perm=rev)
+    assert np.array_equal(again["perm"], rev)
+    assert 1 <= again["levels"] <= nk
+
+
+def test_symbolic_rejects_bad_permutation(oracle):
+    q = sparse_strongly_convex_qp(10, 3, 4, 0.3, seed=1)
+    P, AT, GT = sp.triu(q["P"]), sp.csc_matrix(q["A"]).T, sp.csc_matrix(q["G"]).T
+    bad = np.zeros(17, dtype=np.int32)
+    with pytest.raises(RuntimeError, match="invalid permutation"):
+        _symbolic(P, AT, GT, perm=bad)
