@@ -281,12 +281,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
 
-    # The one collective of the path: rank 0 broadcasts the problem descriptor (batch, seed base) over NCCL/NVLink at
-    # setup; every rank then owns the contiguous shard [rank*B, (rank+1)*B) of the global batch.  No collective follows.
-    desc = torch.tensor([B, 42], dtype=torch.int64, device=dev)
-    if dist:
-        dist.broadcast(desc, src=0)
-    B, seed0 = [int(v) for v in desc.tolist()]
+    # The one collective of the path: rank 0 broadcasts the problem descriptor (global batch, seed base) over NCCL/NVLink at
+    # setup; every rank then owns a contiguous shard of the global batch (weak scaling: `--batch` instances per GPU).
+    # No collective follows inside the IP loop.
+    from piqp_b200.distributed import ShardedBatch
+    sb = ShardedBatch(B * world, 42, dist=dist, device=dev)
+    B, seed0 = sb.local_batch, sb.seed0
+    assert (sb.lo, sb.hi) == (rank * B, (rank + 1) * B)
     data = wl.device_data(B, seed0 + rank * B, dev)
     torch.cuda.synchronize()
     solver = wl.make_solver(local, data)

@@ -335,10 +335,10 @@ void SparseLdltBatchedKKT::copy_from(const SparseLdltBatchedKKT& o) {
 }
 void SparseLdltBatchedKKT::scatter_static(int options) {   // kkt_full.hpp:212-251
     const int nnzPK = (int)S.PKi_rows.size();
-    if ((options & 1) && D->P.nnz) {
-        dim3 g(ceil_div(D->P.nnz, 256), batch);
-        B200_LAUNCH(ldlt_scatter_kernel, g, 256, 0, stream, d_P_to_PK.get(), D->P.nnz, nnzPK, D->Px.get(), PKx.get());
-        sparse_extract_diag(*D, P_diag.get(), stream);
+    if (options & 1) {
+        if (D->P.nnz) { dim3 g(ceil_div(D->P.nnz, 256), batch);
+            B200_LAUNCH(ldlt_scatter_kernel, g, 256, 0, stream, d_P_to_PK.get(), D->P.nnz, nnzPK, D->Px.get(), PKx.get()); }
+        sparse_extract_diag(*D, P_diag.get(), stream);   // zeros where P has no stored diagonal
     }
     if ((options & 2) && D->AT.nnz) { dim3 g(ceil_div(D->AT.nnz, 256), batch);
         B200_LAUNCH(ldlt_scatter_kernel, g, 256, 0, stream, d_AT_to_PK.get(), D->AT.nnz, nnzPK, D->ATx.get(), PKx.get()); }
