@@ -353,6 +353,7 @@ def main():
             if rep > 0:
                 times.append(dt); fl.append(st2.factor_calls * ff + st2.backend_solves * sf)
             del s2
+        print("e2e repetitions (s): %s" % ["%.4f" % t for t in times], file=sys.stderr)
         tmax = torch.tensor([max(times)], dtype=torch.float64, device=dev)      # conservative: slowest repetition
         fsum = torch.tensor([sum(fl) / len(fl)], dtype=torch.float64, device=dev)
         if dist:

@@ -571,6 +571,10 @@ int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
     if ((p > 0 && (!Ap || !b)) || (m > 0 && (!Gp || (!h_l && !h_u)))) return fail(B200_E_INVALID, "b200qp_setup_sparse: missing constraint data");
     B200_TRY(
         B200_CUDA(cudaSetDevice(device));
+        const bool tm = getenv("B200_TIMING") != nullptr;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto t_0 = now(); auto t_prev = t_0;
+        auto lap = [&](const char* what) { if (tm) { cudaDeviceSynchronize(); auto t = now(); fprintf(stderr, "[b200qp_setup_sparse] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count()); t_prev = t; } };
         auto h = std::make_unique<b200qp_handle>();
         h->kind = 1; h->device = device; h->batch = batch; h->n = n; h->p = p; h->m = m;
         if (settings) h->st = *settings; else b200qp_set_default_settings_sparse(&h->st);
@@ -598,9 +602,11 @@ int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
         auto upm = [](DevBuf<int>& d, const std::vector<int>& v) { d.alloc(std::max<size_t>(v.size(), 1)); if (!v.empty()) B200_CUDA(cudaMemcpy(d.get(), v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice)); };
         upm(h->d_P_map, h->P_map); upm(h->d_A_map, h->A_map); upm(h->d_G_map, h->G_map);
         B200_CUDA(cudaDeviceSynchronize());
+        lap("patterns + value buffers");
         B200_CUDA(cudaEventRecord(e0, h->stream));
         h->ip = std::make_unique<BatchedIPSolver>(batch, n, p, m, h->st, h->stream);
         h->ruiz.alloc(batch, n, p, m);
+        lap("IP solver + ruiz alloc");
         h->zero_rows.alloc(std::max<size_t>((size_t)batch * m, 1)); h->zero_rows.zero(h->stream);
         IpDev& d = h->ip->dev();
         fill_d(d.xbs, (size_t)batch * n, 1.0, h->stream);
@@ -608,14 +614,18 @@ int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
         gather_values(h.get(), Ax, h->nnzA_in, h->d_A_map, S.AT.nnz, S.ATx.get(), on_device);
         gather_values(h.get(), Gx, h->nnzG_in, h->d_G_map, S.GT.nnz, S.GTx.get(), on_device);
         load_vectors_and_bounds(h.get(), true, c, b, h_l, h_u, x_l, x_u, on_device);
+        lap("H2D + gather");
         sparse_ruiz_scale(S, h->ruiz, d.c, d.b, d.h_l, d.h_u, d.x_l, d.x_u, d.xbs, false, h->st.preconditioner_scale_cost != 0, h->st.preconditioner_iter, h->stream);
+        lap("ruiz");
         d.pd = h->ruiz.delta.get(); d.pd_inv = h->ruiz.delta_inv.get(); d.pdb = h->ruiz.delta_b.get(); d.pdb_inv = h->ruiz.delta_b_inv.get();
         d.pc = h->ruiz.c.get(); d.pc_inv = h->ruiz.c_inv.get();
         if (h->st.kkt_solver == 5) { h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream); h->be = h->ms.get(); }
         else { h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, nullptr, h->stream); h->be = h->ldlt.get(); }
+        lap("backend ctor");
         h->ip->finish_setup(h->be);
         B200_CUDA(cudaEventRecord(e1, h->stream));
         B200_CUDA(cudaEventSynchronize(e1));
+        lap("finish_setup");
         float ms_ = 0; B200_CUDA(cudaEventElapsedTime(&ms_, e0, e1)); h->setup_ms = ms_;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         *out = h.release();

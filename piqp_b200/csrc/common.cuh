@@ -31,7 +31,22 @@ extern unsigned long long g_launches;  // counted at every kernel launch (b200_k
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// RAII device buffer
+// RAII device buffer.  Allocations come from the device's stream-ordered memory pool (cudaMallocAsync) with the release
+// threshold raised to "never", so that creating and destroying solvers re-uses HBM instead of paying the driver's
+// cudaMalloc / cudaFree (measured: 30-60 ms to allocate and 30-350 ms to free one batched solver's ~100 buffers).
+// Semantics stay those of cudaMalloc / cudaFree: memory is usable from any stream after alloc() returns, and release()
+// waits for the device before handing the memory back.
+inline void pool_setup_once() {
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == configured_dev) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    configured_dev = dev;
+}
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -46,10 +61,17 @@ struct DevBuf {
     void alloc(size_t n_) {
         release();
         n = n_;
-        if (n) { B200_CUDA(cudaMalloc(&p, n * sizeof(T))); }
+        if (n) {
+            pool_setup_once();
+            B200_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), n * sizeof(T), cudaStreamPerThread));
+            B200_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
+        }
     }
     void zero(cudaStream_t s = 0) { if (n) B200_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() {
+        if (p) { cudaDeviceSynchronize(); cudaFreeAsync(p, cudaStreamPerThread); }
+        p = nullptr; n = 0;
+    }
     T* get() const { return p; }
 };
 

@@ -1,7 +1,9 @@
 // piqp_b200/csrc/multistage_backend.cu -- see multistage_backend.hpp
 #include "multistage_backend.hpp"
+#include "multistage_chain.cuh"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 
 namespace b200 {
@@ -159,11 +161,6 @@ double MsStructure::solve_bytes() const {
 // =====================================================================================================
 // device kernels
 // =====================================================================================================
-struct MsDev {
-    const int *start, *diag, *off, *offD, *offB, *offE, *offI;
-    int N, w, n, total, total_inv, dmax, omax;
-};
-
 // out[slot] = sum_list (w[row] *) vals[qa] * vals[qb]
 __global__ void ms_accumulate_kernel(const int* ptr, const int* qa, const int* qb, const int* row, int total, int nnz, int m, const double* vals,
                                      const double* w, double* out, const int* active) {
@@ -405,7 +402,44 @@ MultistageBatchedKKT::MultistageBatchedKKT(SparseData* data, cudaStream_t st) : 
     for (auto f : {0, 1, 2}) for (int i = 0; i < S.N; i++) meta.push_back(f == 0 ? S.bi[i].start : f == 1 ? S.bi[i].diag : S.bi[i].off);
     meta.insert(meta.end(), S.offD.begin(), S.offD.end()); meta.insert(meta.end(), S.offB.begin(), S.offB.end());
     meta.insert(meta.end(), S.offE.begin(), S.offE.end()); meta.insert(meta.end(), S.offI.begin(), S.offI.end());
+    // warp-chain fast path (multistage_chain.cuh): every front d + o + w fits one warp; solve packets per stage and direction
+    warp_chain = S.w <= 32;
+    int max_rows = S.w;
+    for (int i = 0; i + 1 < S.N; i++) max_rows = std::max(max_rows, S.bi[i].diag + ((i + 2 < S.N) ? S.bi[i].off : 0) + S.w);
+    if (max_rows > 32) warp_chain = false;
+    if (const char* e = getenv("B200_MS_GENERIC")) if (e[0] == '1') warp_chain = false;
+    std::vector<int> cls(S.N, 0), pkF(S.N, 0), szF(S.N, 0), pkB(S.N, 0), szB(S.N, 0);
+    size_t slot = 0;
+    pk_stride = 0;
+    if (warp_chain) {
+        auto r2 = [](int v) { return (v + 1) & ~1; };
+        for (int i = 0; i < S.N; i++) { const int d = S.bi[i].diag; cls[i] = d <= 8 ? 8 : (d <= 16 ? 16 : 32); }
+        for (int i = 0; i + 1 < S.N; i++) {
+            const int D = cls[i], PD = i > 0 ? cls[i - 1] : 0, ND = (i + 2 < S.N) ? cls[i + 1] : 0;
+            szF[i] = D * D + D * PD + r2(S.w * D);
+            szB[i] = D * D + D * ND + D * r2(S.w);
+            pkF[i] = (int)pk_stride; pk_stride += szF[i];
+            pkB[i] = (int)pk_stride; pk_stride += szB[i];
+            slot = std::max(slot, (size_t)std::max(szF[i], szB[i]));
+        }
+        chain_rp = (max_rows + 1) / 2;
+        chain_slot = (int)slot;
+        chain_solve_smem = sizeof(double) * ((size_t)((n + 1) & ~1) + 96 + (size_t)(((MS_META * S.N + 1) / 2 + 1) / 2 * 2) + (size_t)MSW_R * chain_slot);
+        if (chain_solve_smem > 227 * 1024 || (size_t)MS_META * S.N * sizeof(int) > 100 * 1024) warp_chain = false;
+    }
+    for (auto* v : {&cls, &pkF, &szF, &pkB, &szB}) meta.insert(meta.end(), v->begin(), v->end());
     upload(d_meta, meta);
+    if (warp_chain) {
+        packets.alloc((size_t)batch * pk_stride);
+        packets.zero(st);
+        B200_CUDA(cudaFuncSetAttribute(msw_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(chain_solve_smem, 48 * 1024)));
+        const int csm = (int)(sizeof(MswChainSmem) + sizeof(int) * MS_META * S.N);
+        B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
+        B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
+        B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
+        B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
+        B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
+    }
     upload(d_P_slot, S.P_slot);
     std::vector<int> diag_var(S.total, -1);
     for (int i = 0; i < n; i++) diag_var[S.diag_slot[i]] = i;
@@ -431,6 +465,7 @@ static MsDev make_dev(const MsStructure& S, const int* meta) {
     MsDev d;
     const int N = S.N;
     d.start = meta; d.diag = meta + N; d.off = meta + 2 * N; d.offD = meta + 3 * N; d.offB = meta + 4 * N; d.offE = meta + 5 * N; d.offI = meta + 6 * N;
+    d.cls = meta + 7 * N; d.pkF = meta + 8 * N; d.szF = meta + 9 * N; d.pkB = meta + 10 * N; d.szB = meta + 11 * N;
     d.N = N; d.w = S.w; d.n = S.n; d.total = S.total; d.total_inv = S.total_inv; d.dmax = std::max(S.dmax, S.w); d.omax = S.omax;
     return d;
 }
@@ -451,7 +486,7 @@ void MultistageBatchedKKT::update_data(int options) {   // :140-178
 }
 void MultistageBatchedKKT::copy_from(const MultistageBatchedKKT& o) {
     auto cp = [&](DevBuf<double>& d, const DevBuf<double>& s) { if (s.n) B200_CUDA(cudaMemcpyAsync(d.get(), s.get(), s.n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); };
-    cp(Pblk, o.Pblk); cp(AtAblk, o.AtAblk); cp(fac, o.fac); cp(Linv, o.Linv); cp(zinv, o.zinv); cp(delta, o.delta);
+    cp(Pblk, o.Pblk); cp(AtAblk, o.AtAblk); cp(fac, o.fac); cp(Linv, o.Linv); cp(zinv, o.zinv); cp(delta, o.delta); cp(packets, o.packets);
 }
 
 void MultistageBatchedKKT::factor(const double* delta_in, const double* x_reg, const double* z_reg, const int* active, int* ok) {   // :180-219
@@ -463,7 +498,18 @@ void MultistageBatchedKKT::factor(const double* delta_in, const double* x_reg, c
                 Pblk.get(), AtAblk.get(), D->GTx.get(), zinv.get(), delta.get(), x_reg, fac.get(), active);
     toc(T_ASSEMBLE);
     tic(T_FACTOR);
-    B200_LAUNCH(ms_factor_kernel, batch, MS_T, factor_smem, stream, make_dev(S, d_meta.get()), fac.get(), Linv.get(), active);
+    if (warp_chain) {
+        const MsDev dv = make_dev(S, d_meta.get());
+        const size_t msm = sizeof(int) * MS_META * S.N;
+#define MSW_FACTOR(RP) B200_LAUNCH(msw_factor_kernel<RP>, batch, 64, msm, stream, dv, fac.get(), Linv.get(), packets.get(), pk_stride, active)
+#define MSW_CHAIN(RP) B200_LAUNCH(msw_factor_chain_kernel<RP>, batch, 64, sizeof(MswChainSmem) + msm, stream, dv, fac.get(), packets.get(), pk_stride, active)
+        if (S.w == 0) { if (chain_rp <= 4) MSW_CHAIN(4); else if (chain_rp <= 8) MSW_CHAIN(8); else if (chain_rp <= 12) MSW_CHAIN(12);
+                        else if (chain_rp <= 14) MSW_CHAIN(14); else MSW_CHAIN(16); }
+        else if (chain_rp <= 4) MSW_FACTOR(4); else if (chain_rp <= 8) MSW_FACTOR(8); else if (chain_rp <= 12) MSW_FACTOR(12);
+        else if (chain_rp <= 14) MSW_FACTOR(14); else MSW_FACTOR(16);
+#undef MSW_FACTOR
+#undef MSW_CHAIN
+    } else B200_LAUNCH(ms_factor_kernel, batch, MS_T, factor_smem, stream, make_dev(S, d_meta.get()), fac.get(), Linv.get(), active);
     toc(T_FACTOR);
     B200_LAUNCH(ms_set_ok_kernel, ceil_div(batch, 256), 256, 0, stream, active, ok, batch);
 }
@@ -475,7 +521,8 @@ void MultistageBatchedKKT::solve(const double* rx, const double* ry, const doubl
     B200_LAUNCH(ms_copy_masked_kernel, gn, 256, 0, stream, rx, lx, n, active);
     if (m > 0) spmv_rows(D->GT, D->GTx.get(), 1.0, rz, m, lx, 1, zinv.get(), nullptr, 0, batch, active, stream);          // lx += GT (zinv .* rz)
     if (p > 0) spmv_rows(D->AT, D->ATx.get(), 1.0, ry, p, lx, 1, nullptr, delta.get(), 1, batch, active, stream);         // lx += AT ry / delta
-    B200_LAUNCH(ms_solve_kernel, batch, MS_T, solve_smem, stream, make_dev(S, d_meta.get()), fac.get(), Linv.get(), lx, active);
+    if (warp_chain) B200_LAUNCH(msw_solve_kernel, batch, 32, chain_solve_smem, stream, make_dev(S, d_meta.get()), chain_slot, Linv.get(), packets.get(), pk_stride, lx, active);
+    else B200_LAUNCH(ms_solve_kernel, batch, MS_T, solve_smem, stream, make_dev(S, d_meta.get()), fac.get(), Linv.get(), lx, active);
     if (p > 0) spmv_cols(D->AT, D->ATx.get(), 1.0, lx, n, ly, ry, 1.0, nullptr, delta.get(), 1, batch, active, stream);    // ly = (A lx - ry) / delta
     if (m > 0) spmv_cols(D->GT, D->GTx.get(), 1.0, lx, n, lz, rz, 1.0, zinv.get(), nullptr, 0, batch, active, stream);     // lz = zinv .* (G lx - rz)
     toc(T_SOLVE);

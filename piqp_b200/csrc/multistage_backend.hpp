@@ -58,7 +58,11 @@ public:
     DevBuf<int> d_a_ptr, d_a_qa, d_a_qb, d_g_ptr, d_g_qa, d_g_qb, d_g_row;
     DevBuf<double> Pblk, AtAblk, fac, Linv;   // [batch][total] x3, [batch][total_inv]
     DevBuf<double> zinv, delta, work_z;
-    size_t factor_smem = 0, solve_smem = 0;
+    size_t factor_smem = 0, solve_smem = 0, chain_solve_smem = 0;
+    bool warp_chain = false;            // fronts of <= 32 rows: one warp walks the chain (multistage_chain.cuh)
+    int chain_slot = 0, chain_rp = 16;  // doubles per ring slot of msw_solve_kernel; ceil(max front rows / 2)
+    DevBuf<double> packets;             // [batch][pk_stride] solve packets (see multistage_chain.cuh)
+    size_t pk_stride = 0;
 private:
     void load_P();
     void compute_AtA();

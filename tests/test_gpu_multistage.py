@@ -38,10 +38,13 @@ def test_structure_detection_matches_reference_print_and_oracle(oracle, b200):
     assert b200.MultistageKKT(P, AT, GT).block_info() == o.multistage_blocks()
 
 
+@pytest.mark.parametrize("path", ["warp_chain", "generic"])
 @pytest.mark.parametrize("case", ["notebook", "mpc", "random_with_G"])
-def test_backend_factor_solve_eval_parity(oracle, b200, case):
+def test_backend_factor_solve_eval_parity(oracle, b200, case, path, monkeypatch):
     """multistage_kkt_test.cpp:24-98 style: same rho/delta/scalings -> same solve and mat-vec results (vs the oracle's
-    multistage AND vs its sparse_ldlt backend)"""
+    multistage AND vs its sparse_ldlt backend).  Both kernel families are exercised: the one-warp-per-QP chain kernels
+    (fronts of <= 32 rows, multistage_chain.cuh) and the general shared-memory kernels (B200_MS_GENERIC=1)."""
+    monkeypatch.setenv("B200_MS_GENERIC", "1" if path == "generic" else "0")
     if case == "notebook":
         q, _ = load_scenario_mpc(); args = setup_args(q)
     elif case == "mpc":
