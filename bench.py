@@ -29,7 +29,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="dense", choices=["dense", "multistage"])
+    ap.add_argument("--workload", default="dense", choices=["dense", "multistage", "sparse"])
+    ap.add_argument("--density", type=float, default=0.01, help="sparse workload: density of P_utri, A, G")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (weak scaling); 0 = workload default")
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--p", type=int, default=0)
@@ -42,7 +43,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
     if a.batch == 0:
-        a.batch = 256 if a.workload == "dense" else 128
+        a.batch = {"dense": 256, "multistage": 128, "sparse": 148}[a.workload]      # sparse: one CTA per QP, one QP per SM
+    if a.workload == "sparse" and (a.n, a.p, a.m) == (1024, 0, 512):      # sparse defaults (random patterns fill in heavily: n_kkt=850 -> nnz(L)=53k, 308 etree levels; 10-17 IP iterations)
+        a.n, a.p, a.m = 500, 100, 250
     return a
 
 
@@ -137,10 +140,13 @@ class DenseWorkload:
         out = []
         for i in range(n_qp):
             q = dense_strongly_convex_qp(self.n, self.p, self.m, seed=seed0 + i)
-            s = pyoracle.DenseSolver(native=native)
-            s.setup(q["P"], q["c"], q["A"] if self.p else None, q["b"] if self.p else None, q["G"] if self.m else None,
-                    q["h_l"] if self.m else None, q["h_u"] if self.m else None, q["x_l"], q["x_u"])
-            out.append(s)
+
+            def make(q=q):
+                s = pyoracle.DenseSolver(native=native)
+                s.setup(q["P"], q["c"], q["A"] if self.p else None, q["b"] if self.p else None, q["G"] if self.m else None,
+                        q["h_l"] if self.m else None, q["h_u"] if self.m else None, q["x_l"], q["x_u"])
+                return s
+            out.append(make)
         return out
 
     roofline_kernel = "gemm_nt_tile_kernel<EPI_ASSEMBLE,true> (K = P + diag + G^T Z^-1 G, DMMA m8n8k4 fp64)"
@@ -196,22 +202,94 @@ class MultistageWorkload:
         out = []
         for k in range(n_qp):
             A = sp.csc_matrix((d["Ax"][k], d["A"].indices, d["A"].indptr), shape=d["A"].shape)
-            s = pyoracle.SparseSolver(pyoracle.default_settings(kkt_solver="sparse_multistage"), native=native)
-            s.setup(d["P"], d["c"][k], A, d["b"][k], None, None, None, d["x_l"][k], d["x_u"][k])
-            out.append(s)
+
+            def make(k=k, A=A):
+                s = pyoracle.SparseSolver(pyoracle.default_settings(kkt_solver="sparse_multistage"), native=native)
+                s.setup(d["P"], d["c"][k], A, d["b"][k], None, None, None, d["x_l"][k], d["x_u"][k])
+                return s
+            out.append(make)
         if self._work is None:
             import ctypes as C
-            f = out[0]._L.orc_multistage_factor_flops(C.c_void_p(out[0]._h))
+            s0 = out[0]()
+            f = s0._L.orc_multistage_factor_flops(C.c_void_p(s0._h))
             n = d["n"]
             self._work = (f, 2.0 * n * 16)     # solve flops only used on the reference arm when no GPU ran: coarse
         return out
 
-    roofline_kernel = "ms_factor_kernel (block-tridiagonal Cholesky chain, one CTA per QP)"
+    roofline_kernel = "msw_factor_chain_kernel (block-tridiagonal Cholesky chain, one warp per QP, fronts in registers)"
+
+
+class SparseWorkload(MultistageWorkload):
+    """BASELINE config 3 / 5 family: random sparse QPs sharing one pattern, kkt_solver = sparse_ldlt (KKT_FULL, n_kkt = n+p+m)."""
+    name = "sparse"
+
+    def __init__(self, a):
+        self.a = a
+        self.n, self.p, self.m, self.density = a.n, a.p, a.m, a.density
+        self._work = None
+
+    def describe(self, B):
+        return ("sparse random QP n=%d p=%d m=%d density=%.3g%% (n_kkt=%d), sparse_ldlt, shared pattern, batch=%d per GPU (BASELINE config 3/5 family), full IP solve per step"
+                % (self.n, self.p, self.m, 100 * self.density, self.n + self.p + self.m, B))
+
+    def working_set_gb(self, B):
+        return B * (self.bytes[0] if getattr(self, "bytes", None) else 0.0) / 1e9
+
+    _keys = ("Px", "Ax", "Gx", "c", "b", "h_l", "h_u", "x_l", "x_u")
+
+    def device_data(self, B, seed0, dev):
+        import torch
+        from piqp_b200.synth import sparse_batch
+        self.pat = sparse_batch(B, self.n, self.p, self.m, self.density, seed0=42)      # one pattern for every rank
+        return {k: torch.from_numpy(self.pat[k]).to(dev) for k in self._keys}
+
+    def make_solver(self, local, data, on_host=False):
+        import piqp_b200
+        s = piqp_b200.SparseSolverBatched(device=local, kkt_solver="sparse_ldlt")
+        g = (lambda k: data[k].numpy()) if on_host else (lambda k: data[k])
+        B = data["c"].shape[0]
+        s.setup(B, self.pat["P"], g("c"), self.pat["A"], g("b"), self.pat["G"], g("h_l"), g("h_u"), g("x_l"), g("x_u"), Px=g("Px"), Ax=g("Ax"), Gx=g("Gx"))
+        w = s.work()
+        self._work = (w[0], w[2])
+        self.bytes = (w[1], w[3])
+        return s
+
+    def h2d_bytes(self, host):
+        return sum(v.numel() * 8 for v in host.values())
+
+    def cpu_solvers(self, n_qp, seed0, native):
+        import scipy.sparse as sp
+        from oracle import pyoracle
+        from piqp_b200.synth import sparse_batch
+        d = sparse_batch(n_qp, self.n, self.p, self.m, self.density, seed0=42)
+        out = []
+        mk = lambda pat, v: sp.csc_matrix((v, pat.indices, pat.indptr), shape=pat.shape)
+        # ordering: the pattern is shared, so the fill-reducing permutation is computed once, OUTSIDE the timed region, by
+        # the product's host-only symbolic phase and handed to every oracle solver (the oracle's own exact minimum-degree
+        # code is O(n^3)-ish and would misrepresent the reference's AMD; both arms then factor the same L pattern)
+        import piqp_b200
+        perm = piqp_b200.sparse_ldlt_symbolic(d["P"], d["A"], d["G"])["perm"]
+        for k in range(n_qp):
+            mats = (mk(d["P"], d["Px"][k]), mk(d["A"], d["Ax"][k]), mk(d["G"], d["Gx"][k]))
+
+            def make(k=k, mats=mats):
+                s = pyoracle.SparseSolver(pyoracle.default_settings(kkt_solver="sparse_ldlt"), native=native, kkt_perm=perm)
+                s.setup(mats[0], d["c"][k], mats[1], d["b"][k], mats[2], d["h_l"][k], d["h_u"][k], d["x_l"][k], d["x_u"][k])
+                return s
+            out.append(make)
+        if self._work is None:
+            nnzL, flops = out[0]().ldlt_stats()[:2]
+            self._work = (float(flops), 4.0 * nnzL + self.n + self.p + self.m)
+        return out
+
+    roofline_kernel = "mf_factor_kernel (supernodal multifrontal sparse LDL^T, one CTA per QP, fronts in shared memory)"
 
 
 def cpu_oracle_sample(wl, n_qp, threads, seed0=1042):
     """The CPU restatement of the reference (oracle, kind "port"): `n_qp` QPs of the workload's shape, one solver per host
-    thread (the reference is single-threaded per solve).  Returns (gflops, qps, seconds, iters, native)."""
+    thread (the reference is single-threaded per solve).  Two clocks: solve() only (comparable with `value`) and
+    setup() + solve() (comparable with the GPU arm's `e2e`, which pays setup + H2D + solve + D2H).
+    Returns (gflops, qps, seconds, iters, native, e2e_gflops, e2e_qps)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle
     try:
@@ -219,18 +297,22 @@ def cpu_oracle_sample(wl, n_qp, threads, seed0=1042):
         native = True
     except Exception:
         native = False
-    solvers = wl.cpu_solvers(n_qp, seed0, native)
+    makers = wl.cpu_solvers(n_qp, seed0, native)
+    ts = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        solvers = list(ex.map(lambda mk: mk(), makers))  # setup(): ctypes releases the GIL inside the oracle
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
         list(ex.map(lambda s: s.solve(), solvers))      # ctypes releases the GIL inside orc_solve
-    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    dt = t1 - t0
     ff, sf = wl.work()
     flops, iters = 0.0, []
     for s in solvers:
         i = s.info()
         flops += i.n_factor * ff + i.n_backend_solve * sf
         iters.append(int(i.iter))
-    return flops / dt * 1e-9, n_qp / dt, dt, iters, native
+    return flops / dt * 1e-9, n_qp / dt, dt, iters, native, flops / (t1 - ts) * 1e-9, n_qp / (t1 - ts)
 
 
 def run_reference(args, wl, rank):
@@ -240,12 +322,12 @@ def run_reference(args, wl, rank):
         return
     threads = min(os.cpu_count() or 1, 32)
     n_qp = args.cpu_sample or (threads if wl.name == "dense" else 8 * threads)
-    vals, qpss, secs = [], [], []
+    vals, qpss, secs, e2ev, e2eq = [], [], [], [], []
     native = False
     for it in range(args.warmup + args.steps):
-        g, q, dt, iters, native = cpu_oracle_sample(wl, n_qp, threads, seed0=1042 + 1000 * it)
+        g, q, dt, iters, native, eg, eq = cpu_oracle_sample(wl, n_qp, threads, seed0=1042 + 1000 * it)
         if it >= args.warmup:
-            vals.append(g); qpss.append(q); secs.append(dt)
+            vals.append(g); qpss.append(q); secs.append(dt); e2ev.append(eg); e2eq.append(eq)
         if it == 0 and dt > 40:      # keep the whole run within a few minutes
             n_qp = max(1, int(n_qp * 20 / dt))
     v = sum(vals) / len(vals)
@@ -256,7 +338,8 @@ def run_reference(args, wl, rank):
         "config": {"workload": wl.describe(n_qp) + " -- CPU: %d QPs per step on %d host threads" % (n_qp, threads)},
         "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": threads, "kind": "port",
                          "sample": "%d QPs per step, one oracle solver per thread, %s build" % (n_qp, "-march=native" if native else "x86-64-v3")},
-        "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": sum(e2ev) / len(e2ev), "unit": "GFLOP/s", "qps": sum(e2eq) / len(e2eq), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "what": "setup() + solve() per QP on the host (the GPU arm's e2e also pays setup)"},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -265,7 +348,7 @@ def run_reference(args, wl, rank):
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = DenseWorkload(args) if args.workload == "dense" else MultistageWorkload(args)
+    wl = {"dense": DenseWorkload, "multistage": MultistageWorkload, "sparse": SparseWorkload}[args.workload](args)
     if args.impl == "reference":
         run_reference(args, wl, rank)
         return
@@ -414,7 +497,8 @@ def main():
             pass
         roofline = {"kernel": wl.roofline_kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "peak_source": hbm_src, "bytes_per_launch": by_launch, "ms_per_launch": ms_launch, "traffic": traffic,
-                    "note": "latency-bound chain of N dependent 16x16 block steps per QP; algorithmic bytes = blocks read + factor written and read once",
+                    "note": ("latency-bound chain of N dependent 16x16 block steps per QP; algorithmic bytes = blocks read + factor written and read once" if wl.name == "multistage"
+                             else "one launch = one numeric factorisation of every QP of the batch; algorithmic bytes = 12 nnz(L) written + 12 nnz(KKT) read per QP (SURVEY 8d); latency-bound walk over the supernodes"),
                     "factor_gflops": (agg["factor_calls"] * ff) / (agg["cholesky_ms"] * 1e-3) * 1e-9 if agg["cholesky_ms"] else None,
                     "backend_solve_gbs": (agg["backend_solves"] * sb) / (agg["backend_solve_ms"] * 1e-3) * 1e-9 if agg["backend_solve_ms"] else None}
 
@@ -422,8 +506,8 @@ def main():
     if not args.no_cpu_baseline:
         threads = min(os.cpu_count() or 1, 32)
         n_qp = args.cpu_sample or (min(threads, 16) if wl.name == "dense" else 16 * threads)
-        g, q, dt, iters, native = cpu_oracle_sample(wl, n_qp, min(threads, n_qp))
-        cpu = {"value": g, "unit": "GFLOP/s", "qps": q, "cores": min(threads, n_qp), "kind": "port",
+        g, q, dt, iters, native, eg, eq = cpu_oracle_sample(wl, n_qp, min(threads, n_qp))
+        cpu = {"value": g, "unit": "GFLOP/s", "qps": q, "cores": min(threads, n_qp), "kind": "port", "setup_plus_solve_gflops": eg, "setup_plus_solve_qps": eq,
                "sample": "%d QPs of the same shape (seeds 1042..), one oracle solver per thread, %.1f s, iters %s, %s build"
                          % (n_qp, dt, sorted(set(iters)), "-march=native" if native else "x86-64-v3")}
 

@@ -185,6 +185,28 @@ class SparseKKT(KKTSolverBase):
 SparseKKT.update_data = MultistageKKT.update_data
 
 
+def sparse_ldlt_symbolic(P, A, G, perm=None):
+    """Host-only symbolic phase of the sparse_ldlt backend (b200_sparse_ldlt_symbolic): fill-reducing ordering of the
+    full KKT (sparse/ordering.hpp:59-125), nnz(L), etree levels and factor flops (sparse/ldlt.hpp:42-99).
+    P (n x n, upper part used), A (p x n) or None, G (m x n) or None: scipy sparse."""
+    import scipy.sparse as sp
+    L = _lib.lib()
+    n = P.shape[0]
+    AT = sp.csc_matrix((n, 0)) if A is None else sp.csc_matrix(sp.csc_matrix(A).T)
+    GT = sp.csc_matrix((n, 0)) if G is None else sp.csc_matrix(sp.csc_matrix(G).T)
+    Pp, Pi, _ = _csc_arrays(P, upper=True)
+    Ap, Ai, _ = _csc_arrays(AT)
+    Gp, Gi, _ = _csc_arrays(GT)
+    p, m = AT.shape[1], GT.shape[1]
+    out = np.zeros(n + p + m, dtype=np.int32)
+    nk, nl, lv, fl = C.c_longlong(), C.c_longlong(), C.c_int(), C.c_double()
+    pin = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+    q = lambda a: a.ctypes.data_as(ip)
+    _lib.check(L.b200_sparse_ldlt_symbolic(n, p, m, q(Pp), q(Pi), q(Ap), q(Ai), q(Gp), q(Gi), None if pin is None else q(pin), q(out),
+                                           C.byref(nk), C.byref(nl), C.byref(lv), C.byref(fl)), "b200_sparse_ldlt_symbolic")
+    return {"perm": out, "nnz_kkt": nk.value, "nnz_L": nl.value, "levels": lv.value, "flops": fl.value}
+
+
 def c_abi_vtable():
     """Function-pointer table of the C-ABI in the layout oracle/oracle_capi.cpp::OrcBackendVTable expects
     (used by tests to put the CUDA backend behind the oracle's KKTSystem + IP loop)."""

@@ -1,0 +1,363 @@
+// piqp_b200/csrc/sparse_frontal.cuh -- supernodal multifrontal LDL^T and supernodal triangular solves, one CTA per QP.
+//
+// Replaces LDLt::factorize_numeric_upper_triangular / solve_inplace (include/piqp/sparse/ldlt.hpp:101-218) for a batch of
+// QPs that share one pattern.  The reference's up-looking algorithm is scalar and serial; a batch offers instance
+// parallelism (one CTA per instance, no kernel launch per column or level) and each supernode offers dense work:
+//
+//   mf_factor_kernel : walks the supernodes in postorder.  For supernode s with columns j0..j1 and update rows U the
+//                      FRONT (|s|+|U|)^2 is built in shared memory (scatter of the permuted KKT entries through a
+//                      precomputed position map, extend-add of the children's update matrices through precomputed
+//                      relative indices), its first |s| pivots are eliminated right-looking by the whole CTA
+//                      (D_k = F_kk, L_ik = F_ik / D_k, F_ic -= F_ik L_ck), the L columns / D go to HBM in the CSC layout
+//                      of L, the Schur complement goes on a per-instance stack for the parent.  Fronts that do not fit in
+//                      shared memory use a per-instance HBM/L2 scratch front with the same code.
+//   mf_solve_kernel  : permuted rhs in shared memory; forward sweep per supernode = unit-lower solve with the |s| x |s|
+//                      triangle, then x_U -= L_Us x_s; D^-1; backward sweep = x_s -= L_Us^T x_U (one warp per column,
+//                      shuffle reduction), then the transposed triangle.  Deterministic: no atomics anywhere.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct MfDev {
+    const int *hdr;        // [nsup][8]: j0, ws, us, Lp[j0], asm_begin, asm_cnt, child_begin, child_cnt
+    const int *crec;       // [children][4]: us of the child, rel_begin, upd_off (lo, hi)
+    const int *rel_idx, *asm_pos, *Li, *perm;
+    const long long* upd_off;
+    int nsup, nk, n, p, m, front_smem_rows, fmax;
+    long long upd_total;
+    size_t nnzL, nnzPK;
+};
+
+constexpr int MF_T = 256;
+constexpr int MF_NB = 32;     // panel width of the blocked elimination used for fronts that live in HBM/L2
+constexpr int MF_TS = 64;     // trailing-update tile
+
+// ---- elimination of the first ws pivots of a front held in SHARED memory (right-looking, one pivot per step)
+__device__ __forceinline__ void mf_eliminate_smem(double* F, int f, int ws, int j0, int lp0, double* lcol, double* Lx, double* Dv, double* Dinv, int* failb) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = MF_T / 32;
+    for (int k = 0; k < ws; k++) {
+        const double d = F[k + k * f];
+        const double* Fk = F + k * f;
+        double* Lcolumn = Lx + (lp0 + k * (f - 1) - (k * (k - 1)) / 2) - (k + 1);      // L(i, j0+k) for front row i > k sits at Lcolumn[i]
+        for (int i = k + 1 + tid; i < f; i += MF_T) { const double l = Fk[i] / d; lcol[i] = l; Lcolumn[i] = l; }
+        if (tid == 0) {
+            if (d == 0.0 && *failb == 0) *failb = j0 + k + 1;           // ldlt.hpp:161
+            Dv[j0 + k] = d; Dinv[j0 + k] = 1.0 / d;
+        }
+        __syncthreads();
+        for (int c = k + 1 + wid; c < f; c += NW) {
+            const double lc = lcol[c];
+            double* Fc = F + c * f;
+#pragma unroll 4
+            for (int i = c + lane; i < f; i += 32) Fc[i] -= Fk[i] * lc;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- blocked elimination of a front held in HBM/L2: panels of MF_NB pivots; per panel (1) LDL^T of the nb x nb diagonal
+// block in shared memory by one warp, (2) one thread per row below solves its row against the block (w = a L11^-T D, l = w / d),
+// (3) the trailing lower triangle is updated tile by tile (64x64, 4x4 per thread) from shared-memory copies of W and L.
+// sm: scratch of at least 2 * MF_TS * MF_NB + MF_NB * (MF_NB + 1) + MF_NB doubles.  Wg / Lg: per-instance panel scratch (f x MF_NB each).
+__device__ void mf_eliminate_big(double* __restrict__ F, int f, int ws, int j0, int lp0, double* sm, double* __restrict__ Wg, double* __restrict__ Lg,
+                                 double* Lx, double* Dv, double* Dinv, int* failb) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double* A11 = sm;                                   // MF_NB x (MF_NB + 1)
+    double* dd = A11 + MF_NB * (MF_NB + 1);             // MF_NB
+    double* Wt = dd + MF_NB;                            // MF_NB x MF_TS  (k-major)
+    double* Lt = Wt + MF_NB * MF_TS;
+    constexpr int LDA = MF_NB + 1;
+    for (int k0 = 0; k0 < ws; k0 += MF_NB) {
+        const int nb = min(MF_NB, ws - k0), r0 = k0 + nb, R = f - r0;
+        // (1) diagonal block
+        for (int e = tid; e < nb * nb; e += MF_T) { const int i = e % nb, c = e / nb; A11[i + c * LDA] = (i >= c) ? F[(size_t)(k0 + i) + (size_t)(k0 + c) * f] : 0.0; }
+        __syncthreads();
+        if (wid == 0) {
+            for (int k = 0; k < nb; k++) {
+                const double d = A11[k + k * LDA];
+                const double wi = (lane > k && lane < nb) ? A11[lane + k * LDA] : 0.0;     // unscaled column k
+                const double li = wi / d;
+                __syncwarp();
+                if (lane > k && lane < nb) A11[lane + k * LDA] = li;
+                __syncwarp();
+                if (lane > k && lane < nb) for (int c = k + 1; c <= lane; c++) A11[lane + c * LDA] -= wi * A11[c + k * LDA];
+                if (lane == 0) dd[k] = d;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < nb; k += MF_T) {
+            const double d = dd[k];
+            if (d == 0.0 && *failb == 0) *failb = j0 + k0 + k + 1;
+            Dv[j0 + k0 + k] = d; Dinv[j0 + k0 + k] = 1.0 / d;
+        }
+        for (int e = tid; e < nb * nb; e += MF_T) {
+            const int i = e % nb, c = e / nb;
+            if (i > c) { const int kk = k0 + c; Lx[(lp0 + kk * (f - 1) - (kk * (kk - 1)) / 2) - (kk + 1) + (k0 + i)] = A11[i + c * LDA]; }
+        }
+        // (2) rows below the block
+        for (int ii = tid; ii < R; ii += MF_T) {
+            const int i = r0 + ii;
+            double w[MF_NB];
+#pragma unroll
+            for (int k = 0; k < MF_NB; k++) w[k] = (k < nb) ? F[(size_t)i + (size_t)(k0 + k) * f] : 0.0;
+#pragma unroll
+            for (int k = 0; k < MF_NB; k++) {
+                if (k < nb) {
+                    double acc = w[k];
+#pragma unroll
+                    for (int q = 0; q < k; q++) acc -= w[q] * A11[k + q * LDA];
+                    w[k] = acc;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < MF_NB; k++) {
+                if (k < nb) {
+                    const double l = w[k] / dd[k];
+                    const int kk = k0 + k;
+                    Wg[(size_t)k * R + ii] = w[k]; Lg[(size_t)k * R + ii] = l;
+                    Lx[(lp0 + kk * (f - 1) - (kk * (kk - 1)) / 2) - (kk + 1) + i] = l;
+                }
+            }
+        }
+        __syncthreads();
+        // (3) trailing update F[i, c] -= sum_k W[i, k] L[c, k],  r0 <= c <= i < f
+        const int nt = (R + MF_TS - 1) / MF_TS;
+        const int ti = tid % 16, tc = tid / 16;
+        for (int bi = 0; bi < nt; bi++) {
+            for (int e = tid; e < nb * MF_TS; e += MF_T) { const int k = e / MF_TS, rr = e % MF_TS, g = bi * MF_TS + rr; Wt[e] = g < R ? Wg[(size_t)k * R + g] : 0.0; }
+            for (int bc = 0; bc <= bi; bc++) {
+                __syncthreads();
+                for (int e = tid; e < nb * MF_TS; e += MF_T) { const int k = e / MF_TS, rr = e % MF_TS, g = bc * MF_TS + rr; Lt[e] = g < R ? Lg[(size_t)k * R + g] : 0.0; }
+                __syncthreads();
+                double acc[4][4];
+#pragma unroll
+                for (int a2 = 0; a2 < 4; a2++)
+#pragma unroll
+                    for (int c2 = 0; c2 < 4; c2++) acc[a2][c2] = 0.0;
+                for (int k = 0; k < nb; k++) {
+                    const double4 wv = *reinterpret_cast<const double4*>(Wt + k * MF_TS + ti * 4);
+                    const double4 lv = *reinterpret_cast<const double4*>(Lt + k * MF_TS + tc * 4);
+                    const double wa[4] = {wv.x, wv.y, wv.z, wv.w}, la[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+                    for (int a2 = 0; a2 < 4; a2++)
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; c2++) acc[a2][c2] += wa[a2] * la[c2];
+                }
+#pragma unroll
+                for (int c2 = 0; c2 < 4; c2++) {
+                    const int gc = bc * MF_TS + tc * 4 + c2;
+#pragma unroll
+                    for (int a2 = 0; a2 < 4; a2++) {
+                        const int gi = bi * MF_TS + ti * 4 + a2;
+                        if (gi < R && gc <= gi) F[(size_t)(r0 + gi) + (size_t)(r0 + gc) * f] -= acc[a2][c2];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// PKasm: the permuted KKT values in ASSEMBLY order (grouped by supernode, see LdltSymbolic::asm_*), so that a front's
+// original entries are one contiguous, coalesced read.
+__global__ void __launch_bounds__(MF_T) mf_factor_kernel(MfDev M, const double* __restrict__ PKasm_all, double* __restrict__ Lx_all, double* __restrict__ Dv_all,
+                                                         double* __restrict__ Dinv_all, double* __restrict__ upd_all, double* __restrict__ big_all,
+                                                         double* __restrict__ panel_all, int* __restrict__ fail, const int* __restrict__ active) {
+    extern __shared__ __align__(16) double mf_sm[];
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = MF_T / 32;
+    const double* PK = PKasm_all + (size_t)b * M.nnzPK;
+    double* Lx = Lx_all + (size_t)b * M.nnzL;
+    double* Dv = Dv_all + (size_t)b * M.nk;
+    double* Dinv = Dinv_all + (size_t)b * M.nk;
+    double* upd = upd_all + (size_t)b * (size_t)M.upd_total;
+    double* big = big_all ? big_all + (size_t)b * (size_t)M.fmax * M.fmax : nullptr;
+    double* Wg = panel_all ? panel_all + (size_t)b * 2 * (size_t)M.fmax * MF_NB : nullptr;
+    double* Lg = Wg ? Wg + (size_t)M.fmax * MF_NB : nullptr;
+    const int fpad = (M.fmax + 1) & ~1;
+    double* lcol = mf_sm;                                  // fmax doubles
+    int* relbuf = reinterpret_cast<int*>(mf_sm + fpad);    // fmax ints
+    double* Fs = mf_sm + ((fpad + fpad / 2 + 3) & ~3);
+    if (tid == 0) fail[b] = 0;
+    const int4* hdr4 = reinterpret_cast<const int4*>(M.hdr);
+    int4 nh0 = hdr4[0], nh1 = hdr4[1];
+    long long noff = M.upd_off[0];
+
+    for (int s = 0; s < M.nsup; s++) {
+        const int4 h0 = nh0, h1 = nh1;
+        const long long my_off = noff;
+        if (s + 1 < M.nsup) { nh0 = hdr4[2 * (s + 1)]; nh1 = hdr4[2 * (s + 1) + 1]; noff = M.upd_off[s + 1]; }     // prefetch the next header
+        const int j0 = h0.x, ws = h0.y, us = h0.z, lp0 = h0.w, ab = h1.x, an = h1.y, cb = h1.z, cn = h1.w;
+        const int f = ws + us;
+        const bool in_smem = f <= M.front_smem_rows;
+        double* F = in_smem ? Fs : big;
+        // original entries of this front: issue the loads before zeroing
+        double av[2]; int ap[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) { const int t = tid + u * MF_T; if (t < an) { ap[u] = M.asm_pos[ab + t]; av[u] = PK[ab + t]; } }
+        if (in_smem) { for (int e = tid; e < f * f; e += MF_T) Fs[e] = 0.0; }
+        else { for (size_t e = tid; e < (size_t)f * f; e += MF_T) big[e] = 0.0; }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; u++) if (tid + u * MF_T < an) F[ap[u]] = av[u];
+        for (int t = tid + 2 * MF_T; t < an; t += MF_T) F[M.asm_pos[ab + t]] = PK[ab + t];
+        for (int c = 0; c < cn; c++) {                       // extend-add, one child at a time (fixed order)
+            const int4 cr = reinterpret_cast<const int4*>(M.crec)[cb + c];
+            const int uc = cr.x;
+            const double* U = upd + (((long long)cr.w << 32) | (unsigned)cr.z);
+            for (int t = tid; t < uc; t += MF_T) relbuf[t] = M.rel_idx[cr.y + t];
+            __syncthreads();                                  // relbuf ready; scatter of the original entries done
+            const int total = uc * uc;
+            for (int e0 = tid; e0 < total; e0 += 4 * MF_T) {
+                double uv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const int e = e0 + u * MF_T; uv[u] = e < total ? U[e] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int e = e0 + u * MF_T;
+                    if (e < total) {
+                        const int col = e / uc, a = e - col * uc;
+                        if (a >= col) { const size_t pos = (size_t)relbuf[a] + (size_t)relbuf[col] * f; if (in_smem) Fs[pos] += uv[u]; else big[pos] += uv[u]; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (cn == 0) __syncthreads();
+        // ---- eliminate the ws pivots of the supernode
+        if (in_smem) mf_eliminate_smem(Fs, f, ws, j0, lp0, lcol, Lx, Dv, Dinv, fail + b);
+        else { mf_eliminate_big(big, f, ws, j0, lp0, Fs, Wg, Lg, Lx, Dv, Dinv, fail + b); __syncthreads(); }
+        // ---- Schur complement -> stack (full us x us square, ld = us; only the lower part is meaningful)
+        if (us > 0) {
+            double* U = upd + my_off;
+            for (int col = wid; col < us; col += NW) {
+                const double* Fc = F + (size_t)(ws + col) * f + ws;
+                for (int a = col + lane; a < us; a += 32) U[a + (size_t)col * us] = Fc[a];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// x: permuted work vector (shared memory when it fits, else the HBM work buffer)
+__global__ void __launch_bounds__(MF_T) mf_solve_kernel(MfDev M, int x_in_smem, const double* __restrict__ Lx_all, const double* __restrict__ Dinv_all,
+                                                        const double* __restrict__ rx, const double* __restrict__ ry, const double* __restrict__ rz,
+                                                        double* __restrict__ lx, double* __restrict__ ly, double* __restrict__ lz, double* __restrict__ work_all,
+                                                        const int* __restrict__ active) {
+    extern __shared__ __align__(16) double mf_sm[];
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = MF_T / 32;
+    const int nk = M.nk, n = M.n, p = M.p, m = M.m;
+    const double* Lx = Lx_all + (size_t)b * M.nnzL;
+    const double* Dinv = Dinv_all + (size_t)b * nk;
+    double* x = x_in_smem ? mf_sm : work_all + (size_t)b * nk;
+    __shared__ double red_fallback[NW];
+    for (int j = tid; j < nk; j += MF_T) {                  // ordering.hpp:102-124, sparse/kkt.hpp:113-147
+        const int v = M.perm[j];
+        x[j] = v < n ? rx[(size_t)b * n + v] : (v < n + p ? ry[(size_t)b * p + (v - n)] : rz[(size_t)b * m + (v - n - p)]);
+    }
+    __syncthreads();
+    const int4* hdr4 = reinterpret_cast<const int4*>(M.hdr);
+    // column j0+k of a supernode starts at lp0 + k (f-1) - k (k-1) / 2 in L; its last |U| entries are the update rows
+    // ---- forward: L y = b.  The first MF_T entries of the NEXT supernode's update panel are prefetched into registers.
+    int4 nh = hdr4[0];
+    double pl = 0.0; int pu = 0;
+    { const int ws = nh.y, us = nh.z; if (ws == 1 && tid < us) { pl = Lx[nh.w + tid]; pu = M.Li[nh.w + tid]; } }
+    for (int s = 0; s < M.nsup; s++) {
+        const int4 h = nh;
+        const double cl = pl; const int cu = pu;
+        if (s + 1 < M.nsup) {
+            nh = hdr4[2 * (s + 1)];
+            if (nh.y == 1 && tid < nh.z) { pl = Lx[nh.w + tid]; pu = M.Li[nh.w + tid]; }
+        }
+        const int j0 = h.x, ws = h.y, us = h.z, lp0 = h.w, f = ws + us;
+        if (ws == 1) {
+            if (us > 0) {
+                const double xk = x[j0];
+                if (tid < us) x[cu] -= cl * xk;
+                for (int t = tid + MF_T; t < us; t += MF_T) x[M.Li[lp0 + t]] -= Lx[lp0 + t] * xk;
+                __syncthreads();
+            }
+            continue;
+        }
+        for (int k = 0; k + 1 < ws; k++) {
+            const double xk = x[j0 + k];
+            const double* Lc = Lx + (lp0 + k * (f - 1) - (k * (k - 1)) / 2);            // rows j0+k+1 .. j1 first
+            for (int i = k + 1 + tid; i < ws; i += MF_T) x[j0 + i] -= Lc[i - k - 1] * xk;
+            __syncthreads();
+        }
+        if (us > 0) {
+            const int* U = M.Li + (lp0 + (ws - 1) * (f - 1) - ((ws - 1) * (ws - 2)) / 2);
+            for (int t = tid; t < us; t += MF_T) {
+                double acc = 0.0;
+                for (int k = 0; k < ws; k++) acc += Lx[(lp0 + k * (f - 1) - (k * (k - 1)) / 2) + (ws - 1 - k) + t] * x[j0 + k];
+                x[U[t]] -= acc;
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = tid; j < nk; j += MF_T) x[j] *= Dinv[j];
+    __syncthreads();
+    // ---- backward: L^T x = y  (same register prefetch, walking the supernodes in reverse)
+    nh = hdr4[2 * (M.nsup - 1)];
+    pl = 0.0; pu = 0;
+    if (nh.y == 1 && tid < nh.z) { pl = Lx[nh.w + tid]; pu = M.Li[nh.w + tid]; }
+    for (int s = M.nsup - 1; s >= 0; s--) {
+        const int4 h = nh;
+        const double cl = pl; const int cu = pu;
+        if (s > 0) {
+            nh = hdr4[2 * (s - 1)];
+            if (nh.y == 1 && tid < nh.z) { pl = Lx[nh.w + tid]; pu = M.Li[nh.w + tid]; }
+        }
+        const int j0 = h.x, ws = h.y, us = h.z, lp0 = h.w, f = ws + us;
+        if (ws == 1) {
+            if (us > 0) {
+                double acc = tid < us ? cl * x[cu] : 0.0;
+                for (int t = tid + MF_T; t < us; t += MF_T) acc += Lx[lp0 + t] * x[M.Li[lp0 + t]];
+                // fixed-tree block reduction (deterministic)
+                acc = warp_sum(acc);
+                double* red = red_fallback;
+                if (lane == 0) red[wid] = acc;
+                __syncthreads();
+                if (tid == 0) { double t2 = 0.0; for (int w2 = 0; w2 < (us + 31) / 32 && w2 < NW; w2++) t2 += red[w2]; x[j0] -= t2; }
+                __syncthreads();
+            }
+            continue;
+        }
+        if (us > 0) {
+            const int* U = M.Li + (lp0 + (ws - 1) * (f - 1) - ((ws - 1) * (ws - 2)) / 2);
+            for (int k = wid; k < ws; k += NW) {
+                const double* Lc = Lx + (lp0 + k * (f - 1) - (k * (k - 1)) / 2) + (ws - 1 - k);
+                double acc = 0.0;
+                for (int t = lane; t < us; t += 32) acc += Lc[t] * x[U[t]];
+                acc = warp_sum(acc);
+                if (lane == 0) x[j0 + k] -= acc;
+            }
+            __syncthreads();
+        }
+        for (int k = ws - 2; k >= 0; k--) {
+            if (wid == 0) {
+                const double* Lc = Lx + (lp0 + k * (f - 1) - (k * (k - 1)) / 2);
+                double acc = 0.0;
+                for (int i = k + 1 + lane; i < ws; i += 32) acc += Lc[i - k - 1] * x[j0 + i];
+                acc = warp_sum(acc);
+                if (lane == 0) x[j0 + k] -= acc;
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = tid; j < nk; j += MF_T) {
+        const int v = M.perm[j];
+        const double val = x[j];
+        if (v < n) lx[(size_t)b * n + v] = val; else if (v < n + p) ly[(size_t)b * p + (v - n)] = val; else lz[(size_t)b * m + (v - n - p)] = val;
+    }
+}
+
+}  // namespace b200

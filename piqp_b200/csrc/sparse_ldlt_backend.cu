@@ -1,5 +1,7 @@
 // piqp_b200/csrc/sparse_ldlt_backend.cu -- see sparse_ldlt_backend.hpp
 #include "sparse_ldlt_backend.hpp"
+#include "sparse_frontal.cuh"
+#include <cstdlib>
 #include <algorithm>
 #include <cstdio>
 #include <set>
@@ -97,10 +99,12 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
     // ---- ordering
     if (user_perm) perm.assign(user_perm, user_perm + nk);
     else perm = minimum_degree_ordering(nk, Kp, Ki);
+    const int nnzK = (int)Ki.size();
+    std::vector<int> flag(nk, -1), Lnz(nk, 0);
+    for (int pass = 0; pass < 2; pass++) {
     iperm.assign(nk, -1);
     for (int k = 0; k < nk; k++) { if (perm[k] < 0 || perm[k] >= nk || iperm[perm[k]] != -1) { error = "sparse_ldlt: invalid permutation"; return false; } iperm[perm[k]] = k; }
     // ---- permuted upper pattern with sorted rows + value map (utils.hpp:31-128)
-    const int nnzK = (int)Ki.size();
     std::vector<int> colcnt(nk + 1, 0), ecol(nnzK), erow(nnzK);
     for (int j = 0; j < nk; j++) for (int q = Kp[j]; q < Kp[j + 1]; q++) {
         const int a = iperm[Ki[q]], b = iperm[j];
@@ -123,11 +127,33 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
     for (int v = 0; v < nk; v++) diagPK[v] = K_to_PK[diagK[v]];
     // ---- elimination tree and pattern of L, row by row (ldlt.hpp:42-99 + the pattern the numeric phase fills, :101-169)
     etree.assign(nk, -1);
-    std::vector<int> flag(nk, -1), Lnz(nk, 0);
+    std::fill(flag.begin(), flag.end(), -1); std::fill(Lnz.begin(), Lnz.end(), 0);
     for (int k = 0; k < nk; k++) {
         flag[k] = k;
         for (int q = PKp[k]; q < PKp[k + 1]; q++)
             for (int i = PKi_rows[q]; flag[i] != k; i = etree[i]) { if (etree[i] == -1) etree[i] = k; Lnz[i]++; flag[i] = k; }
+    }
+    if (pass == 1) break;
+    // ---- postorder the elimination tree (children in increasing order) so that supernodes are runs of consecutive columns;
+    //      an equivalent reordering: same fill, same arithmetic per column.  A postordered input is left unchanged.
+    std::vector<int> head(nk, -1), next(nk, -1), post; post.reserve(nk);
+    for (int j = nk - 1; j >= 0; j--) if (etree[j] >= 0) { next[j] = head[etree[j]]; head[etree[j]] = j; }
+    std::vector<int> stack;
+    for (int r = 0; r < nk; r++) {
+        if (etree[r] >= 0) continue;
+        stack.push_back(r);
+        while (!stack.empty()) {
+            const int v = stack.back();
+            if (head[v] >= 0) { const int c = head[v]; head[v] = next[c]; stack.push_back(c); }
+            else { post.push_back(v); stack.pop_back(); }
+        }
+    }
+    bool identity = true;
+    for (int k = 0; k < nk; k++) if (post[k] != k) { identity = false; break; }
+    if (identity) break;
+    std::vector<int> np(nk);
+    for (int k = 0; k < nk; k++) np[k] = perm[post[k]];
+    perm.swap(np);
     }
     Lp.assign(nk + 1, 0);
     for (int k = 0; k < nk; k++) Lp[k + 1] = Lp[k] + Lnz[k];
@@ -169,6 +195,80 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
     for (int l = 0; l <= maxl; l++) level_ptr[l + 1] += level_ptr[l];
     level_cols.assign(nk, 0);
     { std::vector<int> w(level_ptr.begin(), level_ptr.end() - 1); for (int j = 0; j < nk; j++) level_cols[w[level[j]]++] = j; }
+    // ---- supernodes (maximal runs j, j+1 with parent(j) = j+1 and |struct(L_j)| = |struct(L_{j+1})| + 1) and the multifrontal schedule
+    sup_ptr.clear();
+    std::vector<int> sup_of(nk, 0);
+    for (int j = 0; j < nk; j++) {
+        const bool cont = j > 0 && etree[j - 1] == j && (Lp[j] - Lp[j - 1]) == (Lp[j + 1] - Lp[j]) + 1;
+        if (!cont) sup_ptr.push_back(j);
+        sup_of[j] = (int)sup_ptr.size() - 1;
+    }
+    nsup = (int)sup_ptr.size();
+    sup_ptr.push_back(nk);
+    std::vector<int> psup(nsup, -1);
+    child_ptr.assign(nsup + 1, 0);
+    for (int s2 = 0; s2 < nsup; s2++) { const int j1 = sup_ptr[s2 + 1] - 1; if (etree[j1] >= 0) { psup[s2] = sup_of[etree[j1]]; child_ptr[psup[s2] + 1]++; } }
+    for (int s2 = 0; s2 < nsup; s2++) child_ptr[s2 + 1] += child_ptr[s2];
+    child_idx.assign(child_ptr[nsup], 0);
+    { std::vector<int> w(child_ptr.begin(), child_ptr.end() - 1); for (int s2 = 0; s2 < nsup; s2++) if (psup[s2] >= 0) child_idx[w[psup[s2]]++] = s2; }
+    auto front_row = [&](int s2, int row) -> int {          // position of global row `row` in the front of supernode s2, or -1
+        const int j0 = sup_ptr[s2], j1 = sup_ptr[s2 + 1] - 1;
+        if (row >= j0 && row <= j1) return row - j0;
+        const int* b = &Li[0] + Lp[j1]; const int* e = &Li[0] + Lp[j1 + 1];
+        const int* it = std::lower_bound(b, e, row);
+        if (it == e || *it != row) return -1;
+        return (j1 - j0 + 1) + (int)(it - b);
+    };
+    fmax = 0;
+    rel_ptr.assign(nsup + 1, 0);
+    for (int s2 = 0; s2 < nsup; s2++) {
+        const int j1 = sup_ptr[s2 + 1] - 1, us = Lp[j1 + 1] - Lp[j1];
+        rel_ptr[s2 + 1] = rel_ptr[s2] + us;
+        fmax = std::max(fmax, (j1 - sup_ptr[s2] + 1) + us);
+    }
+    rel_idx.assign(rel_ptr[nsup], 0);
+    for (int s2 = 0; s2 < nsup; s2++) {
+        const int j1 = sup_ptr[s2 + 1] - 1;
+        for (int t = 0; t < rel_ptr[s2 + 1] - rel_ptr[s2]; t++) {
+            const int r = front_row(psup[s2], Li[Lp[j1] + t]);      // us > 0 implies a parent
+            if (r < 0) { error = "sparse_ldlt: internal error (update row missing in the parent front)"; return false; }
+            rel_idx[rel_ptr[s2] + t] = r;
+        }
+    }
+    asm_ptr.assign(nsup + 1, 0);
+    for (int j = 0; j < nk; j++) for (int q = PKp[j]; q < PKp[j + 1]; q++) asm_ptr[sup_of[PKi_rows[q]] + 1]++;
+    for (int s2 = 0; s2 < nsup; s2++) asm_ptr[s2 + 1] += asm_ptr[s2];
+    asm_q.assign(nnzK, 0); asm_pos.assign(nnzK, 0);
+    {
+        std::vector<int> w(asm_ptr.begin(), asm_ptr.end() - 1);
+        for (int j = 0; j < nk; j++) for (int q = PKp[j]; q < PKp[j + 1]; q++) {
+            const int i = PKi_rows[q], s2 = sup_of[i];          // upper entry (i <= j) = lower entry (row j, column i) of the front of i's supernode
+            const int j1 = sup_ptr[s2 + 1] - 1, f = (j1 - sup_ptr[s2] + 1) + (Lp[j1 + 1] - Lp[j1]);
+            const int r = front_row(s2, j);
+            if (r < 0) { error = "sparse_ldlt: internal error (matrix entry outside its front)"; return false; }
+            const int t = w[s2]++;
+            asm_q[t] = q; asm_pos[t] = r + (i - sup_ptr[s2]) * f;
+        }
+    }
+    // update-matrix stack: children sit on top of the stack when their parent is assembled (postorder)
+    upd_off.assign(nsup, 0);
+    long long top = 0; upd_total = 0;
+    for (int s2 = 0; s2 < nsup; s2++) {
+        for (int c = child_ptr[s2]; c < child_ptr[s2 + 1]; c++) { const long long uc = rel_ptr[child_idx[c] + 1] - rel_ptr[child_idx[c]]; top -= uc * uc; }
+        const long long us = rel_ptr[s2 + 1] - rel_ptr[s2];
+        upd_off[s2] = top; top += us * us;
+        upd_total = std::max(upd_total, top);
+    }
+    if (getenv("B200_DEBUG_SYMBOLIC")) {
+        double sf2 = 0, su2 = 0, piv_work = 0; int big = 0, w1 = 0;
+        for (int s2 = 0; s2 < nsup; s2++) {
+            const double ws = sup_ptr[s2 + 1] - sup_ptr[s2], us = rel_ptr[s2 + 1] - rel_ptr[s2], f = ws + us;
+            sf2 += f * f; su2 += us * us; big += f > 150; w1 += ws == 1;
+            for (int k = 0; k < (int)ws; k++) piv_work += (f - k) * (f - k) / 2;
+        }
+        fprintf(stderr, "[sparse_ldlt symbolic] nk=%d nnzL=%zu nsup=%d (width 1: %d) fmax=%d fronts>150: %d  sum f^2=%.3g  sum us^2=%.3g  pivot-update entries=%.3g  flops=%.3g upd_total=%lld\n",
+                nk, Li.size(), nsup, w1, fmax, big, sf2, su2, piv_work, factor_flops(), upd_total);
+    }
     return true;
 }
 double LdltSymbolic::factor_flops() const {
@@ -314,19 +414,71 @@ static void upload(DevBuf<int>& d, const std::vector<int>& h) {
     d.alloc(std::max<size_t>(h.size(), 1));
     if (!h.empty()) B200_CUDA(cudaMemcpy(d.get(), h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
 }
+static MfDev make_mf(const SparseLdltBatchedKKT& K) {
+    MfDev M;
+    M.hdr = K.d_hdr.get(); M.crec = K.d_crec.get(); M.rel_idx = K.d_rel_idx.get(); M.asm_pos = K.d_asm_pos.get(); M.Li = K.d_Li.get(); M.perm = K.d_perm.get();
+    M.upd_off = K.d_upd_off.get();
+    M.nsup = K.S.nsup; M.nk = K.S.nk; M.n = K.n; M.p = K.p; M.m = K.m; M.front_smem_rows = K.front_smem_rows; M.fmax = K.S.fmax;
+    M.upd_total = std::max<long long>(K.S.upd_total, 1);
+    M.nnzL = std::max<size_t>(K.S.Li.size(), 1); M.nnzPK = K.S.PKi_rows.size();
+    return M;
+}
 
 SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_perm, cudaStream_t st) : D(data) {
     batch = D->batch; n = D->n; p = D->p; m = D->m; stream = st;
     if (!S.analyse(D->P, D->AT, D->GT, user_perm)) throw std::runtime_error(S.error);
-    auto compose = [&](const std::vector<int>& toK) { std::vector<int> r(toK.size()); for (size_t q = 0; q < toK.size(); q++) r[q] = S.K_to_PK[toK[q]]; return r; };
+    if (const char* e = getenv("B200_LDLT_LEVELS")) if (e[0] == '1') frontal = false;
+    // value order of PKx: CSC order of the permuted matrix for the level kernels, ASSEMBLY order (grouped by front) for the
+    // multifrontal kernels
+    std::vector<int> order(S.PKi_rows.size());
+    for (size_t q = 0; q < order.size(); q++) order[q] = (int)q;
+    if (frontal) for (size_t t = 0; t < S.asm_q.size(); t++) order[S.asm_q[t]] = (int)t;
+    auto compose = [&](const std::vector<int>& toK) { std::vector<int> r(toK.size()); for (size_t q = 0; q < toK.size(); q++) r[q] = order[S.K_to_PK[toK[q]]]; return r; };
     upload(d_P_to_PK, compose(S.P_to_K)); upload(d_AT_to_PK, compose(S.AT_to_K)); upload(d_GT_to_PK, compose(S.GT_to_K));
-    upload(d_diagPK, S.diagPK); upload(d_PK_to_L, S.PK_to_L); upload(d_PKp, S.PKp);
+    { std::vector<int> dg(S.diagPK.size()); for (size_t v = 0; v < dg.size(); v++) dg[v] = order[S.diagPK[v]]; upload(d_diagPK, dg); }
+    upload(d_PK_to_L, S.PK_to_L); upload(d_PKp, S.PKp);
     upload(d_Lp, S.Lp); upload(d_Li, S.Li); upload(d_Rp, S.Rp); upload(d_Rcol, S.Rcol); upload(d_Rpos, S.Rpos);
     upload(d_level_cols, S.level_cols); upload(d_perm, S.perm);
     const size_t B = batch, nnzPK = S.PKi_rows.size(), nnzL = std::max<size_t>(S.Li.size(), 1);
     PKx.alloc(B * nnzPK); PKx.zero(st);
     P_diag.alloc(std::max<size_t>(B * n, 1));
     Lx.alloc(B * nnzL); Dv.alloc(B * S.nk); Dinv.alloc(B * S.nk); work.alloc(B * S.nk); fail.alloc(B); fail.zero(st);
+    // multifrontal schedule (sparse_frontal.cuh)
+    if (frontal) {
+        std::vector<int> hdr((size_t)8 * S.nsup), crec((size_t)4 * std::max<size_t>(S.child_idx.size(), 1), 0);
+        for (int s2 = 0; s2 < S.nsup; s2++) {
+            const int j0 = S.sup_ptr[s2], j1 = S.sup_ptr[s2 + 1] - 1;
+            int* h = &hdr[(size_t)8 * s2];
+            h[0] = j0; h[1] = j1 - j0 + 1; h[2] = S.Lp[j1 + 1] - S.Lp[j1]; h[3] = S.Lp[j0];
+            h[4] = S.asm_ptr[s2]; h[5] = S.asm_ptr[s2 + 1] - S.asm_ptr[s2]; h[6] = S.child_ptr[s2]; h[7] = S.child_ptr[s2 + 1] - S.child_ptr[s2];
+        }
+        for (size_t c = 0; c < S.child_idx.size(); c++) {
+            const int cs = S.child_idx[c];
+            crec[4 * c] = S.rel_ptr[cs + 1] - S.rel_ptr[cs]; crec[4 * c + 1] = S.rel_ptr[cs];
+            crec[4 * c + 2] = (int)(unsigned)(S.upd_off[cs] & 0xffffffffll); crec[4 * c + 3] = (int)(S.upd_off[cs] >> 32);
+        }
+        upload(d_hdr, hdr); upload(d_crec, crec); upload(d_rel_idx, S.rel_idx); upload(d_asm_pos, S.asm_pos);
+        d_upd_off.alloc(std::max<size_t>(S.upd_off.size(), 1));
+        if (!S.upd_off.empty()) B200_CUDA(cudaMemcpy(d_upd_off.get(), S.upd_off.data(), S.upd_off.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        upd.alloc(B * (size_t)std::max<long long>(S.upd_total, 1));
+        const size_t fpad = (size_t)((S.fmax + 1) & ~1);
+        const size_t smem_cap = 200 * 1024, lcol_bytes = sizeof(double) * ((fpad + fpad / 2 + 3) & ~(size_t)3);      // lcol (doubles) + relbuf (ints)
+        const size_t big_scratch = sizeof(double) * (size_t)(2 * MF_TS * MF_NB + MF_NB * (MF_NB + 2));
+        if (lcol_bytes + big_scratch > smem_cap) throw std::runtime_error("sparse_ldlt: a front of this size is not supported by this build");
+        int fs = S.fmax;
+        while ((size_t)fs * fs * sizeof(double) + lcol_bytes > smem_cap) fs--;
+        if (const char* e = getenv("B200_FRONT_SMEM_ROWS")) { const int v = atoi(e); if (v > 0) fs = std::min(fs, v); }     // tests: force the blocked HBM-front path
+        front_smem_rows = fs;
+        factor_smem = lcol_bytes + (size_t)fs * fs * sizeof(double);
+        if (S.fmax > fs) {
+            factor_smem = std::max(factor_smem, lcol_bytes + big_scratch);
+            bigfront.alloc(B * (size_t)S.fmax * S.fmax); panel.alloc(B * 2 * (size_t)S.fmax * MF_NB);
+        }
+        solve_x_in_smem = (size_t)S.nk * sizeof(double) <= smem_cap;
+        solve_smem = solve_x_in_smem ? (size_t)S.nk * sizeof(double) : 0;
+        B200_CUDA(cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(factor_smem, 48 * 1024)));
+        B200_CUDA(cudaFuncSetAttribute(mf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(solve_smem, 48 * 1024)));
+    }
     scatter_static(7);
 }
 void SparseLdltBatchedKKT::copy_from(const SparseLdltBatchedKKT& o) {
@@ -353,6 +505,14 @@ void SparseLdltBatchedKKT::factor(const double* delta, const double* x_reg, cons
     tic(T_ASSEMBLE);
     { dim3 g(ceil_div(nk, 256), batch);
       B200_LAUNCH(ldlt_set_diag_kernel, g, 256, 0, stream, d_diagPK.get(), n, p, m, nnzPK, P_diag.get(), x_reg, delta, z_reg, PKx.get(), active); }
+    if (frontal) {
+        toc(T_ASSEMBLE);
+        tic(T_FACTOR);
+        B200_LAUNCH(mf_factor_kernel, batch, MF_T, factor_smem, stream, make_mf(*this), PKx.get(), Lx.get(), Dv.get(), Dinv.get(), upd.get(), bigfront.get(), panel.get(), fail.get(), active);
+        toc(T_FACTOR);
+        B200_LAUNCH(ldlt_fail_to_ok_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, ok, batch);
+        return;
+    }
     { dim3 g((unsigned)((nnzL + 255) / 256), batch); B200_LAUNCH(ldlt_zero_kernel, g, 256, 0, stream, Lx.get(), nnzL, active); }
     { dim3 g(ceil_div(nnzPK, 256), batch);
       B200_LAUNCH(ldlt_init_kernel, g, 256, 0, stream, d_PK_to_L.get(), nnzPK, nnzL, nk, PKx.get(), Lx.get(), Dv.get(), active); }
@@ -374,6 +534,11 @@ void SparseLdltBatchedKKT::solve(const double* rx, const double* ry, const doubl
     const int nk = S.nk;
     const size_t nnzL = std::max<size_t>(S.Li.size(), 1);
     tic(T_SOLVE);
+    if (frontal) {
+        B200_LAUNCH(mf_solve_kernel, batch, MF_T, solve_smem, stream, make_mf(*this), (int)solve_x_in_smem, Lx.get(), Dinv.get(), rx, ry, rz, lx, ly, lz, work.get(), active);
+        toc(T_SOLVE);
+        return;
+    }
     dim3 gk(ceil_div(nk, 256), batch);
     B200_LAUNCH(ldlt_gather_rhs_kernel, gk, 256, 0, stream, d_perm.get(), n, p, m, rx, ry, rz, work.get(), active);
     const int nlev = (int)S.level_ptr.size() - 1;
@@ -402,8 +567,8 @@ void SparseLdltBatchedKKT::eval_G(double an, double at, const double* xn, const 
 }
 void SparseLdltBatchedKKT::extract_P_diag(double* out) { sparse_extract_diag(*D, out, stream); }
 void SparseLdltBatchedKKT::print_info() const {
-    printf("b200 sparse_ldlt backend: n_kkt = %d, nnz(KKT upper) = %zu, nnz(L) = %.0f, etree levels = %zu, factor flops = %.3g\n",
-           S.nk, S.PKi_rows.size(), S.nnzL(), S.level_ptr.size() - 1, S.factor_flops());
+    printf("b200 sparse_ldlt backend: n_kkt = %d, nnz(KKT upper) = %zu, nnz(L) = %.0f, etree levels = %zu, supernodes = %d, largest front = %d, factor flops = %.3g\n",
+           S.nk, S.PKi_rows.size(), S.nnzL(), S.level_ptr.size() - 1, S.nsup, S.fmax, S.factor_flops());
 }
 
 }  // namespace b200

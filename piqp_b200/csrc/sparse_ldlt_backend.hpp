@@ -34,6 +34,15 @@ struct LdltSymbolic {   // host
     std::vector<int> Lp, Li, etree, level, level_ptr, level_cols;
     std::vector<int> Rp, Rcol, Rpos;              // row j: columns k < j with L(j,k) != 0 and the position of L(j,k) in column k
     std::vector<int> PK_to_L;                     // value index of PK -> position in L (off-diagonal) or -(j+1) for the diagonal of column j
+    // ---- supernodal multifrontal schedule (columns are postordered, so a supernode is a run of consecutive columns whose
+    //      L patterns are nested: struct(L_j) = {j+1..j1} u U, U = struct(L_j1)); front of supernode s = rows {j0..j1} u U
+    int nsup = 0, fmax = 0;                       // number of supernodes, largest front
+    std::vector<int> sup_ptr;                     // [nsup+1] first column of each supernode
+    std::vector<int> child_ptr, child_idx;        // children (supernodes) of each supernode, in increasing order
+    std::vector<int> rel_ptr, rel_idx;            // per supernode: position of each of ITS update rows in its PARENT's front
+    std::vector<int> asm_ptr, asm_q, asm_pos;     // per supernode: entries of the permuted matrix (value index, offset row + col * f in the front)
+    std::vector<long long> upd_off;               // per supernode: offset of its update matrix (us x us, lower, ld = us) on the per-instance stack
+    long long upd_total = 0;                      // stack size in doubles
     std::string error;
     bool analyse(const Pattern& P, const Pattern& AT, const Pattern& GT, const int* user_perm);
     double nnzL() const { return Lp.empty() ? 0.0 : (double)Lp.back(); }
@@ -68,6 +77,14 @@ public:
     DevBuf<double> Lx, Dv, Dinv;   // [batch][nnz(L)], [batch][nk] x2
     DevBuf<double> work;       // [batch][nk] permuted rhs / solution
     DevBuf<int> fail;
+    // multifrontal path
+    bool frontal = true;       // B200_LDLT_LEVELS=1 selects the level-scheduled simplicial kernels instead
+    int front_smem_rows = 0;   // fronts up to this many rows live in shared memory, larger ones in `bigfront`
+    size_t factor_smem = 0, solve_smem = 0;
+    bool solve_x_in_smem = true;
+    DevBuf<int> d_hdr, d_crec, d_rel_idx, d_asm_pos;
+    DevBuf<long long> d_upd_off;
+    DevBuf<double> upd, bigfront, panel;   // [batch][upd_total], [batch][fmax^2] and [batch][2 fmax NB] (only if fmax > front_smem_rows)
 private:
     void scatter_static(int options);
 };

@@ -181,3 +181,42 @@ def mpc_batch(batch, N=100, nx=12, nu=4, seed0=42, umax=1.0, xmax=5.0):
         x_l[k, :nx] = x0; x_u[k, :nx] = x0
     A0 = sp.csc_matrix((Ax[0], A_pat.indices, A_pat.indptr), shape=(p, n))
     return dict(P=P, A=A0, Ax=Ax, c=c, b=b, x_l=x_l, x_u=x_u, n=n, p=p)
+
+
+def sparse_batch(batch, n=1000, p=500, m=500, density=0.005, seed0=42):
+    """BASELINE config 3 / 5 family: `batch` random sparse strongly convex QPs (random_utils.hpp:211-286) that share one
+    sparsity pattern (the batched sparse API's contract) and differ in values: instance k scales diag(P) by U(1, 1.2),
+    perturbs every entry of A and G by U(0.8, 1.2), draws its own c and x_sol, and gets b = A_k x_sol and bounds around
+    G_k x_sol / x_sol by the reference's recipe (so every instance is feasible).
+    Returns scipy patterns P (upper), A, G and arrays Px, Ax, Gx, c, b, h_l, h_u, x_l, x_u with a leading batch axis."""
+    import scipy.sparse as sp
+    base = sparse_strongly_convex_qp(n, p, m, density, seed=seed0, eig_shift="gershgorin")
+    Pu = sp.csc_matrix(sp.triu(base["P"])); A = sp.csc_matrix(base["A"]); G = sp.csc_matrix(base["G"])
+    Pu.sort_indices(); A.sort_indices(); G.sort_indices()
+    diag_mask = np.repeat(np.arange(n), np.diff(Pu.indptr)) == Pu.indices
+    out = {k: [] for k in ("Px", "Ax", "Gx", "c", "b", "h_l", "h_u", "x_l", "x_u")}
+    for k in range(batch):
+        rng = np.random.default_rng(seed0 + 7919 * (k + 1))
+        Px = Pu.data * np.where(diag_mask, rng.uniform(1.0, 1.2), 1.0)
+        Ax = A.data * rng.uniform(0.8, 1.2, A.nnz)
+        Gx = G.data * rng.uniform(0.8, 1.2, G.nnz)
+        Ak = sp.csc_matrix((Ax, A.indices, A.indptr), shape=A.shape); Gk = sp.csc_matrix((Gx, G.indices, G.indptr), shape=G.shape)
+        x_sol = rng.standard_normal(n)
+        h_l, h_u, x_l, x_u = _bounds(rng, x_sol, Gk @ x_sol, m, n, 0.5)
+        for key, v in (("Px", Px), ("Ax", Ax), ("Gx", Gx), ("c", rng.standard_normal(n)), ("b", Ak @ x_sol), ("h_l", h_l), ("h_u", h_u), ("x_l", x_l), ("x_u", x_u)):
+            out[key].append(v)
+    out = {k: np.stack(v) for k, v in out.items()}
+    out.update(P=Pu, A=A, G=G, n=n, p=p, m=m)
+    return out
+
+
+def kkt_min_degree_perm(P, A, G):
+    """A fill-reducing permutation of the FULL KKT pattern [[P, A^T, G^T], [A, I, 0], [G, 0, I]] from SuperLU's
+    multiple-minimum-degree code (scipy), standing in for Eigen::AMDOrdering (sparse/ordering.hpp:68-84) on the CPU arm."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    n, p, m = P.shape[0], A.shape[0], G.shape[0]
+    Pf = sp.triu(P, 1); Pf = abs(Pf) + abs(Pf.T)
+    K = sp.bmat([[Pf, abs(A.T), abs(G.T)], [abs(A), None, None], [abs(G), None, None]], format="csc") + sp.identity(n + p + m, format="csc") * (1.0 + 4.0 * (n + p + m))
+    lu = spla.splu(K, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+    return np.asarray(lu.perm_c, dtype=np.int32)

@@ -28,10 +28,14 @@ def _random_args(n=80, p=25, m=40, seed=3, sparsity=0.08):
     return (q["P"], q["c"], q["A"], q["b"], q["G"], q["h_l"], q["h_u"], q["x_l"], q["x_u"])
 
 
+@pytest.mark.parametrize("kernels", ["frontal", "frontal_hbm_fronts", "levels"])
 @pytest.mark.parametrize("case", ["notebook", "mpc", "random", "no_eq", "no_ineq"])
 @pytest.mark.parametrize("own_perm", [True, False])
-def test_backend_factor_solve_eval_parity(oracle, b200, case, own_perm):
-    """sparse/kkt_test style (tests/src/sparse/kkt_*_test.cpp): same rho/delta/scalings -> same solve / mat-vec results"""
+def test_backend_factor_solve_eval_parity(oracle, b200, case, own_perm, kernels, monkeypatch):
+    """sparse/kkt_test style (tests/src/sparse/kkt_*_test.cpp): same rho/delta/scalings -> same solve / mat-vec results.
+    Both numeric kernel families: the supernodal multifrontal one (default) and the level-scheduled simplicial one."""
+    monkeypatch.setenv("B200_LDLT_LEVELS", "1" if kernels == "levels" else "0")
+    monkeypatch.setenv("B200_FRONT_SMEM_ROWS", "6" if kernels == "frontal_hbm_fronts" else "0")   # fronts > 6 rows -> blocked HBM-front path
     if case == "notebook":
         q, _ = load_scenario_mpc(); args = setup_args(q)
     elif case == "mpc":
@@ -50,8 +54,7 @@ def test_backend_factor_solve_eval_parity(oracle, b200, case, own_perm):
     be = b200.SparseKKT(P, AT, GT, perm=perm)
     info = be.symbolic_info()
     assert sorted(info["perm"].tolist()) == list(range(nk))
-    if perm is not None:
-        assert np.array_equal(info["perm"], perm)
+    # (a user permutation is composed with a postorder of the elimination tree: an equivalent ordering)
     # oracle with the SAME permutation: identical elimination order -> agreement to rounding
     o2 = oracle.SparseSolver(oracle.default_settings(kkt_solver="sparse_ldlt"), kkt_perm=info["perm"]); o2.setup(*args)
     assert o2.ldlt_stats()[0] == info["nnz_L"]

@@ -60,10 +60,14 @@ def test_symbolic_matches_oracle_under_same_permutation(oracle, name, args):
     # ordering quality: own minimum degree is in the same class as the oracle's
     nnzL_oracle, _ = o.ldlt_stats()
     assert mine["nnz_L"] <= 1.3 * nnzL_oracle + 16
-    # user permutation round trip
+    # user permutation: the backend composes it with a postorder of the elimination tree (supernodes become runs of
+    # consecutive columns); that is an equivalent ordering -- same nnz(L) and flops as the user's -- and is idempotent
     rev = np.arange(nk)[::-1].copy()
     again = _symbolic(P, AT, GT, perm=rev)
-    assert np.array_equal(again["perm"], rev)
+    assert sorted(again["perm"].tolist()) == list(range(nk))
+    o3 = oracle.SparseSolver(oracle.default_settings(kkt_solver="sparse_ldlt"), kkt_perm=rev); o3.setup(*args)
+    assert o3.ldlt_stats()[0] == again["nnz_L"]
+    assert np.array_equal(_symbolic(P, AT, GT, perm=again["perm"])["perm"], again["perm"])
     assert 1 <= again["levels"] <= nk
 
 
