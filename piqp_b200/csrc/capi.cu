@@ -156,7 +156,7 @@ int b200_sparse_ldlt_symbolic(int n, int p, int m, const int* Pp, const int* Pi,
         LdltSymbolic S;
         if (!S.analyse(P, AT, GT, perm_in)) throw std::runtime_error(S.error);
         if (perm_out) std::copy(S.perm.begin(), S.perm.end(), perm_out);
-        if (nnz_kkt) *nnz_kkt = (long long)S.PKi_rows.size();
+        if (nnz_kkt) *nnz_kkt = (long long)S.Ki.size();      // structural entries (supernode amalgamation pads PK with explicit zeros)
         if (nnz_L) *nnz_L = (long long)S.nnzL();
         if (levels) *levels = (int)S.level_ptr.size() - 1;
         if (factor_flops) *factor_flops = S.factor_flops();
@@ -166,7 +166,7 @@ int b200_sparse_ldlt_symbolic(int n, int p, int m, const int* Pp, const int* Pi,
 int b200kkt_sparse_info(b200kkt_handle* h, long long* nnz_kkt, long long* nnz_L, int* levels, int* perm) {
     if (!h || !h->ldlt) return fail(B200_E_INVALID, "not a sparse_ldlt handle");
     const LdltSymbolic& S = h->ldlt->S;
-    if (nnz_kkt) *nnz_kkt = (long long)S.PKi_rows.size();
+    if (nnz_kkt) *nnz_kkt = (long long)S.Ki.size();      // structural entries (supernode amalgamation pads PK with explicit zeros)
     if (nnz_L) *nnz_L = (long long)S.nnzL();
     if (levels) *levels = (int)S.level_ptr.size() - 1;
     if (perm) std::copy(S.perm.begin(), S.perm.end(), perm);

@@ -101,27 +101,32 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
     else perm = minimum_degree_ordering(nk, Kp, Ki);
     const int nnzK = (int)Ki.size();
     std::vector<int> flag(nk, -1), Lnz(nk, 0);
-    for (int pass = 0; pass < 2; pass++) {
+    std::vector<std::pair<int, int>> extra;     // explicit structural zeros (row < col, permuted indices) added by supernode amalgamation
+    nnzL_exact = -1.0; flops_exact = -1.0;
+    for (int pass = 0; pass < 3; pass++) {
     iperm.assign(nk, -1);
     for (int k = 0; k < nk; k++) { if (perm[k] < 0 || perm[k] >= nk || iperm[perm[k]] != -1) { error = "sparse_ldlt: invalid permutation"; return false; } iperm[perm[k]] = k; }
     // ---- permuted upper pattern with sorted rows + value map (utils.hpp:31-128)
+    const int nnzPK = nnzK + (int)extra.size();
     std::vector<int> colcnt(nk + 1, 0), ecol(nnzK), erow(nnzK);
     for (int j = 0; j < nk; j++) for (int q = Kp[j]; q < Kp[j + 1]; q++) {
         const int a = iperm[Ki[q]], b = iperm[j];
         erow[q] = std::min(a, b); ecol[q] = std::max(a, b);
         colcnt[ecol[q] + 1]++;
     }
+    for (const auto& x : extra) colcnt[x.second + 1]++;
     PKp.assign(nk + 1, 0);
     for (int j = 0; j < nk; j++) PKp[j + 1] = PKp[j] + colcnt[j + 1];
-    std::vector<std::pair<int, int>> tmp(nnzK);   // (row, K index) grouped by column
+    std::vector<std::pair<int, int>> tmp(nnzPK);   // (row, K index or -1) grouped by column
     {
         std::vector<int> w(PKp.begin(), PKp.end() - 1);
         for (int q = 0; q < nnzK; q++) tmp[w[ecol[q]]++] = {erow[q], q};
+        for (const auto& x : extra) tmp[w[x.second]++] = {x.first, -1};
     }
-    PKi_rows.assign(nnzK, 0); K_to_PK.assign(nnzK, 0);
+    PKi_rows.assign(nnzPK, 0); K_to_PK.assign(nnzK, 0);
     for (int j = 0; j < nk; j++) {
         std::sort(tmp.begin() + PKp[j], tmp.begin() + PKp[j + 1]);
-        for (int t = PKp[j]; t < PKp[j + 1]; t++) { PKi_rows[t] = tmp[t].first; K_to_PK[tmp[t].second] = t; }
+        for (int t = PKp[j]; t < PKp[j + 1]; t++) { PKi_rows[t] = tmp[t].first; if (tmp[t].second >= 0) K_to_PK[tmp[t].second] = t; }
     }
     diagPK.assign(nk, -1);
     for (int v = 0; v < nk; v++) diagPK[v] = K_to_PK[diagK[v]];
@@ -133,7 +138,59 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
         for (int q = PKp[k]; q < PKp[k + 1]; q++)
             for (int i = PKi_rows[q]; flag[i] != k; i = etree[i]) { if (etree[i] == -1) etree[i] = k; Lnz[i]++; flag[i] = k; }
     }
-    if (pass == 1) break;
+    if (pass == 2) break;
+    if (pass == 1) {
+        // ---- relaxed supernode amalgamation.  Fundamental supernodes of these KKT systems are mostly single columns, so a
+        // multifrontal sweep would pay its per-front overhead once per column.  A chain  s -> parent t  (t starts right after s)
+        // is merged when padding s's columns to t's structure costs few explicit zeros; the padding is added to the PATTERN of
+        // the permuted matrix (values stay 0), after which the symbolic phase below finds the merged supernodes by itself.
+        if (getenv("B200_LDLT_NO_AMALG")) break;
+        auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+        const int k_abs = knob("B200_AMALG_ABS", 256), k_div = std::max(1, knob("B200_AMALG_DIV", 4)), k_grow = knob("B200_AMALG_GROW_PCT", 100);
+        std::vector<int> lp(nk + 1, 0), li, fl(nk, 0);
+        for (int k = 0; k < nk; k++) lp[k + 1] = lp[k] + Lnz[k];
+        li.assign(lp[nk], 0);
+        std::fill(flag.begin(), flag.end(), -1);
+        for (int k = 0; k < nk; k++) {
+            flag[k] = k;
+            for (int q = PKp[k]; q < PKp[k + 1]; q++)
+                for (int i = PKi_rows[q]; flag[i] != k; i = etree[i]) { flag[i] = k; li[lp[i] + fl[i]++] = k; }
+        }
+        nnzL_exact = (double)lp[nk];
+        flops_exact = 0; for (int j = 0; j < nk; j++) { const double c = Lnz[j]; flops_exact += c * c + 2 * c; }
+        std::vector<int> fs;                                   // first columns of the fundamental supernodes
+        for (int j = 0; j < nk; j++) if (!(j > 0 && etree[j - 1] == j && Lnz[j - 1] == Lnz[j] + 1)) fs.push_back(j);
+        fs.push_back(nk);
+        const int nf = (int)fs.size() - 1;
+        for (int s2 = 0; s2 < nf;) {
+            const int a = fs[s2];
+            int t2 = s2;                                       // group = fundamental supernodes s2..t2
+            const int orig_first = Lnz[a];
+            while (t2 + 1 < nf) {
+                const int b = fs[t2 + 1] - 1;                  // last column of the group so far
+                if (etree[b] != b + 1) break;
+                const int bt = fs[t2 + 2] - 1;                 // last column of the candidate parent
+                const int f_t = (bt - b) + Lnz[bt], newrows = f_t - Lnz[b], wcur = b - a + 1;
+                const int padded_first = (bt - a) + Lnz[bt];
+                const bool cheap = (long long)wcur * newrows <= k_abs || newrows <= std::max(2, Lnz[b] / k_div);
+                if (!cheap || padded_first > orig_first + (int)((long long)orig_first * k_grow / 100) + 8) break;
+                t2++;
+            }
+            if (t2 > s2) {
+                const int bg = fs[t2 + 1] - 1;
+                const int* Ub = &li[0] + lp[bg]; const int* Ue = &li[0] + lp[bg + 1];
+                for (int j = a; j < bg; j++) {
+                    // target = {j+1..bg} u U ; add what struct(L_j) lacks
+                    const int* p0 = &li[0] + lp[j]; const int* p1 = &li[0] + lp[j + 1];
+                    for (int r = j + 1; r <= bg; r++) { while (p0 < p1 && *p0 < r) p0++; if (p0 == p1 || *p0 != r) extra.push_back({j, r}); }
+                    for (const int* u = Ub; u < Ue; u++) { while (p0 < p1 && *p0 < *u) p0++; if (p0 == p1 || *p0 != *u) extra.push_back({j, *u}); }
+                }
+            }
+            s2 = t2 + 1;
+        }
+        if (extra.empty()) break;
+        continue;
+    }
     // ---- postorder the elimination tree (children in increasing order) so that supernodes are runs of consecutive columns;
     //      an equivalent reordering: same fill, same arithmetic per column.  A postordered input is left unchanged.
     std::vector<int> head(nk, -1), next(nk, -1), post; post.reserve(nk);
@@ -150,11 +207,12 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
     }
     bool identity = true;
     for (int k = 0; k < nk; k++) if (post[k] != k) { identity = false; break; }
-    if (identity) break;
+    if (identity) continue;
     std::vector<int> np(nk);
     for (int k = 0; k < nk; k++) np[k] = perm[post[k]];
     perm.swap(np);
     }
+    const int nnzPK = (int)PKi_rows.size();
     Lp.assign(nk + 1, 0);
     for (int k = 0; k < nk; k++) Lp[k + 1] = Lp[k] + Lnz[k];
     Li.assign(Lp[nk], 0);
@@ -177,7 +235,7 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
     Rcol.assign(Rp[nk], 0); Rpos.assign(Rp[nk], 0);
     for (int k = 0; k < nk; k++) for (size_t t = 0; t < rows[k].size(); t++) { Rcol[Rp[k] + t] = rows[k][t].first; Rpos[Rp[k] + t] = rows[k][t].second; }
     // ---- scatter map of the permuted matrix into L / D
-    PK_to_L.assign(nnzK, 0);
+    PK_to_L.assign(nnzPK, 0);
     for (int j = 0; j < nk; j++) for (int q = PKp[j]; q < PKp[j + 1]; q++) {
         const int i = PKi_rows[q];
         if (i == j) { PK_to_L[q] = -(j + 1); continue; }
@@ -238,7 +296,7 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
     asm_ptr.assign(nsup + 1, 0);
     for (int j = 0; j < nk; j++) for (int q = PKp[j]; q < PKp[j + 1]; q++) asm_ptr[sup_of[PKi_rows[q]] + 1]++;
     for (int s2 = 0; s2 < nsup; s2++) asm_ptr[s2 + 1] += asm_ptr[s2];
-    asm_q.assign(nnzK, 0); asm_pos.assign(nnzK, 0);
+    asm_q.assign(nnzPK, 0); asm_pos.assign(nnzPK, 0);
     {
         std::vector<int> w(asm_ptr.begin(), asm_ptr.end() - 1);
         for (int j = 0; j < nk; j++) for (int q = PKp[j]; q < PKp[j + 1]; q++) {
@@ -272,6 +330,7 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
     return true;
 }
 double LdltSymbolic::factor_flops() const {
+    if (flops_exact >= 0) return flops_exact;      // algorithmic figure: explicit zeros of amalgamated supernodes are not counted
     double f = 0;
     for (int j = 0; j < nk; j++) { const double c = Lp[j + 1] - Lp[j]; f += c * c + 2 * c; }
     return f;

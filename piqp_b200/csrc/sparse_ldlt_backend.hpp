@@ -45,7 +45,8 @@ struct LdltSymbolic {   // host
     long long upd_total = 0;                      // stack size in doubles
     std::string error;
     bool analyse(const Pattern& P, const Pattern& AT, const Pattern& GT, const int* user_perm);
-    double nnzL() const { return Lp.empty() ? 0.0 : (double)Lp.back(); }
+    double nnzL_exact = -1.0, flops_exact = -1.0; // of the unpadded pattern (what the reference's LDLt would store / compute)
+    double nnzL() const { return nnzL_exact >= 0 ? nnzL_exact : (Lp.empty() ? 0.0 : (double)Lp.back()); }
     double factor_flops() const;                  // sum_j (c_j^2 + 2 c_j), SURVEY 8(d)
 };
 
