@@ -492,7 +492,8 @@ def main():
         achieved = by_launch / (ms_launch * 1e-3) * 1e-9 if ms_launch > 0 else 0.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("ms_factor_kernel_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                "msw_factor_chain_kernel_bytes_per_launch" if wl.name == "multistage" else "mf_factor_kernel_bytes_per_launch")
         except Exception:
             pass
         roofline = {"kernel": wl.roofline_kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
