@@ -1,5 +1,7 @@
 // piqp_b200/csrc/dense_backend.cu -- batched dense KKT backend + dense problem data / Ruiz sweeps.
 #include "dense_backend.hpp"
+#include <string>
+#include <cstdlib>
 #include "dense_kernels.cuh"
 
 namespace b200 {
@@ -362,6 +364,42 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
     Linv.alloc((size_t)batch * Linv_stride); Linv.zero(st);
     set_smem(trsv_kernel, (size_t)(n + 32) * sizeof(double) > 48 * 1024 ? (size_t)(n + 32) * sizeof(double) : 48 * 1024);
     if (p > 0) { AtA.alloc((size_t)batch * D->ld * n); AtA.zero(st); compute_AtA(); }
+    // ---- Ozaki / tcgen05 assembly: B200_DENSE_ASSEMBLE = ozaki | dmma | auto (default: ozaki when the contraction is long enough
+    //      for the integer tensor cores to beat the FP64 DMMA pipe including the digit split)
+    {
+        const char* e = getenv("B200_DENSE_ASSEMBLE");
+        const std::string mode = e ? e : "auto";
+        ozaki = m > 0 && n > 0 && (mode == "ozaki" || (mode == "auto" && n >= 256 && m >= 128));
+    }
+    if (ozaki) {
+        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+        B200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn) throw std::runtime_error("cuTensorMapEncodeTiled is not available");
+        oz_mp = round_up(m, 16);
+        oz_digits.alloc((size_t)batch * OZ_S * n * oz_mp);
+        B200_CUDA(cudaMemsetAsync(oz_digits.get(), 0, oz_digits.n, st));
+        oz_ex.alloc((size_t)batch * n); oz_sw.alloc((size_t)batch * m);
+        std::vector<int> tiles;
+        const int nI = ceil_div(n, OZ_TM), nJ = ceil_div(n, OZ_TN);
+        for (int I = 0; I < nI; I++) for (int J = 0; J < nJ && J * OZ_TN < (I + 1) * OZ_TM; J++) { tiles.push_back(I); tiles.push_back(J); }
+        oz_ntiles = (int)tiles.size() / 2;
+        oz_tiles.alloc(tiles.size());
+        B200_CUDA(cudaMemcpy(oz_tiles.get(), tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice));
+        auto make = [&](unsigned char* out, cuuint32_t box_rows) {
+            cuuint64_t dims[3] = {(cuuint64_t)oz_mp, (cuuint64_t)n, (cuuint64_t)OZ_S * batch};
+            cuuint64_t strides[2] = {(cuuint64_t)oz_mp, (cuuint64_t)n * oz_mp};
+            cuuint32_t box[3] = {(cuuint32_t)OZ_KB, box_rows, (cuuint32_t)OZ_S};
+            cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult r = ((EncodeTiled)fn)(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, oz_digits.get(), dims, strides, box, estr,
+                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed for the digit planes");
+        };
+        static_assert(sizeof(CUtensorMap) <= 128, "CUtensorMap size");
+        make(oz_mapA, OZ_TM); make(oz_mapB, OZ_TN);
+        set_smem(oz_gemm_kernel, OZ_GEMM_SMEM);
+    }
 }
 
 void DenseBatchedKKT::copy_from(const DenseBatchedKKT& o) {
@@ -384,8 +422,28 @@ void DenseBatchedKKT::update_data(int options) {   // dense/kkt.hpp:62-71
     if (options & 2) compute_AtA();
 }
 
+void DenseBatchedKKT::assemble_ozaki(const double* x_reg, const int* active) {   // dense/kkt.hpp:140-160 on tcgen05 (dense_ozaki.cuh)
+    OzArgs a{};
+    a.G = D->GT.get(); a.strideG = D->sG(); a.ldg = D->ld;
+    a.w = zinv.get(); a.stridew = m;
+    a.n = n; a.m = m; a.mp = oz_mp;
+    a.Dg = reinterpret_cast<int8_t*>(oz_digits.get()); a.ex = oz_ex.get(); a.sw = oz_sw.get();
+    a.C = K.get(); a.strideC = D->sP(); a.ldc = D->ld;
+    a.Pf = D->Pf.get(); a.strideP = D->sP();
+    a.AtA = p > 0 ? AtA.get() : nullptr; a.strideAtA = D->sP();
+    a.xreg = x_reg; a.stridex = n; a.delta = delta.get(); a.active = active;
+    a.tile_ij = oz_tiles.get(); a.ntiles = oz_ntiles;
+    const size_t tot = (size_t)batch * m;
+    B200_LAUNCH(oz_sqrt_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, zinv.get(), oz_sw.get(), tot);
+    { dim3 g(ceil_div(n, 128), batch); B200_LAUNCH(oz_rowscale_kernel, g, 128, 0, stream, a); }
+    { dim3 g(ceil_div(n, 32), ceil_div(oz_mp, 128), batch); B200_LAUNCH(oz_split_kernel, g, 256, 0, stream, a); }
+    B200_LAUNCH(oz_gemm_kernel, (unsigned)((size_t)oz_ntiles * batch), 128, OZ_GEMM_SMEM, stream, *reinterpret_cast<const CUtensorMap*>(oz_mapA),
+                *reinterpret_cast<const CUtensorMap*>(oz_mapB), a);
+}
+
 void DenseBatchedKKT::assemble(const double* x_reg, const int* active) {   // dense/kkt.hpp:140-160
     if (n == 0) return;
+    if (ozaki) { assemble_ozaki(x_reg, active); return; }
     GemmArgs g{};
     g.A = D->GT.get(); g.strideA = D->sG(); g.lda = D->ld;
     g.B = g.A; g.strideB = g.strideA; g.ldb = g.lda;

@@ -73,8 +73,16 @@ public:
     DevBuf<int> fail;        // [batch] 0 = ok, else failing column + 1
     DevBuf<double> Linv;     // [batch][n/32 (padded to whole tiles)][32 x 36] inverses of the 32 x 32 diagonal blocks of L
     long long Linv_stride = 0;
+    // Ozaki / tcgen05 assembly path (dense_ozaki.cuh)
+    bool ozaki = false;
+    int oz_mp = 0, oz_ntiles = 0;
+    DevBuf<signed char> oz_digits;   // [batch][8][n][mp]
+    DevBuf<int> oz_ex, oz_tiles;     // [batch][n] row exponents; [ntiles][2] lower tiles (128-row, 64-col)
+    DevBuf<double> oz_sw;            // [batch][m] sqrt(z_reg^-1)
+    unsigned char oz_mapA[128] __attribute__((aligned(64))), oz_mapB[128] __attribute__((aligned(64)));   // CUtensorMap x 2
 private:
     void compute_AtA();
+    void assemble_ozaki(const double* x_reg, const int* active);
 };
 
 }  // namespace b200

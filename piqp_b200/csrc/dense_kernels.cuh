@@ -15,6 +15,7 @@
 // Layout: every matrix is column-major with a padded leading dimension ld (multiple of 8 doubles); the
 // padding rows are zero.  Batched arrays are instance-major with a fixed stride.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 namespace b200 {
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_tile_kernel(GemmArgs 
 }
 
 #include "dense_chol.cuh"
+#include "dense_ozaki.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // trsv: x <- L^{-T} L^{-1} x for one instance per CTA (x in shared memory).

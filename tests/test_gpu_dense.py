@@ -20,6 +20,14 @@ def _rel(a, b):
     return np.abs(a - b).max() / max(1.0, np.abs(b).max())
 
 
+@pytest.fixture(params=["dmma", "ozaki"])
+def assemble_mode(request, monkeypatch):
+    """Both assembly kernels for K = P + diag + AtA/delta + G^T Z^-1 G: the FP64 DMMA tile kernel and the Ozaki-split
+    tcgen05 (s8 tensor core + TMEM + TMA) kernel, forced through B200_DENSE_ASSEMBLE (read when a backend is constructed)."""
+    monkeypatch.setenv("B200_DENSE_ASSEMBLE", request.param)
+    return request.param
+
+
 def _oracle_backend(oracle, dims, seed):
     q = dense_strongly_convex_qp(*dims, seed=seed)
     s = oracle.DenseSolver(); s.setup(*setup_args(q))
@@ -27,7 +35,7 @@ def _oracle_backend(oracle, dims, seed):
 
 
 @pytest.mark.parametrize("dims", [(20, 8, 9), (128, 32, 64), (200, 0, 300), (260, 30, 0), (300, 17, 45), (5, 0, 0)])
-def test_backend_factor_solve_eval_parity(oracle, b200, dims):
+def test_backend_factor_solve_eval_parity(oracle, b200, dims, assemble_mode):
     n, p, m = dims
     q, s, (P, AT, GT) = _oracle_backend(oracle, dims, seed=11)
     be = b200.DenseKKT(P, AT, GT)
@@ -107,7 +115,7 @@ def _vtable(oracle, b200):
 
 
 @pytest.mark.parametrize("dims,seed", [((20, 10, 12), 42), ((128, 32, 64), 42), ((64, 10, 0), 43), ((20, 0, 12), 44), ((150, 20, 200), 45)])
-def test_reference_style_solver_drives_cuda_backend(oracle, b200, dims, seed):
+def test_reference_style_solver_drives_cuda_backend(oracle, b200, dims, seed, assemble_mode):
     """The drop-in: the oracle's KKTSystem + IP loop (the reference's caller) runs on the CUDA backend through the
     C-ABI function table and must take the same iterations to the same solution as with the CPU backend."""
     q = dense_strongly_convex_qp(*dims, seed=seed)
@@ -135,7 +143,7 @@ def _solve_batch(b200, qs, **settings):
 
 
 @pytest.mark.parametrize("dims,batch", [((20, 10, 12), 6), ((128, 32, 64), 4), ((64, 10, 0), 3), ((20, 0, 12), 3), ((64, 0, 0), 2), ((300, 40, 150), 2)])
-def test_batched_solver_matches_oracle(oracle, b200, dims, batch):
+def test_batched_solver_matches_oracle(oracle, b200, dims, batch, assemble_mode):
     """device-resident IP loop vs the CPU oracle: same status, same iteration count, |dx| <= 1e-8 max(1,|x|)"""
     kw = dict(bounds_perc=0.0) if dims[2] == 0 and dims[1] in (10, 0) and dims[0] == 64 else {}
     qs = [dense_strongly_convex_qp(*dims, seed=42 + b, **kw) for b in range(batch)]
@@ -171,7 +179,7 @@ def test_batched_known_answers_and_update(oracle, b200):
     assert np.allclose(r.x[0], [0.2763157, 0.0921056], atol=1e-6) and np.allclose(r.x[1], r.x[0], atol=1e-9)
 
 
-def test_batched_infeasibility_and_special_cases(oracle, b200):
+def test_batched_infeasibility_and_special_cases(oracle, b200, assemble_mode):
     """solver_test.cpp:107-182, 347-377"""
     s, r = _solve_batch(b200, [primal_infeasible_qp()])
     assert r.info[0].status == -2
@@ -189,7 +197,7 @@ def test_batched_infeasibility_and_special_cases(oracle, b200):
         assert r.info[0].status == o.info().status and r.info[0].iter == o.info().iter
 
 
-def test_batched_iterative_refinement_path(oracle, b200):
+def test_batched_iterative_refinement_path(oracle, b200, assemble_mode):
     """iterative_refinement_always_enabled exercises kkt_system.hpp:196-207,256-301 on the device"""
     qs = [dense_strongly_convex_qp(30, 10, 20, seed=60 + b) for b in range(3)]
     s, r = _solve_batch(b200, qs, iterative_refinement_always_enabled=1)
@@ -210,7 +218,7 @@ def test_batched_trace_matches_oracle(oracle, b200):
     assert np.allclose(tg[:, :5], to[:, :5], rtol=1e-6, atol=1e-12)
 
 
-def test_batched_full_size_properties(oracle, b200):
+def test_batched_full_size_properties(oracle, b200, assemble_mode):
     """BASELINE config 2 shape (n=1024, m=512) at a small batch: every instance solves, satisfies the KKT conditions,
     and instance 0 matches the oracle's iteration count and solution."""
     qs = [dense_strongly_convex_qp(1024, 0, 512, seed=42 + b) for b in range(3)]
