@@ -364,12 +364,14 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
     Linv.alloc((size_t)batch * Linv_stride); Linv.zero(st);
     set_smem(trsv_kernel, (size_t)(n + 32) * sizeof(double) > 48 * 1024 ? (size_t)(n + 32) * sizeof(double) : 48 * 1024);
     if (p > 0) { AtA.alloc((size_t)batch * D->ld * n); AtA.zero(st); compute_AtA(); }
-    // ---- Ozaki / tcgen05 assembly: B200_DENSE_ASSEMBLE = ozaki | dmma | auto (default: ozaki when the contraction is long enough
-    //      for the integer tensor cores to beat the FP64 DMMA pipe including the digit split)
+    // ---- Ozaki / tcgen05 assembly: B200_DENSE_ASSEMBLE = ozaki | dmma (default dmma).  Measured on config 2 (profiles/README.md):
+    //      the tcgen05 kernel is exact to the parity bars but its 128 x 64 tiles (TMEM holds 8 accumulators x 64 columns) are bound by
+    //      the L2 -> shared-memory operand stream (8.5 TB/s ceiling measured), 6.6 ms per launch against 5.0 ms for the DMMA kernel;
+    //      it becomes the default once the operand tiles are multicast across a cluster.
     {
         const char* e = getenv("B200_DENSE_ASSEMBLE");
-        const std::string mode = e ? e : "auto";
-        ozaki = m > 0 && n > 0 && (mode == "ozaki" || (mode == "auto" && n >= 256 && m >= 128));
+        const std::string mode = e ? e : "dmma";
+        ozaki = m > 0 && n > 0 && mode == "ozaki";
     }
     if (ozaki) {
         typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -380,7 +382,7 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
         oz_mp = round_up(m, 16);
         oz_digits.alloc((size_t)batch * OZ_S * n * oz_mp);
         B200_CUDA(cudaMemsetAsync(oz_digits.get(), 0, oz_digits.n, st));
-        oz_ex.alloc((size_t)batch * n); oz_sw.alloc((size_t)batch * m);
+        oz_ex.alloc((size_t)batch * n); oz_sw.alloc((size_t)batch * m); oz_sc.alloc((size_t)batch * n);
         std::vector<int> tiles;
         const int nI = ceil_div(n, OZ_TM), nJ = ceil_div(n, OZ_TN);
         for (int I = 0; I < nI; I++) for (int J = 0; J < nJ && J * OZ_TN < (I + 1) * OZ_TM; J++) { tiles.push_back(I); tiles.push_back(J); }
@@ -427,7 +429,7 @@ void DenseBatchedKKT::assemble_ozaki(const double* x_reg, const int* active) {  
     a.G = D->GT.get(); a.strideG = D->sG(); a.ldg = D->ld;
     a.w = zinv.get(); a.stridew = m;
     a.n = n; a.m = m; a.mp = oz_mp;
-    a.Dg = reinterpret_cast<int8_t*>(oz_digits.get()); a.ex = oz_ex.get(); a.sw = oz_sw.get();
+    a.Dg = reinterpret_cast<int8_t*>(oz_digits.get()); a.ex = oz_ex.get(); a.sw = oz_sw.get(); a.sc = oz_sc.get();
     a.C = K.get(); a.strideC = D->sP(); a.ldc = D->ld;
     a.Pf = D->Pf.get(); a.strideP = D->sP();
     a.AtA = p > 0 ? AtA.get() : nullptr; a.strideAtA = D->sP();

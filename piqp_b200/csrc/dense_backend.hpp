@@ -78,7 +78,7 @@ public:
     int oz_mp = 0, oz_ntiles = 0;
     DevBuf<signed char> oz_digits;   // [batch][8][n][mp]
     DevBuf<int> oz_ex, oz_tiles;     // [batch][n] row exponents; [ntiles][2] lower tiles (128-row, 64-col)
-    DevBuf<double> oz_sw;            // [batch][m] sqrt(z_reg^-1)
+    DevBuf<double> oz_sw, oz_sc;     // [batch][m] sqrt(z_reg^-1); [batch][n] per-row output scales
     unsigned char oz_mapA[128] __attribute__((aligned(64))), oz_mapB[128] __attribute__((aligned(64)));   // CUtensorMap x 2
 private:
     void compute_AtA();

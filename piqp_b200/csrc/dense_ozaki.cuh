@@ -32,6 +32,7 @@ struct OzArgs {
     int n, m, mp;                       // mp = m rounded up to 16 (row pitch of a digit plane in bytes)
     int8_t* Dg;                         // [batch][OZ_S][n][mp]
     int* ex;                            // [batch][n]
+    double* sc;                         // [batch][n] 2^(e_i - 34) (NaN when the row holds a non-finite entry): K_ij = V sc_i sc_j
     double* sw;                         // [batch][m] sqrt(w)
     // epilogue
     double* C; long long strideC; int ldc;
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(128) oz_rowscale_kernel(OzArgs a) {
     int e = 0;
     if (mx > 0.0) frexp(mx, &e);                 // mx = f 2^e, f in [0.5, 1)  ->  |B| / 2^e < 1
     a.ex[(size_t)b * a.n + i] = bad ? OZ_EXP_NONFINITE : e;
+    a.sc[(size_t)b * a.n + i] = bad ? __longlong_as_double(0x7ff8000000000000ll) : scalbn(1.0, e - (2 * OZ_F - 8 * (OZ_S - 1)) / 2);
 }
 // block = 256 threads: 32 rows x 128 k.  thread (r = tid % 32, q = tid / 32) converts k = k0 + 16 q .. + 15 of row i0 + r; the digit
 // bytes are transposed through shared memory so that every plane row is written as one 128-byte segment.
@@ -175,13 +177,16 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
             oz_mbar_wait(&full[s], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a0 = oz_smem_u32(sm + (size_t)s * OZ_STAGE), b0 = a0 + OZ_STAGE_A;
-#pragma unroll 1
+            // descriptors differ only in the start-address field (bits [0,14) of the low word, units of 16 B): add constants
+            const uint64_t da0 = oz_desc_sw64(a0), db0 = oz_desc_sw64(b0);
+#pragma unroll
             for (int g = 0; g < OZ_S; g++)                    // weight group g = (a + b) - 2, digit indices 0-based below
+#pragma unroll
                 for (int da = 0; da <= g; da++) {
                     const int db = g - da;
 #pragma unroll
                     for (int kk = 0; kk < 2; kk++)
-                        oz_umma_s8(tmem + (uint32_t)(g * OZ_TN), oz_desc_sw64(a0 + da * (OZ_TM * OZ_KB) + kk * 32), oz_desc_sw64(b0 + db * (OZ_TN * OZ_KB) + kk * 32), idesc,
+                        oz_umma_s8(tmem + (uint32_t)(g * OZ_TN), da0 + (uint64_t)((da * (OZ_TM * OZ_KB) + kk * 32) >> 4), db0 + (uint64_t)((db * (OZ_TN * OZ_KB) + kk * 32) >> 4), idesc,
                                    (it > 0 || da > 0 || kk > 0) ? 1u : 0u);
                 }
             oz_commit(&empty[s]);
@@ -194,23 +199,28 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     const double* Pf = a.Pf + (size_t)b * a.strideP;
     const double* AtA = a.AtA ? a.AtA + (size_t)b * a.strideAtA : nullptr;
     const double dinv = a.AtA ? 1.0 / a.delta[b] : 0.0;
-    const int* ex = a.ex + (size_t)b * a.n;
-    const int ei = gi < a.n ? ex[gi] : 0;
+    const double* sc = a.sc + (size_t)b * a.n;
+    const double si = gi < a.n ? sc[gi] : 0.0;
     const double xr = gi < a.n ? a.xreg[(size_t)b * a.stridex + gi] : 0.0;
+    auto load_base = [&](int c0, double (&base)[8], double (&sj)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int gj = col0 + c0 + j;
+            base[j] = 0.0; sj[j] = 0.0;
+            if (gi < a.n && gj <= gi) { const size_t idx = (size_t)gj * a.ldc + gi; base[j] = Pf[idx]; if (AtA) base[j] += dinv * AtA[idx]; sj[j] = sc[gj]; }
+        }
+    };
+    double base[8], sj[8];
+    load_base(0, base, sj);                       // in flight while the last MMAs run
     oz_mbar_wait(&done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
     for (int c0 = 0; c0 < OZ_TN; c0 += 8) {
-        double base[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int gj = col0 + c0 + j;
-            base[j] = 0.0;
-            if (gi < a.n && gj <= gi) { const size_t idx = (size_t)gj * a.ldc + gi; base[j] = Pf[idx]; if (AtA) base[j] += dinv * AtA[idx]; }
-        }
         uint32_t r[OZ_S][8];
 #pragma unroll
         for (int g = 0; g < OZ_S; g++) oz_tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * OZ_TN + c0), r[g]);
+        double nbase[8], nsj[8];
+        if (c0 + 8 < OZ_TN) load_base(c0 + 8, nbase, nsj);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -219,15 +229,13 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
                 double V = (double)(int)r[0][j];
 #pragma unroll
                 for (int g = 1; g < OZ_S; g++) V = fma(V, 256.0, (double)(int)r[g][j]);
-                const int ej = ex[gj];
-                double val;
-                if (ei == OZ_EXP_NONFINITE || ej == OZ_EXP_NONFINITE) val = __longlong_as_double(0x7ff8000000000000ll);
-                else val = scalbn(V, ei + ej - (2 * OZ_F - 8 * (OZ_S - 1)));
                 double bse = base[j];
                 if (gj == gi) bse += xr;
-                C[(size_t)gj * a.ldc + gi] = bse + val;
+                C[(size_t)gj * a.ldc + gi] = bse + (V * si) * sj[j];
             }
         }
+#pragma unroll
+        for (int j = 0; j < 8; j++) { base[j] = nbase[j]; sj[j] = nsj[j]; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

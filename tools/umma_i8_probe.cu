@@ -221,15 +221,16 @@ __global__ void __launch_bounds__(128) probe_issue(int N, int iters, unsigned lo
 // ------------------------------------------------------------------------------------------------ part C
 // Each CTA streams `nsteps` k-slabs: per slab TMA loads SA slices of A rows (128 x 128 B each) and SB slices of B rows (N x 128 B),
 // then issues `pairs` x 4 MMAs on them (round-robin over the loaded slices).  2-stage ring.
+template <int NST>
 __global__ void __launch_bounds__(128) probe_stream(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int N, int SA, int SB, int pairs,
                                                     int nsteps, int rows_total, unsigned long long* cycles_out) {
     extern __shared__ __align__(1024) uint8_t sm[];
-    __shared__ uint64_t full[2], empty[2], done;
+    __shared__ uint64_t full[NST], empty[NST], done;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
     const size_t stageA = (size_t)SA * 128 * 128, stageB = (size_t)SB * N * 128, stage = stageA + stageB;
     if (warp == 0) tmem_alloc(&tmem_base, 512);
-    if (tid == 0) { for (int s = 0; s < 2; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); } mbar_init(&done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); } mbar_init(&done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -237,8 +238,8 @@ __global__ void __launch_bounds__(128) probe_stream(const __grid_constant__ CUte
     unsigned long long t0 = clock64();
     if (warp == 0 && (tid & 31) == 0) {            // TMA producer
         for (int it = 0; it < nsteps; it++) {
-            const int s = it & 1;
-            if (it >= 2) mbar_wait(&empty[s], ((it >> 1) - 1) & 1);
+            const int s = it % NST;
+            if (it >= NST) mbar_wait(&empty[s], ((it / NST) - 1) & 1);
             mbar_expect_tx(&full[s], (uint32_t)stage);
             uint8_t* base = sm + (size_t)s * stage;
             const int row0 = (int)(((size_t)blockIdx.x * 977 + (size_t)it * 131) % (size_t)(rows_total / 256)) * 256;      // wander over the tensor
@@ -248,8 +249,8 @@ __global__ void __launch_bounds__(128) probe_stream(const __grid_constant__ CUte
     } else if (warp == 1 && (tid & 31) == 0) {     // MMA issuer
         const uint32_t idesc = make_idesc_i8(128, N, 1, 0);
         for (int it = 0; it < nsteps; it++) {
-            const int s = it & 1;
-            mbar_wait(&full[s], (it >> 1) & 1);
+            const int s = it % NST;
+            mbar_wait(&full[s], (it / NST) & 1);
             tc_fence_after();
             const uint32_t a0 = smem_u32(sm + (size_t)s * stage), b0 = a0 + (uint32_t)stageA;
             for (int pq = 0; pq < pairs; pq++) {
@@ -389,27 +390,31 @@ int main() {
     uint8_t *gA, *gB;
     CK(cudaMalloc(&gA, rows_total * kbytes)); CK(cudaMalloc(&gB, rows_total * kbytes));
     CK(cudaMemset(gA, 1, rows_total * kbytes)); CK(cudaMemset(gB, 2, rows_total * kbytes));
-    struct Cfg { int N, SA, SB, pairs; const char* what; };
-    const Cfg cfgs[] = {{128, 1, 1, 1, "plain int8 GEMM tile 128x128 (1 MMA group per loaded slab)"},
-                        {64, 4, 4, 10, "Ozaki half: 4+4 slices, 10 pairs, 128x64"},
-                        {64, 8, 8, 36, "Ozaki full: 8+8 slices, 36 pairs, 128x64"},
-                        {128, 4, 4, 10, "Ozaki half: 4+4 slices, 10 pairs, 128x128"}};
+    struct Cfg { int N, SA, SB, pairs, nst; const char* what; };
+    const Cfg cfgs[] = {{128, 1, 1, 1, 2, "plain int8 GEMM tile 128x128, 32 KB stages, 2 stages"},
+                        {128, 1, 1, 1, 4, "plain int8 GEMM tile 128x128, 32 KB stages, 4 stages"},
+                        {128, 1, 1, 1, 6, "plain int8 GEMM tile 128x128, 32 KB stages, 6 stages"},
+                        {64, 4, 4, 10, 2, "Ozaki half: 4+4 planes, 10 pairs, 128x64, 96 KB stages, 2 stages"},
+                        {64, 2, 2, 3, 4, "2+2 planes, 3 pairs, 128x64, 48 KB stages, 4 stages"}};
     for (const Cfg& c : cfgs) {
         CUtensorMap mA = make_map(enc, gA, rows_total, kbytes, 128), mB = make_map(enc, gB, rows_total, kbytes, (uint32_t)c.N);
-        const size_t stage = (size_t)c.SA * 128 * 128 + (size_t)c.SB * c.N * 128, smem = 2 * stage + 1024;
+        const size_t stage = (size_t)c.SA * 128 * 128 + (size_t)c.SB * c.N * 128, smem = c.nst * stage + 1024;
         if (smem > 227 * 1024) { printf("part C: %s: %zu B of smem do not fit, skipped\n", c.what, smem); continue; }
-        CK(cudaFuncSetAttribute(probe_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int nsteps = 2048;
-        probe_stream<<<nsm, 128, smem>>>(mA, mB, c.N, c.SA, c.SB, c.pairs, nsteps, (int)rows_total, dcyc);
+        auto launch = [&]() {
+            if (c.nst == 2) { CK(cudaFuncSetAttribute(probe_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); probe_stream<2><<<nsm, 128, smem>>>(mA, mB, c.N, c.SA, c.SB, c.pairs, nsteps, (int)rows_total, dcyc); }
+            else if (c.nst == 4) { CK(cudaFuncSetAttribute(probe_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); probe_stream<4><<<nsm, 128, smem>>>(mA, mB, c.N, c.SA, c.SB, c.pairs, nsteps, (int)rows_total, dcyc); }
+            else { CK(cudaFuncSetAttribute(probe_stream<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); probe_stream<6><<<nsm, 128, smem>>>(mA, mB, c.N, c.SA, c.SB, c.pairs, nsteps, (int)rows_total, dcyc); }
+        };
+        launch();
         CK(cudaDeviceSynchronize());
         cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
         CK(cudaEventRecord(e0));
-        probe_stream<<<nsm, 128, smem>>>(mA, mB, c.N, c.SA, c.SB, c.pairs, nsteps, (int)rows_total, dcyc);
+        launch();
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         const double ops = 2.0 * 128 * c.N * 128.0 * c.pairs * nsteps * nsm, bytes = (double)stage * nsteps * nsm;
-        printf("part C: %-62s: %.1f TOP/s, operand stream %.2f TB/s (%.3f ms) -> FP64-equivalent %.1f TFLOP/s at 36 products per FP64 product\n",
-               c.what, ops / (ms * 1e-3) * 1e-12, bytes / (ms * 1e-3) * 1e-12, ms, ops / (ms * 1e-3) * 1e-12 / 36.0);
+        printf("part C: %-68s: %.1f TOP/s, operand stream %.2f TB/s (%.3f ms)\n", c.what, ops / (ms * 1e-3) * 1e-12, bytes / (ms * 1e-3) * 1e-12, ms);
     }
     printf("done\n");
     return 0;
