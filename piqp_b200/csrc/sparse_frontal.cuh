@@ -360,4 +360,137 @@ __global__ void __launch_bounds__(MF_T) mf_solve_kernel(MfDev M, int x_in_smem, 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// mf_solve_ring_kernel: the same supernodal sweeps with the L panels STREAMED through shared memory.  In mf_solve_kernel every
+// triangle step of a multi-column supernode waits for an L2 round trip; but L does not depend on x, so the panel of column block
+// s+1 (one contiguous range of Lx, because the columns of a supernode are adjacent in L's CSC storage) and its row indices are
+// copied with cp.async into the other half of a double buffer while block s is processed.  Supernodes are cut into column blocks
+// whose panel fits the buffer (host: SparseLdltBatchedKKT builds `shdr`).
+// shdr[blk] = {j0, wsb, nbelow, lx_off, len, li_off, 0, 0}
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mf_cp8(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void mf_cp4(int* dst, const int* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__global__ void __launch_bounds__(MF_T) mf_solve_ring_kernel(MfDev M, const int* __restrict__ shdr, int nblk, int PB, int RB, const double* __restrict__ Lx_all,
+                                                             const double* __restrict__ Dinv_all, const double* __restrict__ rx, const double* __restrict__ ry,
+                                                             const double* __restrict__ rz, double* __restrict__ lx, double* __restrict__ ly, double* __restrict__ lz,
+                                                             const int* __restrict__ active) {
+    extern __shared__ __align__(16) double mf_sm[];
+    __shared__ double red[MF_T / 32];
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = MF_T / 32;
+    const int nk = M.nk, n = M.n, p = M.p, m = M.m;
+    const double* Lx = Lx_all + (size_t)b * M.nnzL;
+    const double* Dinv = Dinv_all + (size_t)b * nk;
+    double* x = mf_sm;
+    double* pan = mf_sm + ((nk + 1) & ~1);
+    int* ridx = reinterpret_cast<int*>(pan + 2 * (size_t)PB);
+    const int4* hdr4 = reinterpret_cast<const int4*>(shdr);
+    // headers are prefetched in registers two blocks ahead, panels one block ahead
+    auto prefetch = [&](const int4& h0, const int4& h1, int buf) {
+        const double* src = Lx + h0.w;
+        double* dst = pan + (size_t)buf * PB;
+        for (int e = tid; e < h1.x; e += MF_T) mf_cp8(dst + e, src + e);
+        const int* isrc = M.Li + h1.y;
+        int* idst = ridx + (size_t)buf * RB;
+        for (int e = tid; e < h0.z; e += MF_T) mf_cp4(idst + e, isrc + e);
+    };
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+    int4 c0 = nblk > 0 ? hdr4[0] : zero4, c1 = nblk > 0 ? hdr4[1] : zero4;
+    int4 n0 = nblk > 1 ? hdr4[2] : zero4, n1 = nblk > 1 ? hdr4[3] : zero4;
+    if (nblk > 0) prefetch(c0, c1, 0);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int j = tid; j < nk; j += MF_T) {
+        const int v = M.perm[j];
+        x[j] = v < n ? rx[(size_t)b * n + v] : (v < n + p ? ry[(size_t)b * p + (v - n)] : rz[(size_t)b * m + (v - n - p)]);
+    }
+    // ---- forward
+    for (int s = 0; s < nblk; s++) {
+        int4 m0 = zero4, m1 = zero4;
+        if (s + 2 < nblk) { m0 = hdr4[2 * (s + 2)]; m1 = hdr4[2 * (s + 2) + 1]; }
+        if (s + 1 < nblk) prefetch(n0, n1, (s + 1) & 1);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncthreads();
+        const int j0 = c0.x, wsb = c0.y, nb = c0.z, fb = wsb + nb;
+        const double* P = pan + (size_t)(s & 1) * PB;
+        const int* R = ridx + (size_t)(s & 1) * RB;
+        for (int k = 0; k + 1 < wsb; k++) {
+            const double xk = x[j0 + k];
+            const double* col = P + (k * (fb - 1) - (k * (k - 1)) / 2);
+            for (int i = k + 1 + tid; i < wsb; i += MF_T) x[j0 + i] -= col[i - k - 1] * xk;
+            __syncthreads();
+        }
+        for (int t = tid; t < nb; t += MF_T) {
+            double acc = 0.0;
+            for (int k = 0; k < wsb; k++) acc += P[(k * (fb - 1) - (k * (k - 1)) / 2) + (wsb - 1 - k) + t] * x[j0 + k];
+            x[R[t]] -= acc;
+        }
+        __syncthreads();
+        c0 = n0; c1 = n1; n0 = m0; n1 = m1;
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    for (int j = tid; j < nk; j += MF_T) x[j] *= Dinv[j];
+    __syncthreads();
+    // ---- backward (blocks in reverse; buffer parity follows the block index again)
+    c0 = nblk > 0 ? hdr4[2 * (nblk - 1)] : zero4; c1 = nblk > 0 ? hdr4[2 * (nblk - 1) + 1] : zero4;
+    n0 = nblk > 1 ? hdr4[2 * (nblk - 2)] : zero4; n1 = nblk > 1 ? hdr4[2 * (nblk - 2) + 1] : zero4;
+    if (nblk > 0) prefetch(c0, c1, (nblk - 1) & 1);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int s = nblk - 1; s >= 0; s--) {
+        int4 m0 = zero4, m1 = zero4;
+        if (s >= 2) { m0 = hdr4[2 * (s - 2)]; m1 = hdr4[2 * (s - 2) + 1]; }
+        if (s > 0) prefetch(n0, n1, (s - 1) & 1);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncthreads();
+        const int j0 = c0.x, wsb = c0.y, nb = c0.z, fb = wsb + nb;
+        const double* P = pan + (size_t)(s & 1) * PB;
+        const int* R = ridx + (size_t)(s & 1) * RB;
+        if (nb > 0) {
+            if (wsb == 1 && nb > 64) {                     // one long column: all warps, fixed-tree block reduction
+                double acc = 0.0;
+                for (int t = tid; t < nb; t += MF_T) acc += P[t] * x[R[t]];
+                acc = warp_sum(acc);
+                if (lane == 0) red[wid] = acc;
+                __syncthreads();
+                if (tid == 0) { double t2 = 0.0; for (int w2 = 0; w2 < NW; w2++) t2 += red[w2]; x[j0] -= t2; }
+            } else {
+                for (int k = wid; k < wsb; k += NW) {
+                    const double* col = P + (k * (fb - 1) - (k * (k - 1)) / 2) + (wsb - 1 - k);
+                    double acc = 0.0;
+                    for (int t = lane; t < nb; t += 32) acc += col[t] * x[R[t]];
+                    acc = warp_sum(acc);
+                    if (lane == 0) x[j0 + k] -= acc;
+                }
+            }
+            __syncthreads();
+        }
+        for (int k = wsb - 2; k >= 0; k--) {
+            if (wid == 0) {
+                const double* col = P + (k * (fb - 1) - (k * (k - 1)) / 2);
+                double acc = 0.0;
+                for (int i = k + 1 + lane; i < wsb; i += 32) acc += col[i - k - 1] * x[j0 + i];
+                acc = warp_sum(acc);
+                if (lane == 0) x[j0 + k] -= acc;
+            }
+            __syncthreads();
+        }
+        c0 = n0; c1 = n1; n0 = m0; n1 = m1;
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    for (int j = tid; j < nk; j += MF_T) {
+        const int v = M.perm[j];
+        const double val = x[j];
+        if (v < n) lx[(size_t)b * n + v] = val; else if (v < n + p) ly[(size_t)b * p + (v - n)] = val; else lz[(size_t)b * m + (v - n - p)] = val;
+    }
+}
+
 }  // namespace b200

@@ -537,6 +537,38 @@ SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_per
         solve_smem = solve_x_in_smem ? (size_t)S.nk * sizeof(double) : 0;
         B200_CUDA(cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(factor_smem, 48 * 1024)));
         B200_CUDA(cudaFuncSetAttribute(mf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(solve_smem, 48 * 1024)));
+        // streamed solve (mf_solve_ring_kernel): x + a double-buffered panel + row indices in shared memory
+        ring_solve = false;
+        if (solve_x_in_smem && !getenv("B200_LDLT_SIMPLE_SOLVE")) {
+            const size_t xbytes = sizeof(double) * (size_t)((S.nk + 1) & ~1);
+            const size_t rb = (size_t)((S.fmax + 3) & ~3);
+            const size_t avail = smem_cap > xbytes + 2 * rb * sizeof(int) + 1024 ? smem_cap - xbytes - 2 * rb * sizeof(int) - 1024 : 0;
+            size_t pb = std::min<size_t>(avail / (2 * sizeof(double)), 2048);      // 2 x 16 KB: enough to hide the L2 latency, small enough to keep the default smem carve-out
+            if (const char* e = getenv("B200_RING_PB")) pb = std::min<size_t>(avail / (2 * sizeof(double)), (size_t)std::max(64, atoi(e)));
+            pb = std::max<size_t>(pb, (size_t)S.fmax + 2);
+            pb &= ~(size_t)1;
+            if (pb >= (size_t)S.fmax + 2 && pb >= 256) {
+                std::vector<int> sh;
+                for (int s2 = 0; s2 < S.nsup; s2++) {
+                    const int j0 = S.sup_ptr[s2], j1 = S.sup_ptr[s2 + 1] - 1, us = S.Lp[j1 + 1] - S.Lp[j1];
+                    int c0 = 0; const int ws = j1 - j0 + 1;
+                    while (c0 < ws) {
+                        int c = 1;                             // widest block [c0, c0 + c) whose panel fits
+                        auto panel = [&](int cc) { const long long nbelow = (ws - c0 - cc) + us; return (long long)cc * (cc - 1) / 2 + (long long)cc * nbelow; };
+                        while (c0 + c < ws && panel(c + 1) <= (long long)pb) c++;
+                        const int jb = j0 + c0, jl = jb + c - 1;
+                        const int h[8] = {jb, c, S.Lp[jl + 1] - S.Lp[jl], S.Lp[jb], S.Lp[jl + 1] - S.Lp[jb], S.Lp[jl], 0, 0};
+                        sh.insert(sh.end(), h, h + 8);
+                        c0 += c;
+                    }
+                }
+                ring_nblk = (int)sh.size() / 8; ring_pb = (int)pb; ring_rb = (int)rb;
+                upload(d_shdr, sh);
+                ring_smem = xbytes + 2 * pb * sizeof(double) + 2 * rb * sizeof(int);
+                B200_CUDA(cudaFuncSetAttribute(mf_solve_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ring_smem, 48 * 1024)));
+                ring_solve = true;
+            }
+        }
     }
     scatter_static(7);
 }
@@ -594,7 +626,9 @@ void SparseLdltBatchedKKT::solve(const double* rx, const double* ry, const doubl
     const size_t nnzL = std::max<size_t>(S.Li.size(), 1);
     tic(T_SOLVE);
     if (frontal) {
-        B200_LAUNCH(mf_solve_kernel, batch, MF_T, solve_smem, stream, make_mf(*this), (int)solve_x_in_smem, Lx.get(), Dinv.get(), rx, ry, rz, lx, ly, lz, work.get(), active);
+        if (ring_solve) B200_LAUNCH(mf_solve_ring_kernel, batch, MF_T, ring_smem, stream, make_mf(*this), d_shdr.get(), ring_nblk, ring_pb, ring_rb, Lx.get(), Dinv.get(),
+                                    rx, ry, rz, lx, ly, lz, active);
+        else B200_LAUNCH(mf_solve_kernel, batch, MF_T, solve_smem, stream, make_mf(*this), (int)solve_x_in_smem, Lx.get(), Dinv.get(), rx, ry, rz, lx, ly, lz, work.get(), active);
         toc(T_SOLVE);
         return;
     }

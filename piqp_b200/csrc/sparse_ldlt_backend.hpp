@@ -83,7 +83,10 @@ public:
     int front_smem_rows = 0;   // fronts up to this many rows live in shared memory, larger ones in `bigfront`
     size_t factor_smem = 0, solve_smem = 0;
     bool solve_x_in_smem = true;
-    DevBuf<int> d_hdr, d_crec, d_rel_idx, d_asm_pos;
+    DevBuf<int> d_hdr, d_crec, d_rel_idx, d_asm_pos, d_shdr;
+    bool ring_solve = false;   // mf_solve_ring_kernel: L panels streamed through a cp.async double buffer
+    int ring_nblk = 0, ring_pb = 0, ring_rb = 0;
+    size_t ring_smem = 0;
     DevBuf<long long> d_upd_off;
     DevBuf<double> upd, bigfront, panel;   // [batch][upd_total], [batch][fmax^2] and [batch][2 fmax NB] (only if fmax > front_smem_rows)
 private:
