@@ -364,14 +364,15 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
     Linv.alloc((size_t)batch * Linv_stride); Linv.zero(st);
     set_smem(trsv_kernel, (size_t)(n + 32) * sizeof(double) > 48 * 1024 ? (size_t)(n + 32) * sizeof(double) : 48 * 1024);
     if (p > 0) { AtA.alloc((size_t)batch * D->ld * n); AtA.zero(st); compute_AtA(); }
-    // ---- Ozaki / tcgen05 assembly: B200_DENSE_ASSEMBLE = ozaki | dmma (default dmma).  Measured on config 2 (profiles/README.md):
-    //      the tcgen05 kernel is exact to the parity bars but its 128 x 64 tiles (TMEM holds 8 accumulators x 64 columns) are bound by
-    //      the L2 -> shared-memory operand stream (8.5 TB/s ceiling measured), 6.6 ms per launch against 5.0 ms for the DMMA kernel;
-    //      it becomes the default once the operand tiles are multicast across a cluster.
+    // ---- Ozaki / tcgen05 assembly: B200_DENSE_ASSEMBLE = ozaki | dmma | auto (default).  Measured (profiles/r01b_dense_sweep.jsonl):
+    //      the tcgen05 kernel is exact to the parity bars; its 128 x 64 tiles (TMEM holds 8 accumulators x 64 columns) are bound by the
+    //      L2 -> shared-memory operand stream, so it needs a long contraction to amortise its prologue / epilogue: at m = 512 it takes
+    //      6.6 ms per launch against 5.0 ms for the DMMA kernel, at m = 1024 8.7 vs 9.2 ms, at m = 2048 12.0 vs 18.6 ms
+    //      (= 46 FP64-equivalent TFLOP/s, above the 37 TFLOP/s FP64 pipe).  auto = ozaki from m >= 1024.
     {
         const char* e = getenv("B200_DENSE_ASSEMBLE");
-        const std::string mode = e ? e : "dmma";
-        ozaki = m > 0 && n > 0 && mode == "ozaki";
+        const std::string mode = e ? e : "auto";
+        ozaki = m > 0 && n > 0 && (mode == "ozaki" || (mode == "auto" && m >= 1024 && n >= 512));
     }
     if (ozaki) {
         typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
