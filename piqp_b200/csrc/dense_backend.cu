@@ -381,6 +381,7 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
         B200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
         if (!fn) throw std::runtime_error("cuTensorMapEncodeTiled is not available");
         oz_mp = round_up(m, 16);
+        if (const char* e2 = getenv("B200_OZ_KSTEP")) oz_kb = atoi(e2) == 64 ? 64 : 32;
         oz_digits.alloc((size_t)batch * OZ_S * n * oz_mp);
         B200_CUDA(cudaMemsetAsync(oz_digits.get(), 0, oz_digits.n, st));
         oz_ex.alloc((size_t)batch * n); oz_sw.alloc((size_t)batch * m); oz_sc.alloc((size_t)batch * n);
@@ -393,15 +394,17 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
         auto make = [&](unsigned char* out, cuuint32_t box_rows) {
             cuuint64_t dims[3] = {(cuuint64_t)oz_mp, (cuuint64_t)n, (cuuint64_t)OZ_S * batch};
             cuuint64_t strides[2] = {(cuuint64_t)oz_mp, (cuuint64_t)n * oz_mp};
-            cuuint32_t box[3] = {(cuuint32_t)OZ_KB, box_rows, (cuuint32_t)OZ_S};
+            cuuint32_t box[3] = {(cuuint32_t)oz_kb, box_rows, (cuuint32_t)OZ_S};
             cuuint32_t estr[3] = {1, 1, 1};
             const CUresult r = ((EncodeTiled)fn)(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, oz_digits.get(), dims, strides, box, estr,
-                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, oz_kb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed for the digit planes");
         };
         static_assert(sizeof(CUtensorMap) <= 128, "CUtensorMap size");
         make(oz_mapA, OZ_TM); make(oz_mapB, OZ_TN);
-        set_smem(oz_gemm_kernel, OZ_GEMM_SMEM);
+        set_smem(oz_gemm_kernel<64, 2>, OZ_GEMM_SMEM);
+        set_smem(oz_gemm_kernel<32, 4>, OZ_GEMM_SMEM);
     }
 }
 
@@ -440,8 +443,10 @@ void DenseBatchedKKT::assemble_ozaki(const double* x_reg, const int* active) {  
     B200_LAUNCH(oz_sqrt_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, zinv.get(), oz_sw.get(), tot);
     { dim3 g(ceil_div(n, 128), batch); B200_LAUNCH(oz_rowscale_kernel, g, 128, 0, stream, a); }
     { dim3 g(ceil_div(n, 32), ceil_div(oz_mp, 128), batch); B200_LAUNCH(oz_split_kernel, g, 256, 0, stream, a); }
-    B200_LAUNCH(oz_gemm_kernel, (unsigned)((size_t)oz_ntiles * batch), 128, OZ_GEMM_SMEM, stream, *reinterpret_cast<const CUtensorMap*>(oz_mapA),
-                *reinterpret_cast<const CUtensorMap*>(oz_mapB), a);
+    if (oz_kb == 64) B200_LAUNCH((oz_gemm_kernel<64, 2>), (unsigned)((size_t)oz_ntiles * batch), 128, OZ_GEMM_SMEM, stream, *reinterpret_cast<const CUtensorMap*>(oz_mapA),
+                                 *reinterpret_cast<const CUtensorMap*>(oz_mapB), a);
+    else B200_LAUNCH((oz_gemm_kernel<32, 4>), (unsigned)((size_t)oz_ntiles * batch), 128, OZ_GEMM_SMEM, stream, *reinterpret_cast<const CUtensorMap*>(oz_mapA),
+                     *reinterpret_cast<const CUtensorMap*>(oz_mapB), a);
 }
 
 void DenseBatchedKKT::assemble(const double* x_reg, const int* active) {   // dense/kkt.hpp:140-160

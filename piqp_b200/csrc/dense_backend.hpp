@@ -75,7 +75,7 @@ public:
     long long Linv_stride = 0;
     // Ozaki / tcgen05 assembly path (dense_ozaki.cuh)
     bool ozaki = false;
-    int oz_mp = 0, oz_ntiles = 0;
+    int oz_mp = 0, oz_ntiles = 0, oz_kb = 64;   // k-step bytes: 64 (2 stages, SWIZZLE_64B) or 32 (4 stages, SWIZZLE_32B)
     DevBuf<signed char> oz_digits;   // [batch][8][n][mp]
     DevBuf<int> oz_ex, oz_tiles;     // [batch][n] row exponents; [ntiles][2] lower tiles (128-row, 64-col)
     DevBuf<double> oz_sw, oz_sc;     // [batch][m] sqrt(z_reg^-1); [batch][n] per-row output scales

@@ -20,9 +20,9 @@
 
 constexpr int OZ_S = 8;              // digit planes
 constexpr int OZ_F = 62;             // X = rint(B * 2^(OZ_F - e))
-constexpr int OZ_TM = 128, OZ_TN = 64, OZ_KB = 64;
-constexpr int OZ_STAGE_A = OZ_S * OZ_TM * OZ_KB, OZ_STAGE_B = OZ_S * OZ_TN * OZ_KB, OZ_STAGE = OZ_STAGE_A + OZ_STAGE_B;
-constexpr size_t OZ_GEMM_SMEM = 2 * (size_t)OZ_STAGE + 1024;
+constexpr int OZ_TM = 128, OZ_TN = 64;
+// two pipeline shapes with the same 192 KB of operand stages: KB = 64 B k-steps x 2 stages (SWIZZLE_64B) or 32 B x 4 stages (SWIZZLE_32B)
+constexpr size_t OZ_GEMM_SMEM = (size_t)OZ_S * (OZ_TM + OZ_TN) * 128 + 1024;
 constexpr int OZ_EXP_NONFINITE = 0x7fffffff;
 
 struct OzArgs {
@@ -129,17 +129,22 @@ __device__ __forceinline__ void oz_umma_s8(uint32_t tmem_d, uint64_t adesc, uint
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void oz_commit(uint64_t* bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem_u32(bar)) : "memory"); }
-__device__ __forceinline__ uint64_t oz_desc_sw64(uint32_t smem_addr) {      // K-major, SWIZZLE_64B, 8-row groups 512 B apart (cute::UMMA::SmemDescriptor)
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+// K-major operand descriptor (cute::UMMA::SmemDescriptor): rows of KB bytes, 8-row groups 8*KB bytes apart, SWIZZLE_64B (4) / SWIZZLE_32B (6)
+template <int KB>
+__device__ __forceinline__ uint64_t oz_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((8 * KB) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(KB == 64 ? 4 : 6) << 61);
 }
 __device__ __forceinline__ void oz_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
 }
 
+template <int OZ_KB, int NST>
 __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, OzArgs a) {
+    constexpr int OZ_STAGE_A = OZ_S * OZ_TM * OZ_KB, OZ_STAGE_B = OZ_S * OZ_TN * OZ_KB, OZ_STAGE = OZ_STAGE_A + OZ_STAGE_B;
+    static_assert((size_t)NST * OZ_STAGE + 1024 <= OZ_GEMM_SMEM, "stages do not fit");
     extern __shared__ __align__(1024) unsigned char oz_sm[];
-    __shared__ uint64_t full[2], empty[2], done;
+    __shared__ uint64_t full[NST], empty[NST], done;
     __shared__ uint32_t tmem_base;
     const int b = blockIdx.x / a.ntiles, t = blockIdx.x - b * a.ntiles;
     if (a.active && !a.active[b]) return;
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int s = 0; s < 2; s++) { oz_mbar_init(&full[s], 1); oz_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NST; s++) { oz_mbar_init(&full[s], 1); oz_mbar_init(&empty[s], 1); }
         oz_mbar_init(&done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -163,8 +168,8 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     const int nsteps = (a.m + OZ_KB - 1) / OZ_KB;
     if (warp == 0 && (tid & 31) == 0) {                       // ---- TMA producer
         for (int it = 0; it < nsteps; it++) {
-            const int s = it & 1;
-            if (it >= 2) oz_mbar_wait(&empty[s], ((it >> 1) - 1) & 1);
+            const int s = it % NST;
+            if (it >= NST) oz_mbar_wait(&empty[s], ((it / NST) - 1) & 1);
             oz_expect_tx(&full[s], OZ_STAGE);
             oz_tma_3d(sm + (size_t)s * OZ_STAGE, &mapA, it * OZ_KB, row0, b * OZ_S, &full[s]);
             oz_tma_3d(sm + (size_t)s * OZ_STAGE + OZ_STAGE_A, &mapB, it * OZ_KB, col0, b * OZ_S, &full[s]);
@@ -173,19 +178,19 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
         // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = s8, K-major, N = 64, M = 128
         const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_TN >> 3) << 17) | ((uint32_t)(OZ_TM >> 4) << 24);
         for (int it = 0; it < nsteps; it++) {
-            const int s = it & 1;
-            oz_mbar_wait(&full[s], (it >> 1) & 1);
+            const int s = it % NST;
+            oz_mbar_wait(&full[s], (it / NST) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a0 = oz_smem_u32(sm + (size_t)s * OZ_STAGE), b0 = a0 + OZ_STAGE_A;
             // descriptors differ only in the start-address field (bits [0,14) of the low word, units of 16 B): add constants
-            const uint64_t da0 = oz_desc_sw64(a0), db0 = oz_desc_sw64(b0);
+            const uint64_t da0 = oz_desc<OZ_KB>(a0), db0 = oz_desc<OZ_KB>(b0);
 #pragma unroll
             for (int g = 0; g < OZ_S; g++)                    // weight group g = (a + b) - 2, digit indices 0-based below
 #pragma unroll
                 for (int da = 0; da <= g; da++) {
                     const int db = g - da;
 #pragma unroll
-                    for (int kk = 0; kk < 2; kk++)
+                    for (int kk = 0; kk < OZ_KB / 32; kk++)
                         oz_umma_s8(tmem + (uint32_t)(g * OZ_TN), da0 + (uint64_t)((da * (OZ_TM * OZ_KB) + kk * 32) >> 4), db0 + (uint64_t)((db * (OZ_TN * OZ_KB) + kk * 32) >> 4), idesc,
                                    (it > 0 || da > 0 || kk > 0) ? 1u : 0u);
                 }
