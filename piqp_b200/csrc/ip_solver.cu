@@ -765,15 +765,17 @@ BatchedIPSolver::BatchedIPSolver(int batch_, int n_, int p_, int m_, const b200q
     d.work_x = alloc_d(B * n); d.work_x2 = alloc_d(B * n); d.work_z = alloc_d(B * m); d.P_diag = alloc_d(B * n);
     sc_.alloc(B); sc_.zero(stream); d.sc = sc_.get();
     d.delta_reg = alloc_d(B);
-    d.act = alloc_i(B); d.act2 = alloc_i(B); d.need_factor = alloc_i(2 * B); d.ok = alloc_i(B); d.ir_mask = alloc_i(B);
+    d.need_factor = alloc_i(3 * B); d.act = d.need_factor + 2 * B;      // [need_factor | use_ir | act]: one read-back serves the retry loop and the termination test
+    d.act2 = alloc_i(B); d.ok = alloc_i(B); d.ir_mask = alloc_i(B);
     d.trace = nullptr; d.trace_rows = 0;
     if (st.verbose >= 2) { d.trace_rows = st.max_iter + 1; d.trace = alloc_d(B * d.trace_rows * 10); }
-    B200_CUDA(cudaMallocHost(&h_flags_, sizeof(int) * std::max<size_t>(2 * B, 2)));
+    B200_CUDA(cudaMallocHost(&h_flags_, sizeof(int) * std::max<size_t>(3 * B, 3)));
     for (auto& e : ev_) B200_CUDA(cudaEventCreate(&e));
 }
 BatchedIPSolver::~BatchedIPSolver() {
     if (h_flags_) cudaFreeHost(h_flags_);
     for (auto& e : ev_) cudaEventDestroy(e);
+    for (auto& e : iter_ev_) cudaEventDestroy(e);
 }
 
 void BatchedIPSolver::finish_setup(BatchedKKT* backend) {
@@ -791,17 +793,19 @@ int BatchedIPSolver::count_flags(const int* dev_flags, int count) {
     return c;
 }
 
-void BatchedIPSolver::factor_with_retry() {
+int BatchedIPSolver::factor_with_retry() {
     // at most 1 (enable refinement) + max_factor_retires + 1 rounds
+    int active = 0;
     for (int round = 0; round < d_.st.max_factor_retires + 3; round++) {
         B200_LAUNCH(k_prepare_factor, batch, IPT, 0, stream, d_);
         be_->factor(d_.delta_reg, d_.x_reg, d_.z_reg_ir, d_.need_factor, d_.ok);
         B200_LAUNCH(k_after_factor, ceil_div(batch, 128), 128, 0, stream, d_);
-        const int pending = count_flags(d_.need_factor, 2 * batch);
-        any_ir_ = false;
-        for (int i = 0; i < batch; i++) any_ir_ |= h_flags_[batch + i] != 0;
+        const int pending = count_flags(d_.need_factor, 3 * batch);
+        any_ir_ = false; active = 0;
+        for (int i = 0; i < batch; i++) { any_ir_ |= h_flags_[batch + i] != 0; active += h_flags_[2 * batch + i] != 0; }
         if (pending == 0) break;
     }
+    return active;
 }
 
 void BatchedIPSolver::kkt_solve(const Vars& rhs, const Vars& lhs, const int* mask) {
@@ -874,31 +878,33 @@ void BatchedIPSolver::solve() {
     B200_CUDA(cudaEventElapsedTime(&ms, ev_[1], ev_[2])); stats_.solve_ms += ms;
 
     int L = 0;
+    auto iev = [&](int i) { while ((int)iter_ev_.size() <= i) { cudaEvent_t e; B200_CUDA(cudaEventCreate(&e)); iter_ev_.push_back(e); } return iter_ev_[i]; };
     for (; L < st.max_iter; L++) {
+        // k_head decides per instance (converged / infeasible / continue) and raises need_factor for the active ones; the masks are
+        // read back together with the factorisation flags, so an iteration costs ONE host synchronisation
         B200_LAUNCH(k_head, batch, IPT, 0, stream, d);
-        if (count_flags(d.act) == 0) break;
-        B200_CUDA(cudaEventRecord(ev_[0], stream));
-        factor_with_retry();
-        B200_CUDA(cudaEventRecord(ev_[1], stream));
+        B200_CUDA(cudaEventRecord(iev(3 * L), stream));
+        if (factor_with_retry() == 0) break;
+        B200_CUDA(cudaEventRecord(iev(3 * L + 1), stream));
         B200_LAUNCH(k_predictor, batch, IPT, 0, stream, d);
         kkt_solve(d.r, d.step, d.act);
         B200_LAUNCH(k_corrector, batch, IPT, 0, stream, d);
         kkt_solve(d.r, d.step, d.act2);
-        B200_CUDA(cudaEventRecord(ev_[2], stream));
+        B200_CUDA(cudaEventRecord(iev(3 * L + 2), stream));
         B200_LAUNCH(k_update, batch, IPT, 0, stream, d);
         residuals_nr(d.act);
         B200_LAUNCH(k_resid_nr, batch, IPT, 0, stream, d, d.act, 0);
         B200_LAUNCH(k_reg_update, batch, IPT, 0, stream, d);
-        B200_CUDA(cudaEventRecord(ev_[3], stream));
-        B200_CUDA(cudaEventSynchronize(ev_[3]));
-        B200_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1])); stats_.factor_ms += ms;
-        B200_CUDA(cudaEventElapsedTime(&ms, ev_[1], ev_[2])); stats_.solve_ms += ms;
     }
     stats_.lockstep_iterations = L;
     B200_LAUNCH(k_mark_max_iter, ceil_div(batch, 128), 128, 0, stream, d);
     B200_LAUNCH(k_finish, batch, IPT, 0, stream, d);
     B200_CUDA(cudaEventRecord(ev_[5], stream));
     B200_CUDA(cudaEventSynchronize(ev_[5]));
+    for (int i = 0; i < L; i++) {
+        B200_CUDA(cudaEventElapsedTime(&ms, iter_ev_[3 * i], iter_ev_[3 * i + 1])); stats_.factor_ms += ms;
+        B200_CUDA(cudaEventElapsedTime(&ms, iter_ev_[3 * i + 1], iter_ev_[3 * i + 2])); stats_.solve_ms += ms;
+    }
     B200_CUDA(cudaEventElapsedTime(&ms, ev_[4], ev_[5])); stats_.total_ms = ms;
     stats_.kernel_launches = g_launches - l0;
 }

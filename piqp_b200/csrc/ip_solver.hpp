@@ -67,7 +67,7 @@ public:
 
 private:
     void kkt_solve(const Vars& rhs, const Vars& lhs, const int* mask);   // KKTSystem::solve
-    void factor_with_retry();
+    int factor_with_retry();      // returns the number of instances still active (read back with the factor flags: one host sync)
     void residuals_nr(const int* mask);
     int count_flags(const int* dev_flags, int count = -1);
     IpDev d_{};
@@ -78,6 +78,7 @@ private:
     int* h_flags_ = nullptr;   // pinned
     b200qp_stats stats_{};
     cudaEvent_t ev_[6];
+    std::vector<cudaEvent_t> iter_ev_;   // 3 per IP iteration (factor begin, factor end / solve begin, solve end): read after the loop, no per-iteration sync
     bool any_ir_ = false, invalid_settings_ = false;
     int* ir_was_ = nullptr;
     double* alloc_d(size_t n);
