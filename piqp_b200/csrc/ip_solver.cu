@@ -4,6 +4,7 @@
 // iteration counts match the CPU solver; only reductions (dot / min / max) use a fixed tree instead of a
 // sequential loop.
 #include "ip_solver.hpp"
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 
@@ -771,6 +772,9 @@ BatchedIPSolver::BatchedIPSolver(int batch_, int n_, int p_, int m_, const b200q
     if (st.verbose >= 2) { d.trace_rows = st.max_iter + 1; d.trace = alloc_d(B * d.trace_rows * 10); }
     B200_CUDA(cudaMallocHost(&h_flags_, sizeof(int) * std::max<size_t>(3 * B, 3)));
     for (auto& e : ev_) B200_CUDA(cudaEventCreate(&e));
+    // threads per instance CTA of the O(n+m) kernels: few large instances want more memory-level parallelism per CTA
+    ipt_ = ((size_t)batch <= 296 && (size_t)n + m >= 1536) ? 512 : IPT;
+    if (const char* e = getenv("B200_IPT")) { const int v = atoi(e); if (v == 128 || v == 256 || v == 512) ipt_ = v; }
 }
 BatchedIPSolver::~BatchedIPSolver() {
     if (h_flags_) cudaFreeHost(h_flags_);
@@ -780,7 +784,7 @@ BatchedIPSolver::~BatchedIPSolver() {
 
 void BatchedIPSolver::finish_setup(BatchedKKT* backend) {
     be_ = backend;
-    B200_LAUNCH(k_counts, batch, IPT, 0, stream, d_);
+    B200_LAUNCH(k_counts, batch, ipt_, 0, stream, d_);
     be_->extract_P_diag(d_.P_diag);
 }
 
@@ -797,7 +801,7 @@ int BatchedIPSolver::factor_with_retry() {
     // at most 1 (enable refinement) + max_factor_retires + 1 rounds
     int active = 0;
     for (int round = 0; round < d_.st.max_factor_retires + 3; round++) {
-        B200_LAUNCH(k_prepare_factor, batch, IPT, 0, stream, d_);
+        B200_LAUNCH(k_prepare_factor, batch, ipt_, 0, stream, d_);
         be_->factor(d_.delta_reg, d_.x_reg, d_.z_reg_ir, d_.need_factor, d_.ok);
         B200_LAUNCH(k_after_factor, ceil_div(batch, 128), 128, 0, stream, d_);
         const int pending = count_flags(d_.need_factor, 3 * batch);
@@ -810,7 +814,7 @@ int BatchedIPSolver::factor_with_retry() {
 
 void BatchedIPSolver::kkt_solve(const Vars& rhs, const Vars& lhs, const int* mask) {
     IpDev& d = d_;
-    B200_LAUNCH(k_solve_pre, batch, IPT, 0, stream, d, rhs, mask);
+    B200_LAUNCH(k_solve_pre, batch, ipt_, 0, stream, d, rhs, mask);
     be_->solve(d.rhs_x_bar, rhs.y, d.rhs_z_bar, lhs.x, lhs.y, d.lhs_z, mask);
     // iterative refinement: only instances whose last factorisation enabled it (host knows if there are any)
     if (any_ir_) B200_LAUNCH(k_mask_and_flag, ceil_div(batch, 128), 128, 0, stream, mask, d, d.ir_mask);
@@ -820,25 +824,25 @@ void BatchedIPSolver::kkt_solve(const Vars& rhs, const Vars& lhs, const int* mas
         be_->eval_P_x(1.0, lhs.x, d.err_x, irm);
         be_->eval_A(1.0, 1.0, lhs.x, lhs.y, d.err_y, d.work_x, irm);
         be_->eval_G(1.0, 1.0, lhs.x, d.lhs_z, d.err_z, d.work_x2, irm);
-        B200_LAUNCH(k_ir_err, batch, IPT, 0, stream, d, rhs, lhs.x, lhs.y, d.lhs_z, 0, 0, irm);
+        B200_LAUNCH(k_ir_err, batch, ipt_, 0, stream, d, rhs, lhs.x, lhs.y, d.lhs_z, 0, 0, irm);
         for (int it = 0; it < d.st.iterative_refinement_max_iter; it++) {
             if (count_flags(irm) == 0) break;
             B200_LAUNCH(k_copy_int, ceil_div(batch, 128), 128, 0, stream, irm, was, batch);
             be_->solve(d.err_x, d.err_y, d.err_z, d.ref_x, d.ref_y, d.ref_z, was);
-            B200_LAUNCH(k_ir_accum, batch, IPT, 0, stream, d, lhs.x, lhs.y, d.lhs_z, was);
+            B200_LAUNCH(k_ir_accum, batch, ipt_, 0, stream, d, lhs.x, lhs.y, d.lhs_z, was);
             be_->eval_P_x(1.0, d.ref_x, d.err_x, was);
             be_->eval_A(1.0, 1.0, d.ref_x, d.ref_y, d.err_y, d.work_x, was);
             be_->eval_G(1.0, 1.0, d.ref_x, d.ref_z, d.err_z, d.work_x2, was);
-            B200_LAUNCH(k_ir_err, batch, IPT, 0, stream, d, rhs, d.ref_x, d.ref_y, d.ref_z, 1, it, was);
-            B200_LAUNCH(k_ir_accept, batch, IPT, 0, stream, d, lhs.x, lhs.y, d.lhs_z, was);
+            B200_LAUNCH(k_ir_err, batch, ipt_, 0, stream, d, rhs, d.ref_x, d.ref_y, d.ref_z, 1, it, was);
+            B200_LAUNCH(k_ir_accept, batch, ipt_, 0, stream, d, lhs.x, lhs.y, d.lhs_z, was);
         }
     }
-    B200_LAUNCH(k_solve_post, batch, IPT, 0, stream, d, rhs, lhs, mask);
+    B200_LAUNCH(k_solve_post, batch, ipt_, 0, stream, d, rhs, lhs, mask);
 }
 
 void BatchedIPSolver::residuals_nr(const int* mask) {
     IpDev& d = d_;
-    B200_LAUNCH(k_resid_pre, batch, IPT, 0, stream, d, mask);
+    B200_LAUNCH(k_resid_pre, batch, ipt_, 0, stream, d, mask);
     be_->eval_A(-1.0, 1.0, d.it.x, d.it.y, d.rnr.y, d.work_x, mask);
     be_->eval_G(1.0, 1.0, d.it.x, d.work_z, d.rnr.z_l, d.work_x2, mask);
     be_->eval_P_x(-1.0, d.it.x, d.rnr.x, mask);
@@ -863,16 +867,16 @@ void BatchedIPSolver::solve() {
     if (!ir_was_) ir_was_ = alloc_i(batch);
     any_ir_ = false;
 
-    B200_LAUNCH(k_init, batch, IPT, 0, stream, d);
+    B200_LAUNCH(k_init, batch, ipt_, 0, stream, d);
     B200_CUDA(cudaEventRecord(ev_[0], stream));
     factor_with_retry();
     B200_CUDA(cudaEventRecord(ev_[1], stream));
-    B200_LAUNCH(k_initial_rhs, batch, IPT, 0, stream, d);
+    B200_LAUNCH(k_initial_rhs, batch, ipt_, 0, stream, d);
     kkt_solve(d.r, d.it, d.act);
     B200_CUDA(cudaEventRecord(ev_[2], stream));
-    B200_LAUNCH(k_start_point, batch, IPT, 0, stream, d);
+    B200_LAUNCH(k_start_point, batch, ipt_, 0, stream, d);
     residuals_nr(d.act);
-    B200_LAUNCH(k_resid_nr, batch, IPT, 0, stream, d, d.act, 1);
+    B200_LAUNCH(k_resid_nr, batch, ipt_, 0, stream, d, d.act, 1);
     B200_CUDA(cudaStreamSynchronize(stream));
     B200_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1])); stats_.factor_ms += ms;
     B200_CUDA(cudaEventElapsedTime(&ms, ev_[1], ev_[2])); stats_.solve_ms += ms;
@@ -882,23 +886,23 @@ void BatchedIPSolver::solve() {
     for (; L < st.max_iter; L++) {
         // k_head decides per instance (converged / infeasible / continue) and raises need_factor for the active ones; the masks are
         // read back together with the factorisation flags, so an iteration costs ONE host synchronisation
-        B200_LAUNCH(k_head, batch, IPT, 0, stream, d);
+        B200_LAUNCH(k_head, batch, ipt_, 0, stream, d);
         B200_CUDA(cudaEventRecord(iev(3 * L), stream));
         if (factor_with_retry() == 0) break;
         B200_CUDA(cudaEventRecord(iev(3 * L + 1), stream));
-        B200_LAUNCH(k_predictor, batch, IPT, 0, stream, d);
+        B200_LAUNCH(k_predictor, batch, ipt_, 0, stream, d);
         kkt_solve(d.r, d.step, d.act);
-        B200_LAUNCH(k_corrector, batch, IPT, 0, stream, d);
+        B200_LAUNCH(k_corrector, batch, ipt_, 0, stream, d);
         kkt_solve(d.r, d.step, d.act2);
         B200_CUDA(cudaEventRecord(iev(3 * L + 2), stream));
-        B200_LAUNCH(k_update, batch, IPT, 0, stream, d);
+        B200_LAUNCH(k_update, batch, ipt_, 0, stream, d);
         residuals_nr(d.act);
-        B200_LAUNCH(k_resid_nr, batch, IPT, 0, stream, d, d.act, 0);
-        B200_LAUNCH(k_reg_update, batch, IPT, 0, stream, d);
+        B200_LAUNCH(k_resid_nr, batch, ipt_, 0, stream, d, d.act, 0);
+        B200_LAUNCH(k_reg_update, batch, ipt_, 0, stream, d);
     }
     stats_.lockstep_iterations = L;
     B200_LAUNCH(k_mark_max_iter, ceil_div(batch, 128), 128, 0, stream, d);
-    B200_LAUNCH(k_finish, batch, IPT, 0, stream, d);
+    B200_LAUNCH(k_finish, batch, ipt_, 0, stream, d);
     B200_CUDA(cudaEventRecord(ev_[5], stream));
     B200_CUDA(cudaEventSynchronize(ev_[5]));
     for (int i = 0; i < L; i++) {

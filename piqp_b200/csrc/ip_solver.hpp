@@ -78,6 +78,7 @@ private:
     int* h_flags_ = nullptr;   // pinned
     b200qp_stats stats_{};
     cudaEvent_t ev_[6];
+    int ipt_ = 256;
     std::vector<cudaEvent_t> iter_ev_;   // 3 per IP iteration (factor begin, factor end / solve begin, solve end): read after the loop, no per-iteration sync
     bool any_ir_ = false, invalid_settings_ = false;
     int* ir_was_ = nullptr;
