@@ -61,9 +61,11 @@ typedef struct b200kkt_handle b200kkt_handle;
 int b200kkt_dense_create(b200kkt_handle** out, int n, int p, int m,
                          const double* P_utri, const double* AT, const double* GT, int device);
 
-/* replaces sparse::KKT<T,I,KKT_FULL>::KKT(const Data&) (include/piqp/sparse/kkt.hpp:51-70)
- * CSC of P_utri (upper), AT (n x p), GT (n x m).  mode = KKTMode (kkt_fwd.hpp:15-21), only 0 (FULL)
- * is implemented.  perm: optional fill-reducing ordering of the n+p+m KKT (NULL = own AMD). */
+/* replaces sparse::KKT<T,I,Mode>::KKT(const Data&) (include/piqp/sparse/kkt.hpp:51-70)
+ * CSC of P_utri (upper), AT (n x p), GT (n x m).  mode = KKTMode (kkt_fwd.hpp:15-21): 0 FULL (sparse_ldlt, kkt_full.hpp),
+ * 1 EQ_ELIMINATED (sparse_ldlt_eq_cond, kkt_eq_eliminated.hpp), 2 INEQ_ELIMINATED (sparse_ldlt_ineq_cond,
+ * kkt_ineq_eliminated.hpp), 3 ALL_ELIMINATED (sparse_ldlt_cond, kkt_all_eliminated.hpp).
+ * perm: optional fill-reducing ordering of the KKT of that mode (n + [p] + [m] entries; NULL = own AMD). */
 int b200kkt_sparse_create(b200kkt_handle** out, int n, int p, int m,
                           const int* Pp, const int* Pi, const double* Px,
                           const int* ATp, const int* ATi, const double* ATx,
@@ -77,6 +79,12 @@ int b200kkt_sparse_create(b200kkt_handle** out, int n, int p, int m,
 int b200_sparse_ldlt_symbolic(int n, int p, int m, const int* Pp, const int* Pi, const int* ATp, const int* ATi,
                               const int* GTp, const int* GTi, const int* perm_in, int* perm_out,
                               long long* nnz_kkt, long long* nnz_L, int* etree_levels, double* factor_flops);
+/* the same for any KKTMode, plus the supernodal schedule's size (number of supernodes after relaxed amalgamation, rows of the
+ * largest front).  perm_in / perm_out have n + [p] + [m] entries for that mode.                                      */
+int b200_sparse_ldlt_symbolic_mode(int n, int p, int m, const int* Pp, const int* Pi, const int* ATp, const int* ATi,
+                                   const int* GTp, const int* GTi, int mode, const int* perm_in, int* perm_out,
+                                   long long* nnz_kkt, long long* nnz_L, int* etree_levels, double* factor_flops,
+                                   int* n_supernodes, int* largest_front);
 int b200kkt_sparse_info(b200kkt_handle* h, long long* nnz_kkt, long long* nnz_L, int* etree_levels, int* perm);
 
 /* replaces sparse::MultistageKKT<T,I>::MultistageKKT(const Data&) (include/piqp/sparse/multistage_kkt.hpp:74-133) */
@@ -212,8 +220,9 @@ int b200qp_update_dense(b200qp_handle* h, const double* P, const double* c, cons
 /* Batched twin of piqp_setup_sparse (piqp.h:28, piqp_data_sparse piqp_typedef.h:56-68): all instances share the CSC
  * patterns of P (n x n, upper triangle used), A (p x n) and G (m x n) -- int32 column pointers / row indices on the host --
  * and differ in the value arrays Px[batch][nnz(P)], Ax[batch][nnz(A)], Gx[batch][nnz(G)] and in the vectors.
- * settings->kkt_solver selects the backend: 5 = sparse_multistage (block-tridiagonal-arrow Cholesky; built),
- * 1..4 = sparse_ldlt variants (next round).                                                                        */
+ * settings->kkt_solver selects the backend (settings.hpp:18-26): 1 sparse_ldlt, 2 sparse_ldlt_eq_cond,
+ * 3 sparse_ldlt_ineq_cond, 4 sparse_ldlt_cond (supernodal multifrontal LDL^T on the KKT of that mode),
+ * 5 sparse_multistage (block-tridiagonal-arrow Cholesky).                                                           */
 int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
                         const int* Pp, const int* Pi, const double* Px, const double* c,
                         const int* Ap, const int* Ai, const double* Ax, const double* b,

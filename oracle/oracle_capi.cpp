@@ -5,6 +5,7 @@
 #include "oracle_dense.hpp"
 #include "oracle_sparse.hpp"
 #include "oracle_multistage.hpp"
+#include "oracle_sparse_cond.hpp"
 #include <chrono>
 
 using namespace oracle;
@@ -60,7 +61,8 @@ struct ForeignSparse : KKTBackend {
             vt->create_multistage(&h, S.n, S.p, S.m, S.P.p.data(), S.P.i.data(), S.P.x.data(), S.AT.p.data(), S.AT.i.data(), S.AT.x.data(),
                                   S.GT.p.data(), S.GT.i.data(), S.GT.x.data(), 0);
         else vt->create_sparse(&h, S.n, S.p, S.m, S.P.p.data(), S.P.i.data(), S.P.x.data(), S.AT.p.data(), S.AT.i.data(), S.AT.x.data(),
-                          S.GT.p.data(), S.GT.i.data(), S.GT.x.data(), 0, S.user_perm.empty() ? nullptr : S.user_perm.data(), 0);
+                          S.GT.p.data(), S.GT.i.data(), S.GT.x.data(), (S.kkt_solver_hint >= 2 && S.kkt_solver_hint <= 4) ? S.kkt_solver_hint - 1 : 0,
+                          S.user_perm.empty() ? nullptr : S.user_perm.data(), 0);
     }
     ~ForeignSparse() override { if (h) vt->destroy(h); }
     void update_data(int o) override { vt->update_data(h, o, S.P.x.data(), S.AT.x.data(), S.GT.x.data()); }
@@ -162,8 +164,12 @@ void* orc_sparse_setup(int n, int p, int m,
     M->P = Csc::upper_from(n, Pp, Pi, Px);
     M->AT = Csc::from(n, p, ATp, ATi, ATx);
     M->GT = Csc::from(n, m, GTp, GTi, GTx);
-    if (kkt_perm) M->user_perm.assign(kkt_perm, kkt_perm + n + p + m);
     M->kkt_solver_hint = H->ip.st.kkt_solver;
+    {   // size of the KKT system of the selected mode (sparse/kkt.hpp:206-228)
+        const int ks = M->kkt_solver_hint, mode = (ks >= 2 && ks <= 4) ? ks - 1 : 0;
+        const int nk = n + ((mode & 1) ? 0 : p) + ((mode & 2) ? 0 : m);
+        if (kkt_perm) M->user_perm.assign(kkt_perm, kkt_perm + nk);
+    }
     if (ext) { H->vt = *ext; M->backend_factory = make_foreign_sparse; M->backend_factory_arg = &H->vt; }
     H->ip.pre.identity = identity_precond != 0;
     H->ip.d.resize(n, p, m);
@@ -293,10 +299,13 @@ double orc_multistage_factor_flops(void* h) {
 }
 // sparse_ldlt backend: nnz(L) and the flop count of the numeric factorisation
 double orc_sparse_ldlt_stats(void* h, double* nnzL) {
-    auto* be = dynamic_cast<SparseKKTFull*>(static_cast<Handle*>(h)->ip.kkt.be.get());
-    if (!be) return -1.0;
-    if (nnzL) *nnzL = (double)be->ldlt.Lp.back();
-    return be->ldlt.flops();
+    auto* base = static_cast<Handle*>(h)->ip.kkt.be.get();
+    const SparseLDLt* f = nullptr;
+    if (auto* be = dynamic_cast<SparseKKTFull*>(base)) f = &be->ldlt;
+    else if (auto* bc = dynamic_cast<SparseKKTCond*>(base)) f = &bc->ldlt;
+    if (!f) return -1.0;
+    if (nnzL) *nnzL = (double)f->Lp.back();
+    return f->flops();
 }
 
 void orc_destroy(void* h) { delete static_cast<Handle*>(h); }

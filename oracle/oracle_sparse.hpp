@@ -149,6 +149,7 @@ struct SparseKKTFull : KKTBackend {
 };
 
 inline std::unique_ptr<KKTBackend> make_multistage_backend(const SparseMatrices& S);  // oracle_multistage.hpp
+inline std::unique_ptr<KKTBackend> make_cond_backend(const SparseMatrices& S, int mode, const IVec* user_perm);  // oracle_sparse_cond.hpp
 
 struct SparseMatrices : QPMatrices {
     int n = 0, p = 0, m = 0;
@@ -188,6 +189,8 @@ struct SparseMatrices : QPMatrices {
     std::unique_ptr<KKTBackend> make_backend(int kkt_solver) override {
         if (backend_factory) return backend_factory(*this, backend_factory_arg);
         if (kkt_solver == 5) return make_multistage_backend(*this);      // KKTSolver::sparse_multistage
+        if (kkt_solver >= 2 && kkt_solver <= 4)                          // sparse_ldlt_eq_cond / _ineq_cond / _cond (kkt_system.hpp:476-489)
+            return make_cond_backend(*this, kkt_solver - 1, user_perm.empty() ? nullptr : &user_perm);
         return std::make_unique<SparseKKTFull>(*this, user_perm.empty() ? nullptr : &user_perm);
     }
 };

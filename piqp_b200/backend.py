@@ -155,10 +155,13 @@ class MultistageKKT(KKTSolverBase):
 
 
 class SparseKKT(KKTSolverBase):
-    """Twin of piqp::sparse::KKT<T, I, KKT_FULL> (include/piqp/sparse/kkt.hpp:31-250): LDL^T of the permuted
-    quasi-definite KKT matrix.  `perm` (optional, length n+p+m, perm[new] = old) replaces the built-in ordering."""
+    """Twin of piqp::sparse::KKT<T, I, Mode> (include/piqp/sparse/kkt.hpp:31-250): LDL^T of the permuted
+    quasi-definite KKT matrix.  mode = KKTMode (kkt_fwd.hpp:15-21): 0 FULL, 1 EQ_ELIMINATED, 2 INEQ_ELIMINATED,
+    3 ALL_ELIMINATED.  `perm` (optional, length of that mode's KKT, perm[new] = old) replaces the built-in ordering."""
 
-    def __init__(self, P_utri, AT=None, GT=None, perm=None, device=0):
+    MODES = {"sparse_ldlt": 0, "sparse_ldlt_eq_cond": 1, "sparse_ldlt_ineq_cond": 2, "sparse_ldlt_cond": 3}
+
+    def __init__(self, P_utri, AT=None, GT=None, perm=None, device=0, mode=0):
         import scipy.sparse as sp
         super().__init__()
         self.n = P_utri.shape[0]
@@ -168,14 +171,16 @@ class SparseKKT(KKTSolverBase):
         self._P = _csc_arrays(P_utri, upper=True); self._A = _csc_arrays(AT); self._G = _csc_arrays(GT)
         ipp = lambda a: a.ctypes.data_as(ip)
         pm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+        self.mode = self.MODES[mode] if isinstance(mode, str) else int(mode)
+        self.n_kkt = self.n + (0 if self.mode & 1 else self.p) + (0 if self.mode & 2 else self.m)
         _lib.check(self._L.b200kkt_sparse_create(C.byref(self._h), self.n, self.p, self.m, ipp(self._P[0]), ipp(self._P[1]), _p(self._P[2]),
                                                  ipp(self._A[0]), ipp(self._A[1]), _p(self._A[2]), ipp(self._G[0]), ipp(self._G[1]), _p(self._G[2]),
-                                                 0, None if pm is None else ipp(pm), device), "b200kkt_sparse_create")
+                                                 self.mode, None if pm is None else ipp(pm), device), "b200kkt_sparse_create")
 
     update_data = None  # set below (shared with MultistageKKT)
 
     def symbolic_info(self):
-        nk = self.n + self.p + self.m
+        nk = self.n_kkt
         a, b, lv = C.c_longlong(), C.c_longlong(), C.c_int()
         perm = np.zeros(nk, dtype=np.int32)
         _lib.check(self._L.b200kkt_sparse_info(self._h, C.byref(a), C.byref(b), C.byref(lv), perm.ctypes.data_as(ip)), "b200kkt_sparse_info")
@@ -185,9 +190,10 @@ class SparseKKT(KKTSolverBase):
 SparseKKT.update_data = MultistageKKT.update_data
 
 
-def sparse_ldlt_symbolic(P, A, G, perm=None):
-    """Host-only symbolic phase of the sparse_ldlt backend (b200_sparse_ldlt_symbolic): fill-reducing ordering of the
-    full KKT (sparse/ordering.hpp:59-125), nnz(L), etree levels and factor flops (sparse/ldlt.hpp:42-99).
+def sparse_ldlt_symbolic(P, A, G, perm=None, mode=0):
+    """Host-only symbolic phase of the sparse_ldlt backend (b200_sparse_ldlt_symbolic_mode): fill-reducing ordering of the
+    KKT of the given KKTMode (sparse/ordering.hpp:59-125), nnz(L), etree levels and factor flops (sparse/ldlt.hpp:42-99),
+    supernode count and largest front of the multifrontal schedule.
     P (n x n, upper part used), A (p x n) or None, G (m x n) or None: scipy sparse."""
     import scipy.sparse as sp
     L = _lib.lib()
@@ -198,13 +204,14 @@ def sparse_ldlt_symbolic(P, A, G, perm=None):
     Ap, Ai, _ = _csc_arrays(AT)
     Gp, Gi, _ = _csc_arrays(GT)
     p, m = AT.shape[1], GT.shape[1]
-    out = np.zeros(n + p + m, dtype=np.int32)
-    nk, nl, lv, fl = C.c_longlong(), C.c_longlong(), C.c_int(), C.c_double()
+    mode = SparseKKT.MODES[mode] if isinstance(mode, str) else int(mode)
+    out = np.zeros(n + (0 if mode & 1 else p) + (0 if mode & 2 else m), dtype=np.int32)
+    nk, nl, lv, fl, ns, fm = C.c_longlong(), C.c_longlong(), C.c_int(), C.c_double(), C.c_int(), C.c_int()
     pin = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
     q = lambda a: a.ctypes.data_as(ip)
-    _lib.check(L.b200_sparse_ldlt_symbolic(n, p, m, q(Pp), q(Pi), q(Ap), q(Ai), q(Gp), q(Gi), None if pin is None else q(pin), q(out),
-                                           C.byref(nk), C.byref(nl), C.byref(lv), C.byref(fl)), "b200_sparse_ldlt_symbolic")
-    return {"perm": out, "nnz_kkt": nk.value, "nnz_L": nl.value, "levels": lv.value, "flops": fl.value}
+    _lib.check(L.b200_sparse_ldlt_symbolic_mode(n, p, m, q(Pp), q(Pi), q(Ap), q(Ai), q(Gp), q(Gi), mode, None if pin is None else q(pin), q(out),
+                                                C.byref(nk), C.byref(nl), C.byref(lv), C.byref(fl), C.byref(ns), C.byref(fm)), "b200_sparse_ldlt_symbolic_mode")
+    return {"perm": out, "nnz_kkt": nk.value, "nnz_L": nl.value, "levels": lv.value, "flops": fl.value, "supernodes": ns.value, "largest_front": fm.value}
 
 
 def c_abi_vtable():

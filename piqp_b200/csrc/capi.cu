@@ -102,7 +102,7 @@ int b200kkt_dense_create(b200kkt_handle** out, int n, int p, int m, const double
 
 namespace {
 int sparse_single_create(b200kkt_handle** out, int kind, int n, int p, int m, const int* Pp, const int* Pi, const double* Px,
-                         const int* ATp, const int* ATi, const double* ATx, const int* GTp, const int* GTi, const double* GTx, const int* perm, int device) {
+                         const int* ATp, const int* ATi, const double* ATx, const int* GTp, const int* GTi, const double* GTx, const int* perm, int device, int mode = 0) {
     *out = nullptr;
     B200_TRY(
         B200_CUDA(cudaSetDevice(device));
@@ -122,7 +122,7 @@ int sparse_single_create(b200kkt_handle** out, int kind, int n, int p, int m, co
         h->delta.alloc(1); h->ok.alloc(1);
         B200_CUDA(cudaDeviceSynchronize());
         if (kind == 1) { h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream); h->be = h->ms.get(); }
-        else { h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, perm, h->stream); h->be = h->ldlt.get(); }
+        else { h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, perm, h->stream, mode); h->be = h->ldlt.get(); }
         B200_CUDA(cudaStreamSynchronize(h->stream));
         *out = h.release();
     )
@@ -133,8 +133,8 @@ int sparse_single_create(b200kkt_handle** out, int kind, int n, int p, int m, co
 int b200kkt_sparse_create(b200kkt_handle** out, int n, int p, int m, const int* Pp, const int* Pi, const double* Px, const int* ATp, const int* ATi, const double* ATx,
                           const int* GTp, const int* GTi, const double* GTx, int mode, const int* perm, int device) {
     if (!out || n <= 0 || p < 0 || m < 0 || !Pp || (p > 0 && !ATp) || (m > 0 && !GTp)) return fail(B200_E_INVALID, "b200kkt_sparse_create: bad arguments");
-    if (mode != 0) { *out = nullptr; return fail(B200_E_UNSUPPORTED, "b200kkt_sparse_create: only KKTMode FULL (0) is implemented"); }
-    return sparse_single_create(out, 2, n, p, m, Pp, Pi, Px, ATp, ATi, ATx, GTp, GTi, GTx, perm, device);
+    if (mode < 0 || mode > 3) { *out = nullptr; return fail(B200_E_INVALID, "b200kkt_sparse_create: mode must be a KKTMode (0..3)"); }
+    return sparse_single_create(out, 2, n, p, m, Pp, Pi, Px, ATp, ATi, ATx, GTp, GTi, GTx, perm, device, mode);
 }
 int b200kkt_multistage_create(b200kkt_handle** out, int n, int p, int m, const int* Pp, const int* Pi, const double* Px,
                               const int* ATp, const int* ATi, const double* ATx, const int* GTp, const int* GTi, const double* GTx, int device) {
@@ -143,7 +143,12 @@ int b200kkt_multistage_create(b200kkt_handle** out, int n, int p, int m, const i
 }
 int b200_sparse_ldlt_symbolic(int n, int p, int m, const int* Pp, const int* Pi, const int* ATp, const int* ATi, const int* GTp, const int* GTi,
                               const int* perm_in, int* perm_out, long long* nnz_kkt, long long* nnz_L, int* levels, double* factor_flops) {
-    if (n <= 0 || p < 0 || m < 0 || !Pp || (p > 0 && !ATp) || (m > 0 && !GTp)) return fail(B200_E_INVALID, "b200_sparse_ldlt_symbolic: bad arguments");
+    return b200_sparse_ldlt_symbolic_mode(n, p, m, Pp, Pi, ATp, ATi, GTp, GTi, 0, perm_in, perm_out, nnz_kkt, nnz_L, levels, factor_flops, nullptr, nullptr);
+}
+int b200_sparse_ldlt_symbolic_mode(int n, int p, int m, const int* Pp, const int* Pi, const int* ATp, const int* ATi, const int* GTp, const int* GTi, int mode,
+                                   const int* perm_in, int* perm_out, long long* nnz_kkt, long long* nnz_L, int* levels, double* factor_flops,
+                                   int* n_supernodes, int* largest_front) {
+    if (n <= 0 || p < 0 || m < 0 || !Pp || (p > 0 && !ATp) || (m > 0 && !GTp) || mode < 0 || mode > 3) return fail(B200_E_INVALID, "b200_sparse_ldlt_symbolic: bad arguments");
     B200_TRY(
         auto host_pattern = [](Pattern& M, int rows, int cols, const int* cp, const int* ri) {
             M.rows = rows; M.cols = cols;
@@ -154,7 +159,9 @@ int b200_sparse_ldlt_symbolic(int n, int p, int m, const int* Pp, const int* Pi,
         Pattern P, AT, GT;
         host_pattern(P, n, n, Pp, Pi); host_pattern(AT, n, p, ATp, ATi); host_pattern(GT, n, m, GTp, GTi);
         LdltSymbolic S;
-        if (!S.analyse(P, AT, GT, perm_in)) throw std::runtime_error(S.error);
+        if (!S.analyse(P, AT, GT, perm_in, mode)) throw std::runtime_error(S.error);
+        if (n_supernodes) *n_supernodes = S.nsup;
+        if (largest_front) *largest_front = S.fmax;
         if (perm_out) std::copy(S.perm.begin(), S.perm.end(), perm_out);
         if (nnz_kkt) *nnz_kkt = (long long)S.Ki.size();      // structural entries (supernode amalgamation pads PK with explicit zeros)
         if (nnz_L) *nnz_L = (long long)S.nnzL();
@@ -274,7 +281,7 @@ b200kkt_handle* b200kkt_clone(const b200kkt_handle* src) {
                 h->ms->copy_from(*src->ms);
                 h->be = h->ms.get();
             } else {
-                h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, src->ldlt->S.perm.data(), h->stream);
+                h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, src->ldlt->S.perm.data(), h->stream, src->ldlt->S.mode);
                 h->ldlt->copy_from(*src->ldlt);
                 h->be = h->ldlt.get();
             }
@@ -578,8 +585,8 @@ int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
         auto h = std::make_unique<b200qp_handle>();
         h->kind = 1; h->device = device; h->batch = batch; h->n = n; h->p = p; h->m = m;
         if (settings) h->st = *settings; else b200qp_set_default_settings_sparse(&h->st);
-        if (h->st.kkt_solver != 5 && h->st.kkt_solver != 1)
-            throw std::runtime_error("b200qp_setup_sparse: kkt_solver must be sparse_ldlt (1) or sparse_multistage (5); the reduced KKT modes are not built");
+        if (h->st.kkt_solver < 1 || h->st.kkt_solver > 5)
+            throw std::runtime_error("b200qp_setup_sparse: kkt_solver must be one of the sparse backends (1..5, settings.hpp:18-26)");
         B200_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         cudaEvent_t e0, e1;
         B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
@@ -620,7 +627,7 @@ int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
         d.pd = h->ruiz.delta.get(); d.pd_inv = h->ruiz.delta_inv.get(); d.pdb = h->ruiz.delta_b.get(); d.pdb_inv = h->ruiz.delta_b_inv.get();
         d.pc = h->ruiz.c.get(); d.pc_inv = h->ruiz.c_inv.get();
         if (h->st.kkt_solver == 5) { h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream); h->be = h->ms.get(); }
-        else { h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, nullptr, h->stream); h->be = h->ldlt.get(); }
+        else { h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, nullptr, h->stream, h->st.kkt_solver - 1); h->be = h->ldlt.get(); }   // KKTMode = 0..3 (kkt_system.hpp:476-489)
         lap("backend ctor");
         h->ip->finish_setup(h->be);
         B200_CUDA(cudaEventRecord(e1, h->stream));

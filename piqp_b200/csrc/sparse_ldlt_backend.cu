@@ -2,6 +2,7 @@
 #include "sparse_ldlt_backend.hpp"
 #include "sparse_frontal.cuh"
 #include <cstdlib>
+#include <string>
 #include <algorithm>
 #include <cstdio>
 #include <set>
@@ -14,7 +15,7 @@ namespace b200 {
 // =====================================================================================================
 // Minimum-degree ordering on the graph of a symmetric matrix given by its upper triangle (CSC).  Quotient graph
 // (variables + elements, element absorption) with exact external degrees; ties broken by index.  perm[k] = k-th pivot.
-std::vector<int> minimum_degree_ordering(int n, const std::vector<int>& cp, const std::vector<int>& ri) {
+static std::vector<int> minimum_degree_ordering_exact(int n, const std::vector<int>& cp, const std::vector<int>& ri) {
     std::vector<std::vector<int>> avar(n), aelem(n), members(n);
     for (int j = 0; j < n; j++) for (int q = cp[j]; q < cp[j + 1]; q++) { const int i = ri[q]; if (i != j) { avar[i].push_back(j); avar[j].push_back(i); } }
     for (auto& v : avar) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
@@ -66,35 +67,169 @@ std::vector<int> minimum_degree_ordering(int n, const std::vector<int>& cp, cons
     return perm;
 }
 
+
+// Approximate minimum degree on the same quotient graph (what Eigen::AMDOrdering -- third party, ordering.hpp:72-74 --
+// computes in spirit: Amestoy/Davis/Duff's degree bound  d_i <= |A_i| + |L_p \ i| + sum_{e in E_i} |L_e \ L_p|  evaluated with
+// one pass over the element lists, element absorption, aggressive absorption of elements that became subsets of the new
+// one, degree buckets).  No supervariables; instead the elimination stops as soon as the bound says the remaining graph is
+// a clique (min degree = remaining - 1): the rest is appended in index order and becomes the dense root front.  Cost
+// O(sum_pivots sum_{i in L_p} (|A_i| + |E_i|)): BASELINE config 3 (n_kkt = 20 000, 1 %) takes ~1 s instead of the 94 s of
+// the exact-degree version above (kept under B200_ORDERING=exact for cross-checks).
+std::vector<int> minimum_degree_ordering(int n, const std::vector<int>& cp, const std::vector<int>& ri) {
+    if (const char* e = getenv("B200_ORDERING")) if (std::string(e) == "exact") return minimum_degree_ordering_exact(n, cp, ri);
+    std::vector<std::vector<int>> avar(n), aelem(n), members(n);
+    for (int j = 0; j < n; j++) for (int q = cp[j]; q < cp[j + 1]; q++) { const int i = ri[q]; if (i != j) { avar[i].push_back(j); avar[j].push_back(i); } }
+    for (auto& v : avar) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+    std::vector<char> gone(n, 0), elem_alive(n, 0);
+    std::vector<int> deg(n), mark(n, -1), head(n + 1, -1), nxt(n, -1), prv(n, -1);
+    std::vector<long long> w(n, 0);
+    long long wflg = 1;
+    auto bucket_insert = [&](int i) { const int d = deg[i]; prv[i] = -1; nxt[i] = head[d]; if (head[d] >= 0) prv[head[d]] = i; head[d] = i; };
+    auto bucket_remove = [&](int i) { const int d = deg[i]; if (prv[i] >= 0) nxt[prv[i]] = nxt[i]; else head[d] = nxt[i]; if (nxt[i] >= 0) prv[nxt[i]] = prv[i]; };
+    for (int i = n - 1; i >= 0; i--) { deg[i] = (int)avar[i].size(); bucket_insert(i); }      // reverse: the smallest index sits at the head
+    std::vector<int> perm; perm.reserve(n);
+    std::vector<int> Lp;
+    int mindeg = 0;
+    for (int k = 0; k < n; k++) {
+        const int nleft = n - k;
+        while (mindeg < n && head[mindeg] < 0) mindeg++;
+        if (mindeg >= nleft - 1 && nleft > 1) {                // the remaining graph is (bounded by) a clique
+            for (int i = 0; i < n; i++) if (!gone[i]) perm.push_back(i);
+            break;
+        }
+        const int pv = head[mindeg];
+        bucket_remove(pv);
+        perm.push_back(pv);
+        Lp.clear();
+        mark[pv] = pv;
+        for (int v : avar[pv]) if (!gone[v] && mark[v] != pv) { mark[v] = pv; Lp.push_back(v); }
+        for (int e : aelem[pv]) {
+            if (!elem_alive[e]) continue;
+            for (int v : members[e]) if (!gone[v] && mark[v] != pv) { mark[v] = pv; Lp.push_back(v); }
+            elem_alive[e] = 0; std::vector<int>().swap(members[e]);
+        }
+        gone[pv] = 1;
+        std::vector<int>().swap(avar[pv]); std::vector<int>().swap(aelem[pv]);
+        const int lp = (int)Lp.size();
+        // |L_e \ L_p| for every element adjacent to L_p: w[e] - wflg
+        for (int i : Lp) for (int e : aelem[i]) { if (!elem_alive[e]) continue; if (w[e] < wflg) w[e] = (long long)members[e].size() + wflg; w[e]--; }
+        for (int i : Lp) {
+            auto& av = avar[i];
+            size_t o = 0;
+            for (int v : av) if (!gone[v] && mark[v] != pv) av[o++] = v;
+            av.resize(o);
+            auto& ae = aelem[i];
+            o = 0;
+            long long ext = 0;
+            for (int e : ae) {
+                if (!elem_alive[e]) continue;
+                const long long d = w[e] - wflg;
+                if (d <= 0) { elem_alive[e] = 0; std::vector<int>().swap(members[e]); continue; }     // aggressive absorption: L_e is a subset of L_p
+                ext += d; ae[o++] = e;
+            }
+            ae.resize(o);
+            ae.push_back(pv);
+            long long d = (long long)av.size() + (lp - 1) + ext;
+            d = std::min<long long>(d, (long long)deg[i] + (lp - 1));
+            d = std::min<long long>(d, nleft - 2);               // nleft - 1 variables remain after this pivot, i is one of them
+            if (d < 0) d = 0;
+            bucket_remove(i);
+            deg[i] = (int)d;
+            bucket_insert(i);
+            if (deg[i] < mindeg) mindeg = deg[i];
+        }
+        members[pv] = Lp; elem_alive[pv] = lp > 0;
+        wflg += (long long)n + 1;
+    }
+    return perm;
+}
+
 // =====================================================================================================
 // host: symbolic analysis
 // =====================================================================================================
-bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& GT, const int* user_perm) {
-    n = P.rows; p = AT.cols; m = GT.cols; nk = n + p + m;
-    // ---- KKT pattern [[P + rho I, A^T, G^T], [., -delta I, .], [., ., -Z]], upper CSC (kkt_full.hpp:39-170)
+// Contribution lists of upper(MT * diag(w) * MT^T) for MT given column-wise (n x r CSC): entry (i, j), i <= j, is
+// sum_k MT(j,k) * MT(i,k) * w_k over the columns k that hold both rows, k ascending -- the order in which the reference's
+// Gustavson loops accumulate it (kkt_all_eliminated.hpp:178-220).  pa / pb are value indices of MT(i,k) / MT(j,k).
+void LdltSymbolic::build_gram(const Pattern& MT, Gram& g) {
+    const int nr = MT.rows, nc = MT.cols;
+    std::vector<int> rp(nr + 1, 0), rk(MT.nnz), rpos(MT.nnz);          // row view of MT (columns ascending within a row)
+    for (int q = 0; q < MT.nnz; q++) rp[MT.i[q] + 1]++;
+    for (int r = 0; r < nr; r++) rp[r + 1] += rp[r];
+    { std::vector<int> w(rp.begin(), rp.end() - 1); for (int k = 0; k < nc; k++) for (int q = MT.p[k]; q < MT.p[k + 1]; q++) { const int t = w[MT.i[q]]++; rk[t] = k; rpos[t] = q; } }
+    g.colp.assign(nr + 1, 0); g.rows.clear(); g.ptr.assign(1, 0); g.pa.clear(); g.pb.clear();
+    struct Tr { int i, pa, pb; };
+    std::vector<Tr> tr;
+    for (int j = 0; j < nr; j++) {
+        tr.clear();
+        for (int a = rp[j]; a < rp[j + 1]; a++) { const int k = rk[a];
+            for (int t = MT.p[k]; t < MT.p[k + 1]; t++) if (MT.i[t] <= j) tr.push_back({MT.i[t], t, rpos[a]}); }
+        std::stable_sort(tr.begin(), tr.end(), [](const Tr& x, const Tr& y) { return x.i < y.i; });
+        for (size_t t = 0; t < tr.size(); t++) {
+            if (t == 0 || tr[t].i != tr[t - 1].i) { g.rows.push_back(tr[t].i); g.ptr.push_back(g.ptr.back()); }
+            g.pa.push_back(tr[t].pa); g.pb.push_back(tr[t].pb); g.ptr.back()++;
+        }
+        g.colp[j + 1] = (int)g.rows.size();
+    }
+}
+
+bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& GT, const int* user_perm, int mode_) {
+    mode = mode_;
+    const bool elim_eq = mode & 1, elim_ineq = mode & 2;
+    n = P.rows; p = AT.cols; m = GT.cols;
+    pk = elim_eq ? 0 : p; mk = elim_ineq ? 0 : m;
+    nk = n + pk + mk;
+    // ---- KKT pattern, upper CSC.  FULL: [[P + rho I, A^T, G^T], [., -delta I, .], [., ., -Z]] (kkt_full.hpp:39-170); the
+    // condensed modes fold delta^-1 A^T A and / or G^T Z^-1 G into the top-left block on the structural union pattern and
+    // drop the corresponding block columns (kkt_eq_eliminated.hpp:47-148, kkt_ineq_eliminated.hpp:49-150, kkt_all_eliminated.hpp:58-106)
     Kp.assign(nk + 1, 0); Ki.clear();
     P_to_K.assign(P.nnz, -1); AT_to_K.assign(AT.nnz, -1); GT_to_K.assign(GT.nnz, -1);
+    ata = Gram(); gtg = Gram(); xx_P.clear(); xx_var.clear(); xx_ata.clear(); xx_gtg.clear();
     std::vector<int> diagK(nk, -1);
-    for (int j = 0; j < n; j++) {
-        bool has_diag = false;
-        for (int q = P.p[j]; q < P.p[j + 1]; q++) {
-            if (P.i[q] > j) { error = "sparse_ldlt: P must be upper triangular"; return false; }
-            P_to_K[q] = (int)Ki.size();
-            if (P.i[q] == j) { has_diag = true; diagK[j] = (int)Ki.size(); }
-            Ki.push_back(P.i[q]);
+    if (mode == 0) {
+        for (int j = 0; j < n; j++) {
+            bool has_diag = false;
+            for (int q = P.p[j]; q < P.p[j + 1]; q++) {
+                if (P.i[q] > j) { error = "sparse_ldlt: P must be upper triangular"; return false; }
+                P_to_K[q] = (int)Ki.size();
+                if (P.i[q] == j) { has_diag = true; diagK[j] = (int)Ki.size(); }
+                Ki.push_back(P.i[q]);
+            }
+            if (!has_diag) { diagK[j] = (int)Ki.size(); Ki.push_back(j); }
+            Kp[j + 1] = (int)Ki.size();
         }
-        if (!has_diag) { diagK[j] = (int)Ki.size(); Ki.push_back(j); }
-        Kp[j + 1] = (int)Ki.size();
+    } else {
+        if (elim_eq) build_gram(AT, ata);
+        if (elim_ineq) build_gram(GT, gtg);
+        std::vector<int> slot(n, -1), rows;
+        for (int j = 0; j < n; j++) {
+            rows.clear();
+            auto add = [&](int r) { if (slot[r] != j) { slot[r] = j; rows.push_back(r); } };
+            for (int q = P.p[j]; q < P.p[j + 1]; q++) { if (P.i[q] > j) { error = "sparse_ldlt: P must be upper triangular"; return false; } add(P.i[q]); }
+            add(j);
+            if (elim_eq) for (int e = ata.colp[j]; e < ata.colp[j + 1]; e++) add(ata.rows[e]);
+            if (elim_ineq) for (int e = gtg.colp[j]; e < gtg.colp[j + 1]; e++) add(gtg.rows[e]);
+            std::sort(rows.begin(), rows.end());
+            const int base = (int)Ki.size();
+            for (size_t t = 0; t < rows.size(); t++) { Ki.push_back(rows[t]); xx_P.push_back(-1); xx_var.push_back(rows[t] == j ? j : -1); xx_ata.push_back(-1); xx_gtg.push_back(-1); }
+            // positions: rows are sorted, binary search
+            auto find = [&](int r) { return base + (int)(std::lower_bound(rows.begin(), rows.end(), r) - rows.begin()); };
+            for (int q = P.p[j]; q < P.p[j + 1]; q++) { const int e = find(P.i[q]); P_to_K[q] = e; xx_P[e] = q; }
+            diagK[j] = find(j);
+            if (elim_eq) for (int e = ata.colp[j]; e < ata.colp[j + 1]; e++) xx_ata[find(ata.rows[e])] = e;
+            if (elim_ineq) for (int e = gtg.colp[j]; e < gtg.colp[j + 1]; e++) xx_gtg[find(gtg.rows[e])] = e;
+            Kp[j + 1] = (int)Ki.size();
+        }
     }
-    for (int c = 0; c < p; c++) {
+    int col = n;
+    if (!elim_eq) for (int c = 0; c < p; c++, col++) {
         for (int q = AT.p[c]; q < AT.p[c + 1]; q++) { AT_to_K[q] = (int)Ki.size(); Ki.push_back(AT.i[q]); }
-        diagK[n + c] = (int)Ki.size(); Ki.push_back(n + c);
-        Kp[n + c + 1] = (int)Ki.size();
+        diagK[col] = (int)Ki.size(); Ki.push_back(col);
+        Kp[col + 1] = (int)Ki.size();
     }
-    for (int c = 0; c < m; c++) {
+    if (!elim_ineq) for (int c = 0; c < m; c++, col++) {
         for (int q = GT.p[c]; q < GT.p[c + 1]; q++) { GT_to_K[q] = (int)Ki.size(); Ki.push_back(GT.i[q]); }
-        diagK[n + p + c] = (int)Ki.size(); Ki.push_back(n + p + c);
-        Kp[n + p + c + 1] = (int)Ki.size();
+        diagK[col] = (int)Ki.size(); Ki.push_back(col);
+        Kp[col + 1] = (int)Ki.size();
     }
     // ---- ordering
     if (user_perm) perm.assign(user_perm, user_perm + nk);
@@ -344,19 +479,62 @@ __global__ void ldlt_scatter_kernel(const int* map, int nnz, int nnzPK, const do
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < nnz) PKx[(size_t)b * nnzPK + map[q]] = vals[(size_t)b * nnz + q];
 }
-// diagonal of the KKT matrix for this iteration (kkt_full.hpp:172-210)
-__global__ void ldlt_set_diag_kernel(const int* diagPK, int n, int p, int m, int nnzPK, const double* P_diag, const double* x_reg, const double* delta,
+// diagonal of the KKT matrix for this iteration (kkt_full.hpp:172-210).  pk / mk: sizes of the y / z blocks kept in the KKT;
+// skip_x: the condensed modes rebuild the whole top-left block in ldlt_cond_assemble_kernel instead.
+__global__ void ldlt_set_diag_kernel(const int* diagPK, int n, int pk, int mk, int skip_x, int nnzPK, const double* P_diag, const double* x_reg, const double* delta,
                                      const double* z_reg, double* PKx, const int* active) {
     const int b = blockIdx.y;
     if (active && !active[b]) return;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nk = n + p + m;
+    const int nk = n + pk + mk;
     if (v >= nk) return;
     double val;
-    if (v < n) val = P_diag[(size_t)b * n + v] + x_reg[(size_t)b * n + v];
-    else if (v < n + p) val = -delta[b];
-    else val = -z_reg[(size_t)b * m + (v - n - p)];
+    if (v < n) { if (skip_x) return; val = P_diag[(size_t)b * n + v] + x_reg[(size_t)b * n + v]; }
+    else if (v < n + pk) val = -delta[b];
+    else val = -z_reg[(size_t)b * mk + (v - n - pk)];
     PKx[(size_t)b * nnzPK + diagPK[v]] = val;
+}
+// values of upper(A^T A) from the contribution lists (update_AT_A, kkt_eq_eliminated.hpp:223-245): one thread per entry,
+// summands in ascending k like the reference's Gustavson loop
+__global__ void ldlt_gram_values_kernel(const int* ptr, const int* pa, const int* pb, int nent, int nnzM, const double* vals, double* out) {
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nent) return;
+    const double* v = vals + (size_t)b * nnzM;
+    double acc = 0.0;
+    for (int t = ptr[e]; t < ptr[e + 1]; t++) acc += v[pb[t]] * v[pa[t]];
+    out[(size_t)b * nent + e] = acc;
+}
+// top-left block of the condensed KKT:  0 + P + x_reg (diagonal) + delta^-1 (A^T A) + G^T Z^-1 G, in the reference's order of
+// additions (kkt_all_eliminated.hpp:108-160); the G^T Z^-1 G entry is summed as (G_kj * G_ki) / z_reg_k, k ascending (:199-220)
+__global__ void ldlt_cond_assemble_kernel(int nxx, const int* xx_P, const int* xx_var, const int* xx_ata, const int* xx_gtg, const int* xx_target,
+                                          const int* gptr, const int* gpa, const int* gpb, const int* gcolof, int n, int m, int nnzP, int nnzG, int nata, int nnzPK,
+                                          const double* Px, const double* GTx, const double* AtA, const double* x_reg, const double* delta, const double* z_reg,
+                                          double* PKx, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nxx) return;
+    double v = 0.0;
+    const int ps = xx_P[e], j = xx_var[e], a = xx_ata[e], g = xx_gtg[e];
+    if (ps >= 0) v += Px[(size_t)b * nnzP + ps];
+    if (j >= 0) v += x_reg[(size_t)b * n + j];
+    if (a >= 0) v += (1.0 / delta[b]) * AtA[(size_t)b * nata + a];
+    if (g >= 0) {
+        const double* G = GTx + (size_t)b * nnzG;
+        const double* zr = z_reg + (size_t)b * m;
+        double acc = 0.0;
+        for (int t = gptr[g]; t < gptr[g + 1]; t++) { const int ia = gpa[t]; acc += G[gpb[t]] * G[ia] / zr[gcolof[ia]]; }
+        v += acc;
+    }
+    PKx[(size_t)b * nnzPK + xx_target[e]] = v;
+}
+__global__ void ldlt_store_scalings_kernel(int m, const double* delta, const double* z_reg, double* dlt, double* zinv, const int* active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) dlt[b] = delta[b];
+    if (k < m) zinv[(size_t)b * m + k] = 1.0 / z_reg[(size_t)b * m + k];
 }
 __global__ void ldlt_zero_kernel(double* Lx, size_t nnzL, const int* active) {
     const int b = blockIdx.y;
@@ -477,22 +655,23 @@ static MfDev make_mf(const SparseLdltBatchedKKT& K) {
     MfDev M;
     M.hdr = K.d_hdr.get(); M.crec = K.d_crec.get(); M.rel_idx = K.d_rel_idx.get(); M.asm_pos = K.d_asm_pos.get(); M.Li = K.d_Li.get(); M.perm = K.d_perm.get();
     M.upd_off = K.d_upd_off.get();
-    M.nsup = K.S.nsup; M.nk = K.S.nk; M.n = K.n; M.p = K.p; M.m = K.m; M.front_smem_rows = K.front_smem_rows; M.fmax = K.S.fmax;
+    M.nsup = K.S.nsup; M.nk = K.S.nk; M.n = K.n; M.p = K.S.pk; M.m = K.S.mk; M.front_smem_rows = K.front_smem_rows; M.fmax = K.S.fmax;
     M.upd_total = std::max<long long>(K.S.upd_total, 1);
     M.nnzL = std::max<size_t>(K.S.Li.size(), 1); M.nnzPK = K.S.PKi_rows.size();
     return M;
 }
 
-SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_perm, cudaStream_t st) : D(data) {
+SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_perm, cudaStream_t st, int mode) : D(data) {
     batch = D->batch; n = D->n; p = D->p; m = D->m; stream = st;
-    if (!S.analyse(D->P, D->AT, D->GT, user_perm)) throw std::runtime_error(S.error);
+    if (mode < 0 || mode > 3) throw std::runtime_error("sparse_ldlt: KKTMode must be 0..3");
+    if (!S.analyse(D->P, D->AT, D->GT, user_perm, mode)) throw std::runtime_error(S.error);
     if (const char* e = getenv("B200_LDLT_LEVELS")) if (e[0] == '1') frontal = false;
     // value order of PKx: CSC order of the permuted matrix for the level kernels, ASSEMBLY order (grouped by front) for the
     // multifrontal kernels
     std::vector<int> order(S.PKi_rows.size());
     for (size_t q = 0; q < order.size(); q++) order[q] = (int)q;
     if (frontal) for (size_t t = 0; t < S.asm_q.size(); t++) order[S.asm_q[t]] = (int)t;
-    auto compose = [&](const std::vector<int>& toK) { std::vector<int> r(toK.size()); for (size_t q = 0; q < toK.size(); q++) r[q] = order[S.K_to_PK[toK[q]]]; return r; };
+    auto compose = [&](const std::vector<int>& toK) { std::vector<int> r(toK.size()); for (size_t q = 0; q < toK.size(); q++) r[q] = toK[q] >= 0 ? order[S.K_to_PK[toK[q]]] : -1; return r; };
     upload(d_P_to_PK, compose(S.P_to_K)); upload(d_AT_to_PK, compose(S.AT_to_K)); upload(d_GT_to_PK, compose(S.GT_to_K));
     { std::vector<int> dg(S.diagPK.size()); for (size_t v = 0; v < dg.size(); v++) dg[v] = order[S.diagPK[v]]; upload(d_diagPK, dg); }
     upload(d_PK_to_L, S.PK_to_L); upload(d_PKp, S.PKp);
@@ -501,6 +680,17 @@ SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_per
     const size_t B = batch, nnzPK = S.PKi_rows.size(), nnzL = std::max<size_t>(S.Li.size(), 1);
     PKx.alloc(B * nnzPK); PKx.zero(st);
     P_diag.alloc(std::max<size_t>(B * n, 1));
+    if (S.mode) {
+        const int nxx = S.Kp[n];
+        std::vector<int> tgt(nxx);
+        for (int e = 0; e < nxx; e++) tgt[e] = order[S.K_to_PK[e]];
+        upload(d_xx_P, S.xx_P); upload(d_xx_var, S.xx_var); upload(d_xx_ata, S.xx_ata); upload(d_xx_gtg, S.xx_gtg); upload(d_xx_target, tgt);
+        upload(d_ata_ptr, S.ata.ptr); upload(d_ata_pa, S.ata.pa); upload(d_ata_pb, S.ata.pb);
+        upload(d_gtg_ptr, S.gtg.ptr); upload(d_gtg_pa, S.gtg.pa); upload(d_gtg_pb, S.gtg.pb);
+        AtA.alloc(std::max<size_t>(B * (size_t)S.ata.nnz(), 1));
+        zinv.alloc(std::max<size_t>(B * m, 1)); dlt.alloc(B); crx.alloc(B * (size_t)n);
+        zinv.zero(st); dlt.zero(st);
+    }
     Lx.alloc(B * nnzL); Dv.alloc(B * S.nk); Dinv.alloc(B * S.nk); work.alloc(B * S.nk); fail.alloc(B); fail.zero(st);
     // multifrontal schedule (sparse_frontal.cuh)
     if (frontal) {
@@ -575,18 +765,29 @@ SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_per
 void SparseLdltBatchedKKT::copy_from(const SparseLdltBatchedKKT& o) {
     auto cp = [&](DevBuf<double>& d, const DevBuf<double>& s) { if (s.n) B200_CUDA(cudaMemcpyAsync(d.get(), s.get(), s.n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); };
     cp(PKx, o.PKx); cp(P_diag, o.P_diag); cp(Lx, o.Lx); cp(Dv, o.Dv); cp(Dinv, o.Dinv);
+    cp(AtA, o.AtA); cp(zinv, o.zinv); cp(dlt, o.dlt);
 }
-void SparseLdltBatchedKKT::scatter_static(int options) {   // kkt_full.hpp:212-251
+void SparseLdltBatchedKKT::scatter_static(int options) {   // kkt_full.hpp:212-251; update_data_impl of the condensed modes
     const int nnzPK = (int)S.PKi_rows.size();
-    if (options & 1) {
+    const bool elim_eq = S.mode & 1, elim_ineq = S.mode & 2;
+    if ((options & 1) && S.mode == 0) {          // condensed modes re-add P at every factor (update_kkt_cost_scalings)
         if (D->P.nnz) { dim3 g(ceil_div(D->P.nnz, 256), batch);
             B200_LAUNCH(ldlt_scatter_kernel, g, 256, 0, stream, d_P_to_PK.get(), D->P.nnz, nnzPK, D->Px.get(), PKx.get()); }
         sparse_extract_diag(*D, P_diag.get(), stream);   // zeros where P has no stored diagonal
     }
-    if ((options & 2) && D->AT.nnz) { dim3 g(ceil_div(D->AT.nnz, 256), batch);
-        B200_LAUNCH(ldlt_scatter_kernel, g, 256, 0, stream, d_AT_to_PK.get(), D->AT.nnz, nnzPK, D->ATx.get(), PKx.get()); }
-    if ((options & 4) && D->GT.nnz) { dim3 g(ceil_div(D->GT.nnz, 256), batch);
+    if ((options & 2) && D->AT.nnz) {
+        if (elim_eq) update_AtA();
+        else { dim3 g(ceil_div(D->AT.nnz, 256), batch);
+            B200_LAUNCH(ldlt_scatter_kernel, g, 256, 0, stream, d_AT_to_PK.get(), D->AT.nnz, nnzPK, D->ATx.get(), PKx.get()); }
+    }
+    if ((options & 4) && D->GT.nnz && !elim_ineq) { dim3 g(ceil_div(D->GT.nnz, 256), batch);
         B200_LAUNCH(ldlt_scatter_kernel, g, 256, 0, stream, d_GT_to_PK.get(), D->GT.nnz, nnzPK, D->GTx.get(), PKx.get()); }
+}
+void SparseLdltBatchedKKT::update_AtA() {       // update_AT_A (kkt_eq_eliminated.hpp:223-245)
+    const int nent = S.ata.nnz();
+    if (nent == 0) return;
+    dim3 g(ceil_div(nent, 128), batch);
+    B200_LAUNCH(ldlt_gram_values_kernel, g, 128, 0, stream, d_ata_ptr.get(), d_ata_pa.get(), d_ata_pb.get(), nent, D->AT.nnz, D->ATx.get(), AtA.get());
 }
 void SparseLdltBatchedKKT::update_data(int options) { scatter_static(options); }
 
@@ -595,7 +796,16 @@ void SparseLdltBatchedKKT::factor(const double* delta, const double* x_reg, cons
     const size_t nnzL = std::max<size_t>(S.Li.size(), 1);
     tic(T_ASSEMBLE);
     { dim3 g(ceil_div(nk, 256), batch);
-      B200_LAUNCH(ldlt_set_diag_kernel, g, 256, 0, stream, d_diagPK.get(), n, p, m, nnzPK, P_diag.get(), x_reg, delta, z_reg, PKx.get(), active); }
+      B200_LAUNCH(ldlt_set_diag_kernel, g, 256, 0, stream, d_diagPK.get(), n, S.pk, S.mk, S.mode ? 1 : 0, nnzPK, P_diag.get(), x_reg, delta, z_reg, PKx.get(), active); }
+    if (S.mode) {
+        const int nxx = S.Kp[n];
+        { dim3 g(ceil_div(nxx, 128), batch);
+          B200_LAUNCH(ldlt_cond_assemble_kernel, g, 128, 0, stream, nxx, d_xx_P.get(), d_xx_var.get(), d_xx_ata.get(), d_xx_gtg.get(), d_xx_target.get(),
+                      d_gtg_ptr.get(), d_gtg_pa.get(), d_gtg_pb.get(), D->GT.d_colof.get(), n, m, D->P.nnz, D->GT.nnz, S.ata.nnz(), nnzPK,
+                      D->Px.get(), D->GTx.get(), AtA.get(), x_reg, delta, z_reg, PKx.get(), active); }
+        { dim3 g(ceil_div(std::max(m, 1), 256), batch);
+          B200_LAUNCH(ldlt_store_scalings_kernel, g, 256, 0, stream, m, delta, z_reg, dlt.get(), zinv.get(), active); }
+    }
     if (frontal) {
         toc(T_ASSEMBLE);
         tic(T_FACTOR);
@@ -621,19 +831,34 @@ void SparseLdltBatchedKKT::factor(const double* delta, const double* x_reg, cons
     B200_LAUNCH(ldlt_fail_to_ok_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, ok, batch);
 }
 
-void SparseLdltBatchedKKT::solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) {   // sparse/kkt.hpp:107-147 (FULL)
+void SparseLdltBatchedKKT::solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) {   // sparse/kkt.hpp:107-176
+    const bool elim_eq = S.mode & 1, elim_ineq = S.mode & 2;
+    tic(T_SOLVE);
+    const double* srx = rx;
+    if (S.mode) {      // :113-134: rhs_x += G^T (Z^-1 rhs_z) [ineq eliminated], += delta^-1 A^T rhs_y [eq eliminated]
+        B200_CUDA(cudaMemcpyAsync(crx.get(), rx, sizeof(double) * (size_t)batch * n, cudaMemcpyDeviceToDevice, stream));
+        if (elim_ineq && m > 0) spmv_rows(D->GT, D->GTx.get(), 1.0, rz, m, crx.get(), 1, zinv.get(), nullptr, 0, batch, active, stream);
+        if (elim_eq && p > 0) spmv_rows(D->AT, D->ATx.get(), 1.0, ry, p, crx.get(), 1, nullptr, dlt.get(), 1, batch, active, stream);
+        srx = crx.get();
+    }
+    solve_core(srx, ry, rz, lx, ly, lz, active);
+    // :149-175: y = delta^-1 (A x - rhs_y), z = Z^-1 (G x - rhs_z)
+    if (elim_eq && p > 0) spmv_cols(D->AT, D->ATx.get(), 1.0, lx, n, ly, ry, 1.0, nullptr, dlt.get(), 1, batch, active, stream);
+    if (elim_ineq && m > 0) spmv_cols(D->GT, D->GTx.get(), 1.0, lx, n, lz, rz, 1.0, zinv.get(), nullptr, 0, batch, active, stream);
+    toc(T_SOLVE);
+}
+// LDL^T solve of the (possibly condensed) system; blocks eliminated by the mode are never touched (S.pk / S.mk = 0)
+void SparseLdltBatchedKKT::solve_core(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) {
     const int nk = S.nk;
     const size_t nnzL = std::max<size_t>(S.Li.size(), 1);
-    tic(T_SOLVE);
     if (frontal) {
         if (ring_solve) B200_LAUNCH(mf_solve_ring_kernel, batch, MF_T, ring_smem, stream, make_mf(*this), d_shdr.get(), ring_nblk, ring_pb, ring_rb, Lx.get(), Dinv.get(),
                                     rx, ry, rz, lx, ly, lz, active);
         else B200_LAUNCH(mf_solve_kernel, batch, MF_T, solve_smem, stream, make_mf(*this), (int)solve_x_in_smem, Lx.get(), Dinv.get(), rx, ry, rz, lx, ly, lz, work.get(), active);
-        toc(T_SOLVE);
         return;
     }
     dim3 gk(ceil_div(nk, 256), batch);
-    B200_LAUNCH(ldlt_gather_rhs_kernel, gk, 256, 0, stream, d_perm.get(), n, p, m, rx, ry, rz, work.get(), active);
+    B200_LAUNCH(ldlt_gather_rhs_kernel, gk, 256, 0, stream, d_perm.get(), n, S.pk, S.mk, rx, ry, rz, work.get(), active);
     const int nlev = (int)S.level_ptr.size() - 1;
     for (int l = 1; l < nlev; l++) {     // level 0 rows have empty row patterns
         const int c0 = S.level_ptr[l], nc = S.level_ptr[l + 1] - c0;
@@ -646,8 +871,7 @@ void SparseLdltBatchedKKT::solve(const double* rx, const double* ry, const doubl
         dim3 g(ceil_div(nc, 128), batch);
         B200_LAUNCH(ldlt_bwd_level_kernel, g, 128, 0, stream, d_level_cols.get() + c0, nc, d_Lp.get(), d_Li.get(), nnzL, nk, Lx.get(), work.get(), active);
     }
-    B200_LAUNCH(ldlt_scatter_lhs_kernel, gk, 256, 0, stream, d_perm.get(), n, p, m, work.get(), lx, ly, lz, active);
-    toc(T_SOLVE);
+    B200_LAUNCH(ldlt_scatter_lhs_kernel, gk, 256, 0, stream, d_perm.get(), n, S.pk, S.mk, work.get(), lx, ly, lz, active);
 }
 void SparseLdltBatchedKKT::eval_P_x(double alpha, const double* x, double* z, const int* active) { spmv_sym_upper(D->P, D->Px.get(), alpha, x, z, batch, active, stream); }
 void SparseLdltBatchedKKT::eval_A(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) {

@@ -23,6 +23,13 @@ namespace b200 {
 
 struct LdltSymbolic {   // host
     int n = 0, p = 0, m = 0, nk = 0;
+    int mode = 0, pk = 0, mk = 0;                 // KKTMode (kkt_fwd.hpp:15-21); sizes of the y / z blocks KEPT in the KKT (0 when eliminated)
+    // condensed modes: contribution lists of upper(A^T A) / upper(G^T Z^-1 G) and, per entry of the top-left block of K
+    // (K value index < Kp[n]), where its summands come from (kkt_all_eliminated.hpp:108-160)
+    struct Gram { std::vector<int> colp, rows, ptr, pa, pb; int nnz() const { return (int)rows.size(); } };
+    Gram ata, gtg;
+    std::vector<int> xx_P, xx_var, xx_ata, xx_gtg; // P value index / variable (diagonal entries) / ata entry / gtg entry, -1 = none
+    static void build_gram(const Pattern& MT, Gram& g);
     std::vector<int> perm, iperm;                 // perm[new] = old ; iperm[old] = new   (ordering.P / P_inv)
     // unpermuted KKT (upper CSC) and the maps of kkt_full.hpp:39-170
     std::vector<int> Kp, Ki;
@@ -44,7 +51,7 @@ struct LdltSymbolic {   // host
     std::vector<long long> upd_off;               // per supernode: offset of its update matrix (us x us, lower, ld = us) on the per-instance stack
     long long upd_total = 0;                      // stack size in doubles
     std::string error;
-    bool analyse(const Pattern& P, const Pattern& AT, const Pattern& GT, const int* user_perm);
+    bool analyse(const Pattern& P, const Pattern& AT, const Pattern& GT, const int* user_perm, int mode = 0);
     double nnzL_exact = -1.0, flops_exact = -1.0; // of the unpadded pattern (what the reference's LDLt would store / compute)
     double nnzL() const { return nnzL_exact >= 0 ? nnzL_exact : (Lp.empty() ? 0.0 : (double)Lp.back()); }
     double factor_flops() const;                  // sum_j (c_j^2 + 2 c_j), SURVEY 8(d)
@@ -54,7 +61,7 @@ std::vector<int> minimum_degree_ordering(int n, const std::vector<int>& colptr, 
 
 class SparseLdltBatchedKKT : public BatchedKKT {
 public:
-    SparseLdltBatchedKKT(SparseData* data, const int* user_perm, cudaStream_t st);
+    SparseLdltBatchedKKT(SparseData* data, const int* user_perm, cudaStream_t st, int mode = 0);
     void update_data(int options) override;
     void factor(const double* delta, const double* x_reg, const double* z_reg, const int* active, int* ok) override;
     void solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) override;
@@ -78,6 +85,11 @@ public:
     DevBuf<double> Lx, Dv, Dinv;   // [batch][nnz(L)], [batch][nk] x2
     DevBuf<double> work;       // [batch][nk] permuted rhs / solution
     DevBuf<int> fail;
+    // condensed modes (sparse_ldlt_eq_cond / _ineq_cond / _cond)
+    DevBuf<int> d_xx_P, d_xx_var, d_xx_ata, d_xx_gtg, d_xx_target, d_ata_ptr, d_ata_pa, d_ata_pb, d_gtg_ptr, d_gtg_pa, d_gtg_pb;
+    DevBuf<double> AtA;        // [batch][nnz(upper(A^T A))], recomputed on update_data(A)
+    DevBuf<double> zinv, dlt;  // [batch][m] z_reg^-1 and [batch] delta of the last factor() (m_z_reg_inv / m_delta, sparse/kkt.hpp:36-38)
+    DevBuf<double> crx;        // [batch][n] condensed rhs_x
     // multifrontal path
     bool frontal = true;       // B200_LDLT_LEVELS=1 selects the level-scheduled simplicial kernels instead
     int front_smem_rows = 0;   // fronts up to this many rows live in shared memory, larger ones in `bigfront`
@@ -91,6 +103,8 @@ public:
     DevBuf<double> upd, bigfront, panel;   // [batch][upd_total], [batch][fmax^2] and [batch][2 fmax NB] (only if fmax > front_smem_rows)
 private:
     void scatter_static(int options);
+    void update_AtA();
+    void solve_core(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active);
 };
 
 }  // namespace b200

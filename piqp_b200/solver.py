@@ -115,7 +115,8 @@ class SparseSolverBatched(_BatchedBase):
         self._h = C.c_void_p()
         self.settings = Settings()
         self._L.b200qp_set_default_settings_sparse(C.byref(self.settings))
-        self.settings.kkt_solver = {"sparse_ldlt": 1, "sparse_multistage": 5}[kkt_solver]
+        self.settings.kkt_solver = {"sparse_ldlt": 1, "sparse_ldlt_eq_cond": 2, "sparse_ldlt_ineq_cond": 3, "sparse_ldlt_cond": 4,
+                                    "sparse_multistage": 5}[kkt_solver]      # piqp::KKTSolver (settings.hpp:18-26)
         self.device = device
         self.batch = self.n = self.p = self.m = 0
 

@@ -124,3 +124,35 @@ def test_sparse_ldlt_factor_solve(oracle):
     assert np.allclose(G @ lx - z_reg * lz, rz, atol=1e-8)
     nnzL, flops = s.ldlt_stats()
     assert nnzL > 0 and flops > 0
+
+
+@pytest.mark.parametrize("solver", ["sparse_ldlt_eq_cond", "sparse_ldlt_ineq_cond", "sparse_ldlt_cond"])
+def test_condensed_modes_agree_with_full_kkt(oracle, solver):
+    """TEST_P over the sparse backends (tests/src/sparse/solver_test.cpp:443-451): every KKTMode solves the same QPs;
+    backend level: the condensed solve satisfies the FULL 3x3 system (kkt_*_eliminated tests, tests/src/sparse/kkt_test.cpp:88-162)"""
+    import scipy.sparse as sp
+    from piqp_b200.synth import sparse_strongly_convex_qp
+    for dims in [(20, 10, 12), (60, 20, 30), (64, 10, 0), (20, 0, 12)]:
+        q = sparse_strongly_convex_qp(*dims, 0.15, seed=dims[0])
+        A = q["A"] if dims[1] else None; G = q["G"] if dims[2] else None
+        args = (q["P"], q["c"], A, q["b"] if dims[1] else None, G, q["h_l"] if dims[2] else None, q["h_u"] if dims[2] else None, q["x_l"], q["x_u"])
+        full = oracle.SparseSolver(oracle.default_settings(kkt_solver="sparse_ldlt")); full.setup(*args); assert full.solve() == 1
+        cond = oracle.SparseSolver(oracle.default_settings(kkt_solver=solver)); cond.setup(*args); assert cond.solve() == 1
+        rf, rc = full.result(), cond.result()
+        assert rc.info.iter == rf.info.iter
+        assert np.abs(rc.x - rf.x).max() <= 1e-8 * max(1.0, np.abs(rf.x).max())
+        n, p, m = dims
+        rng = np.random.default_rng(1)
+        x_reg = rng.uniform(0.5, 1.5, n); z_reg = rng.uniform(0.5, 2.0, m); delta = 0.7
+        assert cond.backend_factor(delta, x_reg, z_reg) == 1 and full.backend_factor(delta, x_reg, z_reg) == 1
+        r = (rng.standard_normal(n), rng.standard_normal(p), rng.standard_normal(m))
+        for a, b in zip(cond.backend_solve(*r), full.backend_solve(*r)):
+            if len(b):
+                assert np.abs(a - b).max() <= 1e-9 * max(1.0, np.abs(b).max())
+    # known-answer QP of the reference (sparse/solver_test.cpp:67-107)
+    from helpers import simple_qp
+    q1 = simple_qp()
+    s = oracle.SparseSolver(oracle.default_settings(kkt_solver=solver))
+    s.setup(sp.csc_matrix(q1["P"]), q1["c"], sp.csc_matrix(q1["A"]), q1["b"], sp.csc_matrix(q1["G"]), q1["h_l"], q1["h_u"], q1["x_l"], q1["x_u"])
+    assert s.solve() == 1
+    assert np.allclose(s.result().x, [0.4285714, 0.2142857], atol=1e-6)

@@ -77,3 +77,56 @@ def test_symbolic_rejects_bad_permutation(oracle):
     bad = np.zeros(17, dtype=np.int32)
     with pytest.raises(RuntimeError, match="invalid permutation"):
         _symbolic(P, AT, GT, perm=bad)
+
+
+COND = {"sparse_ldlt_eq_cond": 1, "sparse_ldlt_ineq_cond": 2, "sparse_ldlt_cond": 3}
+
+
+@pytest.mark.parametrize("solver", list(COND))
+@pytest.mark.parametrize("name,args", list(_cases()))
+def test_condensed_mode_symbolic_matches_oracle(oracle, name, args, solver):
+    """KKT pattern of the condensed modes (kkt_{eq,ineq,all}_eliminated.hpp create_kkt_matrix: structural union of P, I,
+    A^T A, G^T G in the top-left block) -> same nnz(KKT), and same nnz(L) / flops as the oracle under the same permutation"""
+    from piqp_b200.backend import sparse_ldlt_symbolic
+    mode = COND[solver]
+    o = oracle.SparseSolver(oracle.default_settings(kkt_solver=solver)); o.setup(*args)
+    P, AT, GT = o.scaled_matrices()
+    n, p, m = P.shape[0], AT.shape[1], GT.shape[1]
+    A = sp.csc_matrix(AT.T) if p else None
+    G = sp.csc_matrix(GT.T) if m else None
+    mine = sparse_ldlt_symbolic(P, A, G, mode=mode)
+    nk = n + (0 if mode & 1 else p) + (0 if mode & 2 else m)
+    assert sorted(mine["perm"].tolist()) == list(range(nk))
+    # structural pattern of the top-left block
+    pat = lambda M: sp.csc_matrix((np.ones(M.nnz), M.indices, M.indptr), shape=M.shape)
+    Pu = pat(sp.csc_matrix(sp.triu(sp.csc_matrix(P))))
+    top = Pu + sp.identity(n, format="csc")
+    if mode & 1 and p:
+        top = top + sp.triu(pat(sp.csc_matrix(AT)) @ pat(sp.csc_matrix(AT)).T)
+    if mode & 2 and m:
+        top = top + sp.triu(pat(sp.csc_matrix(GT)) @ pat(sp.csc_matrix(GT)).T)
+    expect = sp.csc_matrix(top).nnz + (0 if mode & 1 else AT.nnz + p) + (0 if mode & 2 else GT.nnz + m)
+    assert mine["nnz_kkt"] == expect
+    o2 = oracle.SparseSolver(oracle.default_settings(kkt_solver=solver), kkt_perm=mine["perm"]); o2.setup(*args)
+    nnzL, flops = o2.ldlt_stats()
+    assert nnzL == mine["nnz_L"] and flops == pytest.approx(mine["flops"], rel=1e-12)
+    assert mine["nnz_L"] <= 1.3 * o.ldlt_stats()[0] + 16
+    assert mine["supernodes"] >= 1 and 1 <= mine["largest_front"] <= nk
+
+
+def test_approximate_degree_ordering_is_as_good_as_exact_and_scales(monkeypatch):
+    """the quotient-graph approximate minimum degree (the product's default) against the exact-external-degree version
+    kept for cross-checks: fill within a few percent, and a 6 000-variable KKT is ordered in seconds"""
+    import time
+    from piqp_b200.backend import sparse_ldlt_symbolic
+    q = sparse_strongly_convex_qp(600, 200, 300, 0.01, seed=9)
+    amd = sparse_ldlt_symbolic(q["P"], q["A"], q["G"])
+    monkeypatch.setenv("B200_ORDERING", "exact")
+    exact = sparse_ldlt_symbolic(q["P"], q["A"], q["G"])
+    monkeypatch.delenv("B200_ORDERING")
+    assert amd["nnz_L"] <= 1.1 * exact["nnz_L"]
+    q = sparse_strongly_convex_qp(3000, 1500, 1500, 0.005, seed=9)
+    t0 = time.time()
+    big = sparse_ldlt_symbolic(q["P"], q["A"], q["G"])
+    assert time.time() - t0 < 30.0
+    assert sorted(big["perm"].tolist()) == list(range(6000))
