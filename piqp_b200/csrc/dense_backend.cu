@@ -408,6 +408,23 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
     }
 }
 
+void dense_syrk_sub_scaled(const double* A, long long strideA, int lda, const double* w, long long stridew, double* C, long long strideC, int ldc,
+                           int n, int K, int batch, const int* active, cudaStream_t st) {
+    if (n <= 0 || K <= 0 || batch <= 0) return;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    if (dev != configured_dev) { set_smem(gemm_nt_tile_kernel<EPI_SUB, true>, GEMM_SMEM); configured_dev = dev; }
+    GemmArgs g{};
+    g.A = A; g.strideA = strideA; g.lda = lda;
+    g.B = A; g.strideB = strideA; g.ldb = lda;
+    g.w = w; g.stridew = stridew;
+    g.C = C; g.strideC = strideC; g.ldc = ldc;
+    g.n = n; g.rows_valid = n + (n & 1); g.K = K; g.nt = ceil_div(n, TILE); g.tj_fixed = -1; g.tiles = g.nt * (g.nt + 1) / 2;
+    g.active = active;
+    B200_LAUNCH((gemm_nt_tile_kernel<EPI_SUB, true>), (unsigned)((size_t)g.tiles * batch), GEMM_THREADS, GEMM_SMEM, st, g);
+}
+
 void DenseBatchedKKT::copy_from(const DenseBatchedKKT& o) {
     auto cp = [&](DevBuf<double>& d, const DevBuf<double>& s) { if (s.n) B200_CUDA(cudaMemcpyAsync(d.get(), s.get(), s.n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); };
     cp(K, o.K); cp(AtA, o.AtA); cp(zinv, o.zinv); cp(delta, o.delta); cp(Linv, o.Linv);

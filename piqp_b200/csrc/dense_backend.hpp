@@ -85,4 +85,11 @@ private:
     void assemble_ozaki(const double* x_reg, const int* active);
 };
 
+// C (lower 128 x 128 tiles of an n x n matrix, ld = ldc) -= A diag(w) A^T for every instance of a batch, with the DMMA tile
+// kernel of the dense backend (gemm_nt_tile_kernel<EPI_SUB, true>).  A: n x K column-major (lda), w: K scale factors.
+// A, C and their leading dimensions must keep 16-byte alignment of row pairs (even row offsets, even ld); rows up to
+// n + (n & 1) of A must exist in memory.  Used by the sparse backend's whole-GPU blocked LDL^T of large fronts.
+void dense_syrk_sub_scaled(const double* A, long long strideA, int lda, const double* w, long long stridew, double* C, long long strideC, int ldc,
+                           int n, int K, int batch, const int* active, cudaStream_t st);
+
 }  // namespace b200

@@ -1,6 +1,7 @@
 // piqp_b200/csrc/sparse_ldlt_backend.cu -- see sparse_ldlt_backend.hpp
 #include "sparse_ldlt_backend.hpp"
 #include "sparse_frontal.cuh"
+#include "sparse_wide.cuh"
 #include <cstdlib>
 #include <string>
 #include <algorithm>
@@ -661,6 +662,174 @@ static MfDev make_mf(const SparseLdltBatchedKKT& K) {
     return M;
 }
 
+// =====================================================================================================
+// whole-GPU schedule (sparse_wide.cuh)
+// =====================================================================================================
+void SparseLdltBatchedKKT::build_wide() {
+    const int nsup = S.nsup, nk = S.nk;
+    auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    wide_sb = std::min(128, std::max(2, knob("B200_WIDE_SB", 128)));
+    const int ws_min = std::max(2, knob("B200_WIDE_WS", 64));          // supernodes at least this wide are solved blocked over the GPU
+    std::vector<int> sup_of(nk, 0), psup(nsup, -1), slevel(nsup, 0);
+    for (int s2 = 0; s2 < nsup; s2++) for (int j = S.sup_ptr[s2]; j < S.sup_ptr[s2 + 1]; j++) sup_of[j] = s2;
+    int maxl = 0;
+    for (int s2 = 0; s2 < nsup; s2++) {          // postorder: children come before their parent
+        const int j1 = S.sup_ptr[s2 + 1] - 1;
+        if (S.etree[j1] >= 0) { psup[s2] = sup_of[S.etree[j1]]; slevel[psup[s2]] = std::max(slevel[psup[s2]], slevel[s2] + 1); }
+        maxl = std::max(maxl, slevel[s2]);
+    }
+    // every supernode keeps its own update slot (siblings of different subtrees are in flight at the same time)
+    std::vector<long long> off(nsup, 0);
+    upd_total_w = 0;
+    for (int s2 = 0; s2 < nsup; s2++) { const long long us = S.rel_ptr[s2 + 1] - S.rel_ptr[s2]; off[s2] = upd_total_w; upd_total_w += us * us; }
+    std::vector<int> crecw((size_t)4 * std::max<size_t>(S.child_idx.size(), 1), 0);
+    for (size_t c = 0; c < S.child_idx.size(); c++) {
+        const int cs = S.child_idx[c];
+        crecw[4 * c] = S.rel_ptr[cs + 1] - S.rel_ptr[cs]; crecw[4 * c + 1] = S.rel_ptr[cs];
+        crecw[4 * c + 2] = (int)(unsigned)(off[cs] & 0xffffffffll); crecw[4 * c + 3] = (int)(off[cs] >> 32);
+    }
+    upload(d_crecw, crecw);
+    d_upd_off_w.alloc(std::max<size_t>(nsup, 1));
+    B200_CUDA(cudaMemcpy(d_upd_off_w.get(), off.data(), (size_t)nsup * sizeof(long long), cudaMemcpyHostToDevice));
+    upd.alloc((size_t)batch * (size_t)std::max<long long>(upd_total_w, 1));
+    // ---- steps by level
+    std::vector<std::vector<int>> by_level(maxl + 1);
+    for (int s2 = 0; s2 < nsup; s2++) by_level[slevel[s2]].push_back(s2);
+    std::vector<int> list_f, list_s, pull_ptr, pull_child, pull_cc;
+    wf_steps.clear(); ws_steps.clear(); wfronts.clear(); wf_smem.clear();
+    front_stride = 0;
+    size_t small_smem_max = 0;
+    for (int l = 0; l <= maxl; l++) {
+        const int fb = (int)list_f.size(), sb0 = (int)list_s.size();
+        int fmax_l = 0;
+        for (int s2 : by_level[l]) {
+            const int ws = S.sup_ptr[s2 + 1] - S.sup_ptr[s2], us = S.rel_ptr[s2 + 1] - S.rel_ptr[s2], f = ws + us;
+            if (f <= front_smem_rows) { list_f.push_back(s2); fmax_l = std::max(fmax_l, f); }
+            if (ws < ws_min) list_s.push_back(s2);
+        }
+        if ((int)list_f.size() > fb) {
+            const int fpad = (fmax_l + 1) & ~1;
+            const size_t smem = sizeof(double) * ((size_t)((fpad + fpad / 2 + 3) & ~3) + (size_t)fmax_l * fmax_l);
+            wf_steps.push_back({0, fb, (int)list_f.size() - fb, fpad});
+            wf_smem.push_back(smem); small_smem_max = std::max(small_smem_max, smem);
+        }
+        if ((int)list_s.size() > sb0) ws_steps.push_back({0, sb0, (int)list_s.size() - sb0, 0});
+        for (int s2 : by_level[l]) {
+            const int j0 = S.sup_ptr[s2], j1 = S.sup_ptr[s2 + 1] - 1, ws = j1 - j0 + 1, us = S.rel_ptr[s2 + 1] - S.rel_ptr[s2], f = ws + us;
+            if (f > front_smem_rows) {
+                if (us > 65535) throw std::runtime_error("sparse_ldlt: update matrix too large for the wide schedule");
+                WFront w{};
+                w.s = s2; w.j0 = j0; w.ws = ws; w.us = us; w.f = f; w.shift = ws & 1; w.ld = round_up(f + w.shift, 8); w.lp0 = S.Lp[j0];
+                w.ab = S.asm_ptr[s2]; w.an = S.asm_ptr[s2 + 1] - S.asm_ptr[s2]; w.off = off[s2];
+                w.nchild = S.child_ptr[s2 + 1] - S.child_ptr[s2];
+                w.pull_begin = (int)pull_ptr.size();
+                // pull lists: for every front column, the (child record, child column) pairs that map onto it, children in order
+                std::vector<int> cnt(f + 1, 0);
+                for (int c = S.child_ptr[s2]; c < S.child_ptr[s2 + 1]; c++) { const int cs = S.child_idx[c];
+                    for (int t = S.rel_ptr[cs]; t < S.rel_ptr[cs + 1]; t++) cnt[S.rel_idx[t] + 1]++; }
+                const int base = (int)pull_child.size();
+                for (int c = 0; c < f; c++) cnt[c + 1] += cnt[c];
+                for (int c = 0; c <= f; c++) pull_ptr.push_back(base + cnt[c]);
+                pull_child.resize(base + cnt[f]); pull_cc.resize(base + cnt[f]);
+                std::vector<int> fillp(cnt.begin(), cnt.end() - 1);
+                for (int c = S.child_ptr[s2]; c < S.child_ptr[s2 + 1]; c++) { const int cs = S.child_idx[c];
+                    for (int t = S.rel_ptr[cs]; t < S.rel_ptr[cs + 1]; t++) { const int q = base + fillp[S.rel_idx[t]]++; pull_child[q] = c; pull_cc[q] = t - S.rel_ptr[cs]; } }
+                front_stride = std::max(front_stride, (long long)w.ld * f);
+                wf_steps.push_back({1, (int)wfronts.size(), 0, 0});
+                wfronts.push_back(w);
+            }
+            if (ws >= ws_min) ws_steps.push_back({1, s2, 0, 0});
+        }
+    }
+    upload(d_wlist_f, list_f); upload(d_wlist_s, list_s); upload(d_pull_ptr, pull_ptr); upload(d_pull_child, pull_child); upload(d_pull_cc, pull_cc);
+    if (front_stride > 0) bigfront.alloc((size_t)batch * (size_t)front_stride);
+    wtmp.alloc((size_t)batch * wide_sb); wcounter.alloc(batch);
+    B200_CUDA(cudaMemset(wcounter.get(), 0, sizeof(unsigned) * batch));
+    const size_t sbs = (size_t)wide_sb;
+    B200_CUDA(cudaFuncSetAttribute(mfw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(small_smem_max, 48 * 1024)));
+    B200_CUDA(cudaFuncSetAttribute(mfw_fwd_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sizeof(double) * (sbs * (sbs + 1) + 3 * sbs), 48 * 1024)));
+    B200_CUDA(cudaFuncSetAttribute(mfw_bwd_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sizeof(double) * (sbs * (sbs + 1) + 2 * sbs + 32), 48 * 1024)));
+    if (getenv("B200_DEBUG_SYMBOLIC"))
+        fprintf(stderr, "[sparse_ldlt wide] levels=%d factor steps=%zu (HBM fronts %zu) solve steps=%zu upd_total=%lld front_stride=%lld\n", maxl + 1, wf_steps.size(),
+                wfronts.size(), ws_steps.size(), upd_total_w, front_stride);
+}
+
+void SparseLdltBatchedKKT::factor_wide(const int* active) {
+    const MfDev M = make_mf(*this);
+    const size_t nnzL = std::max<size_t>(S.Li.size(), 1);
+    const int nk = S.nk;
+    B200_LAUNCH(ldlt_clear_fail_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, batch);
+    size_t small_i = 0;
+    for (const WStep& st : wf_steps) {
+        if (st.kind == 0) {
+            dim3 g(st.b, batch);
+            B200_LAUNCH(mfw_small_kernel, g, MF_T, wf_smem[small_i], stream, M, d_wlist_f.get() + st.a, st.c, d_crecw.get(), d_upd_off_w.get(), PKx.get(), Lx.get(), Dv.get(),
+                        Dinv.get(), upd.get(), upd_total_w, fail.get(), active);
+            small_i++;
+            continue;
+        }
+        const WFront& w = wfronts[st.a];
+        double* F = bigfront.get();
+        const long long count = (long long)w.ld * w.f;
+        { dim3 g((unsigned)std::min<long long>((count / 2 + 255) / 256, 148 * 16), batch); B200_LAUNCH(mfw_zero_kernel, g, 256, 0, stream, F, front_stride, count, active); }
+        if (w.an > 0) { dim3 g(ceil_div(w.an, 256), batch);
+            B200_LAUNCH(mfw_scatter_kernel, g, 256, 0, stream, F, front_stride, w.ld, w.shift, w.f, d_asm_pos.get(), PKx.get(), M.nnzPK, w.ab, w.an, active); }
+        if (w.nchild > 0) { dim3 g(ceil_div(w.f, MW_T / 32), batch);
+            B200_LAUNCH(mfw_pull_kernel, g, MW_T, 0, stream, F, front_stride, w.ld, w.shift, w.f, d_pull_ptr.get() + w.pull_begin, d_pull_child.get(), d_pull_cc.get(),
+                        d_crecw.get(), d_rel_idx.get(), upd.get(), upd_total_w, active); }
+        int k0 = 0, nb = ((w.ws - 1) % MW_NB) + 1;       // first panel takes the remainder: every later r0 has the parity of ws (16-byte aligned row pairs)
+        while (k0 < w.ws) {
+            const int r0 = k0 + nb, R = w.f - r0;
+            { dim3 g(std::max(1, ceil_div(R, MW_T)), batch);
+              B200_LAUNCH(mfw_panel_kernel, g, MW_T, 0, stream, F, front_stride, w.ld, w.shift, w.f, k0, nb, w.j0, w.lp0, Lx.get(), nnzL, Dv.get(), Dinv.get(), nk, fail.get(), active); }
+            if (R > 0) dense_syrk_sub_scaled(F + w.shift + r0 + (size_t)k0 * w.ld, front_stride, w.ld, Dv.get() + w.j0 + k0, nk,
+                                             F + w.shift + r0 + (size_t)r0 * w.ld, front_stride, w.ld, R, nb, batch, active, stream);
+            k0 += nb; nb = MW_NB;
+        }
+        if (w.us > 0) { dim3 g(ceil_div(w.us, 128), w.us, batch);
+            B200_LAUNCH(mfw_schur_kernel, g, 128, 0, stream, F, front_stride, w.ld, w.shift, w.ws, w.us, upd.get(), upd_total_w, w.off, active); }
+    }
+}
+
+void SparseLdltBatchedKKT::solve_wide(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) {
+    const int nk = S.nk, sb = wide_sb;
+    const size_t nnzL = std::max<size_t>(S.Li.size(), 1);
+    dim3 gk(ceil_div(nk, 256), batch);
+    B200_LAUNCH(ldlt_gather_rhs_kernel, gk, 256, 0, stream, d_perm.get(), n, S.pk, S.mk, rx, ry, rz, work.get(), active);
+    const size_t fsm = sizeof(double) * ((size_t)sb * (sb + 1) + 3 * (size_t)sb), bsm = sizeof(double) * ((size_t)sb * (sb + 1) + 2 * (size_t)sb + 32);
+    for (const WStep& st : ws_steps) {           // L y = b
+        if (st.kind == 0) {
+            dim3 g(ceil_div(st.b, MW_T / 32), batch);
+            B200_LAUNCH(mfw_fwd_small_kernel, g, MW_T, 0, stream, d_wlist_s.get() + st.a, st.b, d_hdr.get(), d_Rp.get(), d_Rcol.get(), d_Rpos.get(), Lx.get(), nnzL, work.get(), nk, active);
+            continue;
+        }
+        const int s2 = st.a, j0 = S.sup_ptr[s2], ws = S.sup_ptr[s2 + 1] - j0, us = S.rel_ptr[s2 + 1] - S.rel_ptr[s2], f = ws + us, lp0 = S.Lp[j0];
+        { dim3 g(ceil_div(ws, MW_T / 32), batch);
+          B200_LAUNCH(mfw_fwd_pull_kernel, g, MW_T, 0, stream, j0, ws, d_Rp.get(), d_Rcol.get(), d_Rpos.get(), Lx.get(), nnzL, work.get(), nk, active); }
+        const int nblk = ceil_div(ws, sb);
+        { dim3 g(1, batch); B200_LAUNCH(mfw_fwd_block_kernel, g, MW_T, fsm, stream, j0, ws, f, lp0, 0, 0, sb, Lx.get(), nnzL, work.get(), nk, active); }
+        for (int t = 0; t + 1 < nblk; t++) { dim3 g(nblk - 1 - t, batch);
+            B200_LAUNCH(mfw_fwd_block_kernel, g, MW_T, fsm, stream, j0, ws, f, lp0, t * sb, sb, sb, Lx.get(), nnzL, work.get(), nk, active); }
+    }
+    B200_LAUNCH(ldlt_dscale_kernel, gk, 256, 0, stream, nk, Dinv.get(), work.get(), active);
+    for (size_t i = ws_steps.size(); i-- > 0;) {   // L^T x = y
+        const WStep& st = ws_steps[i];
+        if (st.kind == 0) {
+            dim3 g(ceil_div(st.b, MW_T / 32), batch);
+            B200_LAUNCH(mfw_bwd_small_kernel, g, MW_T, 0, stream, d_wlist_s.get() + st.a, st.b, d_hdr.get(), d_Lp.get(), d_Li.get(), Lx.get(), nnzL, work.get(), nk, active);
+            continue;
+        }
+        const int s2 = st.a, j0 = S.sup_ptr[s2], j1 = S.sup_ptr[s2 + 1] - 1, ws = j1 - j0 + 1, us = S.rel_ptr[s2 + 1] - S.rel_ptr[s2], f = ws + us, lp0 = S.Lp[j0];
+        const int nblk = ceil_div(ws, sb);
+        for (int t = nblk - 1; t >= 0; t--) {
+            const int c0 = t * sb, cn = std::min(sb, ws - c0);
+            dim3 g(cn, batch);
+            B200_LAUNCH(mfw_bwd_block_kernel, g, MW_T, bsm, stream, j0, ws, f, lp0, d_Li.get() + S.Lp[j1], c0, cn, sb, Lx.get(), nnzL, work.get(), nk, wtmp.get(), wcounter.get(), active);
+        }
+    }
+    B200_LAUNCH(ldlt_scatter_lhs_kernel, gk, 256, 0, stream, d_perm.get(), n, S.pk, S.mk, work.get(), lx, ly, lz, active);
+}
+
 SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_perm, cudaStream_t st, int mode) : D(data) {
     batch = D->batch; n = D->n; p = D->p; m = D->m; stream = st;
     if (mode < 0 || mode > 3) throw std::runtime_error("sparse_ldlt: KKTMode must be 0..3");
@@ -709,27 +878,34 @@ SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_per
         upload(d_hdr, hdr); upload(d_crec, crec); upload(d_rel_idx, S.rel_idx); upload(d_asm_pos, S.asm_pos);
         d_upd_off.alloc(std::max<size_t>(S.upd_off.size(), 1));
         if (!S.upd_off.empty()) B200_CUDA(cudaMemcpy(d_upd_off.get(), S.upd_off.data(), S.upd_off.size() * sizeof(long long), cudaMemcpyHostToDevice));
-        upd.alloc(B * (size_t)std::max<long long>(S.upd_total, 1));
+        // few large QPs: spread each factorisation / solve over the whole GPU (sparse_wide.cuh)
+        wide = batch <= 4 && S.fmax >= 512;
+        if (const char* e = getenv("B200_LDLT_WIDE")) wide = atoi(e) != 0;
+        if (!wide) upd.alloc(B * (size_t)std::max<long long>(S.upd_total, 1));
         const size_t fpad = (size_t)((S.fmax + 1) & ~1);
         const size_t smem_cap = 200 * 1024, lcol_bytes = sizeof(double) * ((fpad + fpad / 2 + 3) & ~(size_t)3);      // lcol (doubles) + relbuf (ints)
         const size_t big_scratch = sizeof(double) * (size_t)(2 * MF_TS * MF_NB + MF_NB * (MF_NB + 2));
-        if (lcol_bytes + big_scratch > smem_cap) throw std::runtime_error("sparse_ldlt: a front of this size is not supported by this build");
+        if (!wide && lcol_bytes + big_scratch > smem_cap) throw std::runtime_error("sparse_ldlt: a front of this size is not supported by this build");
         int fs = S.fmax;
-        while ((size_t)fs * fs * sizeof(double) + lcol_bytes > smem_cap) fs--;
+        if (wide) { while (sizeof(double) * ((size_t)fs * fs + (size_t)(((fs + 1) & ~1) * 3 / 2 + 3)) > smem_cap) fs--; }      // per-level scratch: sized by the level's own fronts
+        else while ((size_t)fs * fs * sizeof(double) + lcol_bytes > smem_cap) fs--;
         if (const char* e = getenv("B200_FRONT_SMEM_ROWS")) { const int v = atoi(e); if (v > 0) fs = std::min(fs, v); }     // tests: force the blocked HBM-front path
         front_smem_rows = fs;
         factor_smem = lcol_bytes + (size_t)fs * fs * sizeof(double);
-        if (S.fmax > fs) {
+        if (S.fmax > fs && !wide) {
             factor_smem = std::max(factor_smem, lcol_bytes + big_scratch);
             bigfront.alloc(B * (size_t)S.fmax * S.fmax); panel.alloc(B * 2 * (size_t)S.fmax * MF_NB);
         }
+        if (wide) build_wide();
         solve_x_in_smem = (size_t)S.nk * sizeof(double) <= smem_cap;
         solve_smem = solve_x_in_smem ? (size_t)S.nk * sizeof(double) : 0;
-        B200_CUDA(cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(factor_smem, 48 * 1024)));
-        B200_CUDA(cudaFuncSetAttribute(mf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(solve_smem, 48 * 1024)));
+        if (!wide) {
+            B200_CUDA(cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(factor_smem, 48 * 1024)));
+            B200_CUDA(cudaFuncSetAttribute(mf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(solve_smem, 48 * 1024)));
+        }
         // streamed solve (mf_solve_ring_kernel): x + a double-buffered panel + row indices in shared memory
         ring_solve = false;
-        if (solve_x_in_smem && !getenv("B200_LDLT_SIMPLE_SOLVE")) {
+        if (!wide && solve_x_in_smem && !getenv("B200_LDLT_SIMPLE_SOLVE")) {
             const size_t xbytes = sizeof(double) * (size_t)((S.nk + 1) & ~1);
             const size_t rb = (size_t)((S.fmax + 3) & ~3);
             const size_t avail = smem_cap > xbytes + 2 * rb * sizeof(int) + 1024 ? smem_cap - xbytes - 2 * rb * sizeof(int) - 1024 : 0;
@@ -809,7 +985,8 @@ void SparseLdltBatchedKKT::factor(const double* delta, const double* x_reg, cons
     if (frontal) {
         toc(T_ASSEMBLE);
         tic(T_FACTOR);
-        B200_LAUNCH(mf_factor_kernel, batch, MF_T, factor_smem, stream, make_mf(*this), PKx.get(), Lx.get(), Dv.get(), Dinv.get(), upd.get(), bigfront.get(), panel.get(), fail.get(), active);
+        if (wide) factor_wide(active);
+        else B200_LAUNCH(mf_factor_kernel, batch, MF_T, factor_smem, stream, make_mf(*this), PKx.get(), Lx.get(), Dv.get(), Dinv.get(), upd.get(), bigfront.get(), panel.get(), fail.get(), active);
         toc(T_FACTOR);
         B200_LAUNCH(ldlt_fail_to_ok_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, ok, batch);
         return;
@@ -851,6 +1028,7 @@ void SparseLdltBatchedKKT::solve(const double* rx, const double* ry, const doubl
 void SparseLdltBatchedKKT::solve_core(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) {
     const int nk = S.nk;
     const size_t nnzL = std::max<size_t>(S.Li.size(), 1);
+    if (frontal && wide) { solve_wide(rx, ry, rz, lx, ly, lz, active); return; }
     if (frontal) {
         if (ring_solve) B200_LAUNCH(mf_solve_ring_kernel, batch, MF_T, ring_smem, stream, make_mf(*this), d_shdr.get(), ring_nblk, ring_pb, ring_rb, Lx.get(), Dinv.get(),
                                     rx, ry, rz, lx, ly, lz, active);

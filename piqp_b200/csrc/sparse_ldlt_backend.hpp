@@ -101,7 +101,23 @@ public:
     size_t ring_smem = 0;
     DevBuf<long long> d_upd_off;
     DevBuf<double> upd, bigfront, panel;   // [batch][upd_total], [batch][fmax^2] and [batch][2 fmax NB] (only if fmax > front_smem_rows)
+    // ---- whole-GPU ("wide") schedule for few large QPs (sparse_wide.cuh): supernodes by etree level, HBM fronts spread over the GPU
+    bool wide = false;
+    int wide_sb = 128;         // column block of the blocked supernodal solves (<= 128)
+    struct WStep { int kind, a, b, c; };      // kind 0: narrow / shared-memory group (list offset a, count b, factor: fpad c); kind 1: wide supernode (factor: index into wfronts, solve: supernode)
+    struct WFront { int s, j0, ws, us, f, ld, shift, lp0, ab, an, pull_begin, nchild; long long off; };
+    std::vector<WStep> wf_steps, ws_steps;
+    std::vector<WFront> wfronts;
+    std::vector<size_t> wf_smem;              // dynamic shared memory of each factor step of kind 0
+    DevBuf<int> d_wlist_f, d_wlist_s, d_crecw, d_pull_ptr, d_pull_child, d_pull_cc;
+    DevBuf<long long> d_upd_off_w;
+    DevBuf<double> wtmp;
+    DevBuf<unsigned> wcounter;
+    long long upd_total_w = 0, front_stride = 0;
 private:
+    void build_wide();
+    void factor_wide(const int* active);
+    void solve_wide(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active);
     void scatter_static(int options);
     void update_AtA();
     void solve_core(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active);

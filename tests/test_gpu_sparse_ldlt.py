@@ -28,14 +28,25 @@ def _random_args(n=80, p=25, m=40, seed=3, sparsity=0.08):
     return (q["P"], q["c"], q["A"], q["b"], q["G"], q["h_l"], q["h_u"], q["x_l"], q["x_u"])
 
 
-@pytest.mark.parametrize("kernels", ["frontal", "frontal_hbm_fronts", "levels"])
+def _select_kernels(monkeypatch, kernels):
+    """kernel families of the sparse_ldlt backend: CTA-per-QP multifrontal (default), the same with fronts forced into HBM,
+    level-scheduled simplicial, and the whole-GPU ("wide") schedule with default / tiny thresholds"""
+    monkeypatch.setenv("B200_LDLT_LEVELS", "1" if kernels == "levels" else "0")
+    monkeypatch.setenv("B200_FRONT_SMEM_ROWS", "6" if kernels in ("frontal_hbm_fronts", "wide_tiny") else "0")   # fronts > 6 rows -> HBM-front path
+    monkeypatch.setenv("B200_LDLT_WIDE", "1" if kernels.startswith("wide") else "0")
+    if kernels == "wide_tiny":
+        monkeypatch.setenv("B200_WIDE_WS", "2"); monkeypatch.setenv("B200_WIDE_SB", "8")
+    else:
+        monkeypatch.delenv("B200_WIDE_WS", raising=False); monkeypatch.delenv("B200_WIDE_SB", raising=False)
+
+
+@pytest.mark.parametrize("kernels", ["frontal", "frontal_hbm_fronts", "levels", "wide", "wide_tiny"])
 @pytest.mark.parametrize("case", ["notebook", "mpc", "random", "no_eq", "no_ineq"])
 @pytest.mark.parametrize("own_perm", [True, False])
 def test_backend_factor_solve_eval_parity(oracle, b200, case, own_perm, kernels, monkeypatch):
     """sparse/kkt_test style (tests/src/sparse/kkt_*_test.cpp): same rho/delta/scalings -> same solve / mat-vec results.
-    Both numeric kernel families: the supernodal multifrontal one (default) and the level-scheduled simplicial one."""
-    monkeypatch.setenv("B200_LDLT_LEVELS", "1" if kernels == "levels" else "0")
-    monkeypatch.setenv("B200_FRONT_SMEM_ROWS", "6" if kernels == "frontal_hbm_fronts" else "0")   # fronts > 6 rows -> blocked HBM-front path
+    All numeric kernel families (see _select_kernels)."""
+    _select_kernels(monkeypatch, kernels)
     if case == "notebook":
         q, _ = load_scenario_mpc(); args = setup_args(q)
     elif case == "mpc":
@@ -79,6 +90,43 @@ def test_backend_factor_solve_eval_parity(oracle, b200, case, own_perm, kernels,
                 assert _rel(a, b) < 1e-12
     cl = be.clone()
     for a, b in zip(cl.solve(rx, ry, rz), be.solve(rx, ry, rz)):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("mode", [0, 3])
+@pytest.mark.parametrize("sb", [128, 32])
+def test_wide_schedule_mid_size_multi_panel(oracle, b200, mode, sb, monkeypatch):
+    """whole-GPU schedule on a problem whose root front spans several 64-column panels, 128 x 128 DMMA tiles and solve blocks
+    (BASELINE config 3 family at n_kkt = 700): agreement with the oracle under the same permutation, residual of the full
+    3x3 system, determinism of a clone; update matrices in per-supernode slots, pull-form extend-add"""
+    monkeypatch.setenv("B200_LDLT_WIDE", "1"); monkeypatch.setenv("B200_LDLT_LEVELS", "0"); monkeypatch.setenv("B200_FRONT_SMEM_ROWS", "0")
+    monkeypatch.setenv("B200_WIDE_SB", str(sb)); monkeypatch.delenv("B200_WIDE_WS", raising=False)
+    q = sparse_strongly_convex_qp(350, 150, 200, 0.03, seed=17)
+    solver = {0: "sparse_ldlt", 3: "sparse_ldlt_cond"}[mode]
+    o = oracle.SparseSolver(oracle.default_settings(kkt_solver=solver))
+    o.setup(q["P"], q["c"], q["A"], q["b"], q["G"], q["h_l"], q["h_u"], q["x_l"], q["x_u"])
+    P, AT, GT = o.scaled_matrices()
+    n, p, m = o.dims[:3]
+    be = b200.SparseKKT(P, AT, GT, mode=mode)
+    info = be.symbolic_info()
+    o2 = oracle.SparseSolver(oracle.default_settings(kkt_solver=solver), kkt_perm=info["perm"])
+    o2.setup(q["P"], q["c"], q["A"], q["b"], q["G"], q["h_l"], q["h_u"], q["x_l"], q["x_u"])
+    rng = np.random.default_rng(0)
+    x_reg = rng.uniform(0.5, 1.5, n); z_reg = rng.uniform(0.5, 2.0, m); delta = 0.9
+    assert o2.backend_factor(delta, x_reg, z_reg) == 1 and be.update_scalings_and_factor(delta, x_reg, z_reg) is True
+    r = (rng.standard_normal(n), rng.standard_normal(p), rng.standard_normal(m))
+    lg = be.solve(*r)
+    for a, b in zip(lg, o2.backend_solve(*r)):
+        assert _rel(a, b) < 1e-10
+    Pf = sp.csc_matrix(P) + sp.triu(sp.csc_matrix(P), 1).T
+    K = sp.bmat([[Pf + sp.diags(x_reg), AT, GT], [AT.T, -delta * sp.eye(p), None], [GT.T, None, -sp.diags(z_reg)]]).tocsc()
+    sol = np.concatenate(lg)
+    assert np.abs(K @ sol - np.concatenate(r)).max() < 1e-9 * max(1.0, np.abs(sol).max())
+    cl = be.clone()
+    for a, b in zip(cl.solve(*r), be.solve(*r)):
+        assert np.array_equal(a, b)
+    assert be.update_scalings_and_factor(delta, x_reg, z_reg) is True       # refactor: bitwise the same factor
+    for a, b in zip(be.solve(*r), lg):
         assert np.array_equal(a, b)
 
 
