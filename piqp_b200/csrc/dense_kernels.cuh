@@ -42,7 +42,8 @@ struct GemmArgs {
     int rows_valid;   // rows of A/B that exist in memory (>= n, padded ld); loads beyond are zero-filled
     int K;            // contraction length
     int nt;           // tiles per dimension
-    int tj_fixed;     // >= 0: column mode (tiles (tj_fixed + t, tj_fixed)); < 0: all lower tiles
+    int tj_fixed;     // >= 0: column mode (tiles (tj_fixed + t, tj_fixed)); < 0: all lower tiles of the tile columns >= tj_start
+    int tj_start;
     int tiles;        // tiles per instance
     // EPI_ASSEMBLE extras
     const double* Pf; long long strideP;     // full symmetric P, ld = ldc
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_tile_kernel(GemmArgs 
     if (g.fail && g.fail[b]) return;
     int ti, tj;
     if (g.tj_fixed >= 0) { tj = g.tj_fixed; ti = tj + t; }
-    else { tj = 0; while (t >= g.nt - tj) { t -= g.nt - tj; tj++; } ti = tj + t; }
+    else { tj = g.tj_start; while (t >= g.nt - tj) { t -= g.nt - tj; tj++; } ti = tj + t; }
     const bool diag = (ti == tj) && (g.A == g.B);
     const double* A = g.A + (size_t)b * g.strideA;
     const double* B = g.B + (size_t)b * g.strideB;

@@ -91,10 +91,14 @@ std::vector<int> minimum_degree_ordering(int n, const std::vector<int>& cp, cons
     std::vector<int> perm; perm.reserve(n);
     std::vector<int> Lp;
     int mindeg = 0;
+    const int dense_pct = getenv("B200_AMD_DENSE_PCT") ? atoi(getenv("B200_AMD_DENSE_PCT")) : 40, dense_abs = 128;
     for (int k = 0; k < n; k++) {
         const int nleft = n - k;
         while (mindeg < n && head[mindeg] < 0) mindeg++;
-        if (mindeg >= nleft - 1 && nleft > 1) {                // the remaining graph is (bounded by) a clique
+        // dense tail: the remaining graph is (bounded by) a clique, or every remaining variable already touches >= 40 % of the
+        // others (and >= 128): eliminating them one by one would create a handful of huge, nearly identical fronts; one dense
+        // root front costs a few percent more flops and runs at tensor-pipe speed
+        if (nleft > 1 && (mindeg >= nleft - 1 || (mindeg >= dense_abs && (long long)mindeg * 100 >= (long long)dense_pct * nleft))) {
             for (int i = 0; i < n; i++) if (!gone[i]) perm.push_back(i);
             break;
         }
@@ -327,10 +331,17 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
         if (extra.empty()) break;
         continue;
     }
-    // ---- postorder the elimination tree (children in increasing order) so that supernodes are runs of consecutive columns;
-    //      an equivalent reordering: same fill, same arithmetic per column.  A postordered input is left unchanged.
+    // ---- postorder the elimination tree so that supernodes are runs of consecutive columns; an equivalent reordering: same
+    //      fill, same arithmetic per column.  Children are visited by increasing column count (ties: by index), so the child
+    //      with the largest structure -- the one a parent can form a supernode with, or be amalgamated with -- comes right
+    //      before its parent.  A postordered input is left unchanged.
     std::vector<int> head(nk, -1), next(nk, -1), post; post.reserve(nk);
-    for (int j = nk - 1; j >= 0; j--) if (etree[j] >= 0) { next[j] = head[etree[j]]; head[etree[j]] = j; }
+    {
+        std::vector<int> byk(nk);
+        for (int j = 0; j < nk; j++) byk[j] = j;
+        std::stable_sort(byk.begin(), byk.end(), [&](int a, int b) { return Lnz[a] < Lnz[b]; });
+        for (int t = nk - 1; t >= 0; t--) { const int j = byk[t]; if (etree[j] >= 0) { next[j] = head[etree[j]]; head[etree[j]] = j; } }
+    }
     std::vector<int> stack;
     for (int r = 0; r < nk; r++) {
         if (etree[r] >= 0) continue;
@@ -460,6 +471,8 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
             sf2 += f * f; su2 += us * us; big += f > 150; w1 += ws == 1;
             for (int k = 0; k < (int)ws; k++) piv_work += (f - k) * (f - k) / 2;
         }
+        for (int s2 = 0; s2 < nsup; s2++) { const int ws = sup_ptr[s2 + 1] - sup_ptr[s2], us = rel_ptr[s2 + 1] - rel_ptr[s2];
+            if (ws + us > 150) fprintf(stderr, "  big front: s=%d j0=%d ws=%d us=%d parent=%d nchild=%d\n", s2, sup_ptr[s2], ws, us, psup[s2], child_ptr[s2 + 1] - child_ptr[s2]); }
         fprintf(stderr, "[sparse_ldlt symbolic] nk=%d nnzL=%zu nsup=%d (width 1: %d) fmax=%d fronts>150: %d  sum f^2=%.3g  sum us^2=%.3g  pivot-update entries=%.3g  flops=%.3g upd_total=%lld\n",
                 nk, Li.size(), nsup, w1, fmax, big, sf2, su2, piv_work, factor_flops(), upd_total);
     }
@@ -665,10 +678,24 @@ static MfDev make_mf(const SparseLdltBatchedKKT& K) {
 // =====================================================================================================
 // whole-GPU schedule (sparse_wide.cuh)
 // =====================================================================================================
+SparseLdltBatchedKKT::~SparseLdltBatchedKKT() {
+    if (ev_col) cudaEventDestroy(ev_col);
+    if (ev_panel) cudaEventDestroy(ev_panel);
+    if (aux_stream) cudaStreamDestroy(aux_stream);
+}
+
 void SparseLdltBatchedKKT::build_wide() {
+    if (!aux_stream && !getenv("B200_WIDE_NO_LOOKAHEAD")) {
+        int prio_lo = 0, prio_hi = 0;
+        B200_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        B200_CUDA(cudaStreamCreateWithPriority(&aux_stream, cudaStreamNonBlocking, prio_hi));      // panel CTAs go first when SMs free up
+        B200_CUDA(cudaEventCreateWithFlags(&ev_col, cudaEventDisableTiming));
+        B200_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
+    }
     const int nsup = S.nsup, nk = S.nk;
     auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
-    wide_sb = std::min(128, std::max(2, knob("B200_WIDE_SB", 128)));
+    wide_sb = 128;
+    { const int v = knob("B200_WIDE_SB", 128); for (int c : {8, 16, 32, 64, 128}) if (v == c) wide_sb = c; }     // power of two <= 128
     const int ws_min = std::max(2, knob("B200_WIDE_WS", 64));          // supernodes at least this wide are solved blocked over the GPU
     std::vector<int> sup_of(nk, 0), psup(nsup, -1), slevel(nsup, 0);
     for (int s2 = 0; s2 < nsup; s2++) for (int j = S.sup_ptr[s2]; j < S.sup_ptr[s2 + 1]; j++) sup_of[j] = s2;
@@ -699,6 +726,7 @@ void SparseLdltBatchedKKT::build_wide() {
     wf_steps.clear(); ws_steps.clear(); wfronts.clear(); wf_smem.clear();
     front_stride = 0;
     size_t small_smem_max = 0;
+    long long tinv_blocks = 0;
     for (int l = 0; l <= maxl; l++) {
         const int fb = (int)list_f.size(), sb0 = (int)list_s.size();
         int fmax_l = 0;
@@ -738,17 +766,19 @@ void SparseLdltBatchedKKT::build_wide() {
                 wf_steps.push_back({1, (int)wfronts.size(), 0, 0});
                 wfronts.push_back(w);
             }
-            if (ws >= ws_min) ws_steps.push_back({1, s2, 0, 0});
+            if (ws >= ws_min) { ws_steps.push_back({1, s2, (int)tinv_blocks, 0}); tinv_blocks += ceil_div(ws, wide_sb); }
         }
     }
     upload(d_wlist_f, list_f); upload(d_wlist_s, list_s); upload(d_pull_ptr, pull_ptr); upload(d_pull_child, pull_child); upload(d_pull_cc, pull_cc);
     if (front_stride > 0) bigfront.alloc((size_t)batch * (size_t)front_stride);
     wtmp.alloc((size_t)batch * wide_sb); wcounter.alloc(batch);
+    tinv_stride = tinv_blocks * wide_sb * wide_sb;
+    Tcm.alloc(std::max<size_t>((size_t)batch * (size_t)tinv_stride, 1)); Trm.alloc(std::max<size_t>((size_t)batch * (size_t)tinv_stride, 1));
     B200_CUDA(cudaMemset(wcounter.get(), 0, sizeof(unsigned) * batch));
     const size_t sbs = (size_t)wide_sb;
     B200_CUDA(cudaFuncSetAttribute(mfw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(small_smem_max, 48 * 1024)));
-    B200_CUDA(cudaFuncSetAttribute(mfw_fwd_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sizeof(double) * (sbs * (sbs + 1) + 3 * sbs), 48 * 1024)));
-    B200_CUDA(cudaFuncSetAttribute(mfw_bwd_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sizeof(double) * (sbs * (sbs + 1) + 2 * sbs + 32), 48 * 1024)));
+    B200_CUDA(cudaFuncSetAttribute(mfw_block_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sizeof(double) * sbs * (sbs + 1), 48 * 1024)));
+    B200_CUDA(cudaFuncSetAttribute(mfw_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MW_PANEL_SMEM));
     if (getenv("B200_DEBUG_SYMBOLIC"))
         fprintf(stderr, "[sparse_ldlt wide] levels=%d factor steps=%zu (HBM fronts %zu) solve steps=%zu upd_total=%lld front_stride=%lld\n", maxl + 1, wf_steps.size(),
                 wfronts.size(), ws_steps.size(), upd_total_w, front_stride);
@@ -777,17 +807,47 @@ void SparseLdltBatchedKKT::factor_wide(const int* active) {
         if (w.nchild > 0) { dim3 g(ceil_div(w.f, MW_T / 32), batch);
             B200_LAUNCH(mfw_pull_kernel, g, MW_T, 0, stream, F, front_stride, w.ld, w.shift, w.f, d_pull_ptr.get() + w.pull_begin, d_pull_child.get(), d_pull_cc.get(),
                         d_crecw.get(), d_rel_idx.get(), upd.get(), upd_total_w, active); }
+        // Blocked right-looking LDL^T with look-ahead.  Panel k: columns [k0, k0 + nb); trailing update k: F22 -= L21 D L21^T.
+        // The first 128-column tile column of update k is all panel k+1 needs, so panel k+1 runs on the auxiliary stream while
+        // the remaining tile columns of update k run on the main stream (they touch disjoint columns of F).
         int k0 = 0, nb = ((w.ws - 1) % MW_NB) + 1;       // first panel takes the remainder: every later r0 has the parity of ws (16-byte aligned row pairs)
+        auto panel = [&](int pk0, int pnb, cudaStream_t st) {
+            const int R = w.f - pk0 - pnb;
+            dim3 g(std::max(1, ceil_div(R, MW_T)), batch);
+            B200_LAUNCH(mfw_panel_kernel, g, MW_T, MW_PANEL_SMEM, st, F, front_stride, w.ld, w.shift, w.f, pk0, pnb, w.j0, w.lp0, Lx.get(), nnzL, Dv.get(), Dinv.get(), nk, fail.get(), active);
+        };
+        auto update = [&](int pk0, int pnb, int part) {
+            const int r0 = pk0 + pnb, R = w.f - r0;
+            if (R > 0) dense_syrk_sub_scaled(F + w.shift + r0 + (size_t)pk0 * w.ld, front_stride, w.ld, Dv.get() + w.j0 + pk0, nk,
+                                             F + w.shift + r0 + (size_t)r0 * w.ld, front_stride, w.ld, R, pnb, batch, active, stream, part);
+        };
+        panel(k0, nb, stream);
         while (k0 < w.ws) {
-            const int r0 = k0 + nb, R = w.f - r0;
-            { dim3 g(std::max(1, ceil_div(R, MW_T)), batch);
-              B200_LAUNCH(mfw_panel_kernel, g, MW_T, 0, stream, F, front_stride, w.ld, w.shift, w.f, k0, nb, w.j0, w.lp0, Lx.get(), nnzL, Dv.get(), Dinv.get(), nk, fail.get(), active); }
-            if (R > 0) dense_syrk_sub_scaled(F + w.shift + r0 + (size_t)k0 * w.ld, front_stride, w.ld, Dv.get() + w.j0 + k0, nk,
-                                             F + w.shift + r0 + (size_t)r0 * w.ld, front_stride, w.ld, R, nb, batch, active, stream);
-            k0 += nb; nb = MW_NB;
+            const int k1 = k0 + nb;                      // next panel starts here (width MW_NB)
+            const bool more = k1 < w.ws;
+            if (more && aux_stream) {
+                update(k0, nb, 1);
+                B200_CUDA(cudaEventRecord(ev_col, stream));
+                B200_CUDA(cudaStreamWaitEvent(aux_stream, ev_col, 0));
+                panel(k1, std::min(MW_NB, w.ws - k1), aux_stream);
+                B200_CUDA(cudaEventRecord(ev_panel, aux_stream));
+                update(k0, nb, 2);
+                B200_CUDA(cudaStreamWaitEvent(stream, ev_panel, 0));
+            } else {
+                update(k0, nb, 0);
+                if (more) panel(k1, std::min(MW_NB, w.ws - k1), stream);
+            }
+            k0 = k1; nb = MW_NB;
         }
         if (w.us > 0) { dim3 g(ceil_div(w.us, 128), w.us, batch);
             B200_LAUNCH(mfw_schur_kernel, g, 128, 0, stream, F, front_stride, w.ld, w.shift, w.ws, w.us, upd.get(), upd_total_w, w.off, active); }
+    }
+    for (const WStep& st : ws_steps) {           // inverses of the diagonal blocks of the supernodes the solves treat blocked
+        if (st.kind != 1) continue;
+        const int s2 = st.a, j0 = S.sup_ptr[s2], ws = S.sup_ptr[s2 + 1] - j0, us = S.rel_ptr[s2 + 1] - S.rel_ptr[s2];
+        dim3 g(ceil_div(ws, wide_sb), batch);
+        B200_LAUNCH(mfw_block_inverse_kernel, g, MW_T, sizeof(double) * (size_t)wide_sb * (wide_sb + 1), stream, ws, ws + us, S.Lp[j0], wide_sb, Lx.get(), nnzL,
+                    Tcm.get(), Trm.get(), tinv_stride, (long long)st.b * wide_sb * wide_sb, active);
     }
 }
 
@@ -796,7 +856,8 @@ void SparseLdltBatchedKKT::solve_wide(const double* rx, const double* ry, const 
     const size_t nnzL = std::max<size_t>(S.Li.size(), 1);
     dim3 gk(ceil_div(nk, 256), batch);
     B200_LAUNCH(ldlt_gather_rhs_kernel, gk, 256, 0, stream, d_perm.get(), n, S.pk, S.mk, rx, ry, rz, work.get(), active);
-    const size_t fsm = sizeof(double) * ((size_t)sb * (sb + 1) + 3 * (size_t)sb), bsm = sizeof(double) * ((size_t)sb * (sb + 1) + 2 * (size_t)sb + 32);
+    const size_t fsm = sizeof(double) * (size_t)(MW_T + sb), bsm = sizeof(double) * (size_t)(MW_T + sb + 32);
+    const int sr = std::min(64, sb);
     for (const WStep& st : ws_steps) {           // L y = b
         if (st.kind == 0) {
             dim3 g(ceil_div(st.b, MW_T / 32), batch);
@@ -807,9 +868,12 @@ void SparseLdltBatchedKKT::solve_wide(const double* rx, const double* ry, const 
         { dim3 g(ceil_div(ws, MW_T / 32), batch);
           B200_LAUNCH(mfw_fwd_pull_kernel, g, MW_T, 0, stream, j0, ws, d_Rp.get(), d_Rcol.get(), d_Rpos.get(), Lx.get(), nnzL, work.get(), nk, active); }
         const int nblk = ceil_div(ws, sb);
-        { dim3 g(1, batch); B200_LAUNCH(mfw_fwd_block_kernel, g, MW_T, fsm, stream, j0, ws, f, lp0, 0, 0, sb, Lx.get(), nnzL, work.get(), nk, active); }
-        for (int t = 0; t + 1 < nblk; t++) { dim3 g(nblk - 1 - t, batch);
-            B200_LAUNCH(mfw_fwd_block_kernel, g, MW_T, fsm, stream, j0, ws, f, lp0, t * sb, sb, sb, Lx.get(), nnzL, work.get(), nk, active); }
+        const long long toff = (long long)st.b * sb * sb;
+        { dim3 g(1, batch); B200_LAUNCH(mfw_fwd_block_kernel, g, MW_T, fsm, stream, j0, ws, f, lp0, 0, 0, sb, Lx.get(), nnzL, Tcm.get(), tinv_stride, toff, work.get(), nk, active); }
+        for (int t = 0; t + 1 < nblk; t++) {
+            const int after = ws - (t + 2) * sb;               // rows of the triangle behind the next block
+            dim3 g(1 + (after > 0 ? ceil_div(after, sr) : 0), batch);
+            B200_LAUNCH(mfw_fwd_block_kernel, g, MW_T, fsm, stream, j0, ws, f, lp0, t * sb, sb, sb, Lx.get(), nnzL, Tcm.get(), tinv_stride, toff, work.get(), nk, active); }
     }
     B200_LAUNCH(ldlt_dscale_kernel, gk, 256, 0, stream, nk, Dinv.get(), work.get(), active);
     for (size_t i = ws_steps.size(); i-- > 0;) {   // L^T x = y
@@ -824,7 +888,8 @@ void SparseLdltBatchedKKT::solve_wide(const double* rx, const double* ry, const 
         for (int t = nblk - 1; t >= 0; t--) {
             const int c0 = t * sb, cn = std::min(sb, ws - c0);
             dim3 g(cn, batch);
-            B200_LAUNCH(mfw_bwd_block_kernel, g, MW_T, bsm, stream, j0, ws, f, lp0, d_Li.get() + S.Lp[j1], c0, cn, sb, Lx.get(), nnzL, work.get(), nk, wtmp.get(), wcounter.get(), active);
+            B200_LAUNCH(mfw_bwd_block_kernel, g, MW_T, bsm, stream, j0, ws, f, lp0, d_Li.get() + S.Lp[j1], c0, cn, sb, Lx.get(), nnzL, Trm.get(), tinv_stride,
+                        (long long)st.b * sb * sb, work.get(), nk, wtmp.get(), wcounter.get(), active);
         }
     }
     B200_LAUNCH(ldlt_scatter_lhs_kernel, gk, 256, 0, stream, d_perm.get(), n, S.pk, S.mk, work.get(), lx, ly, lz, active);
@@ -942,6 +1007,7 @@ void SparseLdltBatchedKKT::copy_from(const SparseLdltBatchedKKT& o) {
     auto cp = [&](DevBuf<double>& d, const DevBuf<double>& s) { if (s.n) B200_CUDA(cudaMemcpyAsync(d.get(), s.get(), s.n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); };
     cp(PKx, o.PKx); cp(P_diag, o.P_diag); cp(Lx, o.Lx); cp(Dv, o.Dv); cp(Dinv, o.Dinv);
     cp(AtA, o.AtA); cp(zinv, o.zinv); cp(dlt, o.dlt);
+    if (wide && o.wide && Tcm.n == o.Tcm.n) { cp(Tcm, o.Tcm); cp(Trm, o.Trm); }
 }
 void SparseLdltBatchedKKT::scatter_static(int options) {   // kkt_full.hpp:212-251; update_data_impl of the condensed modes
     const int nnzPK = (int)S.PKi_rows.size();

@@ -62,6 +62,7 @@ std::vector<int> minimum_degree_ordering(int n, const std::vector<int>& colptr, 
 class SparseLdltBatchedKKT : public BatchedKKT {
 public:
     SparseLdltBatchedKKT(SparseData* data, const int* user_perm, cudaStream_t st, int mode = 0);
+    ~SparseLdltBatchedKKT() override;
     void update_data(int options) override;
     void factor(const double* delta, const double* x_reg, const double* z_reg, const int* active, int* ok) override;
     void solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) override;
@@ -111,9 +112,12 @@ public:
     std::vector<size_t> wf_smem;              // dynamic shared memory of each factor step of kind 0
     DevBuf<int> d_wlist_f, d_wlist_s, d_crecw, d_pull_ptr, d_pull_child, d_pull_cc;
     DevBuf<long long> d_upd_off_w;
-    DevBuf<double> wtmp;
+    DevBuf<double> wtmp, Tcm, Trm;   // dot products of one backward block; inverses of the diagonal blocks of the wide supernodes (column- / row-major)
+    long long tinv_stride = 0;
     DevBuf<unsigned> wcounter;
     long long upd_total_w = 0, front_stride = 0;
+    cudaStream_t aux_stream = nullptr;        // look-ahead: panel k+1 runs here while the rest of trailing update k runs on `stream`
+    cudaEvent_t ev_col = nullptr, ev_panel = nullptr;
 private:
     void build_wide();
     void factor_wide(const int* active);

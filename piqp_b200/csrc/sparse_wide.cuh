@@ -109,76 +109,97 @@ __global__ void __launch_bounds__(MW_T) mfw_pull_kernel(double* __restrict__ F_a
     double* Fc = F_all + (size_t)b * stride + shift + (size_t)c * ld;
     const double* upd = upd_all + (size_t)b * (size_t)upd_stride;
     const int t1 = pull_ptr[c + 1];
-    for (int t = pull_ptr[c]; t < t1; t++) {
-        const int4 cr = reinterpret_cast<const int4*>(crecw)[pull_child[t]];
-        const int cc = pull_cc[t], uc = cr.x;
+    int t = pull_ptr[c];
+    const int4* rec = reinterpret_cast<const int4*>(crecw);
+    int4 cr = make_int4(0, 0, 0, 0); int cc = 0;
+    if (t < t1) { cc = pull_cc[t]; cr = rec[pull_child[t]]; }
+    for (; t < t1; t++) {
+        int4 crn = cr; int ccn = cc;
+        if (t + 1 < t1) { ccn = pull_cc[t + 1]; crn = rec[pull_child[t + 1]]; }      // next child's record: off the dependent chain
+        const int uc = cr.x;
         const double* U = upd + (((long long)cr.w << 32) | (unsigned)cr.z) + (size_t)cc * uc;
         const int* rel = rel_idx + cr.y;
         for (int a = cc + lane; a < uc; a += 32) Fc[rel[a]] += U[a];
+        __syncwarp();                                   // two children may touch the same row from different lanes: keep their order
+        cr = crn; cc = ccn;
     }
 }
 
 // One panel of the blocked LDL^T of an HBM front: columns [k0, k0 + nb) of F (f x f, lower, ld), rows below r0 = k0 + nb.
-// Every CTA factors the nb x nb pivot block in shared memory (A11 in F is only read, never overwritten: L11 goes to Lx, D to
-// Dv), then each thread solves one row of the panel: w = a L11^-T (= l D), l = w / d; F keeps l (operand of the trailing update).
+// Every CTA factors the nb x nb pivot block itself, its entries spread over the registers of the 256 threads and one
+// barrier per pivot (A11 in F is only read, never overwritten: L11 goes to Lx, D to Dv), then each thread solves one row of the panel: w = a L11^-T (= l D), l = w / d; F keeps l (operand of the trailing update).
+// Dynamic shared memory: MW_PANEL_SMEM bytes.
+constexpr int MW_LDA = MW_NB + 1;
+constexpr size_t MW_PANEL_SMEM = sizeof(double) * (2 * MW_NB + MW_NB * MW_NB + MW_NB);
 __global__ void __launch_bounds__(MW_T) mfw_panel_kernel(double* __restrict__ F_all, long long stride, int ld, int shift, int f, int k0, int nb, int j0, int lp0,
                                                          double* __restrict__ Lx_all, size_t nnzL, double* __restrict__ Dv_all, double* __restrict__ Dinv_all, int nk,
                                                          int* __restrict__ fail, const int* __restrict__ active) {
-    __shared__ double A[MW_NB][MW_NB + 1];     // lower: A11, overwritten column by column with L11; upper: the unscaled columns w (transposed); diagonal: D
+    extern __shared__ __align__(16) double psm[];
+    double* col = psm;                            // [2][MW_NB]       double-buffered pivot column (unscaled)
+    double* Lc = psm + 2 * MW_NB;                 // [MW_NB][MW_NB]   16-byte aligned rows of L11 (zero on and beyond the diagonal)
+    double* dd = Lc + MW_NB * MW_NB;              // [MW_NB]
     const int b = blockIdx.y;
     if (active && !active[b]) return;
     const int tid = threadIdx.x;
     double* F = F_all + (size_t)b * stride + shift;
     double* Lx = Lx_all + (size_t)b * nnzL;
-    for (int e = tid; e < MW_NB * MW_NB; e += MW_T) {
-        const int i = e % MW_NB, c = e / MW_NB;
-        if (c <= i) A[i][c] = (i < nb) ? F[(size_t)(k0 + i) + (size_t)(k0 + c) * ld] : 0.0;
+    const int i = tid & (MW_NB - 1), g = tid >> 6;          // this thread owns A11(i, c) for c = g, g + 4, ..., g + 60 -- in REGISTERS
+    double a[MW_NB / 4];
+#pragma unroll
+    for (int m = 0; m < MW_NB / 4; m++) { const int c = g + 4 * m; a[m] = (c <= i && i < nb) ? F[(size_t)(k0 + i) + (size_t)(k0 + c) * ld] : 0.0; }
+#pragma unroll
+    for (int k = 0; k < MW_NB; k++) {
+        if (k < nb) {                             // uniform over the CTA
+            double* ck = col + (k & 1) * MW_NB;
+            if (g == (k & 3) && i >= k) ck[i] = a[k >> 2];                  // column k, unscaled: w_i (and d at i = k)
+            __syncthreads();
+            const double rd = 1.0 / ck[k];
+            if (i > k && i < nb) {
+                const double li = ck[i] * rd;                               // l_i = w_i / d
+#pragma unroll
+                for (int m = 0; m < MW_NB / 4; m++) { const int c = g + 4 * m; if (c > k && c <= i) a[m] -= li * ck[c]; }      // A(i, c) -= l_i w_c
+                if (g == (k & 3)) a[k >> 2] = li;
+            }
+        }
     }
     __syncthreads();
-    for (int k = 0; k < nb; k++) {
-        const double d = A[k][k];
-        if (tid > k && tid < nb) { const double w = A[tid][k]; A[k][tid] = w; A[tid][k] = w / d; }
-        __syncthreads();
-        // A(i, c) -= w_i l_c  for k < c <= i < nb
-        const int rem = nb - k - 1;
-        for (int e = tid; e < rem * rem; e += MW_T) {
-            const int i = k + 1 + e % rem, c = k + 1 + e / rem;
-            if (c <= i) A[i][c] -= A[k][i] * A[c][k];
-        }
-        __syncthreads();
-    }
+#pragma unroll
+    for (int m = 0; m < MW_NB / 4; m++) { const int c = g + 4 * m; Lc[i * MW_NB + c] = c < i ? a[m] : 0.0; if (c == i) dd[i] = i < nb ? a[m] : 1.0; }
+    __syncthreads();
     if (blockIdx.x == 0) {
         for (int k = tid; k < nb; k += MW_T) {
-            const double d = A[k][k];
+            const double d = dd[k];
             if (d == 0.0 && fail[b] == 0) fail[b] = j0 + k0 + k + 1;           // ldlt.hpp:161
             Dv_all[(size_t)b * nk + j0 + k0 + k] = d; Dinv_all[(size_t)b * nk + j0 + k0 + k] = 1.0 / d;
         }
         for (int e = tid; e < nb * nb; e += MW_T) {
-            const int i = e % nb, c = e / nb;
-            if (i > c) Lx[mfw_colbase(lp0, f, k0 + c) + (k0 + i)] = A[i][c];
+            const int r = e % nb, c = e / nb;
+            if (r > c) Lx[mfw_colbase(lp0, f, k0 + c) + (k0 + r)] = Lc[r * MW_NB + c];
         }
     }
     const int r0 = k0 + nb;
-    const int i = r0 + blockIdx.x * MW_T + tid;
-    if (i >= f) return;
+    const int row = r0 + blockIdx.x * MW_T + tid;
+    if (row >= f) return;
     double w[MW_NB];
 #pragma unroll
-    for (int k = 0; k < MW_NB; k++) w[k] = (k < nb) ? F[(size_t)i + (size_t)(k0 + k) * ld] : 0.0;
+    for (int k = 0; k < MW_NB; k++) w[k] = (k < nb) ? F[(size_t)row + (size_t)(k0 + k) * ld] : 0.0;
 #pragma unroll
-    for (int k = 0; k < MW_NB; k++) {
-        if (k < nb) {
-            double acc = w[k];
+    for (int k = 1; k < MW_NB; k++) {             // rows of Lc beyond nb are zero, w beyond nb is zero: no guards needed
+        double acc = w[k];
 #pragma unroll
-            for (int q = 0; q < k; q++) acc -= w[q] * A[k][q];
-            w[k] = acc;
+        for (int q = 0; q < k; q += 2) {
+            const double2 l2 = *reinterpret_cast<const double2*>(Lc + k * MW_NB + q);
+            acc -= w[q] * l2.x;
+            if (q + 1 < k) acc -= w[q + 1] * l2.y;
         }
+        w[k] = acc;
     }
 #pragma unroll
     for (int k = 0; k < MW_NB; k++) {
         if (k < nb) {
-            const double l = w[k] / A[k][k];
-            F[(size_t)i + (size_t)(k0 + k) * ld] = l;
-            Lx[mfw_colbase(lp0, f, k0 + k) + i] = l;
+            const double l = w[k] / dd[k];
+            F[(size_t)row + (size_t)(k0 + k) * ld] = l;
+            Lx[mfw_colbase(lp0, f, k0 + k) + row] = l;
         }
     }
 }
@@ -234,10 +255,44 @@ __global__ void __launch_bounds__(MW_T) mfw_fwd_pull_kernel(int j0, int ws, cons
     acc = warp_sum(acc);
     if (lane == 0) w[j] -= acc;
 }
-// forward, wide supernode, part 2 (one launch per column block): CTA c owns rows [rb + c*sb, +sb) of the supernode's triangle;
-// it subtracts L[rows, gc0 .. gc0+gcn) y[gc0 .. gc0+gcn) (final since the previous launch); CTA 0 then solves its own sb x sb
-// unit-lower triangle, which makes block rb final for the next launch.  smem: sb*(sb+1) + 3*sb doubles.
+// Inverses of the sb x sb unit-lower diagonal blocks of a wide supernode (computed once per factorisation, one CTA per block):
+// the blocked solves below apply them as mat-vecs instead of running sb dependent substitution steps per block (the dense
+// backend does the same with its 32 x 32 blocks).  Tcm[blk][k * sb + r] = inv(r, k) (column-major), Trm[blk][r * sb + k] = inv(r, k).
+// smem: sb * (sb + 1) doubles.
+__global__ void __launch_bounds__(MW_T) mfw_block_inverse_kernel(int ws, int f, int lp0, int sb, const double* __restrict__ Lx_all, size_t nnzL,
+                                                                 double* __restrict__ Tcm_all, double* __restrict__ Trm_all, long long tinv_stride, long long tinv_off,
+                                                                 const int* __restrict__ active) {
+    extern __shared__ __align__(16) double sm[];
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int tid = threadIdx.x, t = blockIdx.x;
+    const int c0 = t * sb, cn = min(sb, ws - c0), ldx = sb + 1;
+    const double* Lx = Lx_all + (size_t)b * nnzL;
+    double* X = sm;
+    for (int e = tid; e < sb * sb; e += MW_T) {
+        const int i = e % sb, k = e / sb;
+        X[i * ldx + k] = (i < cn && k < cn && i > k) ? Lx[mfw_colbase(lp0, f, c0 + k) + (c0 + i)] : (i == k ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    for (int i = 1; i < cn; i++) {               // row i of the inverse from rows < i:  X(i, j) = - sum_{k=j}^{i-1} T(i, k) X(k, j)
+        double acc = 0.0;
+        if (tid < i) for (int k = tid; k < i; k++) acc += X[i * ldx + k] * X[k * ldx + tid];
+        __syncthreads();
+        if (tid < i) X[i * ldx + tid] = -acc;
+        __syncthreads();
+    }
+    double* Tcm = Tcm_all + (size_t)b * tinv_stride + tinv_off + (size_t)t * sb * sb;
+    double* Trm = Trm_all + (size_t)b * tinv_stride + tinv_off + (size_t)t * sb * sb;
+    for (int e = tid; e < sb * sb; e += MW_T) { const int r = e % sb, k = e / sb; Tcm[e] = X[r * ldx + k]; }
+    for (int e = tid; e < sb * sb; e += MW_T) { const int k = e % sb, r = e / sb; Trm[e] = X[r * ldx + k]; }
+}
+// forward, wide supernode, part 2 (one launch per column block [gc0, gc0 + gcn), gcn = 0 for the first launch): CTA 0 owns the
+// rows of the NEXT block [rb, rb + sb), rb = gc0 + gcn; CTAs c >= 1 own 64-row slabs after it.  Every CTA subtracts
+// L[rows, block] y[block] (y[block] is final since the previous launch); threads split the block's columns into MW_T / rows
+// groups whose partial sums are added in a fixed order.  CTA 0 then multiplies its rows by the inverse of their diagonal
+// block, which makes them final for the next launch.  sb: power of two <= 128.  smem: (MW_T + sb) doubles.
 __global__ void __launch_bounds__(MW_T) mfw_fwd_block_kernel(int j0, int ws, int f, int lp0, int gc0, int gcn, int sb, const double* __restrict__ Lx_all, size_t nnzL,
+                                                             const double* __restrict__ Tcm_all, long long tinv_stride, long long tinv_off,
                                                              double* __restrict__ work_all, int nk, const int* __restrict__ active) {
     extern __shared__ __align__(16) double sm[];
     const int b = blockIdx.y;
@@ -245,45 +300,62 @@ __global__ void __launch_bounds__(MW_T) mfw_fwd_block_kernel(int j0, int ws, int
     const int tid = threadIdx.x;
     const double* Lx = Lx_all + (size_t)b * nnzL;
     double* w = work_all + (size_t)b * nk + j0;
-    double* xs = sm;                 // sb
-    double* part = sm + sb;          // 2 * sb  (upper half of the threads)
-    double* T = sm + 3 * sb;         // sb x (sb + 1)
-    const int rb = gc0 + gcn;
-    const int r0 = rb + blockIdx.x * sb, rn = min(sb, ws - r0);
+    double* part = sm;               // MW_T
+    double* xs = sm + MW_T;          // sb
+    const int rb = gc0 + gcn, sr = min(64, sb);
+    const int rows = blockIdx.x == 0 ? sb : sr;
+    const int r0 = blockIdx.x == 0 ? rb : rb + sb + (blockIdx.x - 1) * sr;
+    const int rn = min(rows, ws - r0);
     if (rn <= 0) return;
-    const int half = tid / sb, r = tid - half * sb;       // MW_T >= 2 * sb is not required: threads beyond 2*sb idle in the mat-vec
-    double acc = 0.0;
-    if (half < 2 && r < rn && gcn > 0) {
-        const int i = r0 + r;
-        const int kh = (gcn + 1) / 2, ka = gc0 + half * kh, kb = min(gc0 + gcn, ka + kh);
-        for (int k = ka; k < kb; k++) acc += Lx[mfw_colbase(lp0, f, k) + i] * w[k];
+    const int groups = MW_T / rows, grp = tid / rows, r = tid - grp * rows;
+    {
+        double acc = 0.0;
+        if (r < rn && gcn > 0) {
+            const int i = r0 + r;
+            const int kh = (gcn + groups - 1) / groups, ka = gc0 + grp * kh, kb = min(gc0 + gcn, ka + kh);
+            size_t base = mfw_colbase(lp0, f, ka) + i;
+#pragma unroll 8
+            for (int k = ka; k < kb; k++) { acc += Lx[base] * w[k]; base += (size_t)(f - k - 2); }
+        }
+        part[tid] = acc;
     }
-    if (half == 1 && r < rn) part[r] = acc;
     __syncthreads();
-    if (half == 0 && r < rn) xs[r] = w[r0 + r] - (acc + part[r]);
+    double x = 0.0;
+    if (grp == 0 && r < rn) {
+        double tot = 0.0;
+        for (int g2 = 0; g2 < groups; g2++) tot += part[g2 * rows + r];
+        x = w[r0 + r] - tot;
+    }
     if (blockIdx.x != 0) {
-        if (half == 0 && r < rn) w[r0 + r] = xs[r];
+        if (grp == 0 && r < rn) w[r0 + r] = x;
         return;
     }
-    // CTA 0: unit-lower triangle of block [r0, r0 + rn)
-    for (int e = tid; e < rn * rn; e += MW_T) {
-        const int i = e % rn, k = e / rn;
-        if (i > k) T[i * (sb + 1) + k] = Lx[mfw_colbase(lp0, f, r0 + k) + (r0 + i)];
+    if (grp == 0) xs[r] = r < rn ? x : 0.0;
+    __syncthreads();
+    {   // y_blk = inv(T_blk) x_blk, lower triangular: columns k <= r
+        const double* Tc = Tcm_all + (size_t)b * tinv_stride + tinv_off + (size_t)(r0 / sb) * sb * sb;
+        double acc = 0.0;
+        if (r < rn) {
+            const int kh = (rn + groups - 1) / groups, ka = grp * kh, kb = min(min(rn, r + 1), ka + kh);
+#pragma unroll 8
+            for (int k = ka; k < kb; k++) acc += Tc[(size_t)k * sb + r] * xs[k];
+        }
+        part[tid] = acc;
     }
     __syncthreads();
-    for (int k = 0; k + 1 < rn; k++) {
-        const double xk = xs[k];
-        if (tid > k && tid < rn) xs[tid] -= T[tid * (sb + 1) + k] * xk;
-        __syncthreads();
+    if (grp == 0 && r < rn) {
+        double tot = 0.0;
+        for (int g2 = 0; g2 < groups; g2++) tot += part[g2 * rows + r];
+        w[r0 + r] = tot;
     }
-    if (tid < rn) w[r0 + tid] = xs[tid];
 }
 // backward, wide supernode (one launch per column block [c0, c0 + cn), last block first): CTA k computes
 // dot_k = sum_{i >= c0+cn} L(i, c0+k) x_i  (rows of the triangle below the block, then the update rows through their row
-// indices); the CTA that finishes last subtracts the dots and solves the cn x cn transposed unit triangle.
-// smem: sb*(sb+1) + 2*sb + 32 doubles.
+// indices); the CTA that finishes last subtracts the dots and applies the transposed inverse of the diagonal block.
+// smem: (MW_T + sb + 32) doubles.
 __global__ void __launch_bounds__(MW_T) mfw_bwd_block_kernel(int j0, int ws, int f, int lp0, const int* __restrict__ li_u, int c0, int cn, int sb,
-                                                             const double* __restrict__ Lx_all, size_t nnzL, double* __restrict__ work_all, int nk,
+                                                             const double* __restrict__ Lx_all, size_t nnzL, const double* __restrict__ Trm_all, long long tinv_stride,
+                                                             long long tinv_off, double* __restrict__ work_all, int nk,
                                                              double* __restrict__ tmp_all, unsigned* __restrict__ counter, const int* __restrict__ active) {
     extern __shared__ __align__(16) double sm[];
     __shared__ int is_last;
@@ -293,13 +365,14 @@ __global__ void __launch_bounds__(MW_T) mfw_bwd_block_kernel(int j0, int ws, int
     const double* Lx = Lx_all + (size_t)b * nnzL;
     double* wg = work_all + (size_t)b * nk;
     double* tmp = tmp_all + (size_t)b * sb;
-    double* xs = sm;                 // sb
-    double* red = sm + sb;           // 32
-    double* T = sm + 2 * sb + 32;    // sb x (sb + 1)
+    double* part = sm;               // MW_T
+    double* vs = sm + MW_T;          // sb
+    double* red = vs + sb;           // 32
     const int k = blockIdx.x;
     {
         const size_t base = mfw_colbase(lp0, f, c0 + k);
         double acc = 0.0;
+#pragma unroll 4
         for (int i = c0 + cn + tid; i < f; i += MW_T) {
             const double xi = i < ws ? wg[j0 + i] : wg[li_u[i - ws]];
             acc += Lx[base + i] * xi;
@@ -319,18 +392,25 @@ __global__ void __launch_bounds__(MW_T) mfw_bwd_block_kernel(int j0, int ws, int
     }
     if (!is_last) return;
     __threadfence();
-    for (int e = tid; e < cn * cn; e += MW_T) {
-        const int i = e % cn, kk = e / cn;
-        if (i > kk) T[i * (sb + 1) + kk] = Lx[mfw_colbase(lp0, f, c0 + kk) + (c0 + i)];
-    }
-    if (tid < cn) xs[tid] = wg[j0 + c0 + tid] - __ldcg(tmp + tid);
+    if (tid < sb) vs[tid] = tid < cn ? wg[j0 + c0 + tid] - __ldcg(tmp + tid) : 0.0;
     __syncthreads();
-    for (int i = cn - 1; i > 0; i--) {           // x_k -= L(i, k) x_i for k < i, x_i final
-        const double xi = xs[i];
-        if (tid < i) xs[tid] -= T[i * (sb + 1) + tid] * xi;
+    {   // x_blk = inv(T_blk)^T v:  x_k = sum_{i >= k} inv(i, k) v_i ; Trm[i * sb + k] is coalesced over k
+        const double* Tr = Trm_all + (size_t)b * tinv_stride + tinv_off + (size_t)(c0 / sb) * sb * sb;
+        const int groups = MW_T / sb, grp = tid / sb, kk = tid - grp * sb;
+        double acc = 0.0;
+        if (kk < cn) {
+            const int ih = (cn + groups - 1) / groups, ia = max(kk, grp * ih), ib = min(cn, (grp + 1) * ih);
+#pragma unroll 8
+            for (int i = ia; i < ib; i++) acc += Tr[(size_t)i * sb + kk] * vs[i];
+        }
+        part[tid] = acc;
         __syncthreads();
+        if (grp == 0 && kk < cn) {
+            double tot = 0.0;
+            for (int g2 = 0; g2 < groups; g2++) tot += part[g2 * sb + kk];
+            wg[j0 + c0 + kk] = tot;
+        }
     }
-    if (tid < cn) wg[j0 + c0 + tid] = xs[tid];
     if (tid == 0) counter[b] = 0;
 }
 // backward, narrow supernodes of one level: one warp per supernode, columns in reverse, x_j = y_j - sum_{i>j} L(i,j) x_i
