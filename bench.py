@@ -29,7 +29,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="dense", choices=["dense", "multistage", "sparse"])
+    ap.add_argument("--workload", default="dense", choices=["dense", "multistage", "sparse", "sparse_c3"])
     ap.add_argument("--density", type=float, default=0.01, help="sparse workload: density of P_utri, A, G")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (weak scaling); 0 = workload default")
     ap.add_argument("--n", type=int, default=1024)
@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
     if a.batch == 0:
-        a.batch = {"dense": 256, "multistage": 128, "sparse": 148}[a.workload]      # sparse: one CTA per QP, one QP per SM
+        a.batch = {"dense": 256, "multistage": 128, "sparse": 148, "sparse_c3": 1}[a.workload]      # sparse: one CTA per QP, one QP per SM; sparse_c3: one QP over the whole GPU
     if a.workload == "sparse" and (a.n, a.p, a.m) == (1024, 0, 512):      # sparse defaults (random patterns fill in heavily: n_kkt=850 -> nnz(L)=53k, 308 etree levels; 10-17 IP iterations)
         a.n, a.p, a.m = 500, 100, 250
     return a
@@ -285,6 +285,41 @@ class SparseWorkload(MultistageWorkload):
     roofline_kernel = "mf_factor_kernel (supernodal multifrontal sparse LDL^T, one CTA per QP, fronts in shared memory)"
 
 
+class SparseC3Workload(SparseWorkload):
+    """BASELINE config 3: ONE sparse random QP n=10 000, p=m=5 000, density 1 % (n_kkt = 20 000; the random pattern fills in to
+    a ~10 000-row dense root front, 333 GFLOP per factorisation), kkt_solver = sparse_ldlt.  The backend switches to its
+    whole-GPU schedule (sparse_wide.cuh): the roofline kernel is the DMMA trailing update of the blocked LDL^T of the root.
+    CPU arm: the reference's scalar up-looking LDL^T needs minutes per factorisation at this size, so the bounded CPU sample
+    is the SAME family at n=2 000 (n_kkt = 4 000, 2.4 GFLOP per factorisation), reported in the same size-normalised GFLOP/s."""
+    name = "sparse_c3"
+    CPU_N = 2000
+
+    def __init__(self, a):
+        super().__init__(a)
+        if (a.n, a.p, a.m) == (1024, 0, 512):
+            self.n, self.p, self.m = 10000, 5000, 5000
+        self._cpu_work = None
+
+    def describe(self, B):
+        return ("sparse random QP n=%d p=%d m=%d density=%.3g%% (n_kkt=%d), sparse_ldlt, batch=%d per GPU (BASELINE config 3), full IP solve per step, whole-GPU supernodal schedule"
+                % (self.n, self.p, self.m, 100 * self.density, self.n + self.p + self.m, B))
+
+    def cpu_solvers(self, n_qp, seed0, native):
+        small = SparseWorkload(self.a)
+        small.n, small.p, small.m, small.density = self.CPU_N, self.CPU_N // 2, self.CPU_N // 2, self.density
+        out = small.cpu_solvers(n_qp, seed0, native)
+        self._cpu_work = small.work()
+        return out
+
+    def cpu_work(self):
+        return self._cpu_work
+
+    def cpu_sample_note(self):
+        return "same family at n=%d, p=m=%d (one factorisation at n=%d takes minutes on one core)" % (self.CPU_N, self.CPU_N // 2, self.n)
+
+    roofline_kernel = "gemm_nt_tile_kernel<EPI_SUB,true> (trailing update F22 -= L21 D L21^T of the blocked LDL^T of the root front, DMMA m8n8k4 fp64, K = 64)"
+
+
 def cpu_oracle_sample(wl, n_qp, threads, seed0=1042):
     """The CPU restatement of the reference (oracle, kind "port"): `n_qp` QPs of the workload's shape, one solver per host
     thread (the reference is single-threaded per solve).  Two clocks: solve() only (comparable with `value`) and
@@ -306,7 +341,7 @@ def cpu_oracle_sample(wl, n_qp, threads, seed0=1042):
         list(ex.map(lambda s: s.solve(), solvers))      # ctypes releases the GIL inside orc_solve
     t1 = time.perf_counter()
     dt = t1 - t0
-    ff, sf = wl.work()
+    ff, sf = wl.cpu_work() if hasattr(wl, "cpu_work") else wl.work()
     flops, iters = 0.0, []
     for s in solvers:
         i = s.info()
@@ -321,7 +356,7 @@ def run_reference(args, wl, rank):
     if rank != 0:
         return
     threads = min(os.cpu_count() or 1, 32)
-    n_qp = args.cpu_sample or (threads if wl.name == "dense" else 8 * threads)
+    n_qp = args.cpu_sample or (threads if wl.name in ("dense", "sparse_c3") else 8 * threads)
     vals, qpss, secs, e2ev, e2eq = [], [], [], [], []
     native = False
     for it in range(args.warmup + args.steps):
@@ -348,7 +383,7 @@ def run_reference(args, wl, rank):
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = {"dense": DenseWorkload, "multistage": MultistageWorkload, "sparse": SparseWorkload}[args.workload](args)
+    wl = {"dense": DenseWorkload, "multistage": MultistageWorkload, "sparse": SparseWorkload, "sparse_c3": SparseC3Workload}[args.workload](args)
     if args.impl == "reference":
         run_reference(args, wl, rank)
         return
@@ -485,6 +520,34 @@ def main():
                     "cholesky_tflops": (agg["factor_calls"] * n ** 3 / 3.0) / (agg["cholesky_ms"] * 1e-3) * 1e-12 if agg["cholesky_ms"] else None,
                     "backend_solve_gbs": (agg["backend_solves"] * 8.0 * (n * n + 2 * n * m + 2 * n * p)) / (agg["backend_solve_ms"] * 1e-3) * 1e-9 if agg["backend_solve_ms"] else None,
                     "hbm_peak_gbs": hbm_peak}
+    elif wl.name == "sparse_c3":
+        # the factorisation is one dense-contraction-dominated pass (99 % of its flops are the trailing updates of the root front):
+        # tensor-pipe bound; achieved = algorithmic factor flops (sum c_j^2 + 2 c_j, unpadded) / time of the factor kernels
+        a = torch.randn(6144, 6144, dtype=torch.float64, device=dev); bmat = torch.randn(6144, 6144, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            torch.matmul(a, bmat)
+        best = 1e9
+        for _ in range(4):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, bmat); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        fp64_peak = 2 * 6144 ** 3 / (best * 1e-3) * 1e-12
+        del a, bmat
+        fb, sb = wl.bytes
+        ms_launch = agg["cholesky_ms"] / max(1, agg["cholesky_calls"])
+        achieved = ff / (ms_launch * 1e-3) * 1e-12 if ms_launch > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("sparse_c3_factor_bytes_per_factorisation")
+        except Exception:
+            pass
+        roofline = {"kernel": wl.roofline_kernel, "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp64_peak if fp64_peak else None,
+                    "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json carries no fp64 figure)",
+                    "flops_per_launch": ff, "ms_per_launch": ms_launch, "traffic": traffic,
+                    "note": "one 'launch' = one numeric factorisation (level-parallel leaf fronts, pull-form extend-add, ~157 panel + trailing-update launch pairs on the root front); time = CUDA events around the whole factorisation",
+                    "backend_solve_gbs": (agg["backend_solves"] * sb) / (agg["backend_solve_ms"] * 1e-3) * 1e-9 if agg["backend_solve_ms"] else None,
+                    "hbm_peak_gbs": hbm_peak}
     else:
         fb, sb = wl.bytes
         by_launch = fb * (agg["factor_calls"] / max(1, agg["cholesky_calls"]))
@@ -506,11 +569,11 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         threads = min(os.cpu_count() or 1, 32)
-        n_qp = args.cpu_sample or (min(threads, 16) if wl.name == "dense" else 16 * threads)
+        n_qp = args.cpu_sample or (min(threads, 16) if wl.name in ("dense", "sparse_c3") else 16 * threads)
         g, q, dt, iters, native, eg, eq = cpu_oracle_sample(wl, n_qp, min(threads, n_qp))
         cpu = {"value": g, "unit": "GFLOP/s", "qps": q, "cores": min(threads, n_qp), "kind": "port", "setup_plus_solve_gflops": eg, "setup_plus_solve_qps": eq,
-               "sample": "%d QPs of the same shape (seeds 1042..), one oracle solver per thread, %.1f s, iters %s, %s build"
-                         % (n_qp, dt, sorted(set(iters)), "-march=native" if native else "x86-64-v3")}
+               "sample": "%d QPs of %s (seeds 1042..), one oracle solver per thread, %.1f s, iters %s, %s build"
+                         % (n_qp, wl.cpu_sample_note() if hasattr(wl, "cpu_sample_note") else "the same shape", dt, sorted(set(iters)), "-march=native" if native else "x86-64-v3")}
 
     line = {
         "metric": "KKT factor+solve GFLOP/s fp64", "value": gflops, "unit": "GFLOP/s", "qps": qps,
