@@ -409,7 +409,7 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
 }
 
 void dense_syrk_sub_scaled(const double* A, long long strideA, int lda, const double* w, long long stridew, double* C, long long strideC, int ldc,
-                           int n, int K, int batch, const int* active, cudaStream_t st, int part) {
+                           int n, int K, int batch, const int* active, cudaStream_t st, int tj_start, int tj_end, int ncol) {
     if (n <= 0 || K <= 0 || batch <= 0) return;
     static thread_local int configured_dev = -1;
     int dev = 0;
@@ -420,9 +420,11 @@ void dense_syrk_sub_scaled(const double* A, long long strideA, int lda, const do
     g.B = A; g.strideB = strideA; g.ldb = lda;
     g.w = w; g.stridew = stridew;
     g.C = C; g.strideC = strideC; g.ldc = ldc;
-    g.n = n; g.rows_valid = n + (n & 1); g.K = K; g.nt = ceil_div(n, TILE); g.tj_fixed = -1; g.tj_start = 0; g.tiles = g.nt * (g.nt + 1) / 2;
-    if (part == 1) { g.tj_fixed = 0; g.tiles = g.nt; }
-    if (part == 2) { g.tj_start = 1; g.tiles -= g.nt; }
+    g.n = n; g.rows_valid = n + (n & 1); g.K = K; g.nt = ceil_div(n, TILE); g.tj_fixed = -1;
+    if (tj_end < 0 || tj_end > g.nt) tj_end = g.nt;
+    tj_start = std::max(0, std::min(tj_start, tj_end));
+    g.tj_start = tj_start; g.ncol = ncol; g.tiles = 0;
+    for (int tj = tj_start; tj < tj_end; tj++) g.tiles += g.nt - tj;
     g.active = active;
     if (g.tiles <= 0) return;
     B200_LAUNCH((gemm_nt_tile_kernel<EPI_SUB, true>), (unsigned)((size_t)g.tiles * batch), GEMM_THREADS, GEMM_SMEM, st, g);

@@ -88,9 +88,10 @@ private:
 // C (lower 128 x 128 tiles of an n x n matrix, ld = ldc) -= A diag(w) A^T for every instance of a batch, with the DMMA tile
 // kernel of the dense backend (gemm_nt_tile_kernel<EPI_SUB, true>).  A: n x K column-major (lda), w: K scale factors.
 // A, C and their leading dimensions must keep 16-byte alignment of row pairs (even row offsets, even ld); rows up to
-// n + (n & 1) of A must exist in memory.  part: 0 = all lower tiles, 1 = the first tile column only (columns [0, 128) of C),
-// 2 = everything but the first tile column.  Used by the sparse backend's whole-GPU blocked LDL^T of large fronts.
+// n + (n & 1) of A must exist in memory.  Only the lower tiles of the 128-column tile columns [tj_start, tj_end) are
+// updated (tj_end < 0: to the last one) and, if ncol > 0, only columns < ncol.  Used by the sparse backend's whole-GPU blocked
+// LDL^T of large fronts (window / far / look-ahead updates).
 void dense_syrk_sub_scaled(const double* A, long long strideA, int lda, const double* w, long long stridew, double* C, long long strideC, int ldc,
-                           int n, int K, int batch, const int* active, cudaStream_t st, int part = 0);
+                           int n, int K, int batch, const int* active, cudaStream_t st, int tj_start = 0, int tj_end = -1, int ncol = 0);
 
 }  // namespace b200

@@ -44,6 +44,7 @@ struct GemmArgs {
     int nt;           // tiles per dimension
     int tj_fixed;     // >= 0: column mode (tiles (tj_fixed + t, tj_fixed)); < 0: all lower tiles of the tile columns >= tj_start
     int tj_start;
+    int ncol;         // > 0: only columns < ncol of C are stored (narrow window updates); 0: all n
     int tiles;        // tiles per instance
     // EPI_ASSEMBLE extras
     const double* Pf; long long strideP;     // full symmetric P, ld = ldc
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_tile_kernel(GemmArgs 
         for (int u = 0; u < U; u++) {
             const int cl = (it0 + u) * 4 + (threadIdx.x >> 6);
             const int c = rowB0 + cl;
-            ok[u] = (r + 1 < g.rows_valid + 0) && (c < g.n) && (r < g.n) && (r + 1 >= c);
+            ok[u] = (r + 1 < g.rows_valid + 0) && (c < (g.ncol > 0 ? g.ncol : g.n)) && (r < g.n) && (r + 1 >= c);
             base[u] = make_double2(0.0, 0.0); extra[u] = make_double2(0.0, 0.0);
             if (ok[u]) {
                 const size_t idx = (size_t)c * g.ldc + r;

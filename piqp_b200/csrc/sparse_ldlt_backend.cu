@@ -694,6 +694,7 @@ void SparseLdltBatchedKKT::build_wide() {
     }
     const int nsup = S.nsup, nk = S.nk;
     auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    wide_group = std::min(8, std::max(1, knob("B200_WIDE_GROUP", 4)));
     wide_sb = 128;
     { const int v = knob("B200_WIDE_SB", 128); for (int c : {8, 16, 32, 64, 128}) if (v == c) wide_sb = c; }     // power of two <= 128
     const int ws_min = std::max(2, knob("B200_WIDE_WS", 64));          // supernodes at least this wide are solved blocked over the GPU
@@ -807,37 +808,53 @@ void SparseLdltBatchedKKT::factor_wide(const int* active) {
         if (w.nchild > 0) { dim3 g(ceil_div(w.f, MW_T / 32), batch);
             B200_LAUNCH(mfw_pull_kernel, g, MW_T, 0, stream, F, front_stride, w.ld, w.shift, w.f, d_pull_ptr.get() + w.pull_begin, d_pull_child.get(), d_pull_cc.get(),
                         d_crecw.get(), d_rel_idx.get(), upd.get(), upd_total_w, active); }
-        // Blocked right-looking LDL^T with look-ahead.  Panel k: columns [k0, k0 + nb); trailing update k: F22 -= L21 D L21^T.
-        // The first 128-column tile column of update k is all panel k+1 needs, so panel k+1 runs on the auxiliary stream while
-        // the remaining tile columns of update k run on the main stream (they touch disjoint columns of F).
-        int k0 = 0, nb = ((w.ws - 1) % MW_NB) + 1;       // first panel takes the remainder: every later r0 has the parity of ws (16-byte aligned row pairs)
+        // Blocked right-looking LDL^T, two levels, with look-ahead.  Panels of MW_NB columns are taken in GROUPS of `wide_group`:
+        // inside a group, panel j is followed by a narrow WINDOW update of the group's remaining columns only (K = 64); the rest
+        // of the front gets one FAR update per group with K = 64 * wide_group (the DMMA tile kernel needs a deep contraction to
+        // amortise its epilogue: 13 TFLOP/s at K = 64, 21+ at K = 256).  Look-ahead: the first tile columns of a far update cover
+        // the next group's columns, so the next group's panel / window chain runs on the (high-priority) auxiliary stream while
+        // the remaining tile columns of the far update run on the main stream -- they touch disjoint columns of F.
         auto panel = [&](int pk0, int pnb, cudaStream_t st) {
             const int R = w.f - pk0 - pnb;
             dim3 g(std::max(1, ceil_div(R, MW_T)), batch);
             B200_LAUNCH(mfw_panel_kernel, g, MW_T, MW_PANEL_SMEM, st, F, front_stride, w.ld, w.shift, w.f, pk0, pnb, w.j0, w.lp0, Lx.get(), nnzL, Dv.get(), Dinv.get(), nk, fail.get(), active);
         };
-        auto update = [&](int pk0, int pnb, int part) {
-            const int r0 = pk0 + pnb, R = w.f - r0;
-            if (R > 0) dense_syrk_sub_scaled(F + w.shift + r0 + (size_t)pk0 * w.ld, front_stride, w.ld, Dv.get() + w.j0 + pk0, nk,
-                                             F + w.shift + r0 + (size_t)r0 * w.ld, front_stride, w.ld, R, pnb, batch, active, stream, part);
+        // C[rows >= c_lo, cols in [c_lo, ...)] -= L[:, k_lo .. k_lo + K) D L^T restricted to tile columns [tj0, tj1) / the first ncol columns
+        auto update = [&](int k_lo, int K, int c_lo, cudaStream_t st, int tj0, int tj1, int ncol) {
+            const int R = w.f - c_lo;
+            if (R > 0) dense_syrk_sub_scaled(F + w.shift + c_lo + (size_t)k_lo * w.ld, front_stride, w.ld, Dv.get() + w.j0 + k_lo, nk,
+                                             F + w.shift + c_lo + (size_t)c_lo * w.ld, front_stride, w.ld, R, K, batch, active, st, tj0, tj1, ncol);
         };
-        panel(k0, nb, stream);
-        while (k0 < w.ws) {
-            const int k1 = k0 + nb;                      // next panel starts here (width MW_NB)
-            const bool more = k1 < w.ws;
+        const int nb0 = ((w.ws - 1) % MW_NB) + 1;        // first panel takes the remainder: every later boundary has the parity of ws (16-byte aligned row pairs)
+        const int npan = 1 + (w.ws - nb0) / MW_NB;
+        auto pstart = [&](int j) { return j == 0 ? 0 : nb0 + (j - 1) * MW_NB; };
+        auto pwidth = [&](int j) { return j == 0 ? nb0 : MW_NB; };
+        auto chain = [&](int ja, int jb, cudaStream_t st) {      // panels [ja, jb) of one group with their window updates
+            const int gend = pstart(jb - 1) + pwidth(jb - 1);
+            for (int j = ja; j < jb; j++) {
+                panel(pstart(j), pwidth(j), st);
+                const int r0 = pstart(j) + pwidth(j);
+                if (j + 1 < jb) update(pstart(j), pwidth(j), r0, st, 0, ceil_div(gend - r0, 128), gend - r0);      // 128 = tile width of the DMMA kernel
+            }
+        };
+        const int G = wide_group;
+        chain(0, std::min(G, npan), stream);
+        for (int ja = 0; ja < npan; ja += G) {
+            const int jb = std::min(ja + G, npan), g0 = pstart(ja), g1 = pstart(jb - 1) + pwidth(jb - 1);
+            const bool more = jb < npan;
             if (more && aux_stream) {
-                update(k0, nb, 1);
+                const int jn = std::min(jb + G, npan), next_cols = pstart(jn - 1) + pwidth(jn - 1) - g1, tsplit = ceil_div(next_cols, 128);
+                update(g0, g1 - g0, g1, stream, 0, tsplit, 0);
                 B200_CUDA(cudaEventRecord(ev_col, stream));
                 B200_CUDA(cudaStreamWaitEvent(aux_stream, ev_col, 0));
-                panel(k1, std::min(MW_NB, w.ws - k1), aux_stream);
+                chain(jb, jn, aux_stream);
                 B200_CUDA(cudaEventRecord(ev_panel, aux_stream));
-                update(k0, nb, 2);
+                update(g0, g1 - g0, g1, stream, tsplit, -1, 0);
                 B200_CUDA(cudaStreamWaitEvent(stream, ev_panel, 0));
             } else {
-                update(k0, nb, 0);
-                if (more) panel(k1, std::min(MW_NB, w.ws - k1), stream);
+                update(g0, g1 - g0, g1, stream, 0, -1, 0);
+                if (more) chain(jb, std::min(jb + G, npan), stream);
             }
-            k0 = k1; nb = MW_NB;
         }
         if (w.us > 0) { dim3 g(ceil_div(w.us, 128), w.us, batch);
             B200_LAUNCH(mfw_schur_kernel, g, 128, 0, stream, F, front_stride, w.ld, w.shift, w.ws, w.us, upd.get(), upd_total_w, w.off, active); }

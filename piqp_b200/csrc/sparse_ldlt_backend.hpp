@@ -105,6 +105,7 @@ public:
     // ---- whole-GPU ("wide") schedule for few large QPs (sparse_wide.cuh): supernodes by etree level, HBM fronts spread over the GPU
     bool wide = false;
     int wide_sb = 128;         // column block of the blocked supernodal solves (<= 128)
+    int wide_group = 4;        // panels per group of the two-level blocked LDL^T (far updates contract over 64 * wide_group columns)
     struct WStep { int kind, a, b, c; };      // kind 0: narrow / shared-memory group (list offset a, count b, factor: fpad c); kind 1: wide supernode (factor: index into wfronts, solve: supernode)
     struct WFront { int s, j0, ws, us, f, ld, shift, lp0, ab, an, pull_begin, nchild; long long off; };
     std::vector<WStep> wf_steps, ws_steps;
