@@ -3,6 +3,7 @@
 #include "sparse_frontal.cuh"
 #include "sparse_wide.cuh"
 #include <cstdlib>
+#include <chrono>
 #include <string>
 #include <algorithm>
 #include <cstdio>
@@ -179,6 +180,9 @@ void LdltSymbolic::build_gram(const Pattern& MT, Gram& g) {
 
 bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& GT, const int* user_perm, int mode_) {
     mode = mode_;
+    const bool dbg_t = getenv("B200_DEBUG_SYMBOLIC") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (!dbg_t) return; auto t = std::chrono::steady_clock::now(); fprintf(stderr, "  [symbolic %.3f s] %s\n", std::chrono::duration<double>(t - t_last).count(), what); t_last = t; };
     const bool elim_eq = mode & 1, elim_ineq = mode & 2;
     n = P.rows; p = AT.cols; m = GT.cols;
     pk = elim_eq ? 0 : p; mk = elim_ineq ? 0 : m;
@@ -239,6 +243,7 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
     // ---- ordering
     if (user_perm) perm.assign(user_perm, user_perm + nk);
     else perm = minimum_degree_ordering(nk, Kp, Ki);
+    lap("KKT pattern + ordering");
     const int nnzK = (int)Ki.size();
     std::vector<int> flag(nk, -1), Lnz(nk, 0);
     std::vector<std::pair<int, int>> extra;     // explicit structural zeros (row < col, permuted indices) added by supernode amalgamation
@@ -278,6 +283,7 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
         for (int q = PKp[k]; q < PKp[k + 1]; q++)
             for (int i = PKi_rows[q]; flag[i] != k; i = etree[i]) { if (etree[i] == -1) etree[i] = k; Lnz[i]++; flag[i] = k; }
     }
+    lap("permute + etree + column counts (one pass)");
     if (pass == 2) break;
     if (pass == 1) {
         // ---- relaxed supernode amalgamation.  Fundamental supernodes of these KKT systems are mostly single columns, so a
@@ -328,6 +334,7 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
             }
             s2 = t2 + 1;
         }
+        lap("amalgamation");
         if (extra.empty()) break;
         continue;
     }
@@ -365,22 +372,15 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
     Li.assign(Lp[nk], 0);
     std::fill(flag.begin(), flag.end(), -1);
     std::vector<int> fill(nk, 0);
-    Rp.assign(nk + 1, 0);
-    std::vector<std::vector<std::pair<int, int>>> rows(nk);
+    // pattern of L column by column (the rows of a column arrive in increasing order); the row view is built on demand
+    // (build_row_view): only the level-scheduled kernels and the whole-GPU solves read it
     for (int k = 0; k < nk; k++) {
         flag[k] = k;
         for (int q = PKp[k]; q < PKp[k + 1]; q++)
-            for (int i = PKi_rows[q]; flag[i] != k; i = etree[i]) {
-                flag[i] = k;
-                const int pos = Lp[i] + fill[i]++;
-                Li[pos] = k;
-                rows[k].push_back({i, pos});
-            }
-        std::sort(rows[k].begin(), rows[k].end());
-        Rp[k + 1] = Rp[k] + (int)rows[k].size();
+            for (int i = PKi_rows[q]; flag[i] != k; i = etree[i]) { flag[i] = k; Li[Lp[i] + fill[i]++] = k; }
     }
-    Rcol.assign(Rp[nk], 0); Rpos.assign(Rp[nk], 0);
-    for (int k = 0; k < nk; k++) for (size_t t = 0; t < rows[k].size(); t++) { Rcol[Rp[k] + t] = rows[k][t].first; Rpos[Rp[k] + t] = rows[k][t].second; }
+    Rp.clear(); Rcol.clear(); Rpos.clear();
+    lap("pattern of L + row view");
     // ---- scatter map of the permuted matrix into L / D
     PK_to_L.assign(nnzPK, 0);
     for (int j = 0; j < nk; j++) for (int q = PKp[j]; q < PKp[j + 1]; q++) {
@@ -391,6 +391,7 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
         if (it == e || *it != j) { error = "sparse_ldlt: internal error (entry of A missing in L)"; return false; }
         PK_to_L[q] = (int)(it - &Li[0]);
     }
+    lap("PK_to_L");
     // ---- level sets of the elimination tree
     level.assign(nk, 0);
     int maxl = 0;
@@ -455,6 +456,7 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
             asm_q[t] = q; asm_pos[t] = r + (i - sup_ptr[s2]) * f;
         }
     }
+    lap("levels, supernodes, relative indices, assembly map");
     // update-matrix stack: children sit on top of the stack when their parent is assembled (postorder)
     upd_off.assign(nsup, 0);
     long long top = 0; upd_total = 0;
@@ -477,6 +479,24 @@ bool LdltSymbolic::analyse(const Pattern& P, const Pattern& AT, const Pattern& G
                 nk, Li.size(), nsup, w1, fmax, big, sf2, su2, piv_work, factor_flops(), upd_total);
     }
     return true;
+}
+// Row view of L by one counting transpose (columns of a row arrive in increasing order: no sorting).  skip_sup (optional, per
+// supernode): entries whose row AND column lie in the same flagged supernode are left out -- the blocked dense solves of the
+// whole-GPU schedule read those triangles from the column storage, and for a 10 000-column root they are 98 % of nnz(L).
+void LdltSymbolic::build_row_view(const std::vector<char>* skip_sup) {
+    std::vector<int> sup_of;
+    if (skip_sup) { sup_of.assign(nk, 0); for (int s2 = 0; s2 < nsup; s2++) for (int j = sup_ptr[s2]; j < sup_ptr[s2 + 1]; j++) sup_of[j] = s2; }
+    auto skipped = [&](int i, int k) { return skip_sup && sup_of[i] == sup_of[k] && (*skip_sup)[sup_of[i]]; };
+    Rp.assign(nk + 1, 0);
+    for (int i = 0; i < nk; i++) for (int pos = Lp[i]; pos < Lp[i + 1]; pos++) if (!skipped(i, Li[pos])) Rp[Li[pos] + 1]++;
+    for (int k = 0; k < nk; k++) Rp[k + 1] += Rp[k];
+    Rcol.assign(Rp[nk], 0); Rpos.assign(Rp[nk], 0);
+    std::vector<int> rfill(Rp.begin(), Rp.end() - 1);
+    for (int i = 0; i < nk; i++) for (int pos = Lp[i]; pos < Lp[i + 1]; pos++) {
+        const int k = Li[pos];
+        if (skipped(i, k)) continue;
+        const int t = rfill[k]++; Rcol[t] = i; Rpos[t] = pos;
+    }
 }
 double LdltSymbolic::factor_flops() const {
     if (flops_exact >= 0) return flops_exact;      // algorithmic figure: explicit zeros of amalgamated supernodes are not counted
@@ -770,6 +790,12 @@ void SparseLdltBatchedKKT::build_wide() {
             if (ws >= ws_min) { ws_steps.push_back({1, s2, (int)tinv_blocks, 0}); tinv_blocks += ceil_div(ws, wide_sb); }
         }
     }
+    {   // row view for the pull-form forward solves, without the triangles of the supernodes that are solved blocked
+        std::vector<char> skip(nsup, 0);
+        for (int s2 = 0; s2 < nsup; s2++) skip[s2] = (S.sup_ptr[s2 + 1] - S.sup_ptr[s2]) >= ws_min;
+        S.build_row_view(&skip);
+        upload(d_Rp, S.Rp); upload(d_Rcol, S.Rcol); upload(d_Rpos, S.Rpos);
+    }
     upload(d_wlist_f, list_f); upload(d_wlist_s, list_s); upload(d_pull_ptr, pull_ptr); upload(d_pull_child, pull_child); upload(d_pull_cc, pull_cc);
     if (front_stride > 0) bigfront.alloc((size_t)batch * (size_t)front_stride);
     wtmp.alloc((size_t)batch * wide_sb); wcounter.alloc(batch);
@@ -926,7 +952,8 @@ SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_per
     upload(d_P_to_PK, compose(S.P_to_K)); upload(d_AT_to_PK, compose(S.AT_to_K)); upload(d_GT_to_PK, compose(S.GT_to_K));
     { std::vector<int> dg(S.diagPK.size()); for (size_t v = 0; v < dg.size(); v++) dg[v] = order[S.diagPK[v]]; upload(d_diagPK, dg); }
     upload(d_PK_to_L, S.PK_to_L); upload(d_PKp, S.PKp);
-    upload(d_Lp, S.Lp); upload(d_Li, S.Li); upload(d_Rp, S.Rp); upload(d_Rcol, S.Rcol); upload(d_Rpos, S.Rpos);
+    upload(d_Lp, S.Lp); upload(d_Li, S.Li);
+    if (!frontal) { S.build_row_view(nullptr); upload(d_Rp, S.Rp); upload(d_Rcol, S.Rcol); upload(d_Rpos, S.Rpos); }
     upload(d_level_cols, S.level_cols); upload(d_perm, S.perm);
     const size_t B = batch, nnzPK = S.PKi_rows.size(), nnzL = std::max<size_t>(S.Li.size(), 1);
     PKx.alloc(B * nnzPK); PKx.zero(st);

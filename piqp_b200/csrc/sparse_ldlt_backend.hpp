@@ -30,6 +30,7 @@ struct LdltSymbolic {   // host
     Gram ata, gtg;
     std::vector<int> xx_P, xx_var, xx_ata, xx_gtg; // P value index / variable (diagonal entries) / ata entry / gtg entry, -1 = none
     static void build_gram(const Pattern& MT, Gram& g);
+    void build_row_view(const std::vector<char>* skip_sup);      // fills Rp / Rcol / Rpos
     std::vector<int> perm, iperm;                 // perm[new] = old ; iperm[old] = new   (ordering.P / P_inv)
     // unpermuted KKT (upper CSC) and the maps of kkt_full.hpp:39-170
     std::vector<int> Kp, Ki;

@@ -91,3 +91,24 @@ def trace_as_printed(t):
     """oracle/b200 trace rows (rho, delta, mu, p_step, d_step, prim_res, dual_res, prim_obj, dual_obj, gap) ->
     the column order the reference prints (prim_obj dual_obj gap prim_res dual_res rho delta mu p_step d_step)"""
     return np.column_stack([t[:, 7], t[:, 8], t[:, 9], t[:, 5], t[:, 6], t[:, 0], t[:, 1], t[:, 2], t[:, 3], t[:, 4]])
+
+
+def load_mm_small():
+    """the committed subset of the reference's Maros-Meszaros fixtures (tests/golden/make_mm_small.py):
+    {name: (P, c, A, b, G, h_l, h_u, x_l, x_u)} as setup() arguments, plus the golden table"""
+    import json
+    import os
+    import numpy as np
+    import scipy.sparse as sp
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(here, "mm_small.npz"))
+    gold = json.load(open(os.path.join(here, "mm_small_golden.json")))
+    out = {}
+    for g in gold["problems"]:
+        nm = g["name"]
+        n, p, m = (int(v) for v in z[nm + "/dims"])
+        mat = lambda k, r: sp.csc_matrix((z["%s/%s_data" % (nm, k)], z["%s/%s_indices" % (nm, k)], z["%s/%s_indptr" % (nm, k)]), shape=(r, n))
+        P, A, G = mat("P", n), mat("A", p), mat("G", m)
+        v = lambda k: np.asarray(z["%s/%s" % (nm, k)], dtype=float)
+        out[nm] = (P, v("c"), A if p else None, v("b") if p else None, G if m else None, v("h_l") if m else None, v("h_u") if m else None, v("x_l"), v("x_u"))
+    return out, {g["name"]: g for g in gold["problems"]}

@@ -1,0 +1,50 @@
+"""GPU: the device-resident batched IP loop + sparse LDL^T CUDA backends on real Maros-Meszaros problems (BASELINE config 5
+family; committed subset of the reference's fixtures).  Bar: the reference's assertion (PIQP_SOLVED), the oracle's iteration
+count, |dx|_inf <= 1e-8 max(1, |x|_inf)."""
+import numpy as np
+import pytest
+
+from helpers import load_mm_small
+
+pytestmark = pytest.mark.gpu
+PROBLEMS, GOLD = load_mm_small()
+# LP-like problems whose minimiser is not unique (a flat optimal face): two correct solvers agree on the objective to 1e-13 but
+# land on different points of the face (measured |dx| up to 1.6e-2, profiles/r01c_mm_small_diag.txt) -> objective parity there
+DEGENERATE = {"QADLITTL", "QAFIRO", "QSC205", "QSHARE1B", "QSHARE2B", "QGROW7"}
+# Numerically chaotic problems: LDL^T without pivoting at delta = 1e-10 loses ~10 digits and the iteration path depends on the
+# summation order.  The ORACLE itself needs 29..152 iterations on QRECIPE under 1e-15 data perturbations and hits max_iter on
+# QBEACONF under random elimination orders; the multifrontal kernels hit max_iter on both, the level-scheduled (left-looking,
+# the reference's summation order) kernels solve them.  Tested with that kernel family; iteration parity is not asserted.
+CHAOTIC = {"QBEACONF", "QRECIPE"}
+
+
+def _check(oracle, b200, name, solver, batch=2):
+    args = PROBLEMS[name]
+    o = oracle.SparseSolver(oracle.default_settings(kkt_solver=solver)); o.setup(*args)
+    status = o.solve(); ro = o.result()
+    s = b200.SparseSolverBatched(kkt_solver=solver)
+    s.setup(batch, *args)
+    infos = s.solve(); r = s.result()
+    for k in range(batch):
+        assert infos[k].status == status == 1, (name, infos[k].status, status)
+        assert abs(infos[k].primal_obj - ro.info.primal_obj) <= 1e-8 * max(1.0, abs(ro.info.primal_obj)), name
+        if name in CHAOTIC:
+            continue
+        assert infos[k].iter == ro.info.iter, (name, infos[k].iter, ro.info.iter)
+        if name not in DEGENERATE:
+            assert np.abs(r.x[k] - ro.x).max() <= 1e-8 * max(1.0, np.abs(ro.x).max()), name
+    assert np.array_equal(r.x[0], r.x[batch - 1])
+
+
+@pytest.mark.parametrize("name", sorted(PROBLEMS))
+def test_mm_problem_sparse_ldlt(oracle, b200, name, monkeypatch):
+    monkeypatch.setenv("B200_LDLT_LEVELS", "1" if name in CHAOTIC else "0")
+    _check(oracle, b200, name, "sparse_ldlt")
+    assert GOLD[name]["status"] == 1
+
+
+@pytest.mark.parametrize("solver", ["sparse_ldlt_eq_cond", "sparse_ldlt_ineq_cond", "sparse_ldlt_cond"])
+@pytest.mark.parametrize("name", ["DUALC1", "HS118", "LOTSCHD", "QAFIRO", "QPCBLEND", "QSC205"])
+def test_mm_problem_condensed_modes(oracle, b200, name, solver, monkeypatch):
+    monkeypatch.setenv("B200_LDLT_LEVELS", "0")
+    _check(oracle, b200, name, solver)
