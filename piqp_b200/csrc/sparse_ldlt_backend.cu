@@ -899,7 +899,7 @@ void SparseLdltBatchedKKT::solve_wide(const double* rx, const double* ry, const 
     const size_t nnzL = std::max<size_t>(S.Li.size(), 1);
     dim3 gk(ceil_div(nk, 256), batch);
     B200_LAUNCH(ldlt_gather_rhs_kernel, gk, 256, 0, stream, d_perm.get(), n, S.pk, S.mk, rx, ry, rz, work.get(), active);
-    const size_t fsm = sizeof(double) * (size_t)(MW_T + sb), bsm = sizeof(double) * (size_t)(MW_T + sb + 32);
+    const size_t fsm = sizeof(double) * (size_t)(MW_TS + sb), bsm = sizeof(double) * (size_t)(MW_TS + sb + 32);
     const int sr = std::min(64, sb);
     for (const WStep& st : ws_steps) {           // L y = b
         if (st.kind == 0) {
@@ -912,11 +912,11 @@ void SparseLdltBatchedKKT::solve_wide(const double* rx, const double* ry, const 
           B200_LAUNCH(mfw_fwd_pull_kernel, g, MW_T, 0, stream, j0, ws, d_Rp.get(), d_Rcol.get(), d_Rpos.get(), Lx.get(), nnzL, work.get(), nk, active); }
         const int nblk = ceil_div(ws, sb);
         const long long toff = (long long)st.b * sb * sb;
-        { dim3 g(1, batch); B200_LAUNCH(mfw_fwd_block_kernel, g, MW_T, fsm, stream, j0, ws, f, lp0, 0, 0, sb, Lx.get(), nnzL, Tcm.get(), tinv_stride, toff, work.get(), nk, active); }
+        { dim3 g(1, batch); B200_LAUNCH(mfw_fwd_block_kernel, g, MW_TS, fsm, stream, j0, ws, f, lp0, 0, 0, sb, Lx.get(), nnzL, Tcm.get(), tinv_stride, toff, work.get(), nk, active); }
         for (int t = 0; t + 1 < nblk; t++) {
             const int after = ws - (t + 2) * sb;               // rows of the triangle behind the next block
             dim3 g(1 + (after > 0 ? ceil_div(after, sr) : 0), batch);
-            B200_LAUNCH(mfw_fwd_block_kernel, g, MW_T, fsm, stream, j0, ws, f, lp0, t * sb, sb, sb, Lx.get(), nnzL, Tcm.get(), tinv_stride, toff, work.get(), nk, active); }
+            B200_LAUNCH(mfw_fwd_block_kernel, g, MW_TS, fsm, stream, j0, ws, f, lp0, t * sb, sb, sb, Lx.get(), nnzL, Tcm.get(), tinv_stride, toff, work.get(), nk, active); }
     }
     B200_LAUNCH(ldlt_dscale_kernel, gk, 256, 0, stream, nk, Dinv.get(), work.get(), active);
     for (size_t i = ws_steps.size(); i-- > 0;) {   // L^T x = y
@@ -931,7 +931,7 @@ void SparseLdltBatchedKKT::solve_wide(const double* rx, const double* ry, const 
         for (int t = nblk - 1; t >= 0; t--) {
             const int c0 = t * sb, cn = std::min(sb, ws - c0);
             dim3 g(cn, batch);
-            B200_LAUNCH(mfw_bwd_block_kernel, g, MW_T, bsm, stream, j0, ws, f, lp0, d_Li.get() + S.Lp[j1], c0, cn, sb, Lx.get(), nnzL, Trm.get(), tinv_stride,
+            B200_LAUNCH(mfw_bwd_block_kernel, g, MW_TS, bsm, stream, j0, ws, f, lp0, d_Li.get() + S.Lp[j1], c0, cn, sb, Lx.get(), nnzL, Trm.get(), tinv_stride,
                         (long long)st.b * sb * sb, work.get(), nk, wtmp.get(), wcounter.get(), active);
         }
     }

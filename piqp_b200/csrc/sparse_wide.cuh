@@ -23,6 +23,7 @@ namespace b200 {
 
 constexpr int MW_NB = 64;      // panel width of the blocked LDL^T of an HBM front
 constexpr int MW_T = 256;
+constexpr int MW_TS = 1024;    // threads of the blocked-solve kernels: the block steps are latency chains, more threads = fewer dependent loads per thread
 
 __device__ __forceinline__ size_t mfw_colbase(int lp0, int f, int k) {      // L(i, j0 + k) of a supernode sits at Lx[colbase(k) + i], i = front row > k
     return (size_t)((long long)lp0 + (long long)k * (f - 1) - ((long long)k * (k - 1)) / 2 - (k + 1));
@@ -126,45 +127,56 @@ __global__ void __launch_bounds__(MW_T) mfw_pull_kernel(double* __restrict__ F_a
 }
 
 // One panel of the blocked LDL^T of an HBM front: columns [k0, k0 + nb) of F (f x f, lower, ld), rows below r0 = k0 + nb.
-// Every CTA factors the nb x nb pivot block itself, its entries spread over the registers of the 256 threads and one
-// barrier per pivot (A11 in F is only read, never overwritten: L11 goes to Lx, D to Dv), then each thread solves one row of the panel: w = a L11^-T (= l D), l = w / d; F keeps l (operand of the trailing update).
-// Dynamic shared memory: MW_PANEL_SMEM bytes.
-constexpr int MW_LDA = MW_NB + 1;
-constexpr size_t MW_PANEL_SMEM = sizeof(double) * (2 * MW_NB + MW_NB * MW_NB + MW_NB);
+// Every CTA factors the nb x nb pivot block itself (A11 in F is only read, never overwritten: L11 goes to Lx, D to Dv): thread
+// (i, g) keeps A11(i, c), c = g mod 4, in 16 REGISTERS that are rotated by one slot after every 4 pivots, so that the pivot
+// loop stays rolled (the first, fully unrolled version was instruction-fetch bound: 5.8 no-instruction stalls per issue) and
+// still indexes registers statically; one barrier per pivot through a double-buffered pivot column.  Then each thread solves
+// one row of the panel, l = a L11^-T D^-1, in 16-column chunks: the contributions of earlier chunks come from a private
+// shared-memory column (rolled loop), the 16 x 16 triangle of the chunk stays in registers.  F keeps l (operand of the
+// trailing update).  Dynamic shared memory: MW_PANEL_SMEM bytes.
+constexpr size_t MW_PANEL_SMEM = sizeof(double) * (2 * MW_NB + MW_NB * MW_NB + MW_NB + MW_NB * MW_T);
 __global__ void __launch_bounds__(MW_T) mfw_panel_kernel(double* __restrict__ F_all, long long stride, int ld, int shift, int f, int k0, int nb, int j0, int lp0,
                                                          double* __restrict__ Lx_all, size_t nnzL, double* __restrict__ Dv_all, double* __restrict__ Dinv_all, int nk,
                                                          int* __restrict__ fail, const int* __restrict__ active) {
     extern __shared__ __align__(16) double psm[];
     double* col = psm;                            // [2][MW_NB]       double-buffered pivot column (unscaled)
-    double* Lc = psm + 2 * MW_NB;                 // [MW_NB][MW_NB]   16-byte aligned rows of L11 (zero on and beyond the diagonal)
-    double* dd = Lc + MW_NB * MW_NB;              // [MW_NB]
+    double* LcT = psm + 2 * MW_NB;                // [MW_NB][MW_NB]   LcT[q * MW_NB + k] = L11(k, q) for k > q, zero elsewhere
+    double* dd = LcT + MW_NB * MW_NB;             // [MW_NB]
+    double* wsm = dd + MW_NB;                     // [MW_NB][MW_T]    private column of every row-solve thread
     const int b = blockIdx.y;
     if (active && !active[b]) return;
     const int tid = threadIdx.x;
     double* F = F_all + (size_t)b * stride + shift;
     double* Lx = Lx_all + (size_t)b * nnzL;
-    const int i = tid & (MW_NB - 1), g = tid >> 6;          // this thread owns A11(i, c) for c = g, g + 4, ..., g + 60 -- in REGISTERS
-    double a[MW_NB / 4];
+    const int i = tid & (MW_NB - 1), g = tid >> 6;
+    double a[MW_NB / 4];                          // a[m] = A11(i, g + 4 (kk + m)) while the pivots 4 kk .. 4 kk + 3 are eliminated
 #pragma unroll
     for (int m = 0; m < MW_NB / 4; m++) { const int c = g + 4 * m; a[m] = (c <= i && i < nb) ? F[(size_t)(k0 + i) + (size_t)(k0 + c) * ld] : 0.0; }
+    for (int e = tid; e < MW_NB * MW_NB; e += MW_T) LcT[e] = 0.0;
+    __syncthreads();
+#pragma unroll 1
+    for (int kk = 0; kk < MW_NB / 4; kk++) {
 #pragma unroll
-    for (int k = 0; k < MW_NB; k++) {
-        if (k < nb) {                             // uniform over the CTA
-            double* ck = col + (k & 1) * MW_NB;
-            if (g == (k & 3) && i >= k) ck[i] = a[k >> 2];                  // column k, unscaled: w_i (and d at i = k)
-            __syncthreads();
-            const double rd = 1.0 / ck[k];
-            if (i > k && i < nb) {
-                const double li = ck[i] * rd;                               // l_i = w_i / d
+        for (int j = 0; j < 4; j++) {
+            const int k = 4 * kk + j;
+            if (k < nb) {                         // uniform over the CTA
+                double* ck = col + (j & 1) * MW_NB;
+                if (g == j && i >= k) ck[i] = a[0];                         // column k, unscaled: w_i (and d at i = k)
+                __syncthreads();
+                const double rd = 1.0 / ck[k];
+                if (i > k && i < nb) {
+                    const double li = ck[i] * rd;                           // l_i = w_i / d
 #pragma unroll
-                for (int m = 0; m < MW_NB / 4; m++) { const int c = g + 4 * m; if (c > k && c <= i) a[m] -= li * ck[c]; }      // A(i, c) -= l_i w_c
-                if (g == (k & 3)) a[k >> 2] = li;
+                    for (int m = 0; m < MW_NB / 4; m++) { const int c = g + 4 * (kk + m); if (c > k && c <= i) a[m] -= li * ck[c]; }      // A(i, c) -= l_i w_c
+                    if (g == j) a[0] = li;
+                }
             }
         }
-    }
-    __syncthreads();
+        { const int c = 4 * kk + g; if (c < i) LcT[c * MW_NB + i] = (i < nb) ? a[0] : 0.0; else if (c == i) dd[i] = (i < nb) ? a[0] : 1.0; }
 #pragma unroll
-    for (int m = 0; m < MW_NB / 4; m++) { const int c = g + 4 * m; Lc[i * MW_NB + c] = c < i ? a[m] : 0.0; if (c == i) dd[i] = i < nb ? a[m] : 1.0; }
+        for (int m = 0; m + 1 < MW_NB / 4; m++) a[m] = a[m + 1];
+        a[MW_NB / 4 - 1] = 0.0;
+    }
     __syncthreads();
     if (blockIdx.x == 0) {
         for (int k = tid; k < nb; k += MW_T) {
@@ -174,32 +186,40 @@ __global__ void __launch_bounds__(MW_T) mfw_panel_kernel(double* __restrict__ F_
         }
         for (int e = tid; e < nb * nb; e += MW_T) {
             const int r = e % nb, c = e / nb;
-            if (r > c) Lx[mfw_colbase(lp0, f, k0 + c) + (k0 + r)] = Lc[r * MW_NB + c];
+            if (r > c) Lx[mfw_colbase(lp0, f, k0 + c) + (k0 + r)] = LcT[c * MW_NB + r];
         }
     }
     const int r0 = k0 + nb;
     const int row = r0 + blockIdx.x * MW_T + tid;
     if (row >= f) return;
-    double w[MW_NB];
+    constexpr int CH = 16;
+#pragma unroll 1
+    for (int cb = 0; cb < MW_NB / CH; cb++) {
+        if (cb * CH >= nb) break;
+        double acc[CH];
 #pragma unroll
-    for (int k = 0; k < MW_NB; k++) w[k] = (k < nb) ? F[(size_t)row + (size_t)(k0 + k) * ld] : 0.0;
+        for (int j = 0; j < CH; j++) { const int k = cb * CH + j; acc[j] = (k < nb) ? F[(size_t)row + (size_t)(k0 + k) * ld] : 0.0; }
+#pragma unroll 2
+        for (int q = 0; q < cb * CH; q++) {       // earlier chunks: w_q from the private column, L11(k, q) broadcast as double2
+            const double wq = wsm[q * MW_T + tid];
+            const double2* lrow = reinterpret_cast<const double2*>(LcT + q * MW_NB + cb * CH);
 #pragma unroll
-    for (int k = 1; k < MW_NB; k++) {             // rows of Lc beyond nb are zero, w beyond nb is zero: no guards needed
-        double acc = w[k];
-#pragma unroll
-        for (int q = 0; q < k; q += 2) {
-            const double2 l2 = *reinterpret_cast<const double2*>(Lc + k * MW_NB + q);
-            acc -= w[q] * l2.x;
-            if (q + 1 < k) acc -= w[q + 1] * l2.y;
+            for (int j = 0; j < CH; j += 2) { const double2 l2 = lrow[j / 2]; acc[j] -= wq * l2.x; acc[j + 1] -= wq * l2.y; }
         }
-        w[k] = acc;
-    }
 #pragma unroll
-    for (int k = 0; k < MW_NB; k++) {
-        if (k < nb) {
-            const double l = w[k] / dd[k];
-            F[(size_t)row + (size_t)(k0 + k) * ld] = l;
-            Lx[mfw_colbase(lp0, f, k0 + k) + row] = l;
+        for (int j = 0; j < CH; j++) {            // the chunk's own triangle
+#pragma unroll
+            for (int jj = 0; jj < j; jj++) acc[j] -= acc[jj] * LcT[(cb * CH + jj) * MW_NB + cb * CH + j];
+            wsm[(cb * CH + j) * MW_T + tid] = acc[j];
+        }
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            const int k = cb * CH + j;
+            if (k < nb) {
+                const double l = acc[j] / dd[k];
+                F[(size_t)row + (size_t)(k0 + k) * ld] = l;
+                Lx[mfw_colbase(lp0, f, k0 + k) + row] = l;
+            }
         }
     }
 }
@@ -291,7 +311,7 @@ __global__ void __launch_bounds__(MW_T) mfw_block_inverse_kernel(int ws, int f, 
 // L[rows, block] y[block] (y[block] is final since the previous launch); threads split the block's columns into MW_T / rows
 // groups whose partial sums are added in a fixed order.  CTA 0 then multiplies its rows by the inverse of their diagonal
 // block, which makes them final for the next launch.  sb: power of two <= 128.  smem: (MW_T + sb) doubles.
-__global__ void __launch_bounds__(MW_T) mfw_fwd_block_kernel(int j0, int ws, int f, int lp0, int gc0, int gcn, int sb, const double* __restrict__ Lx_all, size_t nnzL,
+__global__ void __launch_bounds__(MW_TS) mfw_fwd_block_kernel(int j0, int ws, int f, int lp0, int gc0, int gcn, int sb, const double* __restrict__ Lx_all, size_t nnzL,
                                                              const double* __restrict__ Tcm_all, long long tinv_stride, long long tinv_off,
                                                              double* __restrict__ work_all, int nk, const int* __restrict__ active) {
     extern __shared__ __align__(16) double sm[];
@@ -300,14 +320,14 @@ __global__ void __launch_bounds__(MW_T) mfw_fwd_block_kernel(int j0, int ws, int
     const int tid = threadIdx.x;
     const double* Lx = Lx_all + (size_t)b * nnzL;
     double* w = work_all + (size_t)b * nk + j0;
-    double* part = sm;               // MW_T
-    double* xs = sm + MW_T;          // sb
+    double* part = sm;               // MW_TS
+    double* xs = sm + MW_TS;          // sb
     const int rb = gc0 + gcn, sr = min(64, sb);
     const int rows = blockIdx.x == 0 ? sb : sr;
     const int r0 = blockIdx.x == 0 ? rb : rb + sb + (blockIdx.x - 1) * sr;
     const int rn = min(rows, ws - r0);
     if (rn <= 0) return;
-    const int groups = MW_T / rows, grp = tid / rows, r = tid - grp * rows;
+    const int groups = MW_TS / rows, grp = tid / rows, r = tid - grp * rows;
     {
         double acc = 0.0;
         if (r < rn && gcn > 0) {
@@ -352,8 +372,8 @@ __global__ void __launch_bounds__(MW_T) mfw_fwd_block_kernel(int j0, int ws, int
 // backward, wide supernode (one launch per column block [c0, c0 + cn), last block first): CTA k computes
 // dot_k = sum_{i >= c0+cn} L(i, c0+k) x_i  (rows of the triangle below the block, then the update rows through their row
 // indices); the CTA that finishes last subtracts the dots and applies the transposed inverse of the diagonal block.
-// smem: (MW_T + sb + 32) doubles.
-__global__ void __launch_bounds__(MW_T) mfw_bwd_block_kernel(int j0, int ws, int f, int lp0, const int* __restrict__ li_u, int c0, int cn, int sb,
+// smem: (MW_TS + sb + 32) doubles.
+__global__ void __launch_bounds__(MW_TS) mfw_bwd_block_kernel(int j0, int ws, int f, int lp0, const int* __restrict__ li_u, int c0, int cn, int sb,
                                                              const double* __restrict__ Lx_all, size_t nnzL, const double* __restrict__ Trm_all, long long tinv_stride,
                                                              long long tinv_off, double* __restrict__ work_all, int nk,
                                                              double* __restrict__ tmp_all, unsigned* __restrict__ counter, const int* __restrict__ active) {
@@ -365,15 +385,15 @@ __global__ void __launch_bounds__(MW_T) mfw_bwd_block_kernel(int j0, int ws, int
     const double* Lx = Lx_all + (size_t)b * nnzL;
     double* wg = work_all + (size_t)b * nk;
     double* tmp = tmp_all + (size_t)b * sb;
-    double* part = sm;               // MW_T
-    double* vs = sm + MW_T;          // sb
+    double* part = sm;               // MW_TS
+    double* vs = sm + MW_TS;          // sb
     double* red = vs + sb;           // 32
     const int k = blockIdx.x;
     {
         const size_t base = mfw_colbase(lp0, f, c0 + k);
         double acc = 0.0;
 #pragma unroll 4
-        for (int i = c0 + cn + tid; i < f; i += MW_T) {
+        for (int i = c0 + cn + tid; i < f; i += MW_TS) {
             const double xi = i < ws ? wg[j0 + i] : wg[li_u[i - ws]];
             acc += Lx[base + i] * xi;
         }
@@ -382,7 +402,7 @@ __global__ void __launch_bounds__(MW_T) mfw_bwd_block_kernel(int j0, int ws, int
         __syncthreads();
         if (tid == 0) {
             double t2 = 0.0;
-            for (int w2 = 0; w2 < MW_T / 32; w2++) t2 += red[w2];
+            for (int w2 = 0; w2 < MW_TS / 32; w2++) t2 += red[w2];
             tmp[k] = t2;
             __threadfence();
             const unsigned prev = atomicAdd(counter + b, 1u);
@@ -396,7 +416,7 @@ __global__ void __launch_bounds__(MW_T) mfw_bwd_block_kernel(int j0, int ws, int
     __syncthreads();
     {   // x_blk = inv(T_blk)^T v:  x_k = sum_{i >= k} inv(i, k) v_i ; Trm[i * sb + k] is coalesced over k
         const double* Tr = Trm_all + (size_t)b * tinv_stride + tinv_off + (size_t)(c0 / sb) * sb * sb;
-        const int groups = MW_T / sb, grp = tid / sb, kk = tid - grp * sb;
+        const int groups = MW_TS / sb, grp = tid / sb, kk = tid - grp * sb;
         double acc = 0.0;
         if (kk < cn) {
             const int ih = (cn + groups - 1) / groups, ia = max(kk, grp * ih), ib = min(cn, (grp + 1) * ih);
