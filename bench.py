@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- measures the KKT factor+solve hot path (BASELINE.json metric) on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload dense|multistage] [--batch B] ...
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload dense|multistage|sparse|sparse_c3] [--batch B] ...
 
 Default workload (the one BASELINE.json's metric is quoted on, config 2): dense QPs n=1024, p=0, m=512, batch=256 per
 GPU.  One "step" = one batched interior-point solve() of the per-GPU batch, i.e. ~10-15 passes of the hot path
 (assemble + factorise + 2 KKT solves + residual mat-vecs).  `value` = algorithmic factor+solve GFLOP/s
 over the whole step with inputs resident in HBM; `e2e` = the same metric through the public C-ABI with HOST buffers
 (setup H2D + Ruiz + solve + D2H).  `--workload multistage` runs BASELINE config 4 (MPC N=100, nx=12, nu=4, 128 QPs per
-GPU) through the block-tridiagonal-arrow backend.  Prints ONE JSON line on rank 0.
+GPU) through the block-tridiagonal-arrow backend; `--workload sparse` a batch of 148 random sparse QPs (n_kkt = 850) and
+`--workload sparse_c3` BASELINE config 3 (ONE sparse QP, n_kkt = 20 000, whole-GPU schedule) through the supernodal
+multifrontal LDL^T backend.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json

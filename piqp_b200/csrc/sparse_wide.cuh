@@ -134,15 +134,17 @@ __global__ void __launch_bounds__(MW_T) mfw_pull_kernel(double* __restrict__ F_a
 // one row of the panel, l = a L11^-T D^-1, in 16-column chunks: the contributions of earlier chunks come from a private
 // shared-memory column (rolled loop), the 16 x 16 triangle of the chunk stays in registers.  F keeps l (operand of the
 // trailing update).  Dynamic shared memory: MW_PANEL_SMEM bytes.
-constexpr size_t MW_PANEL_SMEM = sizeof(double) * (2 * MW_NB + MW_NB * MW_NB + MW_NB + MW_NB * MW_T);
+constexpr size_t MW_PANEL_SMEM = sizeof(double) * (2 * MW_NB + MW_NB * MW_NB + 2 * MW_NB + 2 + MW_NB * MW_T);
 __global__ void __launch_bounds__(MW_T) mfw_panel_kernel(double* __restrict__ F_all, long long stride, int ld, int shift, int f, int k0, int nb, int j0, int lp0,
                                                          double* __restrict__ Lx_all, size_t nnzL, double* __restrict__ Dv_all, double* __restrict__ Dinv_all, int nk,
                                                          int* __restrict__ fail, const int* __restrict__ active) {
     extern __shared__ __align__(16) double psm[];
     double* col = psm;                            // [2][MW_NB]       double-buffered pivot column (unscaled)
     double* LcT = psm + 2 * MW_NB;                // [MW_NB][MW_NB]   LcT[q * MW_NB + k] = L11(k, q) for k > q, zero elsewhere
-    double* dd = LcT + MW_NB * MW_NB;             // [MW_NB]
-    double* wsm = dd + MW_NB;                     // [MW_NB][MW_T]    private column of every row-solve thread
+    double* dd = LcT + MW_NB * MW_NB;             // [MW_NB]          D
+    double* rdd = dd + MW_NB;                     // [MW_NB]          1 / D (fp64 division costs ~30 instructions: one per pivot, not one per entry)
+    double* rpiv = rdd + MW_NB;                   // [2]              reciprocal of the current pivot, double-buffered like `col`
+    double* wsm = rpiv + 2;                       // [MW_NB][MW_T]    private column of every row-solve thread
     const int b = blockIdx.y;
     if (active && !active[b]) return;
     const int tid = threadIdx.x;
@@ -161,9 +163,9 @@ __global__ void __launch_bounds__(MW_T) mfw_panel_kernel(double* __restrict__ F_
             const int k = 4 * kk + j;
             if (k < nb) {                         // uniform over the CTA
                 double* ck = col + (j & 1) * MW_NB;
-                if (g == j && i >= k) ck[i] = a[0];                         // column k, unscaled: w_i (and d at i = k)
+                if (g == j && i >= k) { ck[i] = a[0]; if (i == k) rpiv[j & 1] = 1.0 / a[0]; }      // column k, unscaled: w_i (and d at i = k)
                 __syncthreads();
-                const double rd = 1.0 / ck[k];
+                const double rd = rpiv[j & 1];
                 if (i > k && i < nb) {
                     const double li = ck[i] * rd;                           // l_i = w_i / d
 #pragma unroll
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(MW_T) mfw_panel_kernel(double* __restrict__ F_
                 }
             }
         }
-        { const int c = 4 * kk + g; if (c < i) LcT[c * MW_NB + i] = (i < nb) ? a[0] : 0.0; else if (c == i) dd[i] = (i < nb) ? a[0] : 1.0; }
+        { const int c = 4 * kk + g; if (c < i) LcT[c * MW_NB + i] = (i < nb) ? a[0] : 0.0; else if (c == i) { const double d = (i < nb) ? a[0] : 1.0; dd[i] = d; rdd[i] = 1.0 / d; } }
 #pragma unroll
         for (int m = 0; m + 1 < MW_NB / 4; m++) a[m] = a[m + 1];
         a[MW_NB / 4 - 1] = 0.0;
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(MW_T) mfw_panel_kernel(double* __restrict__ F_
         for (int j = 0; j < CH; j++) {
             const int k = cb * CH + j;
             if (k < nb) {
-                const double l = acc[j] / dd[k];
+                const double l = acc[j] * rdd[k];
                 F[(size_t)row + (size_t)(k0 + k) * ld] = l;
                 Lx[mfw_colbase(lp0, f, k0 + k) + row] = l;
             }

@@ -19,6 +19,23 @@ def shard_bounds(global_batch, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def lpt_assign(costs, world):
+    """Heterogeneous suites (BASELINE config 5): longest-processing-time-first assignment of work items to ranks.
+    Items are taken by decreasing cost (ties: by index) and given to the currently least-loaded rank (ties: lowest rank), so
+    every rank computes the same assignment from the same cost vector without communicating.  Returns owner[item]."""
+    if world <= 0:
+        raise ValueError("bad world size")
+    costs = [float(c) for c in costs]
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    load = [0.0] * world
+    owner = [0] * len(costs)
+    for i in order:
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += costs[i]
+    return owner
+
+
 class ShardedBatch:
     """Descriptor of a global batch of independent QPs split over the ranks of a process group.
 

@@ -80,3 +80,54 @@ def test_two_rank_gloo_sharding_matches_single_process(tmp_path, oracle, global_
         assert o["tot"][0] == global_batch and o["tot"][1] == ref[:, 1].sum()   # sum over ranks
         assert np.array_equal(o["full"], ref)         # union of shards == single-process batch, bit for bit
     assert outs[0]["hi"] == outs[1]["lo"] and outs[1]["hi"] == global_batch
+
+
+def test_lpt_assignment_is_balanced_and_deterministic():
+    from piqp_b200.distributed import lpt_assign
+    rng = np.random.default_rng(0)
+    costs = np.concatenate([rng.uniform(1, 10, 60), [200.0, 150.0, 90.0]])
+    for world in (1, 2, 4, 8):
+        owner = lpt_assign(costs, world)
+        assert owner == lpt_assign(list(costs), world) and set(owner) <= set(range(world))
+        load = np.bincount(owner, weights=costs, minlength=world)
+        assert load.max() <= max(costs.max(), 4.0 / 3.0 * costs.sum() / world + 1e-9)      # LPT bound: 4/3 OPT, OPT >= max(largest item, mean load)
+    with pytest.raises(ValueError):
+        lpt_assign([1.0], 0)
+
+
+def _suite_worker(rank, world, port, out_dir):
+    """config-5 style heterogeneous suite: every rank solves the QPs LPT assigns to it (oracle on the CPU here, the CUDA
+    solver on the GPU box: tools/mm_suite.py), one all-reduce collects the totals"""
+    import torch.distributed as dist
+    from piqp_b200.distributed import lpt_assign
+    from oracle import pyoracle
+    from helpers import load_mm_small
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        probs, gold = load_mm_small()
+        names = sorted(probs)[:16]
+        owner = lpt_assign([gold[nm]["n"] + gold[nm]["p"] + gold[nm]["m"] for nm in names], world)
+        solved = iters = 0
+        for nm, r in zip(names, owner):
+            if r != rank:
+                continue
+            s = pyoracle.SparseSolver(pyoracle.default_settings(kkt_solver="sparse_ldlt")); s.setup(*probs[nm])
+            solved += int(s.solve() == 1); iters += s.result().info.iter
+        sb = ShardedBatch(len(names), dist=dist)
+        tot = sb.reduce_sum([solved, iters, sum(1 for r in owner if r == rank)])
+        np.savez(os.path.join(out_dir, "suite%d.npz" % rank), tot=np.array(tot))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_heterogeneous_suite(tmp_path, oracle):
+    import torch.multiprocessing as mp
+    from helpers import load_mm_small
+    _, gold = load_mm_small()
+    names = sorted(gold)[:16]
+    port = _free_port()
+    mp.spawn(_suite_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    outs = [np.load(os.path.join(str(tmp_path), "suite%d.npz" % r))["tot"] for r in range(2)]
+    assert np.array_equal(outs[0], outs[1])
+    assert outs[0][0] == 16 and outs[0][2] == 16 and outs[0][1] == sum(gold[nm]["iter"] for nm in names)
