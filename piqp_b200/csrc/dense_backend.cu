@@ -355,6 +355,8 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
     K.alloc((size_t)batch * D->ld * n); K.zero(st);
     zinv.alloc((size_t)batch * m); delta.alloc(batch); fail.alloc(batch); fail.zero(st);
     set_smem(gemm_nt_tile_kernel<EPI_ASSEMBLE, true>, GEMM_SMEM);
+    set_smem(gemm_nt_t64_kernel<EPI_ASSEMBLE, true>, T64_SMEM);
+    gemm_t64 = !(getenv("B200_GEMM_T64") && getenv("B200_GEMM_T64")[0] == '0');      // 128 x 64 tiles, two CTAs per SM (default); 0 = the 128 x 128 kernel
     set_smem(gemm_nt_tile_kernel<EPI_ASSEMBLE, false>, GEMM_SMEM);
     set_smem(gemm_nt_tile_kernel<EPI_SUB, false>, GEMM_SMEM);
     set_smem(gemm_nt_tile_kernel<EPI_STORE, false>, GEMM_SMEM);
@@ -414,7 +416,8 @@ void dense_syrk_sub_scaled(const double* A, long long strideA, int lda, const do
     static thread_local int configured_dev = -1;
     int dev = 0;
     B200_CUDA(cudaGetDevice(&dev));
-    if (dev != configured_dev) { set_smem(gemm_nt_tile_kernel<EPI_SUB, true>, GEMM_SMEM); configured_dev = dev; }
+    static const bool use_t64 = !(getenv("B200_GEMM_T64") && getenv("B200_GEMM_T64")[0] == '0');      // 128 x 64 tiles, two CTAs per SM (default)
+    if (dev != configured_dev) { set_smem(gemm_nt_tile_kernel<EPI_SUB, true>, GEMM_SMEM); set_smem(gemm_nt_t64_kernel<EPI_SUB, true>, T64_SMEM); configured_dev = dev; }
     GemmArgs g{};
     g.A = A; g.strideA = strideA; g.lda = lda;
     g.B = A; g.strideB = strideA; g.ldb = lda;
@@ -427,6 +430,7 @@ void dense_syrk_sub_scaled(const double* A, long long strideA, int lda, const do
     for (int tj = tj_start; tj < tj_end; tj++) g.tiles += g.nt - tj;
     g.active = active;
     if (g.tiles <= 0) return;
+    if (use_t64 && K >= 128) { g.tiles *= 2; B200_LAUNCH((gemm_nt_t64_kernel<EPI_SUB, true>), (unsigned)((size_t)g.tiles * batch), GEMM_THREADS, T64_SMEM, st, g); return; }
     B200_LAUNCH((gemm_nt_tile_kernel<EPI_SUB, true>), (unsigned)((size_t)g.tiles * batch), GEMM_THREADS, GEMM_SMEM, st, g);
 }
 
@@ -483,7 +487,8 @@ void DenseBatchedKKT::assemble(const double* x_reg, const int* active) {   // de
     g.Pf = D->Pf.get(); g.strideP = D->sP();
     g.AtA = p > 0 ? AtA.get() : nullptr; g.strideAtA = D->sP();
     g.xreg = x_reg; g.stridex = n; g.delta = delta.get(); g.active = active; g.fail = nullptr;
-    if (m > 0) B200_LAUNCH((gemm_nt_tile_kernel<EPI_ASSEMBLE, true>), (unsigned)(g.tiles * batch), GEMM_THREADS, GEMM_SMEM, stream, g);
+    if (m > 0 && gemm_t64) { g.tiles *= 2; B200_LAUNCH((gemm_nt_t64_kernel<EPI_ASSEMBLE, true>), (unsigned)(g.tiles * batch), GEMM_THREADS, T64_SMEM, stream, g); }
+    else if (m > 0) B200_LAUNCH((gemm_nt_tile_kernel<EPI_ASSEMBLE, true>), (unsigned)(g.tiles * batch), GEMM_THREADS, GEMM_SMEM, stream, g);
     else { g.A = D->Pf.get(); g.B = g.A; g.K = 0; g.w = nullptr;
            B200_LAUNCH((gemm_nt_tile_kernel<EPI_ASSEMBLE, false>), (unsigned)(g.tiles * batch), GEMM_THREADS, GEMM_SMEM, stream, g); }
 }

@@ -236,6 +236,176 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_tile_kernel(GemmArgs 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// gemm_nt_t64_kernel: the same contraction with a 128 (rows) x 64 (columns) C tile, 8 warps as 4 (M) x 2 (N) with 32 x 32
+// warp tiles -> 32 fp64 accumulators per lane, <= 128 registers, 77 KB of shared memory: TWO CTAs PER SM.  The 128 x 128 kernel
+// above holds one CTA per SM, so its prologue (pipeline fill), its barriers and its epilogue (read-modify-write of the C tile)
+// leave the DMMA pipe idle (ncu: 65 % tensor-pipe active); with two co-resident CTAs one tile's epilogue overlaps the other's
+// main loop.  Tiles: per 128-column tile column tj (units of the 128-kernel, so tj_start / tiles / ncol keep their meaning
+// for the callers) the rows ti >= tj, each split into two 64-column halves.
+// ---------------------------------------------------------------------------------------------------
+constexpr int T64_N = 64;
+constexpr int LDS_B64 = T64_N + 4;
+constexpr size_t T64_STAGE_SMEM = (size_t)STAGES * KB * (LDS_T + LDS_B64) * sizeof(double);
+constexpr size_t T64_TILE_SMEM = (size_t)T64_N * TS_LD * sizeof(double);
+constexpr size_t T64_SMEM = T64_TILE_SMEM > T64_STAGE_SMEM ? T64_TILE_SMEM : T64_STAGE_SMEM;
+
+// stage a 64 x KB panel: smem[k][r] <- M[(row0 + r) + (k0 + k) * ld]
+__device__ __forceinline__ void load_panel64(double* sm, const double* M, int ld, int row0, int rows_valid, int k0, int K) {
+#pragma unroll
+    for (int it = 0; it < (KB * T64_N / 2) / GEMM_THREADS; it++) {
+        const int c = threadIdx.x + it * GEMM_THREADS;
+        const int k = c / (T64_N / 2);
+        const int r = (c % (T64_N / 2)) * 2;
+        const int gr = row0 + r, gk = k0 + k;
+        const bool ok = (gr < rows_valid) && (gk < K);
+        const double* src = ok ? (M + (size_t)gk * ld + gr) : M;
+        cp_async16(sm + k * LDS_B64 + r, src, ok ? 16 : 0);
+    }
+}
+
+template <int EPI, bool HAS_W>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_kernel(GemmArgs g) {
+    extern __shared__ __align__(16) double smem[];
+    const int b = blockIdx.x / g.tiles;
+    int t = blockIdx.x % g.tiles;
+    if (g.active && !g.active[b]) return;
+    if (g.fail && g.fail[b]) return;
+    int tj = g.tj_start;
+    while (t >= 2 * (g.nt - tj)) { t -= 2 * (g.nt - tj); tj++; }
+    const int ti = tj + (t >> 1), half = t & 1;
+    const bool diag = (ti == tj) && (g.A == g.B);          // the B rows are a 64-row slice of the A panel: read it from there
+    const double* A = g.A + (size_t)b * g.strideA;
+    const double* B = g.B + (size_t)b * g.strideB;
+    const double* w = HAS_W ? g.w + (size_t)b * g.stridew : nullptr;
+    const int rowA0 = ti * TILE, rowB0 = tj * TILE + half * T64_N;
+    const int K = g.K, rows_valid = g.rows_valid;
+
+    double* As = smem;                                   // [STAGES][KB][LDS_T]
+    double* Bs = smem + STAGES * KB * LDS_T;             // [STAGES][KB][LDS_B64]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int nkb = (K + KB - 1) / KB;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nkb) {
+            load_panel(As + s * KB * LDS_T, A, g.lda, rowA0, rows_valid, s * KB, K);
+            if (!diag) load_panel64(Bs + s * KB * LDS_B64, B, g.ldb, rowB0, rows_valid, s * KB, K);
+        }
+        cp_async_commit();
+    }
+    double wcur[KB / 4], wnext[KB / 4];
+#pragma unroll
+    for (int kk = 0; kk < KB / 4; kk++) { wcur[kk] = 1.0; wnext[kk] = 1.0; }
+    if (HAS_W) {
+#pragma unroll
+        for (int kk = 0; kk < KB / 4; kk++) { const int gk = kk * 4 + tq; wcur[kk] = gk < K ? w[gk] : 0.0; }
+    }
+    const int ldsb = diag ? LDS_T : LDS_B64;
+    // warp tiles of a diagonal block that lie strictly above the diagonal are never stored: their warps skip the DMMAs (they
+    // still load and synchronise) and leave the tensor pipe to the co-resident CTA
+    const bool skip_mma = (ti == tj) && (half * T64_N + wn * 32 >= wm * 32 + 32);
+    for (int kb = 0; kb < nkb; kb++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nx = kb + STAGES - 1;
+            if (nx < nkb) {
+                const int s = nx % STAGES;
+                load_panel(As + s * KB * LDS_T, A, g.lda, rowA0, rows_valid, nx * KB, K);
+                if (!diag) load_panel64(Bs + s * KB * LDS_B64, B, g.ldb, rowB0, rows_valid, nx * KB, K);
+            }
+            cp_async_commit();
+        }
+        if (HAS_W) {
+#pragma unroll
+            for (int kk = 0; kk < KB / 4; kk++) { const int gk = (kb + 1) * KB + kk * 4 + tq; wnext[kk] = gk < K ? w[gk] : 0.0; }
+        }
+        const int s = kb % STAGES;
+        const double* as = As + s * KB * LDS_T;
+        const double* bs = diag ? (as + half * T64_N) : (Bs + s * KB * LDS_B64);
+        if (!skip_mma) {
+#pragma unroll
+        for (int kk = 0; kk < KB / 4; kk++) {
+            double af[4], bf[4];
+            const int krow = kk * 4 + tq;
+#pragma unroll
+            for (int i = 0; i < 4; i++) af[i] = as[krow * LDS_T + wm * 32 + i * 8 + gq];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { bf[j] = bs[krow * ldsb + wn * 32 + j * 8 + gq]; if (HAS_W) bf[j] *= wcur[kk]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        }
+        if (HAS_W) {
+#pragma unroll
+            for (int kk = 0; kk < KB / 4; kk++) wcur[kk] = wnext[kk];
+        }
+    }
+    cp_async_wait<0>();
+    // ---- epilogue through shared memory (Cs[col * TS_LD + row], 64 columns): coalesced 16-byte global accesses
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) smem[(wn * 32 + j * 8 + tq * 2 + e) * TS_LD + wm * 32 + i * 8 + gq] = acc[i][j][e];
+    __syncthreads();
+    double* __restrict__ C = g.C + (size_t)b * g.strideC;
+    const double dinv = (EPI == EPI_ASSEMBLE) ? 1.0 / g.delta[b] : 0.0;
+    const double* __restrict__ Pf = (EPI == EPI_ASSEMBLE) ? g.Pf + (size_t)b * g.strideP : nullptr;
+    const double* __restrict__ AtA = (EPI == EPI_ASSEMBLE && g.AtA) ? g.AtA + (size_t)b * g.strideAtA : nullptr;
+    const double* __restrict__ xr = (EPI == EPI_ASSEMBLE) ? g.xreg + (size_t)b * g.stridex : nullptr;
+    const int ncol = g.ncol > 0 ? g.ncol : g.n;
+    const int r = rowA0 + (threadIdx.x & 63) * 2;
+    constexpr int U = 4;
+#pragma unroll 1
+    for (int it0 = 0; it0 < T64_N / 4; it0 += U) {
+        double2 base[U], extra[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int cl = (it0 + u) * 4 + (threadIdx.x >> 6);
+            const int c = rowB0 + cl;
+            ok[u] = (r + 1 < g.rows_valid) && (c < ncol) && (r < g.n) && (r + 1 >= c);
+            base[u] = make_double2(0.0, 0.0); extra[u] = make_double2(0.0, 0.0);
+            if (ok[u]) {
+                const size_t idx = (size_t)c * g.ldc + r;
+                if (EPI == EPI_SUB) base[u] = *reinterpret_cast<const double2*>(C + idx);
+                if (EPI == EPI_ASSEMBLE) { base[u] = *reinterpret_cast<const double2*>(Pf + idx); if (AtA) extra[u] = *reinterpret_cast<const double2*>(AtA + idx); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!ok[u]) continue;
+            const int cl = (it0 + u) * 4 + (threadIdx.x >> 6);
+            const int c = rowB0 + cl;
+            const double2 a = *reinterpret_cast<const double2*>(smem + cl * TS_LD + (threadIdx.x & 63) * 2);
+            double v0 = a.x, v1 = a.y;
+            if (EPI == EPI_SUB) { v0 = base[u].x - v0; v1 = base[u].y - v1; }
+            if (EPI == EPI_ASSEMBLE) {
+                double b0 = base[u].x, b1 = base[u].y;
+                if (r == c) b0 += xr[r];
+                if (r + 1 == c) b1 += xr[r + 1];
+                if (AtA) { b0 += dinv * extra[u].x; b1 += dinv * extra[u].y; }
+                v0 = b0 + v0; v1 = b1 + v1;
+            }
+            const size_t idx = (size_t)c * g.ldc + r;
+            if (r >= c && r + 1 < g.n) *reinterpret_cast<double2*>(C + idx) = make_double2(v0, v1);
+            else { if (r >= c && r < g.n) C[idx] = v0; if (r + 1 >= c && r + 1 < g.n) C[idx + 1] = v1; }
+        }
+    }
+}
+
 #include "dense_chol.cuh"
 #include "dense_ozaki.cuh"
 

@@ -20,11 +20,13 @@ def _rel(a, b):
     return np.abs(a - b).max() / max(1.0, np.abs(b).max())
 
 
-@pytest.fixture(params=["dmma", "ozaki"])
+@pytest.fixture(params=["dmma", "dmma_tile128", "ozaki"])
 def assemble_mode(request, monkeypatch):
-    """Both assembly kernels for K = P + diag + AtA/delta + G^T Z^-1 G: the FP64 DMMA tile kernel and the Ozaki-split
-    tcgen05 (s8 tensor core + TMEM + TMA) kernel, forced through B200_DENSE_ASSEMBLE (read when a backend is constructed)."""
-    monkeypatch.setenv("B200_DENSE_ASSEMBLE", request.param)
+    """All assembly kernels for K = P + diag + AtA/delta + G^T Z^-1 G: the FP64 DMMA kernel with 128 x 64 tiles and two CTAs per
+    SM (default), the 128 x 128-tile DMMA kernel (B200_GEMM_T64=0) and the Ozaki-split tcgen05 (s8 tensor core + TMEM + TMA)
+    kernel, forced through B200_DENSE_ASSEMBLE (read when a backend is constructed)."""
+    monkeypatch.setenv("B200_DENSE_ASSEMBLE", "ozaki" if request.param == "ozaki" else "dmma")
+    monkeypatch.setenv("B200_GEMM_T64", "0" if request.param == "dmma_tile128" else "1")
     return request.param
 
 
