@@ -151,7 +151,7 @@ class DenseWorkload:
             out.append(make)
         return out
 
-    roofline_kernel = "gemm_nt_tile_kernel<EPI_ASSEMBLE,true> (K = P + diag + G^T Z^-1 G, DMMA m8n8k4 fp64)"
+    roofline_kernel = "gemm_nt_t64_kernel<EPI_ASSEMBLE,true> (K = P + diag + G^T Z^-1 G, DMMA m8n8k4 fp64, 128x64 tiles, two CTAs per SM)"
 
 
 class MultistageWorkload:
@@ -319,7 +319,7 @@ class SparseC3Workload(SparseWorkload):
     def cpu_sample_note(self):
         return "same family at n=%d, p=m=%d (one factorisation at n=%d takes minutes on one core)" % (self.CPU_N, self.CPU_N // 2, self.n)
 
-    roofline_kernel = "gemm_nt_tile_kernel<EPI_SUB,true> (trailing update F22 -= L21 D L21^T of the blocked LDL^T of the root front, DMMA m8n8k4 fp64, K = 64)"
+    roofline_kernel = "gemm_nt_t64_kernel<EPI_SUB,true> (far updates F22 -= L21 D L21^T of the two-level blocked LDL^T of the root front, DMMA m8n8k4 fp64, K = 256; window updates K = 64)"
 
 
 def cpu_oracle_sample(wl, n_qp, threads, seed0=1042):
