@@ -512,7 +512,7 @@ def main():
         achieved = fl_launch / (ms_launch * 1e-3) * 1e-12 if ms_launch > 0 else 0.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("gemm_nt_tile_kernel_assemble_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("gemm_nt_t64_kernel_assemble_bytes_per_launch")
         except Exception:
             pass
         roofline = {"kernel": wl.roofline_kernel, "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",

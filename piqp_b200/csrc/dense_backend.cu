@@ -535,12 +535,12 @@ void DenseBatchedKKT::solve(const double* rx, const double* ry, const double* rz
     if (m > 0) {
         GemvArgs a = gemv_args(D->GT.get(), D->sG(), D->ld, n, m, rz, m, lx, n, 1.0, active);
         a.s = zinv.get(); a.strides = m; a.accumulate = 1;
-        B200_LAUNCH(gemv_n_kernel, gn, 256, 0, stream, a);
+        B200_LAUNCH(gemv_n_kernel, dim3(ceil_div(n, GEMV_N_ROWS), batch), 256, 0, stream, a);
     }
     if (p > 0) {
         GemvArgs a = gemv_args(D->AT.get(), D->sA(), D->ld, n, p, ry, p, lx, n, 1.0, active);
         a.alpha_v = delta.get(); a.alpha_v_inverse = 1; a.accumulate = 1;
-        B200_LAUNCH(gemv_n_kernel, gn, 256, 0, stream, a);
+        B200_LAUNCH(gemv_n_kernel, dim3(ceil_div(n, GEMV_N_ROWS), batch), 256, 0, stream, a);
     }
     B200_LAUNCH(trsv_kernel, batch, TRSV_THREADS, (size_t)(n + 32) * sizeof(double), stream, K.get(), D->sP(), D->ld, n, Linv.get(), Linv_stride, lx, (long long)n, active);
     if (p > 0) {
@@ -562,7 +562,7 @@ void DenseBatchedKKT::eval_P_x(double alpha, const double* x, double* z, const i
     if (n == 0) return;
     dim3 gn(ceil_div(n, 256), batch);
     GemvArgs a = gemv_args(D->Pf.get(), D->sP(), D->ld, n, n, x, n, z, n, alpha, active);
-    B200_LAUNCH(gemv_n_kernel, gn, 256, 0, stream, a);
+    B200_LAUNCH(gemv_n_kernel, dim3(ceil_div(n, GEMV_N_ROWS), batch), 256, 0, stream, a);
 }
 void DenseBatchedKKT::eval_A(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) {   // :117-123
     if (p > 0) {
@@ -573,7 +573,7 @@ void DenseBatchedKKT::eval_A(double an, double at, const double* xn, const doubl
     if (n > 0) {
         GemvArgs a = gemv_args(D->AT.get(), D->sA(), D->ld, n, p, xt, p, zt, n, at, active);
         dim3 gn(ceil_div(n, 256), batch);
-        B200_LAUNCH(gemv_n_kernel, gn, 256, 0, stream, a);
+        B200_LAUNCH(gemv_n_kernel, dim3(ceil_div(n, GEMV_N_ROWS), batch), 256, 0, stream, a);
     }
 }
 void DenseBatchedKKT::eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) {   // :126-132
@@ -585,7 +585,7 @@ void DenseBatchedKKT::eval_G(double an, double at, const double* xn, const doubl
     if (n > 0) {
         GemvArgs a = gemv_args(D->GT.get(), D->sG(), D->ld, n, m, xt, m, zt, n, at, active);
         dim3 gn(ceil_div(n, 256), batch);
-        B200_LAUNCH(gemv_n_kernel, gn, 256, 0, stream, a);
+        B200_LAUNCH(gemv_n_kernel, dim3(ceil_div(n, GEMV_N_ROWS), batch), 256, 0, stream, a);
     }
 }
 void DenseBatchedKKT::extract_P_diag(double* P_diag) {
