@@ -396,6 +396,7 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout for the one JSON line (NCCL prints its version banner to stdout otherwise)
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
