@@ -52,6 +52,7 @@ struct LdltSymbolic {   // host
     std::vector<long long> upd_off;               // per supernode: offset of its update matrix (us x us, lower, ld = us) on the per-instance stack
     long long upd_total = 0;                      // stack size in doubles
     std::string error;
+    bool want_level_maps = true;                  // build PK_to_L (scatter map of the level-scheduled kernels)
     bool analyse(const Pattern& P, const Pattern& AT, const Pattern& GT, const int* user_perm, int mode = 0);
     double nnzL_exact = -1.0, flops_exact = -1.0; // of the unpadded pattern (what the reference's LDLt would store / compute)
     double nnzL() const { return nnzL_exact >= 0 ? nnzL_exact : (Lp.empty() ? 0.0 : (double)Lp.back()); }
