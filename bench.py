@@ -372,9 +372,11 @@ def run_reference(args, wl, rank):
         "impl": "reference", "metric": "KKT factor+solve GFLOP/s fp64", "value": v, "unit": "GFLOP/s", "qps": sum(qpss) / len(qpss),
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl.describe(n_qp) + " -- CPU: %d QPs per step on %d host threads" % (n_qp, threads)},
-        "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": threads, "kind": "port",
-                         "sample": "%d QPs per step, one oracle solver per thread, %s build" % (n_qp, "-march=native" if native else "x86-64-v3")},
+        "config": {"workload": wl.describe(n_qp) + " -- CPU: %d QPs per step on %d host threads" % (n_qp, threads)
+                               + ((" (" + wl.cpu_sample_note() + ")") if hasattr(wl, "cpu_sample_note") else "")},
+        "cpu_baseline": {"value": v, "unit": "GFLOP/s", "cores": min(threads, n_qp), "kind": "port",
+                         "sample": "%d QPs per step%s, one oracle solver per thread, %s build"
+                                   % (n_qp, (" of " + wl.cpu_sample_note()) if hasattr(wl, "cpu_sample_note") else "", "-march=native" if native else "x86-64-v3")},
         "e2e": {"value": sum(e2ev) / len(e2ev), "unit": "GFLOP/s", "qps": sum(e2eq) / len(e2eq), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "what": "setup() + solve() per QP on the host (the GPU arm's e2e also pays setup)"},
         "gpu_launches": 0,

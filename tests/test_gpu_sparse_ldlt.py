@@ -242,3 +242,32 @@ def test_batched_sparse_ldlt_known_answers_infeasibility_and_update(oracle, b200
         t.setup(1, S(q["P"]), q["c"], S(q["A"]) if q.get("A") is not None else None, q.get("b"), S(q["G"]) if q.get("G") is not None else None,
                 q.get("h_l"), q.get("h_u"), q.get("x_l"), q.get("x_u"))
         assert t.solve()[0].status == status
+
+
+@pytest.mark.parametrize("solver", ["sparse_ldlt", "sparse_ldlt_cond"])
+def test_batched_ip_loop_over_the_wide_schedule(oracle, b200, solver, monkeypatch):
+    """device-resident IP loop (batch of 3, per-instance values, instances retire at different iterations -> `active` masks)
+    over the whole-GPU schedule with tiny thresholds: every wide kernel sees batch strides and inactive instances"""
+    monkeypatch.setenv("B200_LDLT_WIDE", "1"); monkeypatch.setenv("B200_LDLT_LEVELS", "0"); monkeypatch.setenv("B200_FRONT_SMEM_ROWS", "6")
+    monkeypatch.setenv("B200_WIDE_WS", "2"); monkeypatch.setenv("B200_WIDE_SB", "8")
+    B = 3
+    base = sparse_strongly_convex_qp(70, 20, 35, 0.08, seed=21)
+    rng = np.random.default_rng(4)
+    Pu = sp.csc_matrix(sp.triu(base["P"])); A = sp.csc_matrix(base["A"]); G = sp.csc_matrix(base["G"])
+    Pu.sort_indices(); A.sort_indices(); G.sort_indices()
+    Ax = np.stack([A.data * rng.uniform(0.6, 1.4, A.nnz) for _ in range(B)])
+    Gx = np.stack([G.data * rng.uniform(0.6, 1.4, G.nnz) for _ in range(B)])
+    c = np.stack([base["c"] + 0.5 * rng.standard_normal(70) for _ in range(B)])
+    s = b200.SparseSolverBatched(kkt_solver=solver)
+    st = lambda v: np.broadcast_to(v, (B, len(v)))
+    s.setup(B, Pu, c, A, st(base["b"]), G, st(base["h_l"]), st(base["h_u"]), st(base["x_l"]), st(base["x_u"]), Ax=Ax, Gx=Gx)
+    infos = s.solve(); r = s.result()
+    for k in range(B):
+        Ak = sp.csc_matrix((Ax[k], A.indices, A.indptr), shape=A.shape)
+        Gk = sp.csc_matrix((Gx[k], G.indices, G.indptr), shape=G.shape)
+        o = oracle.SparseSolver(oracle.default_settings(kkt_solver=solver))
+        o.setup(Pu, c[k], Ak, base["b"], Gk, base["h_l"], base["h_u"], base["x_l"], base["x_u"])
+        status = o.solve(); ro = o.result()
+        assert infos[k].status == status == 1
+        assert infos[k].iter == ro.info.iter, (k, infos[k].iter, ro.info.iter)
+        assert np.abs(r.x[k] - ro.x).max() <= 1e-8 * max(1.0, np.abs(ro.x).max())
