@@ -190,6 +190,44 @@ class SparseKKT(KKTSolverBase):
 SparseKKT.update_data = MultistageKKT.update_data
 
 
+class LDLTNoPivot:
+    """Twin of piqp::dense::LDLTNoPivot<Mat, UpLo> (include/piqp/dense/ldlt_no_pivot.hpp:276-355 compute, :393-450 solveInPlace;
+    SURVEY a11): LDL^T without pivoting of a dense symmetric (quasi-)definite matrix.  The dense matrix is one supernode of
+    the sparse multifrontal backend -- a single front of n rows -- so it runs on the same kernels: the 64-column panel /
+    DMMA trailing-update blocked LDL^T and the blocked triangular solves of the whole-GPU schedule for n >= 512
+    (piqp_b200/csrc/sparse_wide.cuh), the shared-memory / HBM front kernels below that.  Not on the solver's call path."""
+
+    def __init__(self, device=0):
+        self.device, self._kkt, self._ok, self.n = device, None, False, 0
+
+    def compute(self, P, uplo="lower"):
+        """P: (n, n) array whose `uplo` triangle holds the symmetric matrix (the other triangle is ignored)"""
+        import scipy.sparse as sp
+        P = np.asarray(P, dtype=np.float64)
+        n = P.shape[0]
+        U = np.triu(P) if uplo == "upper" else np.tril(P).T
+        # the FULL upper pattern, zeros stored explicitly: one supernode of width n whatever the values are
+        indptr = np.cumsum([0] + [j + 1 for j in range(n)]).astype(np.int32)
+        indices = np.concatenate([np.arange(j + 1) for j in range(n)]).astype(np.int32)
+        data = np.concatenate([U[:j + 1, j] for j in range(n)])
+        Pu = sp.csc_matrix((data, indices, indptr), shape=(n, n))
+        if self._kkt is None or self.n != n:
+            self._kkt = SparseKKT(Pu, perm=np.arange(n, dtype=np.int32), device=self.device, mode=0)
+            self.n = n
+        else:
+            self._kkt.update_data(1, Pu, None, None)
+        self._ok = bool(self._kkt.update_scalings_and_factor(1.0, np.zeros(n), np.zeros(0)))
+        return self
+
+    def info(self):
+        """True = Eigen::Success"""
+        return self._ok
+
+    def solve(self, b):
+        x, _, _ = self._kkt.solve(np.asarray(b, dtype=np.float64), np.zeros(0), np.zeros(0))
+        return x
+
+
 def sparse_ldlt_symbolic(P, A, G, perm=None, mode=0):
     """Host-only symbolic phase of the sparse_ldlt backend (b200_sparse_ldlt_symbolic_mode): fill-reducing ordering of the
     KKT of the given KKTMode (sparse/ordering.hpp:59-125), nnz(L), etree levels and factor flops (sparse/ldlt.hpp:42-99),
