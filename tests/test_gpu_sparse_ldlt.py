@@ -255,9 +255,9 @@ def test_batched_ip_loop_over_the_wide_schedule(oracle, b200, solver, monkeypatc
     rng = np.random.default_rng(4)
     Pu = sp.csc_matrix(sp.triu(base["P"])); A = sp.csc_matrix(base["A"]); G = sp.csc_matrix(base["G"])
     Pu.sort_indices(); A.sort_indices(); G.sort_indices()
-    Ax = np.stack([A.data * rng.uniform(0.6, 1.4, A.nnz) for _ in range(B)])
-    Gx = np.stack([G.data * rng.uniform(0.6, 1.4, G.nnz) for _ in range(B)])
-    c = np.stack([base["c"] + 0.5 * rng.standard_normal(70) for _ in range(B)])
+    Ax = np.stack([A.data * rng.uniform(0.8, 1.2, A.nnz) for _ in range(B)])
+    Gx = np.stack([G.data * rng.uniform(0.8, 1.2, G.nnz) for _ in range(B)])
+    c = np.stack([base["c"] + 0.3 * rng.standard_normal(70) for _ in range(B)])
     s = b200.SparseSolverBatched(kkt_solver=solver)
     st = lambda v: np.broadcast_to(v, (B, len(v)))
     s.setup(B, Pu, c, A, st(base["b"]), G, st(base["h_l"]), st(base["h_u"]), st(base["x_l"]), st(base["x_u"]), Ax=Ax, Gx=Gx)
