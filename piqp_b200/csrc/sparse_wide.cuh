@@ -14,7 +14,9 @@
 //       mfw_schur_kernel            Schur complement -> the supernode's own update slot
 // Solves (L y = b, D, L^T x = y) use the PULL form as well (row view of L forward, column view backward), so that concurrent
 // supernodes never write the same entry: one warp per narrow supernode per level, and for wide supernodes a blocked dense
-// solve over the GPU (mfw_fwd_block_kernel / mfw_bwd_block_kernel, one launch per 128-column block).
+// solve over the GPU (mfw_fwd_block_kernel / mfw_bwd_block_kernel, one launch per 128-column block: a mat-vec with the block's
+// columns plus the precomputed inverse of its diagonal block).  The blocked LDL^T is two-level (groups of panels, window and
+// far updates) with look-ahead on a second stream: see SparseLdltBatchedKKT::factor_wide.
 // Replaces LDLt::factorize_numeric_upper_triangular / solve_inplace (include/piqp/sparse/ldlt.hpp:101-218).
 #pragma once
 #include "sparse_frontal.cuh"
@@ -310,9 +312,9 @@ __global__ void __launch_bounds__(MW_T) mfw_block_inverse_kernel(int ws, int f, 
 }
 // forward, wide supernode, part 2 (one launch per column block [gc0, gc0 + gcn), gcn = 0 for the first launch): CTA 0 owns the
 // rows of the NEXT block [rb, rb + sb), rb = gc0 + gcn; CTAs c >= 1 own 64-row slabs after it.  Every CTA subtracts
-// L[rows, block] y[block] (y[block] is final since the previous launch); threads split the block's columns into MW_T / rows
+// L[rows, block] y[block] (y[block] is final since the previous launch); threads split the block's columns into MW_TS / rows
 // groups whose partial sums are added in a fixed order.  CTA 0 then multiplies its rows by the inverse of their diagonal
-// block, which makes them final for the next launch.  sb: power of two <= 128.  smem: (MW_T + sb) doubles.
+// block, which makes them final for the next launch.  sb: power of two <= 128.  smem: (MW_TS + sb) doubles.
 __global__ void __launch_bounds__(MW_TS) mfw_fwd_block_kernel(int j0, int ws, int f, int lp0, int gc0, int gcn, int sb, const double* __restrict__ Lx_all, size_t nnzL,
                                                              const double* __restrict__ Tcm_all, long long tinv_stride, long long tinv_off,
                                                              double* __restrict__ work_all, int nk, const int* __restrict__ active) {
