@@ -1039,6 +1039,13 @@ SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_per
         if (!S.upd_off.empty()) B200_CUDA(cudaMemcpy(d_upd_off.get(), S.upd_off.data(), S.upd_off.size() * sizeof(long long), cudaMemcpyHostToDevice));
         // few large QPs: spread each factorisation / solve over the whole GPU (sparse_wide.cuh)
         wide = batch <= 4 && S.fmax >= 512;
+        if (wide) {      // every supernode keeps its own update slot in the wide schedule: stay with the stack discipline if that does not fit
+            double slots = 0;
+            for (int s2 = 0; s2 < S.nsup; s2++) { const double us = S.rel_ptr[s2 + 1] - S.rel_ptr[s2]; slots += us * us; }
+            size_t free_b = 0, total_b = 0;
+            B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            if (slots * sizeof(double) * B > 0.5 * (double)free_b) wide = false;
+        }
         if (const char* e = getenv("B200_LDLT_WIDE")) wide = atoi(e) != 0;
         if (!wide) upd.alloc(B * (size_t)std::max<long long>(S.upd_total, 1));
         const size_t fpad = (size_t)((S.fmax + 1) & ~1);
