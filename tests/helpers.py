@@ -93,7 +93,12 @@ def trace_as_printed(t):
     return np.column_stack([t[:, 7], t[:, 8], t[:, 9], t[:, 5], t[:, 6], t[:, 0], t[:, 1], t[:, 2], t[:, 3], t[:, 4]])
 
 
-def load_mm_small():
+def load_mm_mid():
+    """mid-size real Maros-Meszaros problems (tests/golden/make_mm_mid.py)"""
+    return load_mm_small("mm_mid")
+
+
+def load_mm_small(stem="mm_small"):
     """the committed subset of the reference's Maros-Meszaros fixtures (tests/golden/make_mm_small.py):
     {name: (P, c, A, b, G, h_l, h_u, x_l, x_u)} as setup() arguments, plus the golden table"""
     import json
@@ -101,8 +106,8 @@ def load_mm_small():
     import numpy as np
     import scipy.sparse as sp
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    z = np.load(os.path.join(here, "mm_small.npz"))
-    gold = json.load(open(os.path.join(here, "mm_small_golden.json")))
+    z = np.load(os.path.join(here, stem + ".npz"))
+    gold = json.load(open(os.path.join(here, stem + "_golden.json")))
     out = {}
     for g in gold["problems"]:
         nm = g["name"]

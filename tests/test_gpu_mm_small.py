@@ -50,3 +50,38 @@ def test_mm_problem_condensed_modes(oracle, b200, name, solver, monkeypatch):
     the summation order there (QAFIRO / sparse_ldlt_cond differs by a few iterations), so the bar is status + objective"""
     monkeypatch.setenv("B200_LDLT_LEVELS", "0")
     _check(oracle, b200, name, solver, iter_parity=False)
+
+
+def _mid():
+    from helpers import load_mm_mid
+    return load_mm_mid()
+
+
+@pytest.mark.parametrize("name", ["CVXQP1_M", "CVXQP2_M", "CVXQP3_M", "STCQP2", "CONT-050", "AUG3DCQP", "QSHIP08L", "LISWET1", "DTOC3", "STADAT1"])
+def test_mid_size_mm_problem(b200, name, monkeypatch):
+    """real problems with n_kkt 1 500 .. 25 000 (fronts up to 512 rows: HBM fronts in the CTA-per-QP schedule; STCQP2 takes the
+    whole-GPU schedule): SOLVED, the oracle's objective (tests/golden/mm_mid_golden.json) and its iteration count"""
+    monkeypatch.setenv("B200_LDLT_LEVELS", "0")
+    probs, gold = _mid()
+    s = b200.SparseSolverBatched(kkt_solver="sparse_ldlt")
+    s.setup(1, *probs[name])
+    info = s.solve()[0]
+    g = gold[name]
+    assert info.status == 1 == g["status"], (name, info.status)
+    assert abs(info.primal_obj - g["primal_obj"]) <= 1e-7 * max(1.0, abs(g["primal_obj"])), (name, info.primal_obj, g["primal_obj"])
+    assert abs(info.iter - g["iter"]) <= max(2, g["iter"] // 10), (name, info.iter, g["iter"])
+
+
+def test_stcqp2_both_schedules_agree(b200, monkeypatch):
+    """STCQP2 (largest front 512 rows): the CTA-per-QP schedule and the whole-GPU schedule reach the same solution"""
+    probs, _ = _mid()
+    xs = []
+    for wide in ("0", "1"):
+        monkeypatch.setenv("B200_LDLT_WIDE", wide); monkeypatch.setenv("B200_LDLT_LEVELS", "0")
+        s = b200.SparseSolverBatched(kkt_solver="sparse_ldlt")
+        s.setup(1, *probs["STCQP2"])
+        info = s.solve()[0]
+        assert info.status == 1
+        xs.append((s.result().x[0].copy(), info.iter))
+    assert xs[0][1] == xs[1][1]
+    assert np.abs(xs[0][0] - xs[1][0]).max() <= 1e-8 * max(1.0, np.abs(xs[0][0]).max())

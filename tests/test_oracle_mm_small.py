@@ -33,3 +33,20 @@ def test_oracle_condensed_modes_on_mm(oracle, name, solver):
     s.setup(*PROBLEMS[name])
     assert s.solve() == 1
     assert s.result().info.primal_obj == pytest.approx(GOLD[name]["primal_obj"], rel=1e-6, abs=1e-7)
+
+
+def test_oracle_solves_mid_size_mm_problems(oracle):
+    """mid-size real problems (n_kkt 1 500 .. 25 000): SOLVED like the reference asserts; the oracle takes the product's
+    fill-reducing ordering (host-only symbolic phase) because its own exact minimum degree is meant for small problems"""
+    import scipy.sparse as sp
+    from helpers import load_mm_mid
+    from piqp_b200.backend import sparse_ldlt_symbolic
+    probs, gold = load_mm_mid()
+    for name in ("CVXQP3_M", "STCQP2", "AUG3DCQP", "DTOC3"):
+        a = probs[name]
+        perm = sparse_ldlt_symbolic(sp.triu(a[0]), a[2], a[4])["perm"]
+        s = oracle.SparseSolver(oracle.default_settings(kkt_solver="sparse_ldlt"), kkt_perm=perm); s.setup(*a)
+        assert s.solve() == 1 == gold[name]["status"]
+        r = s.result()
+        assert r.info.iter == gold[name]["iter"]
+        assert r.info.primal_obj == pytest.approx(gold[name]["primal_obj"], rel=1e-9, abs=1e-9)
