@@ -477,13 +477,61 @@ def main():
                 times.append(dt); fl.append(st2.factor_calls * ff + st2.backend_solves * sf)
             del s2
         print("e2e repetitions (s): %s" % ["%.4f" % t for t in times], file=sys.stderr)
+        what = "b200qp_setup_*(host pinned buffers) + b200qp_solve + b200qp_get_result(x -> host), per GPU batch"
+        single_times = list(times)
+        if wl.name == "dense" and B >= 8:
+            # The same public calls with the per-GPU batch cut into 4 sub-batches, one handle (= one CUDA stream) and one host
+            # thread each.  The setups (H2D copies: 3.2 GB per GPU in total, ~60 ms over PCIe) run one after the other; the
+            # interior-point solve of a sub-batch starts as soon as its own setup is done and overlaps the copies of the next ones.
+            # Same inputs (slices of the same pinned buffers), same outputs (slices of hx), every QP solved.
+            from concurrent.futures import ThreadPoolExecutor
+            nchunk = 4
+            bounds = [(B * c // nchunk, B * (c + 1) // nchunk) for c in range(nchunk)]
+            chunks = [{k: v[lo:hi] for k, v in host.items()} for lo, hi in bounds]
+            turn = [threading.Event() for _ in range(nchunk + 1)]
+
+            def run_chunk(ci):
+                torch.cuda.set_device(local)
+                turn[ci].wait()
+                try:
+                    sc = wl.make_solver(local, chunks[ci], on_host=True)
+                finally:
+                    turn[ci + 1].set()
+                infos3 = sc.solve()
+                lo, hi = bounds[ci]
+                piqp_b200._lib.check(sc._L.b200qp_get_result(sc._h, C.cast(hx[lo:hi].data_ptr(), piqp_b200._lib.dp), *([None] * 9), 0), "get_result")
+                st3 = sc.stats()
+                ok = all(i.status == 1 for i in infos3)
+                fl3 = st3.factor_calls * ff + st3.backend_solves * sf
+                del sc
+                return fl3, ok
+            ptimes, pfl = [], []
+            with ThreadPoolExecutor(max_workers=nchunk) as ex:
+                for rep in range(1 + max(2, min(args.steps, 3))):
+                    barrier()
+                    for ev in turn:
+                        ev.clear()
+                    t0 = time.perf_counter()
+                    futs = [ex.submit(run_chunk, ci) for ci in range(nchunk)]
+                    turn[0].set()
+                    res = [f.result() for f in futs]
+                    dt = time.perf_counter() - t0
+                    assert all(r[1] for r in res)
+                    if rep > 0:
+                        ptimes.append(dt); pfl.append(sum(r[0] for r in res))
+            print("e2e repetitions, 4 pipelined sub-batches (s): %s" % ["%.4f" % t for t in ptimes], file=sys.stderr)
+            if max(ptimes) < max(times):
+                times, fl = ptimes, pfl
+                what = ("b200qp_setup_dense(host pinned buffers) + b200qp_solve + b200qp_get_result(x -> host) on 4 sub-batches of the per-GPU batch, one handle / "
+                        "stream / host thread each: setups in turn, each solve overlapping the H2D copies of the following sub-batches")
         tmax = torch.tensor([max(times)], dtype=torch.float64, device=dev)      # conservative: slowest repetition
         fsum = torch.tensor([sum(fl) / len(fl)], dtype=torch.float64, device=dev)
+        tsingle = torch.tensor([max(single_times)], dtype=torch.float64, device=dev)
         if dist:
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(fsum, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(fsum, op=dist.ReduceOp.SUM); dist.all_reduce(tsingle, op=dist.ReduceOp.MAX)
         e2e = {"value": float(fsum.item()) / float(tmax.item()) * 1e-9, "unit": "GFLOP/s", "qps": B * world / float(tmax.item()),
                "seconds_per_step": float(tmax.item()), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "what": "b200qp_setup_*(host pinned buffers) + b200qp_solve + b200qp_get_result(x -> host), per GPU batch"}
+               "single_handle_qps": B * world / float(tsingle.item()), "what": what}
 
     if rank != 0:
         if dist:

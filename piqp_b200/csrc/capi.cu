@@ -399,17 +399,19 @@ void load_problem(b200qp_handle* h, bool first, const double* P, const double* c
     const int B = h->batch, n = h->n, p = h->p, m = h->m;
     cudaStream_t st = h->stream;
     IpDev& d = h->ip->dev();
+    // staging buffers are released in stream order (no device-wide wait): several handles may be set up and solved concurrently
+    // from different host threads, and the H2D copies of one then overlap the kernels of the others
     {
         Staged s;
-        if (P && n > 0) { const double* src = s.get(P, (size_t)B * n * n, on_device, st); dense_pack_sym_upper(src, (long long)n * n, n, 1, h->dd, st); B200_CUDA(cudaStreamSynchronize(st)); }
+        if (P && n > 0) { const double* src = s.get(P, (size_t)B * n * n, on_device, st); dense_pack_sym_upper(src, (long long)n * n, n, 1, h->dd, st); s.buf.release_on(st); }
     }
     {
         Staged s;
-        if (A && p > 0) { const double* src = s.get(A, (size_t)B * p * n, on_device, st); dense_pack_cols(src, (long long)p * n, n, p, n, h->dd.AT.get(), h->dd.sA(), h->dd.ld, B, st); B200_CUDA(cudaStreamSynchronize(st)); }
+        if (A && p > 0) { const double* src = s.get(A, (size_t)B * p * n, on_device, st); dense_pack_cols(src, (long long)p * n, n, p, n, h->dd.AT.get(), h->dd.sA(), h->dd.ld, B, st); s.buf.release_on(st); }
     }
     {
         Staged s;
-        if (G && m > 0) { const double* src = s.get(G, (size_t)B * m * n, on_device, st); dense_pack_cols(src, (long long)m * n, n, m, n, h->dd.GT.get(), h->dd.sG(), h->dd.ld, B, st); B200_CUDA(cudaStreamSynchronize(st)); }
+        if (G && m > 0) { const double* src = s.get(G, (size_t)B * m * n, on_device, st); dense_pack_cols(src, (long long)m * n, n, m, n, h->dd.GT.get(), h->dd.sG(), h->dd.ld, B, st); s.buf.release_on(st); }
     }
     copy_vec(d.c, c, (size_t)B * n, on_device, st);
     copy_vec(d.b, b, (size_t)B * p, on_device, st);
@@ -423,7 +425,8 @@ void load_problem(b200qp_handle* h, bool first, const double* P, const double* c
     dim3 grid(ceil_div(len, 256), B);
     B200_LAUNCH(k_setup_bounds, grid, 256, 0, st, d, dhl, dhu, dxl, dxu, set_hl, set_hu, set_xl, set_xu, h->zero_rows.get());
     if (m > 0 && (set_hl || set_hu)) dense_zero_G_rows(h->dd, h->zero_rows.get(), st);
-    B200_CUDA(cudaStreamSynchronize(st));
+    s1.buf.release_on(st); s2.buf.release_on(st); s3.buf.release_on(st); s4.buf.release_on(st);
+    B200_CUDA(cudaStreamSynchronize(st));      // the caller may reuse its host buffers when this returns
 }
 
 void fill_d(double* p, size_t n, double v, cudaStream_t st) { if (n) B200_LAUNCH(k_fill_d, (unsigned)((n + 255) / 256), 256, 0, st, p, n, v); }

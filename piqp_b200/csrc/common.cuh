@@ -72,6 +72,12 @@ struct DevBuf {
         if (p) { cudaDeviceSynchronize(); cudaFreeAsync(p, cudaStreamPerThread); }
         p = nullptr; n = 0;
     }
+    // stream-ordered release: the memory goes back to the pool once `s` has passed this point -- no device-wide synchronisation
+    // (release() waits for the whole device, which serialises handles that work concurrently on different streams)
+    void release_on(cudaStream_t s) {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr; n = 0;
+    }
     T* get() const { return p; }
 };
 
