@@ -42,3 +42,29 @@ def test_no_device_is_an_error_not_a_fallback():
         assert "failed" in str(e)
     else:
         raise AssertionError("expected a RuntimeError without a CUDA device")
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """the boundary is a C ABI: include/piqp_b200.h compiles as C99 (-pedantic) and a C program links against the library
+    (examples/c_api_demo.c; without a device it prints the error and exits 0 -- no compute here)"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "piqp_b200.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    import piqp_b200
+    piqp_b200.lib()
+    libdir = os.path.join(root, "piqp_b200")
+    exe = str(tmp_path / "c_api_demo")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c_api_demo.c"),
+                    "-L", libdir, "-lpiqp_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    if piqp_b200.lib().b200_device_count() > 0:
+        assert "status 1" in r.stdout and "0.42857" in r.stdout, r.stdout
+    else:
+        assert "no CUDA device" in r.stdout
