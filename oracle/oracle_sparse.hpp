@@ -14,6 +14,7 @@
 // otherwise uses its own exact minimum-degree ordering (quotient-graph free, fine for test sizes).
 #pragma once
 #include "oracle_core.hpp"
+#include "experimental_multifrontal.hpp"
 #include <numeric>
 #include <set>
 
@@ -65,6 +66,7 @@ struct SparseLDLt {
     // :101-169 ; returns n on success, failing row otherwise.  No FMA contraction (see Makefile: -ffp-contract=off).
     int numeric(const Csc& A) {
         const int n = A.rows;
+        if (const char* e = getenv("ORACLE_MULTIFRONTAL")) if (e[0] != '0') return numeric_multifrontal(*this, A, atoi(e) - 1);   // experimental_multifrontal.hpp (study only)
         for (int k = 0; k < n; k++) {
             y[k] = 0.0; int top = n; flag[k] = k; Lnz[k] = 0;
             for (int q = A.p[k]; q < A.p[k + 1]; q++) {
