@@ -47,11 +47,16 @@ __device__ __forceinline__ void mf_eliminate_smem(double* F, int f, int ws, int 
             Dv[j0 + k] = d; Dinv[j0 + k] = 1.0 / d;
         }
         __syncthreads();
+        // multiply and subtract are rounded SEPARATELY, like the reference, which forbids FMA contraction in its LDL^T
+        // (sparse/ldlt.hpp:151-158).  On the numerically chaotic Maros-Meszaros problems a fused update changes the outcome: the
+        // oracle with this very loop restated serially solves QBEACONF / QRECIPE in 17 / 22 iterations without contraction and
+        // needs 250 (max_iter) / 146 with it (oracle/experimental_multifrontal.hpp).  The loop is bound by
+        // its three shared-memory accesses per element, not by the extra FP64 instruction.
         for (int c = k + 1 + wid; c < f; c += NW) {
             const double lc = lcol[c];
             double* Fc = F + c * f;
 #pragma unroll 4
-            for (int i = c + lane; i < f; i += 32) Fc[i] -= Fk[i] * lc;
+            for (int i = c + lane; i < f; i += 32) Fc[i] = __dsub_rn(Fc[i], __dmul_rn(Fk[i], lc));
         }
         __syncthreads();
     }

@@ -85,3 +85,17 @@ def test_stcqp2_both_schedules_agree(b200, monkeypatch):
         xs.append((s.result().x[0].copy(), info.iter))
     assert xs[0][1] == xs[1][1]
     assert np.abs(xs[0][0] - xs[1][0]).max() <= 1e-8 * max(1.0, np.abs(xs[0][0]).max())
+
+
+@pytest.mark.xfail(strict=False, reason="unverified on the GPU: the no-FMA elimination loop was written after the round's GPU budget was spent; the CPU study "
+                                         "(oracle/experimental_multifrontal.hpp) predicts SOLVED")
+@pytest.mark.parametrize("name", sorted(CHAOTIC))
+def test_chaotic_mm_problem_with_multifrontal_kernels(oracle, b200, name, monkeypatch):
+    """QBEACONF / QRECIPE through the default (multifrontal) kernels: with the fused multiply-add of the pivot update they ran into
+    max_iter; the update now rounds multiply and subtract separately like the reference (sparse/ldlt.hpp:151-158)"""
+    monkeypatch.setenv("B200_LDLT_LEVELS", "0")
+    s = b200.SparseSolverBatched(kkt_solver="sparse_ldlt")
+    s.setup(1, *PROBLEMS[name])
+    info = s.solve()[0]
+    assert info.status == 1, (name, info.status, info.iter)
+    assert abs(info.primal_obj - GOLD[name]["primal_obj"]) <= 1e-6 * max(1.0, abs(GOLD[name]["primal_obj"]))
