@@ -50,3 +50,16 @@ def test_oracle_solves_mid_size_mm_problems(oracle):
         r = s.result()
         assert r.info.iter == gold[name]["iter"]
         assert r.info.primal_obj == pytest.approx(gold[name]["primal_obj"], rel=1e-9, abs=1e-9)
+
+
+@pytest.mark.parametrize("name", sorted(PROBLEMS))
+def test_oracle_dense_solver_on_mm_problem(oracle, name):
+    """tests/src/dense/maros_meszaros_tests.cpp:20-60: the reference runs its DENSE solver on every Maros-Meszaros problem with
+    n <= 1000 and p + m <= 1000 and asserts PIQP_SOLVED; the oracle's dense backend on the committed subset, against the sparse
+    backend's objective"""
+    P, c, A, b, G, h_l, h_u, x_l, x_u = PROBLEMS[name]
+    d = lambda M: None if M is None else np.asarray(M.todense())
+    s = oracle.DenseSolver()
+    s.setup(d(P), c, d(A), b, d(G), h_l, h_u, x_l, x_u)
+    assert s.solve() == 1
+    assert s.result().info.primal_obj == pytest.approx(GOLD[name]["primal_obj"], rel=1e-6, abs=1e-7)
