@@ -38,6 +38,7 @@ extern "C" {
 #define B200_E_UNSUPPORTED (-4)
 
 #define B200_INF 1e30
+#define B200_MAX_BATCH 65535 /* instances per b200qp handle (larger batches: several handles) */
 
 /* kkt_fwd.hpp:23-29 (KKTUpdateOptions) */
 #define B200_KKT_UPDATE_NONE 0

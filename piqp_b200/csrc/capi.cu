@@ -77,7 +77,7 @@ void dense_single_upload(b200kkt_handle* h, int options, const double* P, const 
 extern "C" {
 
 const char* b200_last_error(void) { return g_err.c_str(); }
-unsigned long long b200_kernel_launch_count(void) { return g_launches; }
+unsigned long long b200_kernel_launch_count(void) { return g_launches.load(); }
 int b200_device_count(void) { int c = 0; if (cudaGetDeviceCount(&c) != cudaSuccess) return 0; return c; }
 
 int b200kkt_dense_create(b200kkt_handle** out, int n, int p, int m, const double* P_utri, const double* AT, const double* GT, int device) {
@@ -203,9 +203,11 @@ int b200kkt_factor(b200kkt_handle* h, double delta, const double* x_reg, const d
     B200_TRY(
         B200_CUDA(cudaSetDevice(h->device));
         upload(h->delta.get(), &delta, 1, h->stream);
-        upload(h->vx[0].get(), x_reg, h->n, h->stream);
-        upload(h->vz[0].get(), z_reg, h->m, h->stream);
-        h->be->factor(h->delta.get(), h->vx[0].get(), h->vz[0].get(), nullptr, h->ok.get());
+        // x_reg / z_reg live in their own buffers (vx[3], vz[3]): solve / eval_* stage through vx[0..1] and must not clobber
+        // the scalings of the current factorisation (b200kkt_dense_get_kkt re-assembles from them)
+        upload(h->vx[3].get(), x_reg, h->n, h->stream);
+        upload(h->vz[3].get(), z_reg, h->m, h->stream);
+        h->be->factor(h->delta.get(), h->vx[3].get(), h->vz[3].get(), nullptr, h->ok.get());
         B200_CUDA(cudaMemcpyAsync(&ok, h->ok.get(), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         B200_CUDA(cudaStreamSynchronize(h->stream));
     )
@@ -316,8 +318,8 @@ int b200kkt_dense_get_kkt(b200kkt_handle* h, double* kkt_lower, double* chol_low
             for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) dst[i + (size_t)j * n] = i >= j ? buf[i + (size_t)j * ld] : 0.0;
         };
         if (chol_lower) fetch(chol_lower);
-        if (kkt_lower) {   // re-assemble with the scalings of the last factor call (x_reg is still in vx[0])
-            h->dense->assemble(h->vx[0].get(), nullptr);
+        if (kkt_lower) {   // re-assemble with the scalings of the last factor call (kept in vx[3])
+            h->dense->assemble(h->vx[3].get(), nullptr);
             fetch(kkt_lower);
             h->dense->cholesky(nullptr);
             B200_CUDA(cudaStreamSynchronize(h->stream));
@@ -461,6 +463,7 @@ int b200qp_setup_dense(b200qp_handle** out, int batch, int n, int p, int m, cons
                        const b200qp_settings* settings, int device, int on_device) {
     if (!out || batch <= 0 || n <= 0 || p < 0 || m < 0 || !P || !c) return fail(B200_E_INVALID, "b200qp_setup_dense: bad arguments");
     if ((p > 0 && (!A || !b)) || (m > 0 && (!G || (!h_l && !h_u)))) return fail(B200_E_INVALID, "b200qp_setup_dense: missing constraint data");
+    if (batch > B200_MAX_BATCH) return fail(B200_E_UNSUPPORTED, "b200qp_setup_dense: batch > 65535 (the batch index is a gridDim.y / .z coordinate); split the batch over several handles");
     B200_TRY(
         B200_CUDA(cudaSetDevice(device));
         auto h = std::make_unique<b200qp_handle>();
@@ -520,7 +523,11 @@ int b200qp_update_dense(b200qp_handle* h, const double* P, const double* c, cons
         bool reuse = h->st.preconditioner_reuse_on_update != 0;
         if (options == 0) reuse = true;
         scale_problem(h, reuse);
-        if (options & B200_KKT_UPDATE_P) h->dense->extract_P_diag(d.P_diag);
+        // a recomputed preconditioner rescales P, A and G alike: every cached product (AtA) is stale, not only those of the pieces
+        // the caller passed (the reference refreshes only `options`, solver.hpp:290-301, and then factorises a KKT that
+        // disagrees with its own data; deliberate deviation)
+        if (!reuse) options = B200_KKT_UPDATE_P | B200_KKT_UPDATE_A | B200_KKT_UPDATE_G;
+        else if (h_l || h_u) options |= B200_KKT_UPDATE_G;   // disable_inf_constraints may have zeroed rows of G (dense/data.hpp:144-169)
         h->dense->update_data(options);
         h->ip->finish_setup(h->dense.get());
         B200_CUDA(cudaStreamSynchronize(h->stream));
@@ -579,6 +586,7 @@ int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
                         const double* x_l, const double* x_u, const b200qp_settings* settings, int device, int on_device) {
     if (!out || batch <= 0 || n <= 0 || p < 0 || m < 0 || !Pp || !c) return fail(B200_E_INVALID, "b200qp_setup_sparse: bad arguments");
     if ((p > 0 && (!Ap || !b)) || (m > 0 && (!Gp || (!h_l && !h_u)))) return fail(B200_E_INVALID, "b200qp_setup_sparse: missing constraint data");
+    if (batch > B200_MAX_BATCH) return fail(B200_E_UNSUPPORTED, "b200qp_setup_sparse: batch > 65535 (the batch index is a gridDim.y / .z coordinate); split the batch over several handles");
     B200_TRY(
         B200_CUDA(cudaSetDevice(device));
         const bool tm = getenv("B200_TIMING") != nullptr;
@@ -660,6 +668,8 @@ int b200qp_update_sparse(b200qp_handle* h, const double* Px, const double* c, co
         bool reuse = h->st.preconditioner_reuse_on_update != 0;
         if (options == 0) reuse = true;
         sparse_ruiz_scale(S, h->ruiz, d.c, d.b, d.h_l, d.h_u, d.x_l, d.x_u, d.xbs, reuse, h->st.preconditioner_scale_cost != 0, h->st.preconditioner_iter, h->stream);
+        if (!reuse) options = B200_KKT_UPDATE_P | B200_KKT_UPDATE_A | B200_KKT_UPDATE_G;   // see b200qp_update_dense
+        else if (h_l || h_u) options |= B200_KKT_UPDATE_G;
         h->be->update_data(options);
         h->ip->finish_setup(h->be);
         B200_CUDA(cudaStreamSynchronize(h->stream));

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdint>
+#include <atomic>
 #include <stdexcept>
 #include <string>
 
@@ -20,11 +21,11 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 }
 #define B200_CUDA(x) ::b200::cuda_check((x), #x, __FILE__, __LINE__)
 
-extern unsigned long long g_launches;  // counted at every kernel launch (b200_kernel_launch_count)
+extern std::atomic<unsigned long long> g_launches;  // counted at every kernel launch (b200_kernel_launch_count); handles may be driven from several host threads
 #define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                         \
     do {                                                                            \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                 \
-        ++::b200::g_launches;                                                       \
+        ::b200::g_launches.fetch_add(1, std::memory_order_relaxed);                 \
         B200_CUDA(cudaPeekAtLastError());                                           \
     } while (0)
 

@@ -6,7 +6,7 @@
 
 namespace b200 {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 void BatchedKKT::tic(int kind) {
     if (!profile) return;

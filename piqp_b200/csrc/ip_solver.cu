@@ -52,7 +52,7 @@ __device__ __forceinline__ VarsB vb(const Vars& v, const IpDev& d, int b) {
 #define US_PRES_B(v, i) ((v) * q.pdb_inv[i])
 #define US_DRES(v, i) ((v) * q.pc_inv * q.pd_inv[i])
 
-__shared__ double g_red[32 * 12];
+__shared__ double g_red[32 * 12];   // block_reduce scratch: up to 12 values per call
 
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_counts(IpDev d) {   // n_fin = n_h_l + n_h_u + n_x_l + n_x_u ; has_ineq = m + n_x_l + n_x_u > 0
@@ -444,6 +444,7 @@ __global__ void k_head(IpDev d) {
         (!st.check_duality_gap || s.duality_gap < st.eps_duality_gap_abs || s.duality_gap_rel < st.eps_duality_gap_rel)) {
         s.status = ST_SOLVED; stop = true;
     }
+    if (!stop && (s.primal_res != s.primal_res || s.dual_res != s.dual_res)) { s.status = ST_NUMERICS; stop = true; }   // NaN residuals (k_resid_nr)
     if (!stop) {
         ResR rr = residuals_r(d, b, q, s.rho, s.delta, s.primal_res, s.primal_res_rel, s.dual_res, s.dual_res_rel);
         s.primal_res_reg = rr.primal_res_reg; s.primal_res_reg_rel = rr.primal_res_reg_rel; s.dual_res_reg = rr.dual_res_reg;
@@ -587,7 +588,8 @@ __global__ void k_resid_nr(IpDev d, const int* mask, int first) {
     IpScalars& sg = d.sc[b];
     double *wx = PB(d.work_x, d.n), *wx2 = PB(d.work_x2, d.n);
     // v: 0 x'Px  1 c'x  2 b'y  3 -h_l'z_l  4 h_u'z_u  5 -x_l'z_bl  6 x_u'z_bu | 7 dual_rel  8 prim_rel  9 primal_res  10 dual_res
-    double v[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // 11: non-finite flag (fmax drops NaNs, so a NaN iterate would otherwise report residuals of 0)
+    double v[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     FOR_T(i, d.n) {
         double wxi = wx[i] + wx2[i];
         const double mPx = rnr.x[i];
@@ -602,6 +604,7 @@ __global__ void k_resid_nr(IpDev d, const int* mask, int first) {
         rx -= wxi;
         rnr.x[i] = rx;
         v[10] = fmax(v[10], fabs(US_DRES(rx, i)));
+        if (!isfinite(rx)) v[11] = 1.0;
         // box primal residuals (signed maxima, solver.hpp:1077-1095, 1137-1144)
         if (q.hxl[i]) {
             const double t = q.xbs[i] * it.x[i];
@@ -624,6 +627,7 @@ __global__ void k_resid_nr(IpDev d, const int* mask, int first) {
         rnr.y[i] = ry;
         v[8] = fmax(v[8], fabs(US_PRES_EQ(q.bv[i], i)));
         v[9] = fmax(v[9], fabs(US_PRES_EQ(ry, i)));
+        if (!isfinite(ry)) v[11] = 1.0;
     }
     FOR_T(i, d.m) {
         const double Gx = rnr.z_l[i];
@@ -642,14 +646,15 @@ __global__ void k_resid_nr(IpDev d, const int* mask, int first) {
         }
         rnr.z_l[i] = rl; rnr.z_u[i] = ru;
         v[9] = fmax(v[9], fmax(fabs(US_PRES_INEQ(rl, i)), fabs(US_PRES_INEQ(ru, i))));
+        if (!isfinite(rl) || !isfinite(ru)) v[11] = 1.0;
     }
     __syncthreads();
     FOR_T(i, d.n) {   // box part of primal_res_nr: signed (solver.hpp:1137-1144)
-        if (q.hxl[i]) v[9] = fmax(v[9], US_PRES_B(rnr.z_bl[i], i));
-        if (q.hxu[i]) v[9] = fmax(v[9], US_PRES_B(rnr.z_bu[i], i));
+        if (q.hxl[i]) { v[9] = fmax(v[9], US_PRES_B(rnr.z_bl[i], i)); if (!isfinite(rnr.z_bl[i])) v[11] = 1.0; }
+        if (q.hxu[i]) { v[9] = fmax(v[9], US_PRES_B(rnr.z_bu[i], i)); if (!isfinite(rnr.z_bu[i])) v[11] = 1.0; }
     }
-    const int op[11] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_MAX, RED_MAX, RED_MAX, RED_MAX};
-    block_reduce<11>(v, op, g_red);
+    const int op[12] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_MAX, RED_MAX, RED_MAX, RED_MAX, RED_MAX};
+    block_reduce<12>(v, op, g_red);
     if (threadIdx.x == 0) {
         IpScalars s = sg;
         double tmp = -v[0];                       // x'Px
@@ -667,6 +672,10 @@ __global__ void k_resid_nr(IpDev d, const int* mask, int first) {
         s.prev_primal_res = s.primal_res; s.prev_dual_res = s.dual_res;
         s.primal_res = v[9]; s.primal_res_rel = v[9] / fmax(1.0, v[8]);
         s.dual_res = v[10]; s.dual_res_rel = v[10] / fmax(1.0, v[7]);
+        if (v[11] > 0.0) {   // a non-finite iterate: report it (an Eigen inf-norm of the reference would carry the NaN), k_head stops with PIQP_NUMERICS
+            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+            s.primal_res = s.primal_res_rel = s.dual_res = s.dual_res_rel = qnan;
+        }
         if (first) { s.prev_primal_res = s.primal_res; s.prev_dual_res = s.dual_res; }
         sg = s;
     }
@@ -850,7 +859,7 @@ void BatchedIPSolver::residuals_nr(const int* mask) {
 
 void BatchedIPSolver::solve() {
     IpDev& d = d_;
-    const unsigned long long l0 = g_launches;
+    const unsigned long long l0 = g_launches.load();
     stats_ = b200qp_stats{};
     float ms;
     B200_CUDA(cudaEventRecord(ev_[4], stream));
@@ -910,7 +919,7 @@ void BatchedIPSolver::solve() {
         B200_CUDA(cudaEventElapsedTime(&ms, iter_ev_[3 * i + 1], iter_ev_[3 * i + 2])); stats_.solve_ms += ms;
     }
     B200_CUDA(cudaEventElapsedTime(&ms, ev_[4], ev_[5])); stats_.total_ms = ms;
-    stats_.kernel_launches = g_launches - l0;
+    stats_.kernel_launches = g_launches.load() - l0;
 }
 
 std::vector<b200qp_info> BatchedIPSolver::infos() {

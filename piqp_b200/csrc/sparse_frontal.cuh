@@ -27,6 +27,7 @@ struct MfDev {
     int nsup, nk, n, p, m, front_smem_rows, fmax;
     long long upd_total;
     size_t nnzL, nnzPK;
+    long long* prof;       // optional [8] phase clocks of CTA 0 (B200_MF_PROF=1): zero+scatter, extend-add, eliminate (smem), eliminate (HBM), Schur store
 };
 
 constexpr int MF_T = 256;
@@ -62,7 +63,7 @@ __device__ __forceinline__ void mf_eliminate_smem(double* F, int f, int ws, int 
     }
 }
 
-// ---- blocked elimination of a front held in HBM/L2: panels of MF_NB pivots; per panel (1) LDL^T of the nb x nb diagonal
+// ---- blocked elimination of a front held in HBM/L2 (products and sums rounded separately, like mf_eliminate_smem): panels of MF_NB pivots; per panel (1) LDL^T of the nb x nb diagonal
 // block in shared memory by one warp, (2) one thread per row below solves its row against the block (w = a L11^-T D, l = w / d),
 // (3) the trailing lower triangle is updated tile by tile (64x64, 4x4 per thread) from shared-memory copies of W and L.
 // sm: scratch of at least 2 * MF_TS * MF_NB + MF_NB * (MF_NB + 1) + MF_NB doubles.  Wg / Lg: per-instance panel scratch (f x MF_NB each).
@@ -87,7 +88,7 @@ __device__ void mf_eliminate_big(double* __restrict__ F, int f, int ws, int j0, 
                 __syncwarp();
                 if (lane > k && lane < nb) A11[lane + k * LDA] = li;
                 __syncwarp();
-                if (lane > k && lane < nb) for (int c = k + 1; c <= lane; c++) A11[lane + c * LDA] -= wi * A11[c + k * LDA];
+                if (lane > k && lane < nb) for (int c = k + 1; c <= lane; c++) A11[lane + c * LDA] = __dsub_rn(A11[lane + c * LDA], __dmul_rn(wi, A11[c + k * LDA]));   // no FMA contraction (sparse/ldlt.hpp:151-158)
                 if (lane == 0) dd[k] = d;
                 __syncwarp();
             }
@@ -113,7 +114,7 @@ __device__ void mf_eliminate_big(double* __restrict__ F, int f, int ws, int j0, 
                 if (k < nb) {
                     double acc = w[k];
 #pragma unroll
-                    for (int q = 0; q < k; q++) acc -= w[q] * A11[k + q * LDA];
+                    for (int q = 0; q < k; q++) acc = __dsub_rn(acc, __dmul_rn(w[q], A11[k + q * LDA]));
                     w[k] = acc;
                 }
             }
@@ -149,7 +150,7 @@ __device__ void mf_eliminate_big(double* __restrict__ F, int f, int ws, int j0, 
 #pragma unroll
                     for (int a2 = 0; a2 < 4; a2++)
 #pragma unroll
-                        for (int c2 = 0; c2 < 4; c2++) acc[a2][c2] += wa[a2] * la[c2];
+                        for (int c2 = 0; c2 < 4; c2++) acc[a2][c2] = __dadd_rn(acc[a2][c2], __dmul_rn(wa[a2], la[c2]));
                 }
 #pragma unroll
                 for (int c2 = 0; c2 < 4; c2++) {
@@ -193,6 +194,9 @@ __global__ void __launch_bounds__(MF_T) mf_factor_kernel(MfDev M, const double* 
     int4 nh0 = hdr4[0], nh1 = hdr4[1];
     long long noff = M.upd_off[0];
 
+    const bool prof = M.prof != nullptr && b == 0 && tid == 0;
+    long long pc[6] = {0, 0, 0, 0, 0, 0}, t_prev = prof ? clock64() : 0;
+#define MF_LAP(k) do { if (prof) { const long long t_ = clock64(); pc[k] += t_ - t_prev; t_prev = t_; } } while (0)
     for (int s = 0; s < M.nsup; s++) {
         const int4 h0 = nh0, h1 = nh1;
         const long long my_off = noff;
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(MF_T) mf_factor_kernel(MfDev M, const double* 
 #pragma unroll
         for (int u = 0; u < 2; u++) if (tid + u * MF_T < an) F[ap[u]] = av[u];
         for (int t = tid + 2 * MF_T; t < an; t += MF_T) F[M.asm_pos[ab + t]] = PK[ab + t];
+        MF_LAP(0);
         for (int c = 0; c < cn; c++) {                       // extend-add, one child at a time (fixed order)
             const int4 cr = reinterpret_cast<const int4*>(M.crec)[cb + c];
             const int uc = cr.x;
@@ -234,9 +239,10 @@ __global__ void __launch_bounds__(MF_T) mf_factor_kernel(MfDev M, const double* 
             __syncthreads();
         }
         if (cn == 0) __syncthreads();
+        MF_LAP(1);
         // ---- eliminate the ws pivots of the supernode
-        if (in_smem) mf_eliminate_smem(Fs, f, ws, j0, lp0, lcol, Lx, Dv, Dinv, fail + b);
-        else { mf_eliminate_big(big, f, ws, j0, lp0, Fs, Wg, Lg, Lx, Dv, Dinv, fail + b); __syncthreads(); }
+        if (in_smem) { mf_eliminate_smem(Fs, f, ws, j0, lp0, lcol, Lx, Dv, Dinv, fail + b); MF_LAP(2); }
+        else { mf_eliminate_big(big, f, ws, j0, lp0, Fs, Wg, Lg, Lx, Dv, Dinv, fail + b); __syncthreads(); MF_LAP(3); }
         // ---- Schur complement -> stack (full us x us square, ld = us; only the lower part is meaningful)
         if (us > 0) {
             double* U = upd + my_off;
@@ -246,7 +252,10 @@ __global__ void __launch_bounds__(MF_T) mf_factor_kernel(MfDev M, const double* 
             }
         }
         __syncthreads();
+        MF_LAP(4);
     }
+#undef MF_LAP
+    if (prof) for (int k = 0; k < 5; k++) M.prof[k] += pc[k];
 }
 
 // x: permuted work vector (shared memory when it fits, else the HBM work buffer)

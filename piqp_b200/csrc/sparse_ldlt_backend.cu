@@ -741,6 +741,7 @@ static MfDev make_mf(const SparseLdltBatchedKKT& K) {
     M.nsup = K.S.nsup; M.nk = K.S.nk; M.n = K.n; M.p = K.S.pk; M.m = K.S.mk; M.front_smem_rows = K.front_smem_rows; M.fmax = K.S.fmax;
     M.upd_total = std::max<long long>(K.S.upd_total, 1);
     M.nnzL = std::max<size_t>(K.S.Li.size(), 1); M.nnzPK = K.S.PKi_rows.size();
+    M.prof = K.d_prof.n ? K.d_prof.get() : nullptr;
     return M;
 }
 
@@ -748,6 +749,11 @@ static MfDev make_mf(const SparseLdltBatchedKKT& K) {
 // whole-GPU schedule (sparse_wide.cuh)
 // =====================================================================================================
 SparseLdltBatchedKKT::~SparseLdltBatchedKKT() {
+    if (d_prof.n) {
+        long long h[8]; cudaDeviceSynchronize();
+        if (cudaMemcpy(h, d_prof.get(), sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
+            fprintf(stderr, "[mf_factor_kernel phase clocks, CTA 0] zero+scatter %lld  extend-add %lld  eliminate(smem) %lld  eliminate(HBM) %lld  schur store %lld\n", h[0], h[1], h[2], h[3], h[4]);
+    }
     if (ev_col) cudaEventDestroy(ev_col);
     if (ev_panel) cudaEventDestroy(ev_panel);
     if (aux_stream) cudaStreamDestroy(aux_stream);
@@ -1020,6 +1026,7 @@ SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_per
         zinv.zero(st); dlt.zero(st);
     }
     Lx.alloc(B * nnzL); Dv.alloc(B * S.nk); Dinv.alloc(B * S.nk); work.alloc(B * S.nk); fail.alloc(B); fail.zero(st);
+    if (getenv("B200_MF_PROF")) { d_prof.alloc(8); d_prof.zero(st); }
     // multifrontal schedule (sparse_frontal.cuh)
     if (frontal) {
         std::vector<int> hdr((size_t)8 * S.nsup), crec((size_t)4 * std::max<size_t>(S.child_idx.size(), 1), 0);

@@ -88,6 +88,7 @@ public:
     DevBuf<double> Lx, Dv, Dinv;   // [batch][nnz(L)], [batch][nk] x2
     DevBuf<double> work;       // [batch][nk] permuted rhs / solution
     DevBuf<int> fail;
+    DevBuf<long long> d_prof;      // B200_MF_PROF=1: phase clocks of mf_factor_kernel's CTA 0 (diagnostics)
     // condensed modes (sparse_ldlt_eq_cond / _ineq_cond / _cond)
     DevBuf<int> d_xx_P, d_xx_var, d_xx_ata, d_xx_gtg, d_xx_target, d_ata_ptr, d_ata_pa, d_ata_pb, d_gtg_ptr, d_gtg_pa, d_gtg_pb;
     DevBuf<double> AtA;        // [batch][nnz(upper(A^T A))], recomputed on update_data(A)

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(MW_T) mfw_panel_kernel(double* __restrict__ F_
                 if (i > k && i < nb) {
                     const double li = ck[i] * rd;                           // l_i = w_i / d
 #pragma unroll
-                    for (int m = 0; m < MW_NB / 4; m++) { const int c = g + 4 * (kk + m); if (c > k && c <= i) a[m] -= li * ck[c]; }      // A(i, c) -= l_i w_c
+                    for (int m = 0; m < MW_NB / 4; m++) { const int c = g + 4 * (kk + m); if (c > k && c <= i) a[m] = __dsub_rn(a[m], __dmul_rn(li, ck[c])); }      // A(i, c) -= l_i w_c, no FMA contraction (sparse/ldlt.hpp:151-158)
                     if (g == j) a[0] = li;
                 }
             }
@@ -208,12 +208,12 @@ __global__ void __launch_bounds__(MW_T) mfw_panel_kernel(double* __restrict__ F_
             const double wq = wsm[q * MW_T + tid];
             const double2* lrow = reinterpret_cast<const double2*>(LcT + q * MW_NB + cb * CH);
 #pragma unroll
-            for (int j = 0; j < CH; j += 2) { const double2 l2 = lrow[j / 2]; acc[j] -= wq * l2.x; acc[j + 1] -= wq * l2.y; }
+            for (int j = 0; j < CH; j += 2) { const double2 l2 = lrow[j / 2]; acc[j] = __dsub_rn(acc[j], __dmul_rn(wq, l2.x)); acc[j + 1] = __dsub_rn(acc[j + 1], __dmul_rn(wq, l2.y)); }
         }
 #pragma unroll
         for (int j = 0; j < CH; j++) {            // the chunk's own triangle
 #pragma unroll
-            for (int jj = 0; jj < j; jj++) acc[j] -= acc[jj] * LcT[(cb * CH + jj) * MW_NB + cb * CH + j];
+            for (int jj = 0; jj < j; jj++) acc[j] = __dsub_rn(acc[j], __dmul_rn(acc[jj], LcT[(cb * CH + jj) * MW_NB + cb * CH + j]));
             wsm[(cb * CH + j) * MW_T + tid] = acc[j];
         }
 #pragma unroll

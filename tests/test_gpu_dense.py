@@ -181,6 +181,31 @@ def test_batched_known_answers_and_update(oracle, b200):
     assert np.allclose(r.x[0], [0.2763157, 0.0921056], atol=1e-6) and np.allclose(r.x[1], r.x[0], atol=1e-9)
 
 
+@pytest.mark.parametrize("piece", ["P", "A", "G"])
+def test_batched_partial_matrix_update_equals_fresh_setup(b200, piece):
+    """update() of ONE matrix with the default preconditioner_reuse_on_update = 0: Ruiz is recomputed, so P, A and G are all
+    rescaled and every cached product (A^T A) must be refreshed, not only the piece the caller passed (the reference's
+    update_data(options) refreshes only `options`, solver.hpp:290-301).  The bar is a fresh setup() on the same data."""
+    qs = [dense_strongly_convex_qp(40, 12, 25, seed=300 + b) for b in range(3)]
+    s, _ = _solve_batch(b200, qs)
+    qn = [dict(q) for q in qs]
+    rng = np.random.default_rng(5)
+    for q in qn:
+        if piece == "P":
+            q["P"] = q["P"] + np.diag(rng.uniform(0.5, 2.0, 40))
+        else:
+            q[piece] = q[piece] * rng.uniform(0.5, 3.0, q[piece].shape)       # also changes the row / column norms Ruiz sees
+    s.update(**{piece: _stack(qn, piece)})
+    s.solve(); r = s.result()
+    # b, h are unchanged, so a rescaled A / G may be infeasible for the old right-hand sides: compare whatever status comes out
+    f, rf = _solve_batch(b200, qn)
+    for b in range(3):
+        assert r.info[b].status == rf.info[b].status
+        assert r.info[b].iter == rf.info[b].iter, (b, r.info[b].iter, rf.info[b].iter)
+        if rf.info[b].status == 1:
+            assert _rel(r.x[b], rf.x[b]) <= 1e-8
+
+
 def test_batched_infeasibility_and_special_cases(oracle, b200, assemble_mode):
     """solver_test.cpp:107-182, 347-377"""
     s, r = _solve_batch(b200, [primal_infeasible_qp()])

@@ -133,6 +133,33 @@ def test_batched_mpc_matches_oracle(oracle, b200):
         assert np.abs(r.y[k] - ro.y).max() <= 1e-5 * max(1.0, np.abs(ro.y).max())
 
 
+@pytest.mark.parametrize("piece", ["Px", "Ax"])
+def test_batched_partial_matrix_update_equals_fresh_setup(b200, piece):
+    """update() of ONE matrix (Ruiz recomputed): the P and A^T A blocks of the multistage backend must both be refreshed"""
+    B = 3
+    d = mpc_batch(B, N=12)
+    Px0 = np.broadcast_to(d["P"].data, (B, d["P"].nnz)).copy()
+    def make(Px, Ax):
+        s = b200.SparseSolverBatched()
+        s.setup(B, d["P"], d["c"], d["A"], d["b"], None, None, None, d["x_l"], d["x_u"], Px=Px, Ax=Ax)
+        return s
+    s = make(Px0, d["Ax"]); s.solve()
+    rng = np.random.default_rng(9)
+    Px1, Ax1 = Px0, d["Ax"]
+    if piece == "Px":
+        Px1 = Px0 * rng.uniform(2.0, 5.0, Px0.shape)          # P is diagonal for the MPC problems: stays PSD
+        s.update(Px=Px1)
+    else:
+        Ax1 = d["Ax"] * rng.uniform(0.7, 1.4, d["Ax"].shape)
+        s.update(Ax=Ax1)
+    iu = s.solve(); ru = s.result()
+    f = make(Px1, Ax1); i_f = f.solve(); rf = f.result()
+    for b in range(B):
+        assert iu[b].status == i_f[b].status and iu[b].iter == i_f[b].iter, (b, iu[b].status, i_f[b].status, iu[b].iter, i_f[b].iter)
+        if i_f[b].status == 1:
+            assert np.abs(ru.x[b] - rf.x[b]).max() <= 1e-8 * max(1.0, np.abs(rf.x[b]).max())
+
+
 def test_batched_sparse_known_answers_and_update(oracle, b200):
     """sparse/solver_test.cpp:67-107 golden values through the batched sparse API + the update() path"""
     q1 = simple_qp(); q2 = simple_qp_update(q1)

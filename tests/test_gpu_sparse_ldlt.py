@@ -156,6 +156,39 @@ def test_update_data_refreshes_values(oracle, b200):
     assert np.abs(K @ sol - np.concatenate(r)).max() < 1e-9 * max(1.0, np.abs(sol).max())
 
 
+@pytest.mark.parametrize("piece", ["Px", "Ax", "Gx"])
+@pytest.mark.parametrize("solver", ["sparse_ldlt", "sparse_ldlt_eq_cond", "sparse_ldlt_cond"])
+def test_batched_partial_matrix_update_equals_fresh_setup(b200, solver, piece):
+    """update() of ONE matrix with preconditioner_reuse_on_update = 0: Ruiz is recomputed, every matrix is rescaled, so every
+    cached copy (permuted KKT values, A^T A of the condensed modes) must be refreshed; bar: a fresh setup()"""
+    from piqp_b200.synth import sparse_batch
+    B = 3
+    d = sparse_batch(B, 60, 15, 30, 0.08, seed0=7)
+    def run(vals, s=None):
+        if s is None:
+            s = b200.SparseSolverBatched(kkt_solver=solver)
+            s.setup(B, d["P"], d["c"], d["A"], d["b"], d["G"], d["h_l"], d["h_u"], d["x_l"], d["x_u"], Px=vals["Px"], Ax=vals["Ax"], Gx=vals["Gx"])
+        infos = s.solve()
+        return s, infos, s.result()
+    v0 = {k: d[k] for k in ("Px", "Ax", "Gx")}
+    s, _, _ = run(v0)
+    rng = np.random.default_rng(3)
+    v1 = dict(v0)
+    if piece == "Px":
+        diag = np.repeat(np.arange(60), np.diff(d["P"].indptr)) == d["P"].indices
+        v1["Px"] = v0["Px"] * np.where(diag, rng.uniform(1.5, 3.0, diag.shape), 1.0)
+    else:
+        v1[piece] = v0[piece] * rng.uniform(0.5, 3.0, v0[piece].shape)
+    s.update(**{piece: v1[piece]})
+    _, iu, ru = run(v1, s)
+    _, i_f, rf = run(v1)
+    for b in range(B):
+        assert iu[b].status == i_f[b].status
+        assert iu[b].iter == i_f[b].iter, (b, iu[b].iter, i_f[b].iter)
+        if i_f[b].status == 1:
+            assert _rel(ru.x[b], rf.x[b]) <= 1e-8
+
+
 @pytest.mark.parametrize("case", ["notebook", "random"])
 def test_reference_style_solver_drives_cuda_sparse_ldlt(oracle, b200, case):
     """oracle KKTSystem + IP loop -> b200kkt_sparse_* through the C-ABI table: same iterations and solution"""
