@@ -414,7 +414,6 @@ def main():
     data = wl.device_data(B, seed0 + rank * B, dev)
     torch.cuda.synchronize()
     solver = wl.make_solver(local, data)
-    solver.set_profiling(True)
     ff, sf = wl.work()
 
     def barrier():
@@ -441,12 +440,27 @@ def main():
             agg[k] += getattr(st, k)
     barrier()
     wall = time.perf_counter() - t0
+    L1 = piqp_b200.lib().b200_kernel_launch_count()
+    clocks = sampler.stop() if sampler else None
+    # The timed region above runs the product's default path (IP iterations replayed as CUDA graphs, no per-phase events).  The
+    # per-bucket / per-kernel-class device times behind `buckets` and `roofline` come from a SEPARATE profiled pass of the same
+    # solves (events between the phases => stepwise launches), outside the timed region.
+    solver.set_profiling(True)
+    prof_steps = max(1, min(args.steps, 3))
+    prof = {k: 0 for k in keys}
+    for _ in range(prof_steps):
+        solver.solve()
+        st = solver.stats()
+        for k in keys:
+            prof[k] += getattr(st, k)
+    solver.set_profiling(False)
+    for k in ("factor_ms", "solve_ms", "assemble_ms", "assemble_launches", "cholesky_ms", "cholesky_calls", "backend_solve_ms"):
+        agg[k] = prof[k] * (args.steps / float(prof_steps))
+    agg["profiled_total_ms_per_step"] = prof["total_ms"] / prof_steps
     # device time of the timed region: the library's own CUDA events on ITS stream (total_ms); max over ranks
     dev_ms = torch.tensor([agg["total_ms"]], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
-    L1 = piqp_b200.lib().b200_kernel_launch_count()
-    clocks = sampler.stop() if sampler else None
     statuses = [i.status for i in infos]
     flops_local = agg["factor_calls"] * ff + agg["backend_solves"] * sf
     tot = torch.tensor([flops_local, float(B * args.steps), float(agg["ip_iterations"])], dtype=torch.float64, device=dev)

@@ -56,6 +56,7 @@ public:
     void eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) override;
     void extract_P_diag(double* P_diag) override;
     void print_info() const override;
+    bool graph_capturable() const override { return true; }
     double factor_flops() const override;
     double factor_bytes() const override;
     double solve_flops() const override;

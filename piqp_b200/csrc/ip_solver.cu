@@ -784,9 +784,11 @@ BatchedIPSolver::BatchedIPSolver(int batch_, int n_, int p_, int m_, const b200q
     // threads per instance CTA of the O(n+m) kernels: few large instances want more memory-level parallelism per CTA
     ipt_ = ((size_t)batch <= 296 && (size_t)n + m >= 1536) ? 512 : IPT;
     if (const char* e = getenv("B200_IPT")) { const int v = atoi(e); if (v == 128 || v == 256 || v == 512) ipt_ = v; }
+    if (const char* e = getenv("B200_NO_GRAPH")) use_graphs_ = e[0] != '1';
 }
 BatchedIPSolver::~BatchedIPSolver() {
     if (h_flags_) cudaFreeHost(h_flags_);
+    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
     for (auto& e : ev_) cudaEventDestroy(e);
     for (auto& e : iter_ev_) cudaEventDestroy(e);
 }
@@ -806,19 +808,70 @@ int BatchedIPSolver::count_flags(const int* dev_flags, int count) {
     return c;
 }
 
-int BatchedIPSolver::factor_with_retry() {
+// one round of the factor ladder: vector part, backend factorisation, retry bookkeeping (no host synchronisation)
+void BatchedIPSolver::factor_round() {
+    B200_LAUNCH(k_prepare_factor, batch, ipt_, 0, stream, d_);
+    be_->factor(d_.delta_reg, d_.x_reg, d_.z_reg_ir, d_.need_factor, d_.ok);
+    B200_LAUNCH(k_after_factor, ceil_div(batch, 128), 128, 0, stream, d_);
+}
+// read back [need_factor | use_ir | act] (ONE host synchronisation); returns the number of instances whose factorisation is still pending
+int BatchedIPSolver::read_factor_flags(int& active) {
+    const int pending = count_flags(d_.need_factor, 3 * batch);
+    any_ir_ = false; active = 0;
+    for (int i = 0; i < batch; i++) { any_ir_ |= h_flags_[batch + i] != 0; active += h_flags_[2 * batch + i] != 0; }
+    return pending;
+}
+// `first_round_done`: the first round was already enqueued (as the tail of the captured iteration graph)
+int BatchedIPSolver::factor_with_retry(bool first_round_done) {
     // at most 1 (enable refinement) + max_factor_retires + 1 rounds
     int active = 0;
     for (int round = 0; round < d_.st.max_factor_retires + 3; round++) {
-        B200_LAUNCH(k_prepare_factor, batch, ipt_, 0, stream, d_);
-        be_->factor(d_.delta_reg, d_.x_reg, d_.z_reg_ir, d_.need_factor, d_.ok);
-        B200_LAUNCH(k_after_factor, ceil_div(batch, 128), 128, 0, stream, d_);
-        const int pending = count_flags(d_.need_factor, 3 * batch);
-        any_ir_ = false; active = 0;
-        for (int i = 0; i < batch; i++) { any_ir_ |= h_flags_[batch + i] != 0; active += h_flags_[2 * batch + i] != 0; }
-        if (pending == 0) break;
+        if (!(round == 0 && first_round_done)) factor_round();
+        if (read_factor_flags(active) == 0) break;
     }
     return active;
+}
+
+// everything of one IP iteration after its factorisation (solver.hpp:716-880): predictor / corrector solves, step, residuals, regularisation
+void BatchedIPSolver::iteration_body(cudaEvent_t after_solves) {
+    IpDev& d = d_;
+    B200_LAUNCH(k_predictor, batch, ipt_, 0, stream, d);
+    kkt_solve(d.r, d.step, d.act);
+    B200_LAUNCH(k_corrector, batch, ipt_, 0, stream, d);
+    kkt_solve(d.r, d.step, d.act2);
+    if (after_solves) B200_CUDA(cudaEventRecord(after_solves, stream));
+    B200_LAUNCH(k_update, batch, ipt_, 0, stream, d);
+    residuals_nr(d.act);
+    B200_LAUNCH(k_resid_nr, batch, ipt_, 0, stream, d, d.act, 0);
+    B200_LAUNCH(k_reg_update, batch, ipt_, 0, stream, d);
+}
+
+// CUDA graph of [iteration body ; loop head of the next iteration ; first factor round]: an IP iteration is ~35-60 small kernels
+// whose launch latency dominates the latency-bound backends (multistage: ~40 % of a step).  Valid while no instance uses iterative
+// refinement (its trip count is decided on the host) -- instances whose factorisation fails are caught by the flag read-back that
+// follows every replay and go through the stepwise retry ladder.  Re-captured when the settings change.
+bool BatchedIPSolver::ensure_graph() {
+    if (graph_exec_) return true;
+    if (graph_failed_) return false;
+    const unsigned long long l0 = g_launches.load();
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); graph_failed_ = true; return false; }
+    bool ok = true;
+    try {
+        iteration_body(nullptr);
+        B200_LAUNCH(k_head, batch, ipt_, 0, stream, d_);
+        factor_round();
+    } catch (const std::exception&) { ok = false; }
+    if (cudaStreamEndCapture(stream, &g) != cudaSuccess || !g) { cudaGetLastError(); ok = false; }
+    if (ok && cudaGraphInstantiate(&graph_exec_, g, 0) != cudaSuccess) { cudaGetLastError(); graph_exec_ = nullptr; ok = false; }
+    if (g) cudaGraphDestroy(g);
+    graph_launches_ = g_launches.load() - l0;
+    if (!ok) graph_failed_ = true;
+    return ok;
+}
+void BatchedIPSolver::drop_graph() {
+    if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    graph_failed_ = false;
 }
 
 void BatchedIPSolver::kkt_solve(const Vars& rhs, const Vars& lhs, const int* mask) {
@@ -878,7 +931,7 @@ void BatchedIPSolver::solve() {
 
     B200_LAUNCH(k_init, batch, ipt_, 0, stream, d);
     B200_CUDA(cudaEventRecord(ev_[0], stream));
-    factor_with_retry();
+    factor_with_retry(false);
     B200_CUDA(cudaEventRecord(ev_[1], stream));
     B200_LAUNCH(k_initial_rhs, batch, ipt_, 0, stream, d);
     kkt_solve(d.r, d.it, d.act);
@@ -892,29 +945,38 @@ void BatchedIPSolver::solve() {
 
     int L = 0;
     auto iev = [&](int i) { while ((int)iter_ev_.size() <= i) { cudaEvent_t e; B200_CUDA(cudaEventCreate(&e)); iter_ev_.push_back(e); } return iter_ev_[i]; };
-    for (; L < st.max_iter; L++) {
-        // k_head decides per instance (converged / infeasible / continue) and raises need_factor for the active ones; the masks are
-        // read back together with the factorisation flags, so an iteration costs ONE host synchronisation
+    // The reference's per-bucket timers (info.kkt_factor_time / kkt_solve_time, solver.hpp:442-471,484-492) need event records between
+    // the phases: with compute_timings or backend profiling on, the iteration is enqueued stepwise; otherwise as one graph replay.
+    const bool want_graph = use_graphs_ && be_->graph_capturable() && !be_->profile && !st.compute_timings;
+    bucket_timers_ = !want_graph;
+    // k_head decides per instance (converged / infeasible / continue) and raises need_factor for the active ones; the masks are
+    // read back together with the factorisation flags, so an iteration costs ONE host synchronisation
+    B200_LAUNCH(k_head, batch, ipt_, 0, stream, d);
+    if (bucket_timers_) B200_CUDA(cudaEventRecord(iev(0), stream));
+    int active = factor_with_retry(false);
+    while (active > 0) {
+        const bool last = L + 1 >= st.max_iter;
+        if (want_graph && !any_ir_ && !last && ensure_graph()) {
+            B200_CUDA(cudaGraphLaunch(graph_exec_, stream));
+            g_launches.fetch_add(graph_launches_, std::memory_order_relaxed);
+            L++;
+            active = factor_with_retry(true);
+            continue;
+        }
+        if (bucket_timers_) B200_CUDA(cudaEventRecord(iev(3 * L + 1), stream));
+        iteration_body(bucket_timers_ ? iev(3 * L + 2) : nullptr);
+        L++;
+        if (last) break;
         B200_LAUNCH(k_head, batch, ipt_, 0, stream, d);
-        B200_CUDA(cudaEventRecord(iev(3 * L), stream));
-        if (factor_with_retry() == 0) break;
-        B200_CUDA(cudaEventRecord(iev(3 * L + 1), stream));
-        B200_LAUNCH(k_predictor, batch, ipt_, 0, stream, d);
-        kkt_solve(d.r, d.step, d.act);
-        B200_LAUNCH(k_corrector, batch, ipt_, 0, stream, d);
-        kkt_solve(d.r, d.step, d.act2);
-        B200_CUDA(cudaEventRecord(iev(3 * L + 2), stream));
-        B200_LAUNCH(k_update, batch, ipt_, 0, stream, d);
-        residuals_nr(d.act);
-        B200_LAUNCH(k_resid_nr, batch, ipt_, 0, stream, d, d.act, 0);
-        B200_LAUNCH(k_reg_update, batch, ipt_, 0, stream, d);
+        if (bucket_timers_) B200_CUDA(cudaEventRecord(iev(3 * L), stream));
+        active = factor_with_retry(false);
     }
     stats_.lockstep_iterations = L;
     B200_LAUNCH(k_mark_max_iter, ceil_div(batch, 128), 128, 0, stream, d);
     B200_LAUNCH(k_finish, batch, ipt_, 0, stream, d);
     B200_CUDA(cudaEventRecord(ev_[5], stream));
     B200_CUDA(cudaEventSynchronize(ev_[5]));
-    for (int i = 0; i < L; i++) {
+    if (bucket_timers_) for (int i = 0; i < L; i++) {
         B200_CUDA(cudaEventElapsedTime(&ms, iter_ev_[3 * i], iter_ev_[3 * i + 1])); stats_.factor_ms += ms;
         B200_CUDA(cudaEventElapsedTime(&ms, iter_ev_[3 * i + 1], iter_ev_[3 * i + 2])); stats_.solve_ms += ms;
     }

@@ -60,14 +60,22 @@ public:
     IpDev& dev() { return d_; }
     std::vector<b200qp_info> infos();
     b200qp_stats stats() const { return stats_; }
-    void set_settings(const b200qp_settings& st) { d_.st = st; }
+    void set_settings(const b200qp_settings& st) { d_.st = st; drop_graph(); }      // settings travel in the kernel arguments: re-capture
+    void drop_graph();
     int batch, n, p, m;
     cudaStream_t stream;
     bool identity_precond = false;
 
 private:
     void kkt_solve(const Vars& rhs, const Vars& lhs, const int* mask);   // KKTSystem::solve
-    int factor_with_retry();      // returns the number of instances still active (read back with the factor flags: one host sync)
+    int factor_with_retry(bool first_round_done);      // returns the number of instances still active (read back with the factor flags: one host sync)
+    void factor_round();
+    int read_factor_flags(int& active);
+    void iteration_body(cudaEvent_t after_solves);
+    bool ensure_graph();
+    cudaGraphExec_t graph_exec_ = nullptr;
+    unsigned long long graph_launches_ = 0;
+    bool graph_failed_ = false, use_graphs_ = true, bucket_timers_ = true;
     void residuals_nr(const int* mask);
     int count_flags(const int* dev_flags, int count = -1);
     IpDev d_{};

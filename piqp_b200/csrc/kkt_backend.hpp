@@ -30,6 +30,9 @@ struct BatchedKKT {
     // diag(P) for KKTSystem's static regularisation (kkt_system.hpp:198,430-453): P_diag[batch][n]
     virtual void extract_P_diag(double* P_diag) = 0;
     virtual void print_info() const {}
+    // true if factor / solve / eval_* only enqueue work on `stream` (no host synchronisation, no other streams): the IP driver
+    // may then capture a whole iteration into a CUDA graph
+    virtual bool graph_capturable() const { return false; }
     // algorithmic work per call and instance, for GFLOP/s and roofline reporting
     virtual double factor_flops() const = 0;
     virtual double factor_bytes() const = 0;

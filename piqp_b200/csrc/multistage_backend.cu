@@ -1,6 +1,8 @@
 // piqp_b200/csrc/multistage_backend.cu -- see multistage_backend.hpp
 #include "multistage_backend.hpp"
 #include "multistage_chain.cuh"
+#include "multistage_partition.cuh"
+#include <cmath>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -414,10 +416,12 @@ MultistageBatchedKKT::MultistageBatchedKKT(SparseData* data, cudaStream_t st) : 
     if (warp_chain) {
         auto r2 = [](int v) { return (v + 1) & ~1; };
         for (int i = 0; i < S.N; i++) { const int d = S.bi[i].diag; cls[i] = d <= 8 ? 8 : (d <= 16 ? 16 : 32); }
+        plan_partition(cls);
         for (int i = 0; i + 1 < S.N; i++) {
             const int D = cls[i], PD = i > 0 ? cls[i - 1] : 0, ND = (i + 2 < S.N) ? cls[i + 1] : 0;
             szF[i] = D * D + D * PD + r2(S.w * D);
             szB[i] = D * D + D * ND + D * r2(S.w);
+            if (part_K > 1 && part_dsep[i] > 0) { szF[i] += part_dsep[i] * D; szB[i] += D * part_dsep[i]; }      // spike blocks Y^T / Y (multistage_partition.cuh)
             pkF[i] = (int)pk_stride; pk_stride += szF[i];
             pkB[i] = (int)pk_stride; pk_stride += szB[i];
             slot = std::max(slot, (size_t)std::max(szF[i], szB[i]));
@@ -425,10 +429,11 @@ MultistageBatchedKKT::MultistageBatchedKKT(SparseData* data, cudaStream_t st) : 
         chain_rp = (max_rows + 1) / 2;
         chain_slot = (int)slot;
         chain_solve_smem = sizeof(double) * ((size_t)((n + 1) & ~1) + 96 + (size_t)(((MS_META * S.N + 1) / 2 + 1) / 2 * 2) + (size_t)MSW_R * chain_slot);
-        if (chain_solve_smem > 227 * 1024 || (size_t)MS_META * S.N * sizeof(int) > 100 * 1024) warp_chain = false;
+        if (chain_solve_smem > 227 * 1024 || (size_t)MS_META * S.N * sizeof(int) > 100 * 1024) { warp_chain = false; part_K = 1; }
     }
     for (auto* v : {&cls, &pkF, &szF, &pkB, &szB}) meta.insert(meta.end(), v->begin(), v->end());
     upload(d_meta, meta);
+    if (warp_chain && part_K > 1) build_partition(cls, st);
     if (warp_chain) {
         packets.alloc((size_t)batch * pk_stride);
         packets.zero(st);
@@ -487,6 +492,7 @@ void MultistageBatchedKKT::update_data(int options) {   // :140-178
 void MultistageBatchedKKT::copy_from(const MultistageBatchedKKT& o) {
     auto cp = [&](DevBuf<double>& d, const DevBuf<double>& s) { if (s.n) B200_CUDA(cudaMemcpyAsync(d.get(), s.get(), s.n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); };
     cp(Pblk, o.Pblk); cp(AtAblk, o.AtAblk); cp(fac, o.fac); cp(Linv, o.Linv); cp(zinv, o.zinv); cp(delta, o.delta); cp(packets, o.packets);
+    if (part_K > 1 && o.part_K == part_K) { cp(rfac, o.rfac); cp(rpackets, o.rpackets); }
 }
 
 void MultistageBatchedKKT::factor(const double* delta_in, const double* x_reg, const double* z_reg, const int* active, int* ok) {   // :180-219
@@ -502,8 +508,9 @@ void MultistageBatchedKKT::factor(const double* delta_in, const double* x_reg, c
         const MsDev dv = make_dev(S, d_meta.get());
         const size_t msm = sizeof(int) * MS_META * S.N;
 #define MSW_FACTOR(RP) B200_LAUNCH(msw_factor_kernel<RP>, batch, 64, msm, stream, dv, fac.get(), Linv.get(), packets.get(), pk_stride, active)
-#define MSW_CHAIN(RP) B200_LAUNCH(msw_factor_chain_kernel<RP>, batch, 64, sizeof(MswChainSmem) + msm, stream, dv, fac.get(), packets.get(), pk_stride, active)
-        if (S.w == 0) { if (chain_rp <= 4) MSW_CHAIN(4); else if (chain_rp <= 8) MSW_CHAIN(8); else if (chain_rp <= 12) MSW_CHAIN(12);
+#define MSW_CHAIN(RP) B200_LAUNCH(msw_factor_chain_kernel<RP>, batch, 64, sizeof(MswChainSmem) + msm, stream, dv, fac.get(), packets.get(), pk_stride, active, (const int*)nullptr, (double*)nullptr)
+        if (part_K > 1) factor_partitioned(dv, active);
+        else if (S.w == 0) { if (chain_rp <= 4) MSW_CHAIN(4); else if (chain_rp <= 8) MSW_CHAIN(8); else if (chain_rp <= 12) MSW_CHAIN(12);
                         else if (chain_rp <= 14) MSW_CHAIN(14); else MSW_CHAIN(16); }
         else if (chain_rp <= 4) MSW_FACTOR(4); else if (chain_rp <= 8) MSW_FACTOR(8); else if (chain_rp <= 12) MSW_FACTOR(12);
         else if (chain_rp <= 14) MSW_FACTOR(14); else MSW_FACTOR(16);
@@ -521,12 +528,144 @@ void MultistageBatchedKKT::solve(const double* rx, const double* ry, const doubl
     B200_LAUNCH(ms_copy_masked_kernel, gn, 256, 0, stream, rx, lx, n, active);
     if (m > 0) spmv_rows(D->GT, D->GTx.get(), 1.0, rz, m, lx, 1, zinv.get(), nullptr, 0, batch, active, stream);          // lx += GT (zinv .* rz)
     if (p > 0) spmv_rows(D->AT, D->ATx.get(), 1.0, ry, p, lx, 1, nullptr, delta.get(), 1, batch, active, stream);         // lx += AT ry / delta
-    if (warp_chain) B200_LAUNCH(msw_solve_kernel, batch, 32, chain_solve_smem, stream, make_dev(S, d_meta.get()), chain_slot, Linv.get(), packets.get(), pk_stride, lx, active);
+    if (warp_chain && part_K > 1) solve_partitioned(lx, active);
+    else if (warp_chain) B200_LAUNCH(msw_solve_kernel, batch, 32, chain_solve_smem, stream, make_dev(S, d_meta.get()), chain_slot, Linv.get(), packets.get(), pk_stride, lx, active);
     else B200_LAUNCH(ms_solve_kernel, batch, MS_T, solve_smem, stream, make_dev(S, d_meta.get()), fac.get(), Linv.get(), lx, active);
     if (p > 0) spmv_cols(D->AT, D->ATx.get(), 1.0, lx, n, ly, ry, 1.0, nullptr, delta.get(), 1, batch, active, stream);    // ly = (A lx - ry) / delta
     if (m > 0) spmv_cols(D->GT, D->GTx.get(), 1.0, lx, n, lz, rz, 1.0, zinv.get(), nullptr, 0, batch, active, stream);     // lz = zinv .* (G lx - rz)
     toc(T_SOLVE);
 }
+
+// =====================================================================================================
+// parallel-in-horizon partition (multistage_partition.cuh)
+// =====================================================================================================
+// Chooses K-1 separator stages.  Cost model (measured stage latencies: factor chain 3.1 us, spike / solve stage ~0.6 us):
+// factor ~ (N/K) (3.1 + 0.8) + 3.1 K, solve ~ 2 (N/K) 0.65 + 2 K 0.5  =>  K ~ sqrt(1.25 N).
+void MultistageBatchedKKT::plan_partition(const std::vector<int>& cls) {
+    part_K = 1; part_dsep.assign(S.N, 0); part_bounds.clear(); part_sep.clear();
+    const int nreal = S.N - 1;
+    if (!warp_chain || S.w != 0 || nreal < 16) return;
+    if (const char* e = getenv("B200_MS_NO_PARTITION")) if (e[0] == '1') return;
+    int K = (int)std::lround(std::sqrt(1.25 * nreal));
+    if (const char* e = getenv("B200_MS_SEGMENTS")) K = atoi(e);
+    K = std::max(1, std::min(K, std::min(32, nreal / 3)));
+    if (K < 2) return;
+    std::vector<int> sep;
+    for (int k = 1; k < K; k++) sep.push_back((int)((long long)k * nreal / K));          // stages 1 .. nreal-2, at least one interior stage in between
+    for (size_t k = 0; k < sep.size(); k++) {
+        const int lo = k == 0 ? 0 : sep[k - 1] + 2;
+        if (sep[k] < std::max(lo, 1) || sep[k] > nreal - 2) return;
+    }
+    // every reduced front (separator k + coupling rows of separator k+1) must fit one warp like the original fronts
+    for (size_t k = 0; k < sep.size(); k++) {
+        const int d = S.bi[sep[k]].diag, o = k + 1 < sep.size() ? S.bi[sep[k + 1] - 1].off : 0;
+        if (d + o > 32 || S.bi[sep[k] - 1].off > d) return;
+    }
+    part_K = K; part_sep = sep;
+    for (int r = 0; r < K; r++) {
+        const int i0 = r == 0 ? 0 : sep[r - 1] + 1, i1 = r + 1 < K ? sep[r] : nreal;
+        part_bounds.push_back(i0); part_bounds.push_back(i1);
+        if (r > 0) for (int i = i0; i < i1; i++) part_dsep[i] = cls[sep[r - 1]];
+    }
+}
+
+void MultistageBatchedKKT::build_partition(const std::vector<int>& cls, cudaStream_t st) {
+    const int K = part_K, NR = K;                        // reduced chain: K-1 stages + the (empty) arrow entry, like S.bi
+    auto r2 = [](int v) { return (v + 1) & ~1; };
+    std::vector<int> rs(NR, 0), rd(NR, 0), ro(NR, 0), rD(NR, 0), rB(NR, 0), rE(NR, 0), rI(NR, 0), rc(NR, 8), rpF(NR, 0), rsF(NR, 0), rpB(NR, 0), rsB(NR, 0);
+    int pos = 0, tot = 0, toti = 0, rmax = 0;
+    for (int k = 0; k < K - 1; k++) {
+        const int d = S.bi[part_sep[k]].diag, o = k + 1 < K - 1 ? S.bi[part_sep[k + 1] - 1].off : 0;
+        rs[k] = pos; rd[k] = d; ro[k] = o; pos += d;
+        rD[k] = tot; tot += d * d; rB[k] = tot; tot += o * d; rE[k] = tot; rI[k] = toti; toti += d * d;
+        rc[k] = cls[part_sep[k]];
+        rmax = std::max(rmax, d + o);
+    }
+    rs[NR - 1] = pos; part_rn = pos; part_rtotal = std::max(tot, 1);
+    size_t rstride = 0, rslot = 0;
+    for (int k = 0; k < K - 1; k++) {
+        const int D = rc[k], PD = k > 0 ? rc[k - 1] : 0, ND = (k + 2 < NR) ? rc[k + 1] : 0;
+        rsF[k] = D * D + D * PD; rsB[k] = D * D + D * ND;
+        rpF[k] = (int)rstride; rstride += rsF[k]; rpB[k] = (int)rstride; rstride += rsB[k];
+        rslot = std::max(rslot, (size_t)std::max(rsF[k], rsB[k]));
+    }
+    part_rpk_stride = std::max<size_t>(rstride, 2); part_rslot = (int)rslot; part_rrp = (rmax + 1) / 2;
+    std::vector<int> meta;
+    for (auto* v : {&rs, &rd, &ro, &rD, &rB, &rE, &rI, &rc, &rpF, &rsF, &rpB, &rsB}) meta.insert(meta.end(), v->begin(), v->end());
+    upload(d_rmeta, meta);
+    std::vector<int> aux(part_bounds);                    // seg_bounds[2K] | sep[K-1] | rstart[K] | roffD[K-1] | roffB[K-1]
+    aux.insert(aux.end(), part_sep.begin(), part_sep.end());
+    aux.insert(aux.end(), rs.begin(), rs.end());
+    aux.insert(aux.end(), rD.begin(), rD.begin() + (K - 1));
+    aux.insert(aux.end(), rB.begin(), rB.begin() + (K - 1));
+    upload(d_part, aux);
+    part_seg_len = 0; part_dsep_max = 8;
+    for (int r = 0; r < K; r++) {
+        const int i0 = part_bounds[2 * r], i1 = part_bounds[2 * r + 1];
+        part_seg_len = std::max(part_seg_len, S.bi[i1 - 1].start + S.bi[i1 - 1].diag - S.bi[i0].start);
+        if (r > 0) part_dsep_max = std::max(part_dsep_max, cls[part_sep[r - 1]]);
+    }
+    part_seg_len = r2(part_seg_len);
+    rfac.alloc((size_t)batch * part_rtotal); rfac.zero(st);
+    rpackets.alloc((size_t)batch * part_rpk_stride); rpackets.zero(st);
+    carry.alloc((size_t)batch * K * 1024); carry.zero(st);
+    zbuf.alloc((size_t)batch * K * 32); zbuf.zero(st);
+    xred.alloc((size_t)batch * std::max(part_rn, 1)); xred.zero(st);
+    const size_t meta_d = (size_t)(((MS_META * S.N + 1) / 2 + 1) / 2 * 2);
+    part_seg_smem = sizeof(double) * ((size_t)part_seg_len + 96 + 64 + meta_d + (size_t)MSW_R * chain_slot);
+    part_spike_smem = sizeof(double) * ((size_t)MSP_R * chain_slot + (size_t)part_dsep_max * (part_seg_len + 64));
+    part_rsolve_smem = sizeof(double) * ((size_t)((part_rn + 1) & ~1) + 96 + (size_t)(((MS_META * NR + 1) / 2 + 1) / 2 * 2) + (size_t)MSW_R * part_rslot);
+    if (part_seg_smem > 227 * 1024 || part_spike_smem > 227 * 1024 || part_rsolve_smem > 227 * 1024) { part_K = 1; return; }
+    B200_CUDA(cudaFuncSetAttribute(msp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(part_seg_smem, 48 * 1024)));
+    B200_CUDA(cudaFuncSetAttribute(msp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(part_seg_smem, 48 * 1024)));
+    B200_CUDA(cudaFuncSetAttribute(msp_spike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(part_spike_smem, 48 * 1024)));
+}
+
+static MsDev make_rdev(const int* meta, int NR, int rn, int rtotal) {
+    MsDev d;
+    d.start = meta; d.diag = meta + NR; d.off = meta + 2 * NR; d.offD = meta + 3 * NR; d.offB = meta + 4 * NR; d.offE = meta + 5 * NR; d.offI = meta + 6 * NR;
+    d.cls = meta + 7 * NR; d.pkF = meta + 8 * NR; d.szF = meta + 9 * NR; d.pkB = meta + 10 * NR; d.szB = meta + 11 * NR;
+    d.N = NR; d.w = 0; d.n = rn; d.total = rtotal; d.total_inv = 0; d.dmax = 32; d.omax = 32;
+    return d;
+}
+MsPart MultistageBatchedKKT::make_part() const {
+    MsPart P;
+    const int K = part_K;
+    const int* a = d_part.get();
+    P.seg_bounds = a; P.sep = a + 2 * K; P.rstart = a + 2 * K + (K - 1); P.roffD = a + 2 * K + (K - 1) + K; P.roffB = P.roffD + (K - 1);
+    P.K = K; P.rn = part_rn; P.rtotal = part_rtotal;
+    return P;
+}
+
+void MultistageBatchedKKT::factor_partitioned(const MsDev& dv, const int* active) {
+    const int K = part_K;
+    const MsPart P = make_part();
+    const size_t msm = sizeof(int) * MS_META * S.N;
+    dim3 gseg(batch, K);
+#define MSP_CHAIN(RP) B200_LAUNCH(msw_factor_chain_kernel<RP>, gseg, 64, sizeof(MswChainSmem) + msm, stream, dv, fac.get(), packets.get(), pk_stride, active, P.seg_bounds, carry.get())
+    if (chain_rp <= 4) MSP_CHAIN(4); else if (chain_rp <= 8) MSP_CHAIN(8); else if (chain_rp <= 12) MSP_CHAIN(12); else if (chain_rp <= 14) MSP_CHAIN(14); else MSP_CHAIN(16);
+#undef MSP_CHAIN
+    B200_LAUNCH(msp_spike_kernel, dim3(batch, K - 1), 32 * part_dsep_max, part_spike_smem, stream, dv, P, chain_slot, part_seg_len, fac.get(), packets.get(), pk_stride, active);
+    B200_LAUNCH(msp_reduce_assemble_kernel, dim3(batch, K - 1), 256, 0, stream, dv, P, fac.get(), packets.get(), pk_stride, carry.get(), rfac.get(), active);
+    const MsDev rd = make_rdev(d_rmeta.get(), K, part_rn, part_rtotal);
+    const size_t rmsm = sizeof(int) * MS_META * K;
+#define MSP_RCHAIN(RP) B200_LAUNCH(msw_factor_chain_kernel<RP>, batch, 64, sizeof(MswChainSmem) + rmsm, stream, rd, rfac.get(), rpackets.get(), part_rpk_stride, active, (const int*)nullptr, (double*)nullptr)
+    if (part_rrp <= 4) MSP_RCHAIN(4); else if (part_rrp <= 8) MSP_RCHAIN(8); else if (part_rrp <= 12) MSP_RCHAIN(12); else if (part_rrp <= 14) MSP_RCHAIN(14); else MSP_RCHAIN(16);
+#undef MSP_RCHAIN
+}
+
+void MultistageBatchedKKT::solve_partitioned(double* lx, const int* active) {
+    const int K = part_K;
+    const MsPart P = make_part();
+    const MsDev dv = make_dev(S, d_meta.get());
+    dim3 gseg(batch, K);
+    B200_LAUNCH(msp_fwd_kernel, gseg, 32, part_seg_smem, stream, dv, P, chain_slot, part_seg_len, packets.get(), pk_stride, lx, zbuf.get(), active);
+    B200_LAUNCH(msp_gather_kernel, dim3(batch, ceil_div(K - 1, 4)), 128, 0, stream, dv, P, packets.get(), pk_stride, lx, zbuf.get(), xred.get(), active);
+    const MsDev rd = make_rdev(d_rmeta.get(), K, part_rn, part_rtotal);
+    B200_LAUNCH(msw_solve_kernel, batch, 32, std::max<size_t>(part_rsolve_smem, 1), stream, rd, part_rslot, (const double*)nullptr, rpackets.get(), part_rpk_stride, xred.get(), active);
+    B200_LAUNCH(msp_bwd_kernel, gseg, 32, part_seg_smem, stream, dv, P, chain_slot, part_seg_len, packets.get(), pk_stride, lx, xred.get(), active);
+}
+
 void MultistageBatchedKKT::eval_P_x(double alpha, const double* x, double* z, const int* active) { spmv_sym_upper(D->P, D->Px.get(), alpha, x, z, batch, active, stream); }
 void MultistageBatchedKKT::eval_A(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) {
     if (p > 0) spmv_cols(D->AT, D->ATx.get(), an, xn, n, zn, nullptr, 0.0, nullptr, nullptr, 0, batch, active, stream);

@@ -12,6 +12,7 @@
 #include <string>
 #include "kkt_backend.hpp"
 #include "sparse_data.hpp"
+#include <vector>
 
 namespace b200 {
 
@@ -45,6 +46,7 @@ public:
     void eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) override;
     void extract_P_diag(double* P_diag) override;
     void print_info() const override;
+    bool graph_capturable() const override { return true; }
     double factor_flops() const override { return S.factor_flops(); }
     double factor_bytes() const override { return S.factor_bytes(); }
     double solve_flops() const override { return S.solve_flops(); }
@@ -63,9 +65,21 @@ public:
     int chain_slot = 0, chain_rp = 16;  // doubles per ring slot of msw_solve_kernel; ceil(max front rows / 2)
     DevBuf<double> packets;             // [batch][pk_stride] solve packets (see multistage_chain.cuh)
     size_t pk_stride = 0;
+    // ---- parallel-in-horizon partition (multistage_partition.cuh): K runs of stages separated by K-1 separator stages
+    int part_K = 1;                     // 1 = off
+    std::vector<int> part_bounds, part_sep, part_dsep;     // [2K] stage ranges of the runs; separator stages; per stage: class of the separator on the left of its run (0: none)
+    int part_rn = 0, part_rtotal = 0, part_rslot = 0, part_rrp = 16, part_seg_len = 0, part_dsep_max = 8;
+    size_t part_rpk_stride = 0, part_seg_smem = 0, part_spike_smem = 0, part_rsolve_smem = 0;
+    DevBuf<int> d_rmeta, d_part;
+    DevBuf<double> rfac, rpackets, carry, zbuf, xred;
 private:
     void load_P();
     void compute_AtA();
+    void plan_partition(const std::vector<int>& cls);
+    void build_partition(const std::vector<int>& cls, cudaStream_t st);
+    struct MsPart make_part() const;
+    void factor_partitioned(const struct MsDev& dv, const int* active);
+    void solve_partitioned(double* lx, const int* active);
 };
 
 }  // namespace b200

@@ -218,9 +218,12 @@ __device__ __forceinline__ void msw_cp_async8(double* dst_smem, const double* sr
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src) : "memory");
 }
 
+// Segment mode (parallel-in-horizon, multistage_partition.cuh): blockIdx.y selects a run of stages [seg_bounds[2y], seg_bounds[2y+1])
+// that is factorised as an independent chain (the separator stages between the runs are left out); the Schur complement the last
+// stage of the run leaves on its coupling rows is exported to carry_all[b][y][32 x 32] for the reduced (separator) system.
 template <int RP>
 __global__ void __launch_bounds__(64) msw_factor_chain_kernel(MsDev s, const double* __restrict__ fac_all, double* __restrict__ pk_all, size_t pk_stride,
-                                                              const int* __restrict__ active) {
+                                                              const int* __restrict__ active, const int* __restrict__ seg_bounds, double* __restrict__ carry_all) {
     extern __shared__ __align__(16) unsigned char msw_raw[];
     MswChainSmem& sm = *reinterpret_cast<MswChainSmem*>(msw_raw);
     int* meta = reinterpret_cast<int*>(msw_raw + sizeof(MswChainSmem));
@@ -229,7 +232,9 @@ __global__ void __launch_bounds__(64) msw_factor_chain_kernel(MsDev s, const dou
     const double* fac = fac_all + (size_t)b * s.total;
     double* pk = pk_all + (size_t)b * pk_stride;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int N = s.N, nst = N - 1;
+    const int N = s.N;
+    int i0 = 0, nst = N - 1;                          // stages [i0, nst)
+    if (seg_bounds) { i0 = seg_bounds[2 * blockIdx.y]; nst = seg_bounds[2 * blockIdx.y + 1]; }
     for (int e = threadIdx.x; e < MS_META * N; e += 64) meta[e] = s.start[e];
     for (int e = threadIdx.x; e < 64 * 65; e += 64) (&sm.S[0][0])[e] = 0.0;
     __syncthreads();
@@ -247,13 +252,13 @@ __global__ void __launch_bounds__(64) msw_factor_chain_kernel(MsDev s, const dou
         if (src) for (int c = 0; c < d; c++) msw_cp_async8(Fb + lane * 33 + c, src + (size_t)c * ld);
         msw_cp_commit();
     };
-    if (warp == 0) { if (nst > 0) prepare(0); } else { if (nst > 1) prepare(1); }
+    if (warp == 0) { if (nst > i0) prepare(i0); } else { if (nst > i0 + 1) prepare(i0 + 1); }
     msw_cp_wait<0>();
     __syncthreads();
 
     if (warp == 0) {
         int dprev = 0;
-        for (int i = 0; i < nst; i++) {
+        for (int i = i0; i < nst; i++) {
             const int d = m_diag[i];
             double v[2 * RP];
             {
@@ -292,8 +297,12 @@ __global__ void __launch_bounds__(64) msw_factor_chain_kernel(MsDev s, const dou
             dprev = d;
             __syncthreads();
         }
+        if (carry_all && nst > i0) {                 // Schur complement on the coupling rows of the run's last stage (lower part is meaningful)
+            double* C = carry_all + ((size_t)b * gridDim.y + blockIdx.y) * 1024;
+            for (int c = 0; c < 32; c++) C[lane + 32 * c] = sm.S[dprev + lane][dprev + c];
+        }
     } else {
-        for (int i = 0; i < nst; i++) {
+        for (int i = i0; i < nst; i++) {
             __syncthreads();
             if (i + 2 < nst) prepare(i + 2);        // F[i & 1] was consumed by the chain warp at the start of stage i
             const int d = m_diag[i], o = (i + 2 < N) ? m_off[i] : 0;

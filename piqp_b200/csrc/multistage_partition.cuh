@@ -1,0 +1,264 @@
+// piqp_b200/csrc/multistage_partition.cuh -- PARALLEL-IN-HORIZON factorisation and solves of the multistage backend.
+//
+// factor_kkt / solve_llt_in_place (include/piqp/sparse/multistage_kkt.hpp:1253-1352, 1709-1816) walk the N stages of the
+// block-tridiagonal KKT one after the other, and so do the warp-chain kernels of multistage_chain.cuh: their time is N x (latency
+// of one stage).  Here the horizon is cut at K-1 SEPARATOR stages g_1 < ... < g_{K-1} into K runs of consecutive stages:
+//
+//      [ run 0 ] g_1 [ run 1 ] g_2 ... g_{K-1} [ run K-1 ]
+//
+// Without the separators the runs are independent block-tridiagonal chains, so (a partitioned / substructuring Cholesky, i.e. the
+// same factorisation under the elimination order  run 0, ..., run K-1, g_1, ..., g_{K-1}):
+//   1. msw_factor_chain_kernel in SEGMENT MODE factorises all runs of all QPs at once (grid = batch x K);
+//   2. msp_spike_kernel computes the spike Y_s = L_s^-1 K[run s, g_s] of every run s >= 1 (the separator on its LEFT couples only
+//      to the first stage of the run, but the forward substitution fills the whole run): d(g_s) right-hand sides per run, one
+//      warp each, the run's forward packets staged once per CTA;
+//   3. msp_reduce_assemble_kernel builds the reduced system on the separators, which is again block tridiagonal with the stage
+//      shape of the original chain:  D~_k = D(g_k) + carry(run k-1) - Y_k^T Y_k ,  B~_k = -(B L^-T)(last stage of run k) Y_k[last];
+//   4. msw_factor_chain_kernel factorises the reduced chain (K-1 stages).
+// Chain length N/K + K instead of N.  The solves follow the same split: msp_fwd_kernel (runs in parallel, also accumulates
+// Y_s^T y_s), msp_gather_kernel (reduced right-hand side), msw_solve_kernel on the reduced chain, msp_bwd_kernel (runs in
+// parallel: x_s = L_s^-T (y_s - Y_s x(g_s)) with the coupling to g_{s+1} through the ordinary backward packet).
+// The spikes ride in the solve packets of the run's stages: forward packet + Y^T block [Dsep x D], backward packet + Y block [D x Dsep].
+#pragma once
+#include "multistage_chain.cuh"
+
+namespace b200 {
+
+struct MsPart {
+    const int* seg_bounds;     // [2K]  stages [i0, i1) of run s
+    const int* sep;            // [K-1] separator stages g_1 .. g_{K-1}
+    const int* rstart;         // [K]   start of separator k in the reduced vector (last entry = its length)
+    const int* roffD;          // [K-1] offsets of D~_k / B~_k in the reduced block storage
+    const int* roffB;
+    int K, rn, rtotal;
+};
+
+__device__ __forceinline__ int msp_yF(const int* m_cls, int i) { const int D = m_cls[i]; return D * D + D * (i > 0 ? m_cls[i - 1] : 0); }
+__device__ __forceinline__ int msp_yB(const int* m_cls, int i, int N) { const int D = m_cls[i]; return D * D + D * ((i + 2 < N) ? m_cls[i + 1] : 0); }
+
+constexpr int MSP_R = 4;       // ring depth of the CTA-wide packet ring of the spike kernel
+
+// ---- 2. spikes: CTA per (QP, run s >= 1), warp j = column j of the separator block; smem: ring[MSP_R][slot] | per warp xs[seg_len_max + 64] | meta
+__global__ void __launch_bounds__(1024) msp_spike_kernel(MsDev s, MsPart P, int slot_doubles, int seg_len_max, const double* __restrict__ fac_all,
+                                                         double* __restrict__ pk_all, size_t pk_stride, const int* __restrict__ active) {
+    extern __shared__ __align__(16) double sp_sm[];
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    const int run = blockIdx.y + 1;
+    const int tid = threadIdx.x, lane = tid & 31, j = tid >> 5, nth = blockDim.x;
+    const int N = s.N;
+    const int i0 = P.seg_bounds[2 * run], i1 = P.seg_bounds[2 * run + 1], g = i0 - 1;
+    double* ring = sp_sm;
+    double* xs = ring + (size_t)MSP_R * slot_doubles + (size_t)j * (seg_len_max + 64);
+    double* tmp = xs + seg_len_max + 32;
+    const double* fac = fac_all + (size_t)b * s.total;
+    double* pk = pk_all + (size_t)b * pk_stride;
+    const int dg = s.diag[g], og = s.off[g], Dsep = s.cls[g];
+    const int base = s.start[i0];
+    for (int e = lane; e < seg_len_max + 64; e += 32) xs[e] = 0.0;
+    __syncwarp();
+    if (j < dg && lane < og) xs[lane] = __ldg(fac + s.offB[g] + lane + (size_t)j * og);      // column j of B(g): rows = first og variables of the run
+    auto issue = [&](int i) {                        // inv(L_i) | B_{i-1} of the forward packet
+        const int D = s.cls[i];
+        const int sz = D * D + D * (i > 0 ? s.cls[i - 1] : 0);
+        const double* src = pk + s.pkF[i];
+        double* dst = ring + (size_t)((i - i0) % MSP_R) * slot_doubles;
+        for (int e = 2 * tid; e < sz; e += 2 * nth) msw_cp_async16(dst + e, src + e);
+    };
+    for (int q = 0; q < MSP_R - 1; q++) { if (i0 + q < i1) issue(i0 + q); msw_cp_commit(); }
+    for (int i = i0; i < i1; i++) {
+        msw_cp_wait<MSP_R - 2>();
+        __syncthreads();                             // packet i landed for every thread; everyone is done with slot (i - 1) % MSP_R
+        if (i + MSP_R - 1 < i1) issue(i + MSP_R - 1);
+        msw_cp_commit();
+        const int d = s.diag[i], D = s.cls[i], st = s.start[i] - base;
+        const int PD = i > i0 ? s.cls[i - 1] : 0, pst = i > i0 ? s.start[i - 1] - base : 0;
+        const double* pkt = ring + (size_t)((i - i0) % MSP_R) * slot_doubles;
+        if (D == 16) msw_fwd_stage<16>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
+        else if (D == 8) msw_fwd_stage<8>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
+        else msw_fwd_stage<32>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
+    }
+    msw_cp_wait<0>();
+    // Y into the packets of the run's stages, both orientations, zero-padded to the class sizes
+    if (j < Dsep) {
+        for (int i = i0; i < i1; i++) {
+            const int d = s.diag[i], D = s.cls[i], st = s.start[i] - base;
+            if (lane < D) {
+                const double v = (lane < d && j < dg) ? xs[st + lane] : 0.0;
+                pk[s.pkB[i] + msp_yB(s.cls, i, N) + lane + j * D] = v;            // Y  [D x Dsep]
+                pk[s.pkF[i] + msp_yF(s.cls, i) + j + lane * Dsep] = v;            // Y^T [Dsep x D]
+            }
+        }
+    }
+}
+
+// ---- 3. reduced system: CTA per (QP, separator k)
+__global__ void __launch_bounds__(256) msp_reduce_assemble_kernel(MsDev s, MsPart P, const double* __restrict__ fac_all, const double* __restrict__ pk_all, size_t pk_stride,
+                                                                  const double* __restrict__ carry_all, double* __restrict__ rfac_all, const int* __restrict__ active) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    if (active && !active[b]) return;
+    const int tid = threadIdx.x, N = s.N;
+    const int g = P.sep[k];
+    const int d = s.diag[g], ol = s.off[g - 1];
+    const int r0 = P.seg_bounds[2 * (k + 1)], r1 = P.seg_bounds[2 * (k + 1) + 1];      // the run on the RIGHT of separator k
+    const double* fac = fac_all + (size_t)b * s.total;
+    const double* pk = pk_all + (size_t)b * pk_stride;
+    const double* carry = carry_all + ((size_t)b * P.K + k) * 1024;                     // the run on the LEFT
+    double* rfac = rfac_all + (size_t)b * P.rtotal;
+    for (int e = tid; e < d * d; e += 256) {
+        const int r = e % d, c = e / d;
+        double v = 0.0;
+        if (r >= c) {
+            v = fac[s.offD[g] + e];
+            if (r < ol) v += carry[r + 32 * c];
+            double acc = 0.0;
+            for (int i = r0; i < r1; i++) {
+                const int D = s.cls[i];
+                const double* Y = pk + s.pkB[i] + msp_yB(s.cls, i, N);
+                for (int q = 0; q < D; q++) acc += Y[q + r * D] * Y[q + c * D];
+            }
+            v -= acc;
+        }
+        rfac[P.roffD[k] + e] = v;
+    }
+    if (k + 1 < P.K - 1) {          // coupling to the next separator through the run in between: -(B L^-T)(last stage) Y[last stage]
+        const int il = r1 - 1, o2 = s.off[il], D = s.cls[il];
+        const double* BT = pk + s.pkB[il] + D * D;                                      // B^T [D x ND]: BT[q + r2 * D]
+        const double* Y = pk + s.pkB[il] + msp_yB(s.cls, il, N);
+        for (int e = tid; e < o2 * d; e += 256) {
+            const int r2 = e % o2, c = e / o2;
+            double acc = 0.0;
+            for (int q = 0; q < D; q++) acc += BT[q + r2 * D] * Y[q + c * D];
+            rfac[P.roffB[k] + e] = -acc;
+        }
+    }
+}
+
+// ---- solves.  smem of msp_fwd / msp_bwd: xs[seg_len_max + 96] | tmp[32] | z[32] | meta | ring[MSW_R][slot]
+__global__ void __launch_bounds__(32) msp_fwd_kernel(MsDev s, MsPart P, int slot_doubles, int seg_len_max, const double* __restrict__ pk_all, size_t pk_stride,
+                                                     double* __restrict__ X, double* __restrict__ zbuf, const int* __restrict__ active) {
+    extern __shared__ __align__(16) double xs[];
+    const int b = blockIdx.x, run = blockIdx.y;
+    if (active && !active[b]) return;
+    const int lane = threadIdx.x, N = s.N;
+    const int i0 = P.seg_bounds[2 * run], i1 = P.seg_bounds[2 * run + 1], NS = i1 - i0;
+    double* tmp = xs + seg_len_max + 96;
+    double* z = tmp + 32;
+    int* meta = reinterpret_cast<int*>(z + 32);
+    double* ring = z + 32 + ((MS_META * N + 1) / 2 + 1) / 2 * 2;
+    for (int e = lane; e < MS_META * N; e += 32) meta[e] = s.start[e];
+    const int *m_start = meta, *m_diag = meta + N, *m_cls = meta + 7 * N, *m_pkF = meta + 8 * N, *m_szF = meta + 9 * N;
+    __syncwarp();
+    const double* pk = pk_all + (size_t)b * pk_stride;
+    const int base = m_start[i0], len = m_start[i1 - 1] + m_diag[i1 - 1] - base;
+    double* x = X + (size_t)b * s.n + base;
+    const int Dsep = run > 0 ? m_cls[i0 - 1] : 0;
+    for (int q = 0; q < MSW_PF; q++) { if (q < NS) msw_issue(pk + m_pkF[i0 + q], m_szF[i0 + q], ring + (size_t)(q % MSW_R) * slot_doubles, lane); msw_cp_commit(); }
+    for (int e = lane; e < seg_len_max + 96; e += 32) xs[e] = e < len ? x[e] : 0.0;
+    z[lane] = 0.0;
+    for (int t = 0; t < NS; t++) {
+        const int i = i0 + t;
+        msw_cp_wait<MSW_PF - 1>();
+        __syncwarp();
+        const int d = m_diag[i], st = m_start[i] - base, D = m_cls[i];
+        const int PD = t > 0 ? m_cls[i - 1] : 0, pst = t > 0 ? m_start[i - 1] - base : 0;
+        const double* pkt = ring + (size_t)(t % MSW_R) * slot_doubles;
+        if (D == 16) msw_fwd_stage<16>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
+        else if (D == 8) msw_fwd_stage<8>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
+        else msw_fwd_stage<32>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
+        if (run > 0) {                               // z += Y_i^T y_i (off the dependent chain)
+            const double* YT = pkt + msp_yF(m_cls, i);
+            if (lane < 32) tmp[lane] = lane < d ? xs[st + lane] : 0.0;       // zero-padded copy: the padded columns of Y^T are zero, the entries of xs behind the stage are not
+            __syncwarp();
+            double acc;
+            if (Dsep == 16) { acc = msw_matvec_dyn<16>(YT, tmp, D, lane % 16, lane / 16); acc = msw_reduce_h<16>(acc); if (lane < 16) z[lane] += acc; }
+            else if (Dsep == 8) { acc = msw_matvec_dyn<8>(YT, tmp, D, lane % 8, lane / 8); acc = msw_reduce_h<8>(acc); if (lane < 8) z[lane] += acc; }
+            else { acc = msw_matvec_dyn<32>(YT, tmp, D, lane, 0); z[lane] += acc; }
+        }
+        __syncwarp();
+        const int jn = t + MSW_PF;
+        if (jn < NS) msw_issue(pk + m_pkF[i0 + jn], m_szF[i0 + jn], ring + (size_t)(jn % MSW_R) * slot_doubles, lane);
+        msw_cp_commit();
+    }
+    msw_cp_wait<0>();
+    __syncwarp();
+    for (int e = lane; e < len; e += 32) x[e] = xs[e];
+    zbuf[((size_t)b * P.K + run) * 32 + lane] = z[lane];
+}
+
+// reduced right-hand side of separator k: x(g) - (B L^-T)(last stage of the run on the left) y(last) - Y^T y (run on the right); warp per separator
+__global__ void msp_gather_kernel(MsDev s, MsPart P, const double* __restrict__ pk_all, size_t pk_stride, const double* __restrict__ X, const double* __restrict__ zbuf,
+                                  double* __restrict__ xr, const int* __restrict__ active) {
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    const int lane = threadIdx.x & 31, k = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= P.K - 1) return;
+    const int g = P.sep[k], il = g - 1;
+    const int d = s.diag[g], D = s.cls[g], dl = s.diag[il], PD = s.cls[il];
+    const double* pk = pk_all + (size_t)b * pk_stride;
+    const double* x = X + (size_t)b * s.n;
+    const double* Bs = pk + s.pkF[g] + D * D;          // (B L^-T)(il) as [D x PD], column-major
+    if (lane < d) {
+        double acc = 0.0;
+        for (int q = 0; q < dl; q++) acc += Bs[lane + q * D] * x[s.start[il] + q];
+        xr[(size_t)b * P.rn + P.rstart[k] + lane] = x[s.start[g] + lane] - acc - zbuf[((size_t)b * P.K + (k + 1)) * 32 + lane];
+    }
+    (void)PD;
+}
+
+__global__ void __launch_bounds__(32) msp_bwd_kernel(MsDev s, MsPart P, int slot_doubles, int seg_len_max, const double* __restrict__ pk_all, size_t pk_stride,
+                                                     double* __restrict__ X, const double* __restrict__ xr_all, const int* __restrict__ active) {
+    extern __shared__ __align__(16) double xs[];
+    const int b = blockIdx.x, run = blockIdx.y;
+    if (active && !active[b]) return;
+    const int lane = threadIdx.x, N = s.N;
+    const int i0 = P.seg_bounds[2 * run], i1 = P.seg_bounds[2 * run + 1], NS = i1 - i0;
+    double* tmp = xs + seg_len_max + 96;
+    double* xl = tmp + 32;
+    int* meta = reinterpret_cast<int*>(xl + 32);
+    double* ring = xl + 32 + ((MS_META * N + 1) / 2 + 1) / 2 * 2;
+    for (int e = lane; e < MS_META * N; e += 32) meta[e] = s.start[e];
+    const int *m_start = meta, *m_diag = meta + N, *m_cls = meta + 7 * N, *m_pkB = meta + 10 * N, *m_szB = meta + 11 * N;
+    __syncwarp();
+    const double* pk = pk_all + (size_t)b * pk_stride;
+    const double* xr = xr_all + (size_t)b * P.rn;
+    const int base = m_start[i0], len = m_start[i1 - 1] + m_diag[i1 - 1] - base;
+    double* x = X + (size_t)b * s.n + base;
+    const int Dsep = run > 0 ? m_cls[i0 - 1] : 0;
+    for (int q = 0; q < MSW_PF; q++) { const int t = NS - 1 - q; if (t >= 0) msw_issue(pk + m_pkB[i0 + t], m_szB[i0 + t], ring + (size_t)(t % MSW_R) * slot_doubles, lane); msw_cp_commit(); }
+    for (int e = lane; e < seg_len_max + 96; e += 32) xs[e] = e < len ? x[e] : 0.0;
+    __syncwarp();
+    if (run + 1 < P.K) {                              // solution of the separator on the right sits where the next stage's x is read; it also goes back to X
+        const int g = P.sep[run], d = m_diag[g];
+        if (lane < d) { const double v = xr[P.rstart[run] + lane]; xs[len + lane] = v; X[(size_t)b * s.n + m_start[g] + lane] = v; }
+    }
+    { const int dl = run > 0 ? m_diag[i0 - 1] : 0; xl[lane] = lane < dl ? xr[P.rstart[run - (run > 0)] + lane] : 0.0; }
+    __syncwarp();
+    for (int t = NS - 1; t >= 0; t--) {
+        const int i = i0 + t;
+        msw_cp_wait<MSW_PF - 1>();
+        __syncwarp();
+        const int d = m_diag[i], st = m_start[i] - base, D = m_cls[i];
+        const int ND = (i + 2 < N) ? m_cls[i + 1] : 0, nst = st + d;
+        const double* pkt = ring + (size_t)(t % MSW_R) * slot_doubles;
+        if (run > 0) {                               // y_i -= Y_i x(separator on the left)
+            const double* Y = pkt + msp_yB(m_cls, i, N);
+            double acc;
+            if (D == 16) { acc = msw_matvec_dyn<16>(Y, xl, Dsep, lane % 16, lane / 16); acc = msw_reduce_h<16>(acc); if (lane < 16 && lane < d) xs[st + lane] -= acc; }
+            else if (D == 8) { acc = msw_matvec_dyn<8>(Y, xl, Dsep, lane % 8, lane / 8); acc = msw_reduce_h<8>(acc); if (lane < 8 && lane < d) xs[st + lane] -= acc; }
+            else { acc = msw_matvec_dyn<32>(Y, xl, Dsep, lane, 0); if (lane < d) xs[st + lane] -= acc; }
+            __syncwarp();
+        }
+        if (D == 16) msw_bwd_stage<16>(pkt, ND, xs, st, nst, d, 0, s.n, tmp, lane);
+        else if (D == 8) msw_bwd_stage<8>(pkt, ND, xs, st, nst, d, 0, s.n, tmp, lane);
+        else msw_bwd_stage<32>(pkt, ND, xs, st, nst, d, 0, s.n, tmp, lane);
+        const int jn = t - MSW_PF;
+        if (jn >= 0) msw_issue(pk + m_pkB[i0 + jn], m_szB[i0 + jn], ring + (size_t)(jn % MSW_R) * slot_doubles, lane);
+        msw_cp_commit();
+    }
+    msw_cp_wait<0>();
+    __syncwarp();
+    for (int e = lane; e < len; e += 32) x[e] = xs[e];
+}
+
+}  // namespace b200

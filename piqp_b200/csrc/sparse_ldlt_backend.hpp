@@ -73,6 +73,7 @@ public:
     void eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) override;
     void extract_P_diag(double* P_diag) override;
     void print_info() const override;
+    bool graph_capturable() const override { return !wide; }      // the whole-GPU schedule forks onto an auxiliary stream (look-ahead)
     double factor_flops() const override { return S.factor_flops(); }
     double factor_bytes() const override { return 12.0 * S.nnzL() + 12.0 * (double)S.PKi_rows.size(); }
     double solve_flops() const override { return 4.0 * S.nnzL() + S.nk; }

@@ -38,6 +38,43 @@ def test_structure_detection_matches_reference_print_and_oracle(oracle, b200):
     assert b200.MultistageKKT(P, AT, GT).block_info() == o.multistage_blocks()
 
 
+@pytest.mark.parametrize("N,segments", [(30, None), (30, "2"), (30, "7"), (30, "10"), (100, None), (100, "4"), (57, "12")])
+def test_parallel_in_horizon_partition_matches_sequential_chain_and_oracle(oracle, b200, N, segments, monkeypatch):
+    """the horizon cut into K runs at K-1 separator stages (runs factorised / substituted concurrently, spikes,
+    reduced chain on the separators; multistage_partition.cuh) == the sequential warp chain (B200_MS_NO_PARTITION=1) == the oracle's
+    factor_kkt / solve_llt_in_place restatement, for default and forced K, including runs of 1-2 stages"""
+    d = mpc_batch(1, N=N)
+    args = (d["P"], d["c"][0], d["A"], d["b"][0], None, None, None, d["x_l"][0], d["x_u"][0])
+    o = oracle.SparseSolver(oracle.default_settings(kkt_solver="sparse_multistage")); o.setup(*args)
+    P, AT, GT = o.scaled_matrices()
+    n, p, m = o.dims[:3]
+    rng = np.random.default_rng(N)
+    x_reg = rng.uniform(0.5, 1.5, n); z_reg = np.zeros(m); delta = 0.7
+    r = (rng.standard_normal(n), rng.standard_normal(p), np.zeros(m))
+    assert o.backend_factor(delta, x_reg, z_reg) == 1
+    ref = o.backend_solve(*r)
+    out = {}
+    for mode in ("partition", "sequential"):
+        monkeypatch.setenv("B200_MS_NO_PARTITION", "1" if mode == "sequential" else "0")
+        if segments and mode == "partition":
+            monkeypatch.setenv("B200_MS_SEGMENTS", segments)
+        else:
+            monkeypatch.delenv("B200_MS_SEGMENTS", raising=False)
+        be = b200.MultistageKKT(P, AT, GT)
+        assert be.update_scalings_and_factor(delta, x_reg, z_reg) is True
+        out[mode] = be.solve(*r)
+        assert be.update_scalings_and_factor(0.3, x_reg * 2, z_reg) is True       # refactor with other scalings, then back: no stale state
+        assert be.update_scalings_and_factor(delta, x_reg, z_reg) is True
+        for a, b in zip(be.solve(*r), out[mode]):
+            assert np.array_equal(a, b)
+        cl = be.clone()
+        for a, b in zip(cl.solve(*r), out[mode]):
+            assert np.array_equal(a, b)
+    for a, b, c in zip(out["partition"], out["sequential"], ref):
+        if len(c):
+            assert _rel(a, b) < 1e-10 and _rel(a, c) < 1e-9, (_rel(a, b), _rel(a, c))
+
+
 @pytest.mark.parametrize("path", ["warp_chain", "generic"])
 @pytest.mark.parametrize("case", ["notebook", "mpc", "random_with_G"])
 def test_backend_factor_solve_eval_parity(oracle, b200, case, path, monkeypatch):
