@@ -31,7 +31,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="dense", choices=["dense", "multistage", "sparse", "sparse_c3"])
+    ap.add_argument("--workload", default="all", choices=["all", "dense", "multistage", "sparse", "sparse_c3", "mm_suite"],
+                    help="all (default): the headline dense config 2 as the line's value + configs 4, 3 and 5 under config.workloads")
+    ap.add_argument("--sub-steps", type=int, default=0, help="timed steps of the secondary workloads of --workload all (0 = auto)")
+    ap.add_argument("--mm-max-kkt", type=int, default=30000)
+    ap.add_argument("--mm-replicas", type=int, default=8)
     ap.add_argument("--density", type=float, default=0.01, help="sparse workload: density of P_utri, A, G")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (weak scaling); 0 = workload default")
     ap.add_argument("--n", type=int, default=1024)
@@ -44,11 +48,20 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
-    if a.batch == 0:
-        a.batch = {"dense": 256, "multistage": 128, "sparse": 148, "sparse_c3": 1}[a.workload]      # sparse: one CTA per QP, one QP per SM; sparse_c3: one QP over the whole GPU
-    if a.workload == "sparse" and (a.n, a.p, a.m) == (1024, 0, 512):      # sparse defaults (random patterns fill in heavily: n_kkt=850 -> nnz(L)=53k, 308 etree levels; 10-17 IP iterations)
-        a.n, a.p, a.m = 500, 100, 250
     return a
+
+
+def workload_args(a, name):
+    """per-workload copy of the arguments with that workload's default batch / shape"""
+    b = argparse.Namespace(**vars(a))
+    b.workload = name
+    if b.batch == 0 or a.workload == "all":
+        b.batch = {"dense": 256, "multistage": 128, "sparse": 148, "sparse_c3": 1}.get(name, 1)      # sparse: one CTA per QP, one QP per SM; sparse_c3: one QP over the whole GPU
+        if a.workload == "all" and name == "dense" and a.batch:
+            b.batch = a.batch
+    if name == "sparse" and (b.n, b.p, b.m) == (1024, 0, 512):      # sparse defaults (random patterns fill in heavily: n_kkt=850 -> nnz(L)=53k, 308 etree levels; 10-17 IP iterations)
+        b.n, b.p, b.m = 500, 100, 250
+    return b
 
 
 class ClockSampler:
@@ -316,6 +329,36 @@ class SparseC3Workload(SparseWorkload):
     def cpu_work(self):
         return self._cpu_work
 
+    def cpu_factor_solve_sample(self, threads):
+        """CPU arm of config 3 (oracle port of sparse::KKT<FULL> + sparse::LDLt): `threads` solvers of the same family at n = CPU_N,
+        each timing setup-free  1 x update_scalings_and_factor + 2 x backend solve  (one IP iteration's worth of the hot path) under
+        the product's permutation; size-normalised GFLOP/s.  One factorisation at the full n = 10 000 needs ~5 minutes on a core."""
+        from concurrent.futures import ThreadPoolExecutor
+        import numpy as np
+        from oracle import pyoracle
+        try:
+            pyoracle.build(native=True); native = True
+        except Exception:
+            native = False
+        makers = self.cpu_solvers(threads, 1042, native)
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            solvers = list(ex.map(lambda mk: mk(), makers))
+        ff, sf = self._cpu_work
+        n, p, m = solvers[0].dims[:3]
+        rng = np.random.default_rng(1)
+        x_reg, z_reg = rng.uniform(0.5, 1.5, n), rng.uniform(0.5, 2.0, m)
+        r = (rng.standard_normal(n), rng.standard_normal(p), rng.standard_normal(m))
+
+        def one(s):
+            s.backend_factor(0.9, x_reg, z_reg); s.backend_solve(*r); s.backend_solve(*r)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(one, solvers))
+        dt = time.perf_counter() - t0
+        return {"value": threads * (ff + 2 * sf) / dt * 1e-9, "unit": "GFLOP/s", "cores": threads, "kind": "port", "seconds": dt,
+                "sample": "%d oracle solvers (one per thread), each 1 factorisation + 2 backend solves of the same family at n=%d, p=m=%d under the product's permutation, %s build"
+                          % (threads, self.CPU_N, self.CPU_N // 2, "-march=native" if native else "x86-64-v3")}
+
     def cpu_sample_note(self):
         return "same family at n=%d, p=m=%d (one factorisation at n=%d takes minutes on one core)" % (self.CPU_N, self.CPU_N // 2, self.n)
 
@@ -352,6 +395,76 @@ def cpu_oracle_sample(wl, n_qp, threads, seed0=1042):
     return flops / dt * 1e-9, n_qp / dt, dt, iters, native, flops / (t1 - ts) * 1e-9, n_qp / (t1 - ts)
 
 
+def blas_proxy_dense(n, p, m, iters, n_qp, threads):
+    """The closest stand-in for the reference's Eigen::LLT + Eigen GEBP products that exists in this image: the same sequence of
+    dense kernels per IP iteration through OpenBLAS (scipy.linalg.blas / lapack), one QP per host thread, BLAS itself
+    single-threaded (the reference is single-threaded per solve):  dsyrk (G^T Z^-1 G, n x m) + dpotrf (n) + 2 x (2 dtrsv + the
+    G / A mat-vecs).  Returns (GFLOP/s with the algorithmic flop count of SURVEY 8d, QP/s, seconds)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from scipy.linalg import blas, lapack
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        threadpool_limits = None
+    rng = np.random.default_rng(0)
+    probs = []
+    for _ in range(n_qp):
+        G = np.asfortranarray(rng.standard_normal((m, n))) if m else None
+        A = np.asfortranarray(rng.standard_normal((p, n))) if p else None
+        P = np.asfortranarray(np.eye(n) * (n + m))
+        probs.append((P, G, A, rng.uniform(0.5, 2.0, max(m, 1)), rng.standard_normal(n)))
+
+    def one(q):
+        P, G, A, z, r = q
+        for _ in range(iters):
+            K = P.copy(order="F")
+            if G is not None:
+                W = np.asfortranarray(G * np.sqrt(z[:m])[:, None])
+                K = blas.dsyrk(1.0, W, beta=1.0, c=K, trans=1, lower=1, overwrite_c=1)
+            if A is not None:
+                K = blas.dsyrk(1.0, A, beta=1.0, c=K, trans=1, lower=1, overwrite_c=1)
+            L, info = lapack.dpotrf(K, lower=1, overwrite_a=1)
+            for _s in range(2):
+                x = r.copy()
+                if G is not None:
+                    x = x + G.T @ (z[:m] * (G @ r)[:m])
+                x = blas.dtrsv(L, x, lower=1, trans=0); x = blas.dtrsv(L, x, lower=1, trans=1)
+                if G is not None:
+                    _ = G @ x
+                if A is not None:
+                    _ = A @ x
+        return 0
+
+    def run():
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(one, probs))
+        return time.perf_counter() - t0
+    if threadpool_limits is not None:
+        with threadpool_limits(limits=1):
+            run(); dt = run()
+    else:
+        run(); dt = run()
+    fn, fp, fm = float(n), float(p), float(m)
+    flops = n_qp * iters * ((fn * fn * fm + fn ** 3 / 3.0) + 2 * (2 * fn * fn + 4 * fn * fm + 4 * fn * fp))
+    return flops / dt * 1e-9, n_qp / dt, dt
+
+
+def blas_proxy_root_front(f, algorithmic_flops):
+    """config 3: 99 % of the factorisation is the dense root front of the fill-in; a supernodal CPU code would run it as one
+    LAPACK dpotrf with every host core (OpenBLAS threading on).  Returns (GFLOP/s on the algorithmic flops, seconds)."""
+    import numpy as np
+    from scipy.linalg import lapack
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((f, 64))
+    K = np.asfortranarray(A @ A.T + np.eye(f) * f)
+    t0 = time.perf_counter()
+    lapack.dpotrf(K, lower=1, overwrite_a=1)
+    dt = time.perf_counter() - t0
+    return algorithmic_flops / dt * 1e-9, dt
+
+
 def run_reference(args, wl, rank):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  The real PIQP cannot be built
     here (Eigen absent), so this times the oracle port; rank 0 only, bounded sample per step."""
@@ -384,24 +497,12 @@ def run_reference(args, wl, rank):
     print(json.dumps(line))
 
 
-def main():
-    args = parse()
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = {"dense": DenseWorkload, "multistage": MultistageWorkload, "sparse": SparseWorkload, "sparse_c3": SparseC3Workload}[args.workload](args)
-    if args.impl == "reference":
-        run_reference(args, wl, rank)
-        return
+def measure(args, wl, ctx):
+    """one workload on this rank's GPU: device-resident value, e2e, roofline, cpu_baseline -> the JSON line (rank 0) or None"""
     import ctypes as C
     import torch
     import piqp_b200
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout for the one JSON line (NCCL prints its version banner to stdout otherwise)
-        import torch.distributed as dist_
-        dist = dist_
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, local, dev, dist = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"], ctx["dist"]
     B = args.batch
 
     # The one collective of the path: rank 0 broadcasts the problem descriptor (global batch, seed base) over NCCL/NVLink at
@@ -548,9 +649,7 @@ def main():
                "single_handle_qps": B * world / float(tsingle.item()), "what": what}
 
     if rank != 0:
-        if dist:
-            dist.destroy_process_group()
-        return
+        return None
 
     peaks = {}
     try:
@@ -634,13 +733,28 @@ def main():
                     "backend_solve_gbs": (agg["backend_solves"] * sb) / (agg["backend_solve_ms"] * 1e-3) * 1e-9 if agg["backend_solve_ms"] else None}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only (the driver's scaling runs do not repeat it)
         threads = min(os.cpu_count() or 1, 32)
-        n_qp = args.cpu_sample or (min(threads, 16) if wl.name in ("dense", "sparse_c3") else 16 * threads)
-        g, q, dt, iters, native, eg, eq = cpu_oracle_sample(wl, n_qp, min(threads, n_qp))
-        cpu = {"value": g, "unit": "GFLOP/s", "qps": q, "cores": min(threads, n_qp), "kind": "port", "setup_plus_solve_gflops": eg, "setup_plus_solve_qps": eq,
-               "sample": "%d QPs of %s (seeds 1042..), one oracle solver per thread, %.1f s, iters %s, %s build"
-                         % (n_qp, wl.cpu_sample_note() if hasattr(wl, "cpu_sample_note") else "the same shape", dt, sorted(set(iters)), "-march=native" if native else "x86-64-v3")}
+        if wl.name == "sparse_c3":
+            cpu = wl.cpu_factor_solve_sample(min(threads, 8))
+            f_root = int(solver.symbolic()["largest_front"]) if hasattr(solver, "symbolic") else wl.n
+            bg, bdt = blas_proxy_root_front(f_root, ff)
+            cpu["blas_proxy"] = {"value": bg, "unit": "GFLOP/s", "cores": os.cpu_count(), "seconds": bdt,
+                                 "what": "LAPACK dpotrf (OpenBLAS, all host threads) of one dense %d x %d front = the root front that carries 99 %% of this factorisation, "
+                                         "credited with the algorithmic factor flops of the FULL-SIZE problem; what a supernodal CPU code would reach, not what the reference's "
+                                         "scalar up-looking LDL^T does (measured once in the build container: 329 s for this factorisation on one core = 1.0 GFLOP/s)" % (f_root, f_root)}
+        else:
+            n_qp = args.cpu_sample or (min(threads, 16) if wl.name == "dense" else 16 * threads)
+            g, q, dt, iters, native, eg, eq = cpu_oracle_sample(wl, n_qp, min(threads, n_qp))
+            cpu = {"value": g, "unit": "GFLOP/s", "qps": q, "cores": min(threads, n_qp), "kind": "port", "setup_plus_solve_gflops": eg, "setup_plus_solve_qps": eq,
+                   "sample": "%d QPs of %s (seeds 1042..), one oracle solver per thread, %.1f s, iters %s, %s build"
+                             % (n_qp, wl.cpu_sample_note() if hasattr(wl, "cpu_sample_note") else "the same shape", dt, sorted(set(iters)), "-march=native" if native else "x86-64-v3")}
+            if wl.name == "dense":
+                it = max(1, int(round(agg["ip_iterations"] / float(B * args.steps))))
+                bg, bq, bdt = blas_proxy_dense(wl.n, wl.p, wl.m, it, min(threads, 16), min(threads, 16))
+                cpu["blas_proxy"] = {"value": bg, "unit": "GFLOP/s", "qps": bq, "cores": min(threads, 16), "seconds": bdt,
+                                     "what": "per IP iteration dsyrk + dpotrf + 2 x (2 dtrsv + mat-vecs) through OpenBLAS (scipy), %d iterations per QP, one QP per host thread, "
+                                             "BLAS single-threaded: stand-in for the reference's Eigen::LLT / GEBP path (Eigen is not in this image)" % it}
 
     line = {
         "metric": "KKT factor+solve GFLOP/s fp64", "value": gflops, "unit": "GFLOP/s", "qps": qps,
@@ -658,7 +772,62 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(L1 - L0), "clocks": clocks,
     }
-    print(json.dumps(line))
+    return line
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    classes = {"dense": DenseWorkload, "multistage": MultistageWorkload, "sparse": SparseWorkload, "sparse_c3": SparseC3Workload}
+    primary = "dense" if args.workload in ("all", "mm_suite") else args.workload
+    if args.impl == "reference":
+        a = workload_args(args, primary)
+        run_reference(a, classes[primary](a), rank)
+        return
+    import torch
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout for the one JSON line (NCCL prints its version banner to stdout otherwise)
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = {"rank": rank, "world": world, "local": local, "dev": dev, "dist": dist}
+    if args.workload == "mm_suite":
+        from tools import mm_suite
+        line = mm_suite.run(ctx, max_kkt=args.mm_max_kkt, replicas=args.mm_replicas)
+    else:
+        a = workload_args(args, primary)
+        line = measure(a, classes[primary](a), ctx)
+    if args.workload == "all":
+        # BASELINE configs 4, 3 and 5 ride in the same line (config.workloads): same measurement contract per workload, fewer steps,
+        # so that the driver's N = 1, 2, 4, 8 runs see config 4 at batch 128 per GPU (1024 over 8) and the config-5 suite sharded 1 -> 8
+        subs = {}
+        sub_steps = args.sub_steps or max(3, min(args.steps, 10))
+        for key, name in (("multistage_c4", "multistage"), ("sparse_c3", "sparse_c3")):
+            a = workload_args(args, name)
+            a.steps, a.warmup = (sub_steps, 3) if name == "multistage" else (max(2, sub_steps // 3), 3)
+            t0 = time.perf_counter()
+            try:
+                sub = measure(a, classes[name](a), ctx)
+            except Exception as e:      # a secondary workload must not take the headline down with it
+                sub = {"error": repr(e)} if rank == 0 else None
+            if rank == 0:
+                sub["bench_seconds"] = time.perf_counter() - t0
+                subs[key] = sub
+        t0 = time.perf_counter()
+        try:
+            from tools import mm_suite
+            sub = mm_suite.run(ctx, max_kkt=args.mm_max_kkt, replicas=args.mm_replicas)
+        except Exception as e:
+            sub = {"error": repr(e)} if rank == 0 else None
+        if rank == 0:
+            sub["bench_seconds"] = time.perf_counter() - t0
+            subs["mm_suite"] = sub
+            line["config"]["workloads"] = subs
+    if rank == 0:
+        print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
 

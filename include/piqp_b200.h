@@ -229,6 +229,16 @@ int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
                         const int* Ap, const int* Ai, const double* Ax, const double* b,
                         const int* Gp, const int* Gi, const double* Gx, const double* h_l, const double* h_u,
                         const double* x_l, const double* x_u, const b200qp_settings* settings, int device, int on_device);
+/* The same with a caller-supplied fill-reducing ordering of the KKT matrix of the selected mode (kkt_perm[new] = old,
+ * n + [p] + [m] entries, sparse/ordering.hpp:59-125; NULL = own AMD).  In the multi-GPU mode rank 0 runs the symbolic analysis
+ * once and the permutation rides the setup broadcast (b200qp_get_sparse_perm on rank 0 -> NCCL -> kkt_perm elsewhere). */
+int b200qp_setup_sparse_ex(b200qp_handle** out, int batch, int n, int p, int m,
+                           const int* Pp, const int* Pi, const double* Px, const double* c,
+                           const int* Ap, const int* Ai, const double* Ax, const double* b,
+                           const int* Gp, const int* Gi, const double* Gx, const double* h_l, const double* h_u,
+                           const double* x_l, const double* x_u, const b200qp_settings* settings, int device, int on_device, const int* kkt_perm);
+/* ordering in use by a sparse_ldlt-family handle: copies min(cap, n_kkt) entries, returns n_kkt */
+int b200qp_get_sparse_perm(b200qp_handle* h, int* perm, int cap);
 /* Batched twin of piqp_update_sparse (piqp.h:36): same patterns, new values; NULL = keep. */
 int b200qp_update_sparse(b200qp_handle* h, const double* Px, const double* c, const double* Ax, const double* b, const double* Gx,
                          const double* h_l, const double* h_u, const double* x_l, const double* x_u, int on_device);

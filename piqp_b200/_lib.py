@@ -67,7 +67,7 @@ SYMBOLS = [
     "b200kkt_factor", "b200kkt_solve", "b200kkt_eval_P_x", "b200kkt_eval_A_xn_and_AT_xt", "b200kkt_eval_G_xn_and_GT_xt",
     "b200kkt_clone", "b200kkt_print_info", "b200kkt_destroy", "b200kkt_dense_get_kkt",
     "b200qp_set_default_settings_dense", "b200qp_set_default_settings_sparse", "b200qp_setup_dense",
-    "b200qp_update_dense", "b200qp_setup_sparse", "b200qp_update_sparse", "b200qp_multistage_blocks", "b200kkt_multistage_blocks", "b200qp_update_settings", "b200qp_solve", "b200qp_get_result", "b200qp_get_info",
+    "b200qp_update_dense", "b200qp_setup_sparse", "b200qp_setup_sparse_ex", "b200qp_get_sparse_perm", "b200qp_update_sparse", "b200qp_multistage_blocks", "b200kkt_multistage_blocks", "b200qp_update_settings", "b200qp_solve", "b200qp_get_result", "b200qp_get_info",
     "b200qp_get_stats", "b200qp_get_trace", "b200qp_set_profiling", "b200qp_get_work", "b200qp_cleanup", "b200qp_bench_factor_solve",
 ]
 

@@ -584,6 +584,19 @@ int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
                         const int* Ap, const int* Ai, const double* Ax, const double* b,
                         const int* Gp, const int* Gi, const double* Gx, const double* h_l, const double* h_u,
                         const double* x_l, const double* x_u, const b200qp_settings* settings, int device, int on_device) {
+    return b200qp_setup_sparse_ex(out, batch, n, p, m, Pp, Pi, Px, c, Ap, Ai, Ax, b, Gp, Gi, Gx, h_l, h_u, x_l, x_u, settings, device, on_device, nullptr);
+}
+int b200qp_get_sparse_perm(b200qp_handle* h, int* perm, int cap) {
+    if (!h || !h->ldlt) return fail(B200_E_INVALID, "not a sparse_ldlt handle");
+    const std::vector<int>& pv = h->ldlt->S.perm;
+    if (perm) for (int i = 0; i < (int)pv.size() && i < cap; i++) perm[i] = pv[i];
+    return (int)pv.size();
+}
+int b200qp_setup_sparse_ex(b200qp_handle** out, int batch, int n, int p, int m,
+                           const int* Pp, const int* Pi, const double* Px, const double* c,
+                           const int* Ap, const int* Ai, const double* Ax, const double* b,
+                           const int* Gp, const int* Gi, const double* Gx, const double* h_l, const double* h_u,
+                           const double* x_l, const double* x_u, const b200qp_settings* settings, int device, int on_device, const int* kkt_perm) {
     if (!out || batch <= 0 || n <= 0 || p < 0 || m < 0 || !Pp || !c) return fail(B200_E_INVALID, "b200qp_setup_sparse: bad arguments");
     if ((p > 0 && (!Ap || !b)) || (m > 0 && (!Gp || (!h_l && !h_u)))) return fail(B200_E_INVALID, "b200qp_setup_sparse: missing constraint data");
     if (batch > B200_MAX_BATCH) return fail(B200_E_UNSUPPORTED, "b200qp_setup_sparse: batch > 65535 (the batch index is a gridDim.y / .z coordinate); split the batch over several handles");
@@ -638,7 +651,7 @@ int b200qp_setup_sparse(b200qp_handle** out, int batch, int n, int p, int m,
         d.pd = h->ruiz.delta.get(); d.pd_inv = h->ruiz.delta_inv.get(); d.pdb = h->ruiz.delta_b.get(); d.pdb_inv = h->ruiz.delta_b_inv.get();
         d.pc = h->ruiz.c.get(); d.pc_inv = h->ruiz.c_inv.get();
         if (h->st.kkt_solver == 5) { h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream); h->be = h->ms.get(); }
-        else { h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, nullptr, h->stream, h->st.kkt_solver - 1); h->be = h->ldlt.get(); }   // KKTMode = 0..3 (kkt_system.hpp:476-489)
+        else { h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, kkt_perm, h->stream, h->st.kkt_solver - 1); h->be = h->ldlt.get(); }   // KKTMode = 0..3 (kkt_system.hpp:476-489)
         lap("backend ctor");
         h->ip->finish_setup(h->be);
         B200_CUDA(cudaEventRecord(e1, h->stream));

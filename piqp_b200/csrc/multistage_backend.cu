@@ -547,6 +547,14 @@ void MultistageBatchedKKT::plan_partition(const std::vector<int>& cls) {
     if (!warp_chain || S.w != 0 || nreal < 16) return;
     if (const char* e = getenv("B200_MS_NO_PARTITION")) if (e[0] == '1') return;
     int K = (int)std::lround(std::sqrt(1.25 * nreal));
+    // The runs of all QPs must be RESIDENT together (a second wave of CTAs would double the chain again): one run's CTA of the
+    // factor kernel holds sizeof(MswChainSmem) = 42 KB of shared memory => 5 per SM.  BASELINE config 4 (batch 128 per GPU): K = 5.
+    {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int per_sm = std::max(1, (int)((227 * 1024) / (sizeof(MswChainSmem) + 1024)));
+        K = std::min(K, (sms * per_sm) / std::max(batch, 1));
+    }
     if (const char* e = getenv("B200_MS_SEGMENTS")) K = atoi(e);
     K = std::max(1, std::min(K, std::min(32, nreal / 3)));
     if (K < 2) return;
@@ -611,9 +619,8 @@ void MultistageBatchedKKT::build_partition(const std::vector<int>& cls, cudaStre
     carry.alloc((size_t)batch * K * 1024); carry.zero(st);
     zbuf.alloc((size_t)batch * K * 32); zbuf.zero(st);
     xred.alloc((size_t)batch * std::max(part_rn, 1)); xred.zero(st);
-    const size_t meta_d = (size_t)(((MS_META * S.N + 1) / 2 + 1) / 2 * 2);
-    part_seg_smem = sizeof(double) * ((size_t)part_seg_len + 96 + 64 + meta_d + (size_t)MSW_R * chain_slot);
-    part_spike_smem = sizeof(double) * ((size_t)MSP_R * chain_slot + (size_t)part_dsep_max * (part_seg_len + 64));
+    part_seg_smem = sizeof(double) * ((size_t)part_seg_len + 96 + 64 + (size_t)MSP_PF * chain_slot);
+    part_spike_smem = sizeof(double) * ((size_t)MSP_R * chain_slot + (size_t)part_dsep_max * 96);
     part_rsolve_smem = sizeof(double) * ((size_t)((part_rn + 1) & ~1) + 96 + (size_t)(((MS_META * NR + 1) / 2 + 1) / 2 * 2) + (size_t)MSW_R * part_rslot);
     if (part_seg_smem > 227 * 1024 || part_spike_smem > 227 * 1024 || part_rsolve_smem > 227 * 1024) { part_K = 1; return; }
     B200_CUDA(cudaFuncSetAttribute(msp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(part_seg_smem, 48 * 1024)));
@@ -640,12 +647,11 @@ MsPart MultistageBatchedKKT::make_part() const {
 void MultistageBatchedKKT::factor_partitioned(const MsDev& dv, const int* active) {
     const int K = part_K;
     const MsPart P = make_part();
-    const size_t msm = sizeof(int) * MS_META * S.N;
     dim3 gseg(batch, K);
-#define MSP_CHAIN(RP) B200_LAUNCH(msw_factor_chain_kernel<RP>, gseg, 64, sizeof(MswChainSmem) + msm, stream, dv, fac.get(), packets.get(), pk_stride, active, P.seg_bounds, carry.get())
+#define MSP_CHAIN(RP) B200_LAUNCH(msw_factor_chain_kernel<RP>, gseg, 64, sizeof(MswChainSmem), stream, dv, fac.get(), packets.get(), pk_stride, active, P.seg_bounds, carry.get())
     if (chain_rp <= 4) MSP_CHAIN(4); else if (chain_rp <= 8) MSP_CHAIN(8); else if (chain_rp <= 12) MSP_CHAIN(12); else if (chain_rp <= 14) MSP_CHAIN(14); else MSP_CHAIN(16);
 #undef MSP_CHAIN
-    B200_LAUNCH(msp_spike_kernel, dim3(batch, K - 1), 32 * part_dsep_max, part_spike_smem, stream, dv, P, chain_slot, part_seg_len, fac.get(), packets.get(), pk_stride, active);
+    B200_LAUNCH(msp_spike_kernel, dim3(batch, K - 1), 32 * part_dsep_max, part_spike_smem, stream, dv, P, chain_slot, fac.get(), packets.get(), pk_stride, active);
     B200_LAUNCH(msp_reduce_assemble_kernel, dim3(batch, K - 1), 256, 0, stream, dv, P, fac.get(), packets.get(), pk_stride, carry.get(), rfac.get(), active);
     const MsDev rd = make_rdev(d_rmeta.get(), K, part_rn, part_rtotal);
     const size_t rmsm = sizeof(int) * MS_META * K;

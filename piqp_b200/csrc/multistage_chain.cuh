@@ -210,7 +210,7 @@ struct MswChainSmem {
     double L[2][32][32];
     double rs[2][32];
     double F[2][32][33];
-    double S[64][65];
+    double S[32][33];         // register rows of the previous stage; the next stage reads its Schur part at [d_prev + lane][d_prev + c]
 };
 
 __device__ __forceinline__ void msw_cp_async8(double* dst_smem, const double* src) {
@@ -235,8 +235,11 @@ __global__ void __launch_bounds__(64) msw_factor_chain_kernel(MsDev s, const dou
     const int N = s.N;
     int i0 = 0, nst = N - 1;                          // stages [i0, nst)
     if (seg_bounds) { i0 = seg_bounds[2 * blockIdx.y]; nst = seg_bounds[2 * blockIdx.y + 1]; }
-    for (int e = threadIdx.x; e < MS_META * N; e += 64) meta[e] = s.start[e];
-    for (int e = threadIdx.x; e < 64 * 65; e += 64) (&sm.S[0][0])[e] = 0.0;
+    // segment mode keeps the meta block in global memory (L1-resident, read off the dependent chain): 42 KB of shared memory per CTA
+    // instead of 47 KB = five CTAs per SM, which is what bounds the number of runs that are in flight at once
+    if (!seg_bounds) { for (int e = threadIdx.x; e < MS_META * N; e += 64) meta[e] = s.start[e]; }
+    else meta = const_cast<int*>(s.start);
+    for (int e = threadIdx.x; e < 32 * 33; e += 64) (&sm.S[0][0])[e] = 0.0;
     __syncthreads();
     const int *m_diag = meta + N, *m_off = meta + 2 * N, *m_offD = meta + 3 * N, *m_offB = meta + 4 * N, *m_cls = meta + 7 * N, *m_pkF = meta + 8 * N,
               *m_pkB = meta + 10 * N;
@@ -263,9 +266,11 @@ __global__ void __launch_bounds__(64) msw_factor_chain_kernel(MsDev s, const dou
             double v[2 * RP];
             {
                 const double* Frow = &sm.F[i & 1][lane][0];
-                const double* Srow = &sm.S[dprev + lane][dprev];
+                const bool rowok = dprev + lane < 32;
+                const double* Srow = &sm.S[rowok ? dprev + lane : 0][dprev];
+                const int cmax = rowok ? 32 - dprev : 0;          // the Schur complement of the previous front; zero beyond it
 #pragma unroll
-                for (int c = 0; c < 2 * RP; c++) v[c] = Frow[c] + Srow[c];
+                for (int c = 0; c < 2 * RP; c++) v[c] = Frow[c] + (c < cmax ? Srow[c] : 0.0);
             }
             __syncwarp();
             double (*Lb)[32] = sm.L[i & 1];
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(64) msw_factor_chain_kernel(MsDev s, const dou
         }
         if (carry_all && nst > i0) {                 // Schur complement on the coupling rows of the run's last stage (lower part is meaningful)
             double* C = carry_all + ((size_t)b * gridDim.y + blockIdx.y) * 1024;
-            for (int c = 0; c < 32; c++) C[lane + 32 * c] = sm.S[dprev + lane][dprev + c];
+            for (int c = 0; c < 32; c++) C[lane + 32 * c] = (dprev + lane < 32 && dprev + c < 32) ? sm.S[dprev + lane][dprev + c] : 0.0;
         }
     } else {
         for (int i = i0; i < nst; i++) {

@@ -37,9 +37,10 @@ __device__ __forceinline__ int msp_yF(const int* m_cls, int i) { const int D = m
 __device__ __forceinline__ int msp_yB(const int* m_cls, int i, int N) { const int D = m_cls[i]; return D * D + D * ((i + 2 < N) ? m_cls[i + 1] : 0); }
 
 constexpr int MSP_R = 4;       // ring depth of the CTA-wide packet ring of the spike kernel
+constexpr int MSP_PF = 6;      // packets in flight per warp of msp_fwd / msp_bwd (smem per CTA decides how many runs are resident per SM)
 
-// ---- 2. spikes: CTA per (QP, run s >= 1), warp j = column j of the separator block; smem: ring[MSP_R][slot] | per warp xs[seg_len_max + 64] | meta
-__global__ void __launch_bounds__(1024) msp_spike_kernel(MsDev s, MsPart P, int slot_doubles, int seg_len_max, const double* __restrict__ fac_all,
+// ---- 2. spikes: CTA per (QP, run s >= 1), warp j = column j of the separator block; smem: ring[MSP_R][slot] | per warp y[2][32] + tmp[32]
+__global__ void __launch_bounds__(1024) msp_spike_kernel(MsDev s, MsPart P, int slot_doubles, const double* __restrict__ fac_all,
                                                          double* __restrict__ pk_all, size_t pk_stride, const int* __restrict__ active) {
     extern __shared__ __align__(16) double sp_sm[];
     const int b = blockIdx.x;
@@ -49,15 +50,11 @@ __global__ void __launch_bounds__(1024) msp_spike_kernel(MsDev s, MsPart P, int 
     const int N = s.N;
     const int i0 = P.seg_bounds[2 * run], i1 = P.seg_bounds[2 * run + 1], g = i0 - 1;
     double* ring = sp_sm;
-    double* xs = ring + (size_t)MSP_R * slot_doubles + (size_t)j * (seg_len_max + 64);
-    double* tmp = xs + seg_len_max + 32;
+    double* y = ring + (size_t)MSP_R * slot_doubles + (size_t)j * 96;      // y[0..31], y[32..63]: the stage's vector and the previous one (alternating)
+    double* tmp = y + 64;
     const double* fac = fac_all + (size_t)b * s.total;
     double* pk = pk_all + (size_t)b * pk_stride;
     const int dg = s.diag[g], og = s.off[g], Dsep = s.cls[g];
-    const int base = s.start[i0];
-    for (int e = lane; e < seg_len_max + 64; e += 32) xs[e] = 0.0;
-    __syncwarp();
-    if (j < dg && lane < og) xs[lane] = __ldg(fac + s.offB[g] + lane + (size_t)j * og);      // column j of B(g): rows = first og variables of the run
     auto issue = [&](int i) {                        // inv(L_i) | B_{i-1} of the forward packet
         const int D = s.cls[i];
         const int sz = D * D + D * (i > 0 ? s.cls[i - 1] : 0);
@@ -66,30 +63,32 @@ __global__ void __launch_bounds__(1024) msp_spike_kernel(MsDev s, MsPart P, int 
         for (int e = 2 * tid; e < sz; e += 2 * nth) msw_cp_async16(dst + e, src + e);
     };
     for (int q = 0; q < MSP_R - 1; q++) { if (i0 + q < i1) issue(i0 + q); msw_cp_commit(); }
+    // right-hand side: column j of B(g), rows = the first og variables of the run's first stage
+    y[lane] = (j < dg && lane < og) ? __ldg(fac + s.offB[g] + lane + (size_t)j * og) : 0.0;
+    y[32 + lane] = 0.0;
     for (int i = i0; i < i1; i++) {
         msw_cp_wait<MSP_R - 2>();
         __syncthreads();                             // packet i landed for every thread; everyone is done with slot (i - 1) % MSP_R
         if (i + MSP_R - 1 < i1) issue(i + MSP_R - 1);
         msw_cp_commit();
-        const int d = s.diag[i], D = s.cls[i], st = s.start[i] - base;
-        const int PD = i > i0 ? s.cls[i - 1] : 0, pst = i > i0 ? s.start[i - 1] - base : 0;
-        const double* pkt = ring + (size_t)((i - i0) % MSP_R) * slot_doubles;
-        if (D == 16) msw_fwd_stage<16>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
-        else if (D == 8) msw_fwd_stage<8>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
-        else msw_fwd_stage<32>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
+        const int t = i - i0, cur = (t & 1) * 32, prev = 32 - cur;
+        const int d = s.diag[i], D = s.cls[i];
+        const int PD = t > 0 ? s.cls[i - 1] : 0;
+        const double* pkt = ring + (size_t)(t % MSP_R) * slot_doubles;
+        if (D == 16) msw_fwd_stage<16>(pkt, PD, y, cur, prev, d, 0, tmp, nullptr, lane);
+        else if (D == 8) msw_fwd_stage<8>(pkt, PD, y, cur, prev, d, 0, tmp, nullptr, lane);
+        else msw_fwd_stage<32>(pkt, PD, y, cur, prev, d, 0, tmp, nullptr, lane);
+        // Y into the packets of this stage, both orientations, zero-padded to the class sizes
+        if (j < Dsep && lane < D) {
+            const double v = (lane < d && j < dg) ? y[cur + lane] : 0.0;
+            pk[s.pkB[i] + msp_yB(s.cls, i, N) + lane + j * D] = v;            // Y  [D x Dsep]
+            pk[s.pkF[i] + msp_yF(s.cls, i) + j + lane * Dsep] = v;            // Y^T [Dsep x D]
+        }
+        __syncwarp();
+        y[prev + lane] = 0.0;                        // becomes the next stage's vector: zero right-hand side beyond the first stage
+        __syncwarp();
     }
     msw_cp_wait<0>();
-    // Y into the packets of the run's stages, both orientations, zero-padded to the class sizes
-    if (j < Dsep) {
-        for (int i = i0; i < i1; i++) {
-            const int d = s.diag[i], D = s.cls[i], st = s.start[i] - base;
-            if (lane < D) {
-                const double v = (lane < d && j < dg) ? xs[st + lane] : 0.0;
-                pk[s.pkB[i] + msp_yB(s.cls, i, N) + lane + j * D] = v;            // Y  [D x Dsep]
-                pk[s.pkF[i] + msp_yF(s.cls, i) + j + lane * Dsep] = v;            // Y^T [Dsep x D]
-            }
-        }
-    }
 }
 
 // ---- 3. reduced system: CTA per (QP, separator k)
@@ -134,7 +133,7 @@ __global__ void __launch_bounds__(256) msp_reduce_assemble_kernel(MsDev s, MsPar
     }
 }
 
-// ---- solves.  smem of msp_fwd / msp_bwd: xs[seg_len_max + 96] | tmp[32] | z[32] | meta | ring[MSW_R][slot]
+// ---- solves.  smem of msp_fwd / msp_bwd: xs[seg_len_max + 96] | tmp[32] | z[32] | ring[MSP_PF][slot]; the meta block is read from global memory
 __global__ void __launch_bounds__(32) msp_fwd_kernel(MsDev s, MsPart P, int slot_doubles, int seg_len_max, const double* __restrict__ pk_all, size_t pk_stride,
                                                      double* __restrict__ X, double* __restrict__ zbuf, const int* __restrict__ active) {
     extern __shared__ __align__(16) double xs[];
@@ -144,25 +143,23 @@ __global__ void __launch_bounds__(32) msp_fwd_kernel(MsDev s, MsPart P, int slot
     const int i0 = P.seg_bounds[2 * run], i1 = P.seg_bounds[2 * run + 1], NS = i1 - i0;
     double* tmp = xs + seg_len_max + 96;
     double* z = tmp + 32;
-    int* meta = reinterpret_cast<int*>(z + 32);
-    double* ring = z + 32 + ((MS_META * N + 1) / 2 + 1) / 2 * 2;
-    for (int e = lane; e < MS_META * N; e += 32) meta[e] = s.start[e];
+    double* ring = z + 32;
+    const int* meta = s.start;
     const int *m_start = meta, *m_diag = meta + N, *m_cls = meta + 7 * N, *m_pkF = meta + 8 * N, *m_szF = meta + 9 * N;
-    __syncwarp();
     const double* pk = pk_all + (size_t)b * pk_stride;
     const int base = m_start[i0], len = m_start[i1 - 1] + m_diag[i1 - 1] - base;
     double* x = X + (size_t)b * s.n + base;
     const int Dsep = run > 0 ? m_cls[i0 - 1] : 0;
-    for (int q = 0; q < MSW_PF; q++) { if (q < NS) msw_issue(pk + m_pkF[i0 + q], m_szF[i0 + q], ring + (size_t)(q % MSW_R) * slot_doubles, lane); msw_cp_commit(); }
+    for (int q = 0; q < MSP_PF; q++) { if (q < NS) msw_issue(pk + m_pkF[i0 + q], m_szF[i0 + q], ring + (size_t)(q % MSP_PF) * slot_doubles, lane); msw_cp_commit(); }
     for (int e = lane; e < seg_len_max + 96; e += 32) xs[e] = e < len ? x[e] : 0.0;
     z[lane] = 0.0;
     for (int t = 0; t < NS; t++) {
         const int i = i0 + t;
-        msw_cp_wait<MSW_PF - 1>();
+        msw_cp_wait<MSP_PF - 1>();
         __syncwarp();
         const int d = m_diag[i], st = m_start[i] - base, D = m_cls[i];
         const int PD = t > 0 ? m_cls[i - 1] : 0, pst = t > 0 ? m_start[i - 1] - base : 0;
-        const double* pkt = ring + (size_t)(t % MSW_R) * slot_doubles;
+        const double* pkt = ring + (size_t)(t % MSP_PF) * slot_doubles;
         if (D == 16) msw_fwd_stage<16>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
         else if (D == 8) msw_fwd_stage<8>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
         else msw_fwd_stage<32>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
@@ -176,8 +173,8 @@ __global__ void __launch_bounds__(32) msp_fwd_kernel(MsDev s, MsPart P, int slot
             else { acc = msw_matvec_dyn<32>(YT, tmp, D, lane, 0); z[lane] += acc; }
         }
         __syncwarp();
-        const int jn = t + MSW_PF;
-        if (jn < NS) msw_issue(pk + m_pkF[i0 + jn], m_szF[i0 + jn], ring + (size_t)(jn % MSW_R) * slot_doubles, lane);
+        const int jn = t + MSP_PF;
+        if (jn < NS) msw_issue(pk + m_pkF[i0 + jn], m_szF[i0 + jn], ring + (size_t)(jn % MSP_PF) * slot_doubles, lane);
         msw_cp_commit();
     }
     msw_cp_wait<0>();
@@ -215,17 +212,15 @@ __global__ void __launch_bounds__(32) msp_bwd_kernel(MsDev s, MsPart P, int slot
     const int i0 = P.seg_bounds[2 * run], i1 = P.seg_bounds[2 * run + 1], NS = i1 - i0;
     double* tmp = xs + seg_len_max + 96;
     double* xl = tmp + 32;
-    int* meta = reinterpret_cast<int*>(xl + 32);
-    double* ring = xl + 32 + ((MS_META * N + 1) / 2 + 1) / 2 * 2;
-    for (int e = lane; e < MS_META * N; e += 32) meta[e] = s.start[e];
+    double* ring = xl + 32;
+    const int* meta = s.start;
     const int *m_start = meta, *m_diag = meta + N, *m_cls = meta + 7 * N, *m_pkB = meta + 10 * N, *m_szB = meta + 11 * N;
-    __syncwarp();
     const double* pk = pk_all + (size_t)b * pk_stride;
     const double* xr = xr_all + (size_t)b * P.rn;
     const int base = m_start[i0], len = m_start[i1 - 1] + m_diag[i1 - 1] - base;
     double* x = X + (size_t)b * s.n + base;
     const int Dsep = run > 0 ? m_cls[i0 - 1] : 0;
-    for (int q = 0; q < MSW_PF; q++) { const int t = NS - 1 - q; if (t >= 0) msw_issue(pk + m_pkB[i0 + t], m_szB[i0 + t], ring + (size_t)(t % MSW_R) * slot_doubles, lane); msw_cp_commit(); }
+    for (int q = 0; q < MSP_PF; q++) { const int t = NS - 1 - q; if (t >= 0) msw_issue(pk + m_pkB[i0 + t], m_szB[i0 + t], ring + (size_t)(t % MSP_PF) * slot_doubles, lane); msw_cp_commit(); }
     for (int e = lane; e < seg_len_max + 96; e += 32) xs[e] = e < len ? x[e] : 0.0;
     __syncwarp();
     if (run + 1 < P.K) {                              // solution of the separator on the right sits where the next stage's x is read; it also goes back to X
@@ -236,11 +231,11 @@ __global__ void __launch_bounds__(32) msp_bwd_kernel(MsDev s, MsPart P, int slot
     __syncwarp();
     for (int t = NS - 1; t >= 0; t--) {
         const int i = i0 + t;
-        msw_cp_wait<MSW_PF - 1>();
+        msw_cp_wait<MSP_PF - 1>();
         __syncwarp();
         const int d = m_diag[i], st = m_start[i] - base, D = m_cls[i];
         const int ND = (i + 2 < N) ? m_cls[i + 1] : 0, nst = st + d;
-        const double* pkt = ring + (size_t)(t % MSW_R) * slot_doubles;
+        const double* pkt = ring + (size_t)(t % MSP_PF) * slot_doubles;
         if (run > 0) {                               // y_i -= Y_i x(separator on the left)
             const double* Y = pkt + msp_yB(m_cls, i, N);
             double acc;
@@ -252,8 +247,8 @@ __global__ void __launch_bounds__(32) msp_bwd_kernel(MsDev s, MsPart P, int slot
         if (D == 16) msw_bwd_stage<16>(pkt, ND, xs, st, nst, d, 0, s.n, tmp, lane);
         else if (D == 8) msw_bwd_stage<8>(pkt, ND, xs, st, nst, d, 0, s.n, tmp, lane);
         else msw_bwd_stage<32>(pkt, ND, xs, st, nst, d, 0, s.n, tmp, lane);
-        const int jn = t - MSW_PF;
-        if (jn >= 0) msw_issue(pk + m_pkB[i0 + jn], m_szB[i0 + jn], ring + (size_t)(jn % MSW_R) * slot_doubles, lane);
+        const int jn = t - MSP_PF;
+        if (jn >= 0) msw_issue(pk + m_pkB[i0 + jn], m_szB[i0 + jn], ring + (size_t)(jn % MSP_PF) * slot_doubles, lane);
         msw_cp_commit();
     }
     msw_cp_wait<0>();

@@ -1045,7 +1045,7 @@ SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_per
         d_upd_off.alloc(std::max<size_t>(S.upd_off.size(), 1));
         if (!S.upd_off.empty()) B200_CUDA(cudaMemcpy(d_upd_off.get(), S.upd_off.data(), S.upd_off.size() * sizeof(long long), cudaMemcpyHostToDevice));
         // few large QPs: spread each factorisation / solve over the whole GPU (sparse_wide.cuh)
-        wide = batch <= 4 && S.fmax >= 512;
+        wide = (batch <= 4 && S.fmax >= 512) || (batch <= 16 && S.fmax >= 1024);      // few large QPs: spread every front over the GPU (a 1024-row front is 0.36 GFLOP: one CTA would need ~1 ms for it)
         if (wide) {      // every supernode keeps its own update slot in the wide schedule: stay with the stack discipline if that does not fit
             double slots = 0;
             for (int s2 = 0; s2 < S.nsup; s2++) { const double us = S.rel_ptr[s2 + 1] - S.rel_ptr[s2]; slots += us * us; }

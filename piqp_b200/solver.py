@@ -135,7 +135,8 @@ class SparseSolverBatched(_BatchedBase):
             return _Arg(torch.from_numpy(np.ascontiguousarray(M_data)).to(like.device).unsqueeze(0).expand(self.batch, nnz).contiguous(), (self.batch, nnz))
         return _Arg(np.broadcast_to(M_data, (self.batch, nnz)), (self.batch, nnz))
 
-    def setup(self, batch, P, c, A=None, b=None, G=None, h_l=None, h_u=None, x_l=None, x_u=None, Px=None, Ax=None, Gx=None):
+    def setup(self, batch, P, c, A=None, b=None, G=None, h_l=None, h_u=None, x_l=None, x_u=None, Px=None, Ax=None, Gx=None, kkt_perm=None):
+        """kkt_perm: optional fill-reducing ordering of the KKT of the selected mode (e.g. the one rank 0 computed and broadcast)"""
         ipp = lambda a: a.ctypes.data_as(_lib.ip)
         self.batch, self.n = int(batch), P.shape[0]
         self.p = 0 if A is None else A.shape[0]
@@ -154,10 +155,18 @@ class SparseSolverBatched(_BatchedBase):
         if self._h.value:
             self._L.b200qp_cleanup(self._h)
             self._h = C.c_void_p()
-        _lib.check(self._L.b200qp_setup_sparse(C.byref(self._h), B, n, p, m, ipp(self._P[0]), ipp(self._P[1]), a[0].ptr, a[1].ptr,
-                                               ipp(self._A[0]) if p else None, ipp(self._A[1]) if p else None, a[2].ptr, a[3].ptr,
-                                               ipp(self._G[0]) if m else None, ipp(self._G[1]) if m else None, a[4].ptr, a[5].ptr, a[6].ptr, a[7].ptr, a[8].ptr,
-                                               C.byref(self.settings), self.device, on_dev), "b200qp_setup_sparse")
+        self._perm_keep = None if kkt_perm is None else np.ascontiguousarray(kkt_perm, dtype=np.int32)
+        _lib.check(self._L.b200qp_setup_sparse_ex(C.byref(self._h), B, n, p, m, ipp(self._P[0]), ipp(self._P[1]), a[0].ptr, a[1].ptr,
+                                                  ipp(self._A[0]) if p else None, ipp(self._A[1]) if p else None, a[2].ptr, a[3].ptr,
+                                                  ipp(self._G[0]) if m else None, ipp(self._G[1]) if m else None, a[4].ptr, a[5].ptr, a[6].ptr, a[7].ptr, a[8].ptr,
+                                                  C.byref(self.settings), self.device, on_dev, None if self._perm_keep is None else ipp(self._perm_keep)), "b200qp_setup_sparse_ex")
+
+    def kkt_perm(self):
+        """the fill-reducing ordering in use (sparse_ldlt family)"""
+        nk = _lib.check(self._L.b200qp_get_sparse_perm(self._h, None, 0), "b200qp_get_sparse_perm")
+        out = np.zeros(nk, dtype=np.int32)
+        _lib.check(self._L.b200qp_get_sparse_perm(self._h, out.ctypes.data_as(_lib.ip), nk), "b200qp_get_sparse_perm")
+        return out
 
     def update(self, Px=None, c=None, Ax=None, b=None, Gx=None, h_l=None, h_u=None, x_l=None, x_u=None):
         B, n, p, m = self.batch, self.n, self.p, self.m
