@@ -88,7 +88,7 @@ int b200kkt_dense_create(b200kkt_handle** out, int n, int p, int m, const double
         h->device = device; h->n = n; h->p = p; h->m = m;
         B200_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->dd.alloc(1, n, p, m);
-        B200_CUDA(cudaDeviceSynchronize());
+        B200_CUDA(device_synchronize_shared());
         dense_single_upload(h.get(), 7, P_utri, AT, GT);
         for (int i = 0; i < 4; i++) { h->vx[i].alloc(std::max(n, 1)); h->vy[i].alloc(std::max(p, 1)); h->vz[i].alloc(std::max(m, 1)); }
         h->delta.alloc(1); h->ok.alloc(1);
@@ -120,7 +120,7 @@ int sparse_single_create(b200kkt_handle** out, int kind, int n, int p, int m, co
         if (S.GT.nnz) B200_CUDA(cudaMemcpy(S.GTx.get(), GTx, sizeof(double) * S.GT.nnz, cudaMemcpyHostToDevice));
         for (int i = 0; i < 4; i++) { h->vx[i].alloc(std::max(n, 1)); h->vy[i].alloc(std::max(p, 1)); h->vz[i].alloc(std::max(m, 1)); }
         h->delta.alloc(1); h->ok.alloc(1);
-        B200_CUDA(cudaDeviceSynchronize());
+        B200_CUDA(device_synchronize_shared());
         if (kind == 1) { h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream); h->be = h->ms.get(); }
         else { h->ldlt = std::make_unique<SparseLdltBatchedKKT>(&h->sd, perm, h->stream, mode); h->be = h->ldlt.get(); }
         B200_CUDA(cudaStreamSynchronize(h->stream));
@@ -277,7 +277,7 @@ b200kkt_handle* b200kkt_clone(const b200kkt_handle* src) {
             cpv(S.Px, O.Px); cpv(S.ATx, O.ATx); cpv(S.GTx, O.GTx);
             for (int i = 0; i < 4; i++) { h->vx[i].alloc(std::max(h->n, 1)); h->vy[i].alloc(std::max(h->p, 1)); h->vz[i].alloc(std::max(h->m, 1)); }
             h->delta.alloc(1); h->ok.alloc(1);
-            B200_CUDA(cudaDeviceSynchronize());
+            B200_CUDA(device_synchronize_shared());
             if (src->kind == 1) {
                 h->ms = std::make_unique<MultistageBatchedKKT>(&h->sd, h->stream);
                 h->ms->copy_from(*src->ms);
@@ -291,7 +291,7 @@ b200kkt_handle* b200kkt_clone(const b200kkt_handle* src) {
             return h.release();
         }
         h->dd.alloc(1, h->n, h->p, h->m);
-        B200_CUDA(cudaDeviceSynchronize());
+        B200_CUDA(device_synchronize_shared());
         auto cp = [&](DevBuf<double>& d, const DevBuf<double>& s) { if (s.n) B200_CUDA(cudaMemcpyAsync(d.get(), s.get(), s.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream)); };
         cp(h->dd.Pf, src->dd.Pf); cp(h->dd.AT, src->dd.AT); cp(h->dd.GT, src->dd.GT);
         for (int i = 0; i < 4; i++) { h->vx[i].alloc(std::max(h->n, 1)); h->vy[i].alloc(std::max(h->p, 1)); h->vz[i].alloc(std::max(h->m, 1)); }
@@ -476,7 +476,7 @@ int b200qp_setup_dense(b200qp_handle** out, int batch, int n, int p, int m, cons
         auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         double t_0 = now();
         h->dd.alloc(batch, n, p, m);
-        B200_CUDA(cudaDeviceSynchronize());
+        B200_CUDA(device_synchronize_shared());
         B200_CUDA(cudaEventRecord(e0, h->stream));
         h->ip = std::make_unique<BatchedIPSolver>(batch, n, p, m, h->st, h->stream);
         h->ruiz.alloc(batch, n, p, m);
@@ -605,7 +605,7 @@ int b200qp_setup_sparse_ex(b200qp_handle** out, int batch, int n, int p, int m,
         const bool tm = getenv("B200_TIMING") != nullptr;
         auto now = [] { return std::chrono::steady_clock::now(); };
         auto t_0 = now(); auto t_prev = t_0;
-        auto lap = [&](const char* what) { if (tm) { cudaDeviceSynchronize(); auto t = now(); fprintf(stderr, "[b200qp_setup_sparse] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count()); t_prev = t; } };
+        auto lap = [&](const char* what) { if (tm) { device_synchronize_shared(); auto t = now(); fprintf(stderr, "[b200qp_setup_sparse] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count()); t_prev = t; } };
         auto h = std::make_unique<b200qp_handle>();
         h->kind = 1; h->device = device; h->batch = batch; h->n = n; h->p = p; h->m = m;
         if (settings) h->st = *settings; else b200qp_set_default_settings_sparse(&h->st);
@@ -632,7 +632,7 @@ int b200qp_setup_sparse_ex(b200qp_handle** out, int batch, int n, int p, int m,
         S.alloc_values(batch);
         auto upm = [](DevBuf<int>& d, const std::vector<int>& v) { d.alloc(std::max<size_t>(v.size(), 1)); if (!v.empty()) B200_CUDA(cudaMemcpy(d.get(), v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice)); };
         upm(h->d_P_map, h->P_map); upm(h->d_A_map, h->A_map); upm(h->d_G_map, h->G_map);
-        B200_CUDA(cudaDeviceSynchronize());
+        B200_CUDA(device_synchronize_shared());
         lap("patterns + value buffers");
         B200_CUDA(cudaEventRecord(e0, h->stream));
         h->ip = std::make_unique<BatchedIPSolver>(batch, n, p, m, h->st, h->stream);

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <atomic>
+#include <shared_mutex>
 #include <stdexcept>
 #include <string>
 
@@ -28,6 +29,12 @@ extern std::atomic<unsigned long long> g_launches;  // counted at every kernel l
         ::b200::g_launches.fetch_add(1, std::memory_order_relaxed);                 \
         B200_CUDA(cudaPeekAtLastError());                                           \
     } while (0)
+
+// A device-wide synchronisation is illegal while ANY thread captures a stream into a CUDA graph (the IP driver captures one iteration
+// per handle, ip_solver.cu: ensure_graph), and handles may be driven from several host threads.  Captures hold this mutex exclusively
+// (~0.2 ms, once per handle), device-wide synchronisations hold it shared.
+inline std::shared_mutex& capture_mutex() { static std::shared_mutex m; return m; }
+inline cudaError_t device_synchronize_shared() { std::shared_lock<std::shared_mutex> lk(capture_mutex()); return cudaDeviceSynchronize(); }
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -70,7 +77,7 @@ struct DevBuf {
     }
     void zero(cudaStream_t s = 0) { if (n) B200_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
     void release() {
-        if (p) { cudaDeviceSynchronize(); cudaFreeAsync(p, cudaStreamPerThread); }
+        if (p) { device_synchronize_shared(); cudaFreeAsync(p, cudaStreamPerThread); }
         p = nullptr; n = 0;
     }
     // stream-ordered release: the memory goes back to the pool once `s` has passed this point -- no device-wide synchronisation

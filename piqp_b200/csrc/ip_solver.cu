@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 
 namespace b200 {
 
@@ -855,6 +856,7 @@ bool BatchedIPSolver::ensure_graph() {
     if (graph_failed_) return false;
     const unsigned long long l0 = g_launches.load();
     cudaGraph_t g = nullptr;
+    std::unique_lock<std::shared_mutex> capture_lock(capture_mutex());      // no device-wide synchronisation from other threads meanwhile
     if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); graph_failed_ = true; return false; }
     bool ok = true;
     try {
@@ -863,6 +865,7 @@ bool BatchedIPSolver::ensure_graph() {
         factor_round();
     } catch (const std::exception&) { ok = false; }
     if (cudaStreamEndCapture(stream, &g) != cudaSuccess || !g) { cudaGetLastError(); ok = false; }
+    capture_lock.unlock();
     if (ok && cudaGraphInstantiate(&graph_exec_, g, 0) != cudaSuccess) { cudaGetLastError(); graph_exec_ = nullptr; ok = false; }
     if (g) cudaGraphDestroy(g);
     graph_launches_ = g_launches.load() - l0;

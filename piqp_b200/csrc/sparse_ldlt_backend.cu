@@ -750,7 +750,7 @@ static MfDev make_mf(const SparseLdltBatchedKKT& K) {
 // =====================================================================================================
 SparseLdltBatchedKKT::~SparseLdltBatchedKKT() {
     if (d_prof.n) {
-        long long h[8]; cudaDeviceSynchronize();
+        long long h[8]; device_synchronize_shared();
         if (cudaMemcpy(h, d_prof.get(), sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
             fprintf(stderr, "[mf_factor_kernel phase clocks, CTA 0] zero+scatter %lld  extend-add %lld  eliminate(smem) %lld  eliminate(HBM) %lld  schur store %lld\n", h[0], h[1], h[2], h[3], h[4]);
     }
