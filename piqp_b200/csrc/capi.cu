@@ -464,6 +464,7 @@ int b200qp_setup_dense(b200qp_handle** out, int batch, int n, int p, int m, cons
     if (!out || batch <= 0 || n <= 0 || p < 0 || m < 0 || !P || !c) return fail(B200_E_INVALID, "b200qp_setup_dense: bad arguments");
     if ((p > 0 && (!A || !b)) || (m > 0 && (!G || (!h_l && !h_u)))) return fail(B200_E_INVALID, "b200qp_setup_dense: missing constraint data");
     if (batch > B200_MAX_BATCH) return fail(B200_E_UNSUPPORTED, "b200qp_setup_dense: batch > 65535 (the batch index is a gridDim.y / .z coordinate); split the batch over several handles");
+    B200_ZONE("piqp::Solver::setup");
     B200_TRY(
         B200_CUDA(cudaSetDevice(device));
         auto h = std::make_unique<b200qp_handle>();
@@ -510,6 +511,7 @@ int b200qp_update_dense(b200qp_handle* h, const double* P, const double* c, cons
                         const double* h_l, const double* h_u, const double* x_l, const double* x_u, int on_device) {
     if (!h) return fail(B200_E_INVALID, "null handle");
     if (h->kind != 0) return fail(B200_E_INVALID, "b200qp_update_dense on a sparse handle");
+    B200_ZONE("piqp::Solver::update");
     B200_TRY(
         B200_CUDA(cudaSetDevice(h->device));
         IpDev& d = h->ip->dev();
@@ -600,6 +602,7 @@ int b200qp_setup_sparse_ex(b200qp_handle** out, int batch, int n, int p, int m,
     if (!out || batch <= 0 || n <= 0 || p < 0 || m < 0 || !Pp || !c) return fail(B200_E_INVALID, "b200qp_setup_sparse: bad arguments");
     if ((p > 0 && (!Ap || !b)) || (m > 0 && (!Gp || (!h_l && !h_u)))) return fail(B200_E_INVALID, "b200qp_setup_sparse: missing constraint data");
     if (batch > B200_MAX_BATCH) return fail(B200_E_UNSUPPORTED, "b200qp_setup_sparse: batch > 65535 (the batch index is a gridDim.y / .z coordinate); split the batch over several handles");
+    B200_ZONE("piqp::Solver::setup");
     B200_TRY(
         B200_CUDA(cudaSetDevice(device));
         const bool tm = getenv("B200_TIMING") != nullptr;
@@ -668,6 +671,7 @@ int b200qp_update_sparse(b200qp_handle* h, const double* Px, const double* c, co
                          const double* h_l, const double* h_u, const double* x_l, const double* x_u, int on_device) {
     if (!h) return fail(B200_E_INVALID, "null handle");
     if (h->kind != 1) return fail(B200_E_INVALID, "b200qp_update_sparse on a dense handle");
+    B200_ZONE("piqp::Solver::update");
     B200_TRY(
         B200_CUDA(cudaSetDevice(h->device));
         IpDev& d = h->ip->dev();

@@ -1,6 +1,7 @@
 // piqp_b200/csrc/common.cuh -- shared device/host helpers for libpiqp_b200 (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdio>
 #include <cstdint>
 #include <atomic>
@@ -29,6 +30,18 @@ extern std::atomic<unsigned long long> g_launches;  // counted at every kernel l
         ::b200::g_launches.fetch_add(1, std::memory_order_relaxed);                 \
         B200_CUDA(cudaPeekAtLastError());                                           \
     } while (0)
+
+// NVTX ranges named after the reference's Tracy zones (include/piqp/utils/tracy.hpp:11-25, PIQP_TRACY_ZoneScopedN("piqp::...")): a
+// Nsight Systems timeline of the product then reads like a Tracy capture of the reference.  Header-only NVTX v3: a no-op (one
+// predictable branch) unless a profiler injected itself.
+struct NvtxZone {
+    explicit NvtxZone(const char* name) { nvtxRangePushA(name); }
+    ~NvtxZone() { nvtxRangePop(); }
+    NvtxZone(const NvtxZone&) = delete;
+};
+#define B200_ZONE_CAT2(a, b) a##b
+#define B200_ZONE_CAT(a, b) B200_ZONE_CAT2(a, b)
+#define B200_ZONE(name) ::b200::NvtxZone B200_ZONE_CAT(nvtx_zone_, __LINE__)(name)
 
 // A device-wide synchronisation is illegal while ANY thread captures a stream into a CUDA graph (the IP driver captures one iteration
 // per handle, ip_solver.cu: ensure_graph), and handles may be driven from several host threads.  Captures hold this mutex exclusively

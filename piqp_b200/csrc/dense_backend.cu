@@ -451,6 +451,7 @@ void DenseBatchedKKT::compute_AtA() {   // dense/kkt.hpp:53,68
 }
 
 void DenseBatchedKKT::update_data(int options) {   // dense/kkt.hpp:62-71
+    B200_ZONE("piqp::KKT::update_data");
     if (options & 2) compute_AtA();
 }
 
@@ -508,6 +509,7 @@ void DenseBatchedKKT::cholesky(const int* active) {   // Eigen::LLT<Lower>::comp
 }
 
 void DenseBatchedKKT::factor(const double* delta_in, const double* x_reg, const double* z_reg, const int* active, int* ok) {
+    B200_ZONE("piqp::KKT::update_scalings_and_factor");
     const size_t nz = (size_t)batch * m;
     const size_t tot = std::max(nz, (size_t)batch);
     B200_LAUNCH(inv_and_copy_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, z_reg, zinv.get(), nz, delta_in, delta.get(), batch);
@@ -529,6 +531,7 @@ static GemvArgs gemv_args(const double* M, long long sM, int ld, int rows, int c
 void DenseBatchedKKT::solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) {
     // dense/kkt.hpp:86-105
     if (n == 0) return;
+    B200_ZONE("piqp::KKT::solve");
     tic(T_SOLVE);
     dim3 gn(ceil_div(n, 256), batch);
     B200_LAUNCH(copy_masked_kernel, gn, 256, 0, stream, rx, lx, n, active);
@@ -559,6 +562,7 @@ void DenseBatchedKKT::solve(const double* rx, const double* ry, const double* rz
 }
 
 void DenseBatchedKKT::eval_P_x(double alpha, const double* x, double* z, const int* active) {   // dense/kkt.hpp:108-114
+    B200_ZONE("piqp::KKT::eval_P_x");
     if (n == 0) return;
     dim3 gn(ceil_div(n, 256), batch);
     GemvArgs a = gemv_args(D->Pf.get(), D->sP(), D->ld, n, n, x, n, z, n, alpha, active);

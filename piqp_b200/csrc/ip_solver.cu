@@ -811,6 +811,7 @@ int BatchedIPSolver::count_flags(const int* dev_flags, int count) {
 
 // one round of the factor ladder: vector part, backend factorisation, retry bookkeeping (no host synchronisation)
 void BatchedIPSolver::factor_round() {
+    B200_ZONE("piqp::KKTSystem::update_scalings_and_factor");
     B200_LAUNCH(k_prepare_factor, batch, ipt_, 0, stream, d_);
     be_->factor(d_.delta_reg, d_.x_reg, d_.z_reg_ir, d_.need_factor, d_.ok);
     B200_LAUNCH(k_after_factor, ceil_div(batch, 128), 128, 0, stream, d_);
@@ -878,6 +879,7 @@ void BatchedIPSolver::drop_graph() {
 }
 
 void BatchedIPSolver::kkt_solve(const Vars& rhs, const Vars& lhs, const int* mask) {
+    B200_ZONE("piqp::KKTSystem::solve");
     IpDev& d = d_;
     B200_LAUNCH(k_solve_pre, batch, ipt_, 0, stream, d, rhs, mask);
     be_->solve(d.rhs_x_bar, rhs.y, d.rhs_z_bar, lhs.x, lhs.y, d.lhs_z, mask);
@@ -906,6 +908,7 @@ void BatchedIPSolver::kkt_solve(const Vars& rhs, const Vars& lhs, const int* mas
 }
 
 void BatchedIPSolver::residuals_nr(const int* mask) {
+    B200_ZONE("piqp::Solver::update_residuals_nr");
     IpDev& d = d_;
     B200_LAUNCH(k_resid_pre, batch, ipt_, 0, stream, d, mask);
     be_->eval_A(-1.0, 1.0, d.it.x, d.it.y, d.rnr.y, d.work_x, mask);
@@ -914,6 +917,7 @@ void BatchedIPSolver::residuals_nr(const int* mask) {
 }
 
 void BatchedIPSolver::solve() {
+    B200_ZONE("piqp::Solver::solve");
     IpDev& d = d_;
     const unsigned long long l0 = g_launches.load();
     stats_ = b200qp_stats{};

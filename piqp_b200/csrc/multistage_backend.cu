@@ -22,6 +22,7 @@ inline u64 fl_potrf(u64 n) { return n * n * n / 3; }
 }  // namespace
 
 bool MsStructure::detect(const Pattern& P, const Pattern& AT, const Pattern& GT) {
+    B200_ZONE("piqp::MultistageKKT::extract_arrow_structure");
     n = P.rows;
     // structural upper pattern of C = P + I + A^T A + G^T G, row by row (sorted, unique)
     std::vector<std::vector<int>> up(n);
@@ -496,6 +497,7 @@ void MultistageBatchedKKT::copy_from(const MultistageBatchedKKT& o) {
 }
 
 void MultistageBatchedKKT::factor(const double* delta_in, const double* x_reg, const double* z_reg, const int* active, int* ok) {   // :180-219
+    B200_ZONE("piqp::MultistageKKT::update_scalings_and_factor");
     const size_t nz = (size_t)batch * m, tot = std::max(nz, (size_t)batch);
     B200_LAUNCH(ms_inv_copy_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, z_reg, zinv.get(), nz, delta_in, delta.get(), batch);
     tic(T_ASSEMBLE);
@@ -522,6 +524,7 @@ void MultistageBatchedKKT::factor(const double* delta_in, const double* x_reg, c
 }
 
 void MultistageBatchedKKT::solve(const double* rx, const double* ry, const double* rz, double* lx, double* ly, double* lz, const int* active) {   // :221-288
+    B200_ZONE("piqp::MultistageKKT::solve");
     if (n == 0) return;
     tic(T_SOLVE);
     dim3 gn(ceil_div(n, 256), batch);
@@ -620,7 +623,7 @@ void MultistageBatchedKKT::build_partition(const std::vector<int>& cls, cudaStre
     zbuf.alloc((size_t)batch * K * 32); zbuf.zero(st);
     xred.alloc((size_t)batch * std::max(part_rn, 1)); xred.zero(st);
     part_seg_smem = sizeof(double) * ((size_t)part_seg_len + 96 + 64 + (size_t)MSP_PF * chain_slot);
-    part_spike_smem = sizeof(double) * ((size_t)MSP_R * chain_slot + (size_t)part_dsep_max * 96);
+    part_spike_smem = sizeof(double) * ((size_t)MSP_R * chain_slot + (size_t)part_dsep_max * 128);
     part_rsolve_smem = sizeof(double) * ((size_t)((part_rn + 1) & ~1) + 96 + (size_t)(((MS_META * NR + 1) / 2 + 1) / 2 * 2) + (size_t)MSW_R * part_rslot);
     if (part_seg_smem > 227 * 1024 || part_spike_smem > 227 * 1024 || part_rsolve_smem > 227 * 1024) { part_K = 1; return; }
     B200_CUDA(cudaFuncSetAttribute(msp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(part_seg_smem, 48 * 1024)));
@@ -644,32 +647,69 @@ MsPart MultistageBatchedKKT::make_part() const {
     return P;
 }
 
+// B200_MS_TIMING=1: CUDA events between the launches of the partitioned factor / solve (in-situ device times per kernel, warm caches;
+// adds one stream synchronisation per call, so only for diagnostics)
+struct MsPartTimer {
+    static constexpr int MAXE = 8;
+    cudaEvent_t ev[MAXE]; double acc[2][MAXE] = {}; long calls[2] = {0, 0}; bool on = false;
+    MsPartTimer() { on = getenv("B200_MS_TIMING") != nullptr; if (on) for (auto& e : ev) cudaEventCreate(&e); }
+    ~MsPartTimer() {
+        if (!on) return;
+        const char* nf[] = {"chain(runs)", "spike", "reduce_assemble", "chain(reduced)"};
+        const char* ns[] = {"fwd(runs)", "gather", "solve(reduced)", "bwd(runs)"};
+        for (int w = 0; w < 2; w++) { if (!calls[w]) continue; fprintf(stderr, "[B200_MS_TIMING] %s, %ld calls, us per call:", w ? "solve" : "factor", calls[w]);
+            for (int k = 0; k < 4; k++) fprintf(stderr, "  %s %.1f", w ? ns[k] : nf[k], 1e3 * acc[w][k] / calls[w]); fprintf(stderr, "\n"); }
+    }
+    void mark(int k, cudaStream_t st) { if (on) cudaEventRecord(ev[k], st); }
+    void done(int which, int n, cudaStream_t st) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        for (int k = 0; k < n; k++) { float ms = 0; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); acc[which][k] += ms; }
+        calls[which]++;
+    }
+};
+static MsPartTimer g_ms_timer;
+bool MultistageBatchedKKT::graph_capturable() const { return !g_ms_timer.on; }
+
 void MultistageBatchedKKT::factor_partitioned(const MsDev& dv, const int* active) {
+    B200_ZONE("piqp::MultistageKKT::factor_kkt");
     const int K = part_K;
     const MsPart P = make_part();
     dim3 gseg(batch, K);
+    g_ms_timer.mark(0, stream);
 #define MSP_CHAIN(RP) B200_LAUNCH(msw_factor_chain_kernel<RP>, gseg, 64, sizeof(MswChainSmem), stream, dv, fac.get(), packets.get(), pk_stride, active, P.seg_bounds, carry.get())
     if (chain_rp <= 4) MSP_CHAIN(4); else if (chain_rp <= 8) MSP_CHAIN(8); else if (chain_rp <= 12) MSP_CHAIN(12); else if (chain_rp <= 14) MSP_CHAIN(14); else MSP_CHAIN(16);
 #undef MSP_CHAIN
-    B200_LAUNCH(msp_spike_kernel, dim3(batch, K - 1), 32 * part_dsep_max, part_spike_smem, stream, dv, P, chain_slot, fac.get(), packets.get(), pk_stride, active);
-    B200_LAUNCH(msp_reduce_assemble_kernel, dim3(batch, K - 1), 256, 0, stream, dv, P, fac.get(), packets.get(), pk_stride, carry.get(), rfac.get(), active);
+    g_ms_timer.mark(1, stream);
+    B200_LAUNCH(msp_spike_kernel, dim3(batch, K - 1), 32 * part_dsep_max, part_spike_smem, stream, dv, P, chain_slot, fac.get(), packets.get(), pk_stride, carry.get(), rfac.get(), active);
+    g_ms_timer.mark(2, stream);
+    g_ms_timer.mark(3, stream);
     const MsDev rd = make_rdev(d_rmeta.get(), K, part_rn, part_rtotal);
     const size_t rmsm = sizeof(int) * MS_META * K;
 #define MSP_RCHAIN(RP) B200_LAUNCH(msw_factor_chain_kernel<RP>, batch, 64, sizeof(MswChainSmem) + rmsm, stream, rd, rfac.get(), rpackets.get(), part_rpk_stride, active, (const int*)nullptr, (double*)nullptr)
     if (part_rrp <= 4) MSP_RCHAIN(4); else if (part_rrp <= 8) MSP_RCHAIN(8); else if (part_rrp <= 12) MSP_RCHAIN(12); else if (part_rrp <= 14) MSP_RCHAIN(14); else MSP_RCHAIN(16);
 #undef MSP_RCHAIN
+    g_ms_timer.mark(4, stream);
+    g_ms_timer.done(0, 4, stream);
 }
 
 void MultistageBatchedKKT::solve_partitioned(double* lx, const int* active) {
+    B200_ZONE("piqp::MultistageKKT::solve_llt_in_place");
     const int K = part_K;
     const MsPart P = make_part();
     const MsDev dv = make_dev(S, d_meta.get());
     dim3 gseg(batch, K);
+    g_ms_timer.mark(0, stream);
     B200_LAUNCH(msp_fwd_kernel, gseg, 32, part_seg_smem, stream, dv, P, chain_slot, part_seg_len, packets.get(), pk_stride, lx, zbuf.get(), active);
+    g_ms_timer.mark(1, stream);
     B200_LAUNCH(msp_gather_kernel, dim3(batch, ceil_div(K - 1, 4)), 128, 0, stream, dv, P, packets.get(), pk_stride, lx, zbuf.get(), xred.get(), active);
     const MsDev rd = make_rdev(d_rmeta.get(), K, part_rn, part_rtotal);
+    g_ms_timer.mark(2, stream);
     B200_LAUNCH(msw_solve_kernel, batch, 32, std::max<size_t>(part_rsolve_smem, 1), stream, rd, part_rslot, (const double*)nullptr, rpackets.get(), part_rpk_stride, xred.get(), active);
+    g_ms_timer.mark(3, stream);
     B200_LAUNCH(msp_bwd_kernel, gseg, 32, part_seg_smem, stream, dv, P, chain_slot, part_seg_len, packets.get(), pk_stride, lx, xred.get(), active);
+    g_ms_timer.mark(4, stream);
+    g_ms_timer.done(1, 4, stream);
 }
 
 void MultistageBatchedKKT::eval_P_x(double alpha, const double* x, double* z, const int* active) { spmv_sym_upper(D->P, D->Px.get(), alpha, x, z, batch, active, stream); }

@@ -46,7 +46,7 @@ public:
     void eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) override;
     void extract_P_diag(double* P_diag) override;
     void print_info() const override;
-    bool graph_capturable() const override { return true; }
+    bool graph_capturable() const override;
     double factor_flops() const override { return S.factor_flops(); }
     double factor_bytes() const override { return S.factor_bytes(); }
     double solve_flops() const override { return S.solve_flops(); }

@@ -12,7 +12,7 @@
 //   2. msp_spike_kernel computes the spike Y_s = L_s^-1 K[run s, g_s] of every run s >= 1 (the separator on its LEFT couples only
 //      to the first stage of the run, but the forward substitution fills the whole run): d(g_s) right-hand sides per run, one
 //      warp each, the run's forward packets staged once per CTA;
-//   3. msp_reduce_assemble_kernel builds the reduced system on the separators, which is again block tridiagonal with the stage
+//   3. the same kernel accumulates Y^T Y and emits the reduced system on the separators, which is again block tridiagonal with the stage
 //      shape of the original chain:  D~_k = D(g_k) + carry(run k-1) - Y_k^T Y_k ,  B~_k = -(B L^-T)(last stage of run k) Y_k[last];
 //   4. msw_factor_chain_kernel factorises the reduced chain (K-1 stages).
 // Chain length N/K + K instead of N.  The solves follow the same split: msp_fwd_kernel (runs in parallel, also accumulates
@@ -39,19 +39,26 @@ __device__ __forceinline__ int msp_yB(const int* m_cls, int i, int N) { const in
 constexpr int MSP_R = 4;       // ring depth of the CTA-wide packet ring of the spike kernel
 constexpr int MSP_PF = 6;      // packets in flight per warp of msp_fwd / msp_bwd (smem per CTA decides how many runs are resident per SM)
 
-// ---- 2. spikes: CTA per (QP, run s >= 1), warp j = column j of the separator block; smem: ring[MSP_R][slot] | per warp y[2][32] + tmp[32]
+// ---- 2 + 3. spikes and the reduced system: CTA per (QP, run s >= 1), warp j = column j of the separator block on the run's left.
+// Warp j substitutes column j of K[run, g] through the run (Y = L^-1 K[run, g]) with the run's forward packets staged once per CTA in
+// a shared-memory ring, writes Y / Y^T into the solve packets, and accumulates row j of the Gram matrix Y^T Y from the columns the
+// other warps hold in shared memory.  At the end the CTA emits the reduced blocks of separator k = run - 1:
+//     D~_k = D(g_k) + carry(run k-1... the run on the left) - Y^T Y ,   B~_k = -(B L^-T)(last stage of this run) Y[last stage]
+// smem: ring[MSP_R][slot] | per warp y[3][32] + tmp[32]
 __global__ void __launch_bounds__(1024) msp_spike_kernel(MsDev s, MsPart P, int slot_doubles, const double* __restrict__ fac_all,
-                                                         double* __restrict__ pk_all, size_t pk_stride, const int* __restrict__ active) {
+                                                         double* __restrict__ pk_all, size_t pk_stride, const double* __restrict__ carry_all,
+                                                         double* __restrict__ rfac_all, const int* __restrict__ active) {
     extern __shared__ __align__(16) double sp_sm[];
     const int b = blockIdx.x;
     if (active && !active[b]) return;
-    const int run = blockIdx.y + 1;
+    const int run = blockIdx.y + 1, k = run - 1;
     const int tid = threadIdx.x, lane = tid & 31, j = tid >> 5, nth = blockDim.x;
     const int N = s.N;
     const int i0 = P.seg_bounds[2 * run], i1 = P.seg_bounds[2 * run + 1], g = i0 - 1;
     double* ring = sp_sm;
-    double* y = ring + (size_t)MSP_R * slot_doubles + (size_t)j * 96;      // y[0..31], y[32..63]: the stage's vector and the previous one (alternating)
-    double* tmp = y + 64;
+    double* ybase = ring + (size_t)MSP_R * slot_doubles;                    // warp w: ybase + 128 w : y[3][32] | tmp[32]
+    double* y = ybase + (size_t)j * 128;
+    double* tmp = y + 96;
     const double* fac = fac_all + (size_t)b * s.total;
     double* pk = pk_all + (size_t)b * pk_stride;
     const int dg = s.diag[g], og = s.off[g], Dsep = s.cls[g];
@@ -65,70 +72,70 @@ __global__ void __launch_bounds__(1024) msp_spike_kernel(MsDev s, MsPart P, int 
     for (int q = 0; q < MSP_R - 1; q++) { if (i0 + q < i1) issue(i0 + q); msw_cp_commit(); }
     // right-hand side: column j of B(g), rows = the first og variables of the run's first stage
     y[lane] = (j < dg && lane < og) ? __ldg(fac + s.offB[g] + lane + (size_t)j * og) : 0.0;
-    y[32 + lane] = 0.0;
+    y[32 + lane] = 0.0; y[64 + lane] = 0.0;
+    double gram = 0.0;                               // (Y^T Y)(j, lane)
+    auto gram_add = [&](int buf) {                   // += sum_r Y_stage(r, j) Y_stage(r, lane), columns of the other warps from shared memory
+        if (lane < Dsep) {
+            const double* mine = y + buf * 32;
+            const double* other = ybase + (size_t)lane * 128 + buf * 32;
+            double a = 0.0;
+#pragma unroll 8
+            for (int r = 0; r < 32; r++) a += mine[r] * other[r];      // rows >= d of a stage vector are zero
+            gram += a;
+        }
+    };
     for (int i = i0; i < i1; i++) {
         msw_cp_wait<MSP_R - 2>();
-        __syncthreads();                             // packet i landed for every thread; everyone is done with slot (i - 1) % MSP_R
+        __syncthreads();                             // packet i landed for every thread; every warp finished stage i - 1
         if (i + MSP_R - 1 < i1) issue(i + MSP_R - 1);
         msw_cp_commit();
-        const int t = i - i0, cur = (t & 1) * 32, prev = 32 - cur;
+        const int t = i - i0, cur = (t % 3) * 32, prev = ((t + 2) % 3) * 32, nxt = ((t + 1) % 3) * 32;
+        if (t > 0) gram_add((t + 2) % 3);
         const int d = s.diag[i], D = s.cls[i];
         const int PD = t > 0 ? s.cls[i - 1] : 0;
         const double* pkt = ring + (size_t)(t % MSP_R) * slot_doubles;
         if (D == 16) msw_fwd_stage<16>(pkt, PD, y, cur, prev, d, 0, tmp, nullptr, lane);
         else if (D == 8) msw_fwd_stage<8>(pkt, PD, y, cur, prev, d, 0, tmp, nullptr, lane);
         else msw_fwd_stage<32>(pkt, PD, y, cur, prev, d, 0, tmp, nullptr, lane);
+        if (lane >= d) y[cur + lane] = 0.0;          // keep the vector zero-padded (the Gram sums run over 32 rows)
         // Y into the packets of this stage, both orientations, zero-padded to the class sizes
         if (j < Dsep && lane < D) {
             const double v = (lane < d && j < dg) ? y[cur + lane] : 0.0;
             pk[s.pkB[i] + msp_yB(s.cls, i, N) + lane + j * D] = v;            // Y  [D x Dsep]
             pk[s.pkF[i] + msp_yF(s.cls, i) + j + lane * Dsep] = v;            // Y^T [Dsep x D]
         }
-        __syncwarp();
-        y[prev + lane] = 0.0;                        // becomes the next stage's vector: zero right-hand side beyond the first stage
+        // the buffer of stage t - 2 becomes the vector of stage t + 1 (zero right-hand side): every warp read it for its Gram row
+        // before the barrier at the top of this iteration
+        y[nxt + lane] = 0.0;
         __syncwarp();
     }
     msw_cp_wait<0>();
-}
-
-// ---- 3. reduced system: CTA per (QP, separator k)
-__global__ void __launch_bounds__(256) msp_reduce_assemble_kernel(MsDev s, MsPart P, const double* __restrict__ fac_all, const double* __restrict__ pk_all, size_t pk_stride,
-                                                                  const double* __restrict__ carry_all, double* __restrict__ rfac_all, const int* __restrict__ active) {
-    const int b = blockIdx.x, k = blockIdx.y;
-    if (active && !active[b]) return;
-    const int tid = threadIdx.x, N = s.N;
-    const int g = P.sep[k];
-    const int d = s.diag[g], ol = s.off[g - 1];
-    const int r0 = P.seg_bounds[2 * (k + 1)], r1 = P.seg_bounds[2 * (k + 1) + 1];      // the run on the RIGHT of separator k
-    const double* fac = fac_all + (size_t)b * s.total;
-    const double* pk = pk_all + (size_t)b * pk_stride;
-    const double* carry = carry_all + ((size_t)b * P.K + k) * 1024;                     // the run on the LEFT
+    __syncthreads();
+    const int tl = i1 - 1 - i0, lastbuf = tl % 3;
+    gram_add(lastbuf);
+    // ---- reduced blocks of separator k (lower triangle of D~, upper part zero like the assembled blocks of the chain)
     double* rfac = rfac_all + (size_t)b * P.rtotal;
-    for (int e = tid; e < d * d; e += 256) {
-        const int r = e % d, c = e / d;
-        double v = 0.0;
-        if (r >= c) {
-            v = fac[s.offD[g] + e];
-            if (r < ol) v += carry[r + 32 * c];
-            double acc = 0.0;
-            for (int i = r0; i < r1; i++) {
-                const int D = s.cls[i];
-                const double* Y = pk + s.pkB[i] + msp_yB(s.cls, i, N);
-                for (int q = 0; q < D; q++) acc += Y[q + r * D] * Y[q + c * D];
+    if (j < dg) {
+        const int ol = s.off[g - 1];
+        const double* carry = carry_all + ((size_t)b * P.K + k) * 1024;      // Schur complement the run on the LEFT left on its coupling rows
+        if (lane < dg) {
+            double v = 0.0;
+            if (j >= lane) {                         // row j, column lane
+                v = fac[s.offD[g] + j + (size_t)lane * dg];
+                if (j < ol) v += carry[j + 32 * lane];
+                v -= gram;
             }
-            v -= acc;
+            rfac[P.roffD[k] + j + lane * dg] = v;
         }
-        rfac[P.roffD[k] + e] = v;
-    }
-    if (k + 1 < P.K - 1) {          // coupling to the next separator through the run in between: -(B L^-T)(last stage) Y[last stage]
-        const int il = r1 - 1, o2 = s.off[il], D = s.cls[il];
-        const double* BT = pk + s.pkB[il] + D * D;                                      // B^T [D x ND]: BT[q + r2 * D]
-        const double* Y = pk + s.pkB[il] + msp_yB(s.cls, il, N);
-        for (int e = tid; e < o2 * d; e += 256) {
-            const int r2 = e % o2, c = e / o2;
-            double acc = 0.0;
-            for (int q = 0; q < D; q++) acc += BT[q + r2 * D] * Y[q + c * D];
-            rfac[P.roffB[k] + e] = -acc;
+        if (k + 1 < P.K - 1) {                       // B~_k(:, j) = -(B L^-T)(last stage) Y_last(:, j)
+            const int il = i1 - 1, o2 = s.off[il], D = s.cls[il], dl = s.diag[il];
+            const double* BT = pk + s.pkB[il] + D * D;                        // B^T [D x ND]: BT[q + r2 * D], written by the chain kernel
+            const double* yl = y + lastbuf * 32;
+            if (lane < o2) {
+                double a = 0.0;
+                for (int q = 0; q < dl; q++) a += BT[q + lane * D] * yl[q];
+                rfac[P.roffB[k] + lane + j * o2] = -a;
+            }
         }
     }
 }
