@@ -555,7 +555,7 @@ void MultistageBatchedKKT::plan_partition(const std::vector<int>& cls) {
     {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int per_sm = std::max(1, (int)((227 * 1024) / (sizeof(MswChainSmem) + 1024)));
+        const int per_sm = std::max(1, (int)((227 * 1024) / (sizeof(MswChainSmem) + sizeof(int) * MS_META * MSP_META_MAX + 1024)));
         K = std::min(K, (sms * per_sm) / std::max(batch, 1));
     }
     if (const char* e = getenv("B200_MS_SEGMENTS")) K = atoi(e);
@@ -622,8 +622,12 @@ void MultistageBatchedKKT::build_partition(const std::vector<int>& cls, cudaStre
     carry.alloc((size_t)batch * K * 1024); carry.zero(st);
     zbuf.alloc((size_t)batch * K * 32); zbuf.zero(st);
     xred.alloc((size_t)batch * std::max(part_rn, 1)); xred.zero(st);
-    part_seg_smem = sizeof(double) * ((size_t)part_seg_len + 96 + 64 + (size_t)MSP_PF * chain_slot);
-    part_spike_smem = sizeof(double) * ((size_t)MSP_R * chain_slot + (size_t)part_dsep_max * 128);
+    const size_t meta_d = (size_t)(MS_META * MSP_META_MAX + 1) / 2;
+    part_seg_smem = sizeof(double) * ((size_t)part_seg_len + 96 + 64 + meta_d + (size_t)MSP_PF * chain_slot);
+    part_spike_slot = 2;
+    for (int i = 1; i + 1 < S.N; i++) part_spike_slot = std::max(part_spike_slot, cls[i] * cls[i] + cls[i] * cls[i - 1]);
+    part_spike_smem = sizeof(double) * ((size_t)3 * 32 * MSP_LDY + meta_d + (size_t)MSP_PF * part_spike_slot);
+    for (int r = 0; r < K; r++) if (part_bounds[2 * r + 1] - part_bounds[2 * r] + 2 > MSP_META_MAX) { part_K = 1; return; }      // run-local meta copies
     part_rsolve_smem = sizeof(double) * ((size_t)((part_rn + 1) & ~1) + 96 + (size_t)(((MS_META * NR + 1) / 2 + 1) / 2 * 2) + (size_t)MSW_R * part_rslot);
     if (part_seg_smem > 227 * 1024 || part_spike_smem > 227 * 1024 || part_rsolve_smem > 227 * 1024) { part_K = 1; return; }
     B200_CUDA(cudaFuncSetAttribute(msp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(part_seg_smem, 48 * 1024)));
@@ -677,11 +681,11 @@ void MultistageBatchedKKT::factor_partitioned(const MsDev& dv, const int* active
     const MsPart P = make_part();
     dim3 gseg(batch, K);
     g_ms_timer.mark(0, stream);
-#define MSP_CHAIN(RP) B200_LAUNCH(msw_factor_chain_kernel<RP>, gseg, 64, sizeof(MswChainSmem), stream, dv, fac.get(), packets.get(), pk_stride, active, P.seg_bounds, carry.get())
+#define MSP_CHAIN(RP) B200_LAUNCH(msw_factor_chain_kernel<RP>, gseg, 64, sizeof(MswChainSmem) + sizeof(int) * MS_META * MSP_META_MAX, stream, dv, fac.get(), packets.get(), pk_stride, active, P.seg_bounds, carry.get())
     if (chain_rp <= 4) MSP_CHAIN(4); else if (chain_rp <= 8) MSP_CHAIN(8); else if (chain_rp <= 12) MSP_CHAIN(12); else if (chain_rp <= 14) MSP_CHAIN(14); else MSP_CHAIN(16);
 #undef MSP_CHAIN
     g_ms_timer.mark(1, stream);
-    B200_LAUNCH(msp_spike_kernel, dim3(batch, K - 1), 32 * part_dsep_max, part_spike_smem, stream, dv, P, chain_slot, fac.get(), packets.get(), pk_stride, carry.get(), rfac.get(), active);
+    B200_LAUNCH(msp_spike_kernel, dim3(batch, K - 1), 32, part_spike_smem, stream, dv, P, part_spike_slot, fac.get(), packets.get(), pk_stride, carry.get(), rfac.get(), active);
     g_ms_timer.mark(2, stream);
     g_ms_timer.mark(3, stream);
     const MsDev rd = make_rdev(d_rmeta.get(), K, part_rn, part_rtotal);

@@ -235,14 +235,18 @@ __global__ void __launch_bounds__(64) msw_factor_chain_kernel(MsDev s, const dou
     const int N = s.N;
     int i0 = 0, nst = N - 1;                          // stages [i0, nst)
     if (seg_bounds) { i0 = seg_bounds[2 * blockIdx.y]; nst = seg_bounds[2 * blockIdx.y + 1]; }
-    // segment mode keeps the meta block in global memory (L1-resident, read off the dependent chain): 42 KB of shared memory per CTA
-    // instead of 47 KB = five CTAs per SM, which is what bounds the number of runs that are in flight at once
+    // segment mode stages only the run's SLICE of the meta block (stages i0 .. nst, 12 x (len + 1) ints ~ 1 KB) so that five CTAs of
+    // 43 KB fit one SM; a meta read from global memory would put an L2 round trip on every stage of the dependent chain
+    int ms = N, mb = 0;                               // array stride and first stage of what `meta` holds
     if (!seg_bounds) { for (int e = threadIdx.x; e < MS_META * N; e += 64) meta[e] = s.start[e]; }
-    else meta = const_cast<int*>(s.start);
+    else {
+        ms = nst - i0 + 1; mb = i0;
+        for (int e = threadIdx.x; e < MS_META * ms; e += 64) { const int a = e / ms, i = e - a * ms; meta[e] = s.start[a * N + mb + i]; }
+    }
     for (int e = threadIdx.x; e < 32 * 33; e += 64) (&sm.S[0][0])[e] = 0.0;
     __syncthreads();
-    const int *m_diag = meta + N, *m_off = meta + 2 * N, *m_offD = meta + 3 * N, *m_offB = meta + 4 * N, *m_cls = meta + 7 * N, *m_pkF = meta + 8 * N,
-              *m_pkB = meta + 10 * N;
+    const int *m_diag = meta + ms - mb, *m_off = meta + 2 * ms - mb, *m_offD = meta + 3 * ms - mb, *m_offB = meta + 4 * ms - mb, *m_cls = meta + 7 * ms - mb,
+              *m_pkF = meta + 8 * ms - mb, *m_pkB = meta + 10 * ms - mb;
     // front of stage j -> F[j & 1] (one warp)
     auto prepare = [&](int j) {
         double* Fb = &sm.F[j & 1][0][0];

@@ -39,104 +39,176 @@ __device__ __forceinline__ int msp_yB(const int* m_cls, int i, int N) { const in
 constexpr int MSP_R = 4;       // ring depth of the CTA-wide packet ring of the spike kernel
 constexpr int MSP_PF = 6;      // packets in flight per warp of msp_fwd / msp_bwd (smem per CTA decides how many runs are resident per SM)
 
-// ---- 2 + 3. spikes and the reduced system: CTA per (QP, run s >= 1), warp j = column j of the separator block on the run's left.
-// Warp j substitutes column j of K[run, g] through the run (Y = L^-1 K[run, g]) with the run's forward packets staged once per CTA in
-// a shared-memory ring, writes Y / Y^T into the solve packets, and accumulates row j of the Gram matrix Y^T Y from the columns the
-// other warps hold in shared memory.  At the end the CTA emits the reduced blocks of separator k = run - 1:
-//     D~_k = D(g_k) + carry(run k-1... the run on the left) - Y^T Y ,   B~_k = -(B L^-T)(last stage of this run) Y[last stage]
-// smem: ring[MSP_R][slot] | per warp y[3][32] + tmp[32]
-__global__ void __launch_bounds__(1024) msp_spike_kernel(MsDev s, MsPart P, int slot_doubles, const double* __restrict__ fac_all,
-                                                         double* __restrict__ pk_all, size_t pk_stride, const double* __restrict__ carry_all,
-                                                         double* __restrict__ rfac_all, const int* __restrict__ active) {
+// run-local copy of the meta block: arrays of stride ml holding stages ib .. ib + ml - 1 (the separator on the left, the run, the separator
+// on the right).  A meta read from global memory would put an L2 round trip on every stage of the dependent chains.
+struct MspMeta {
+    const int* m; int ml, ib;
+    __device__ __forceinline__ int at(int a, int i) const { return m[a * ml + (i - ib)]; }
+    __device__ __forceinline__ int start(int i) const { return at(0, i); }
+    __device__ __forceinline__ int diag(int i) const { return at(1, i); }
+    __device__ __forceinline__ int off(int i) const { return at(2, i); }
+    __device__ __forceinline__ int offD(int i) const { return at(3, i); }
+    __device__ __forceinline__ int offB(int i) const { return at(4, i); }
+    __device__ __forceinline__ int cls(int i) const { return (i < ib) ? 0 : at(7, i); }
+    __device__ __forceinline__ int pkF(int i) const { return at(8, i); }
+    __device__ __forceinline__ int szF(int i) const { return at(9, i); }
+    __device__ __forceinline__ int pkB(int i) const { return at(10, i); }
+    __device__ __forceinline__ int szB(int i) const { return at(11, i); }
+    __device__ __forceinline__ int yF(int i) const { const int D = cls(i); return D * D + D * (i > 0 ? cls(i - 1) : 0); }
+    __device__ __forceinline__ int yB(int i, int N) const { const int D = cls(i); return D * D + D * ((i + 2 < N) ? cls(i + 1) : 0); }
+};
+constexpr int MSP_META_MAX = 40;      // stages per run + 2 that the run-local meta copy can hold (host checks)
+__device__ __forceinline__ MspMeta msp_load_meta(int* dst, const MsDev& s, int i0, int i1, int lane, int nth) {
+    MspMeta M;
+    M.ib = i0 > 0 ? i0 - 1 : 0;
+    const int ie = min(i1, s.N - 1);                 // inclusive: the stage after the run (a separator, or the arrow entry)
+    M.ml = ie - M.ib + 1; M.m = dst;
+    for (int e = lane; e < MS_META * M.ml; e += nth) { const int a = e / M.ml, i = e - a * M.ml; dst[e] = s.start[a * s.N + M.ib + i]; }
+    return M;
+}
+
+// acc(8 ri + gq, 8 ci + 2 tq + e) += sum_k A(row, k) B(k, col): A at As[row + k * lda] (column-major), B at Bs[k * ldb + col] (row-major), K multiple of 4
+__device__ __forceinline__ void msp_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void msp_mma(double (&acc)[4][4][2], const double* As, int lda, const double* Bs, int ldb, int K, int nr, int nc, int lane) {
+    const int gq = lane >> 2, tq = lane & 3;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int ri = 0; ri < 4; ri++) a[ri] = ri < nr ? As[ri * 8 + gq + (k0 + tq) * lda] : 0.0;
+#pragma unroll
+        for (int ci = 0; ci < 4; ci++) b[ci] = ci < nc ? Bs[(k0 + tq) * ldb + ci * 8 + gq] : 0.0;
+#pragma unroll
+        for (int ri = 0; ri < 4; ri++)
+#pragma unroll
+            for (int ci = 0; ci < 4; ci++) if (ri < nr && ci < nc) msp_dmma(acc[ri][ci][0], acc[ri][ci][1], a[ri], b[ci]);
+    }
+}
+__device__ __forceinline__ void msp_zero(double (&acc)[4][4][2]) {
+#pragma unroll
+    for (int ri = 0; ri < 4; ri++)
+#pragma unroll
+        for (int ci = 0; ci < 4; ci++) { acc[ri][ci][0] = 0.0; acc[ri][ci][1] = 0.0; }
+}
+constexpr int MSP_LDY = 36;           // row stride (doubles) of the 32 x 32 spike tiles in shared memory
+
+// ---- 2 + 3. spikes and the reduced system: ONE WARP per (QP, run s >= 1).  The spike Y = L^-1 K[run, g] has d(g) <= 32 columns; a stage
+// is two small matrix products on the FP64 tensor pipe (DMMA m8n8k4):  V = rhs - (B L^-T)(i-1) Y(i-1) ,  Y(i) = inv(L_i) V ,  plus
+// the Gram update G += Y(i)^T Y(i).  Forward packets stream through a per-warp cp.async ring; Y / Y^T go into the solve packets.  At the
+// end the warp emits the reduced blocks of separator k = run - 1:
+//     D~_k = D(g_k) + carry(run on the left) - Y^T Y ,   B~_k = -(B L^-T)(last stage of this run) Y(last stage)
+// smem: Yp, Yc, Vs [32][MSP_LDY] | meta | ring[MSP_PF][slot_spike]
+__global__ void __launch_bounds__(32) msp_spike_kernel(MsDev s, MsPart P, int slot_doubles, const double* __restrict__ fac_all,
+                                                       double* __restrict__ pk_all, size_t pk_stride, const double* __restrict__ carry_all,
+                                                       double* __restrict__ rfac_all, const int* __restrict__ active) {
     extern __shared__ __align__(16) double sp_sm[];
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     const int run = blockIdx.y + 1, k = run - 1;
-    const int tid = threadIdx.x, lane = tid & 31, j = tid >> 5, nth = blockDim.x;
+    const int lane = threadIdx.x, gq = lane >> 2, tq = lane & 3;
     const int N = s.N;
-    const int i0 = P.seg_bounds[2 * run], i1 = P.seg_bounds[2 * run + 1], g = i0 - 1;
-    double* ring = sp_sm;
-    double* ybase = ring + (size_t)MSP_R * slot_doubles;                    // warp w: ybase + 128 w : y[3][32] | tmp[32]
-    double* y = ybase + (size_t)j * 128;
-    double* tmp = y + 96;
+    const int i0 = P.seg_bounds[2 * run], i1 = P.seg_bounds[2 * run + 1], g = i0 - 1, NS = i1 - i0;
+    double* Yp = sp_sm;
+    double* Yc = Yp + 32 * MSP_LDY;
+    double* Vs = Yc + 32 * MSP_LDY;
+    int* metab = reinterpret_cast<int*>(Vs + 32 * MSP_LDY);
+    double* ring = Vs + 32 * MSP_LDY + (MS_META * MSP_META_MAX + 1) / 2;
+    const MspMeta M = msp_load_meta(metab, s, i0, i1, lane, 32);
+    __syncwarp();
     const double* fac = fac_all + (size_t)b * s.total;
     double* pk = pk_all + (size_t)b * pk_stride;
-    const int dg = s.diag[g], og = s.off[g], Dsep = s.cls[g];
-    auto issue = [&](int i) {                        // inv(L_i) | B_{i-1} of the forward packet
-        const int D = s.cls[i];
-        const int sz = D * D + D * (i > 0 ? s.cls[i - 1] : 0);
-        const double* src = pk + s.pkF[i];
-        double* dst = ring + (size_t)((i - i0) % MSP_R) * slot_doubles;
-        for (int e = 2 * tid; e < sz; e += 2 * nth) msw_cp_async16(dst + e, src + e);
+    const int dg = M.diag(g), og = M.off(g), Dsep = M.cls(g), nc = Dsep / 8;
+    auto issue = [&](int t) {                        // inv(L_i) | (B L^-T)(i-1) of the forward packet
+        const int i = i0 + t, D = M.cls(i);
+        msw_issue(pk + M.pkF(i), D * D + D * (i > 0 ? M.cls(i - 1) : 0), ring + (size_t)(t % MSP_PF) * slot_doubles, lane);
     };
-    for (int q = 0; q < MSP_R - 1; q++) { if (i0 + q < i1) issue(i0 + q); msw_cp_commit(); }
-    // right-hand side: column j of B(g), rows = the first og variables of the run's first stage
-    y[lane] = (j < dg && lane < og) ? __ldg(fac + s.offB[g] + lane + (size_t)j * og) : 0.0;
-    y[32 + lane] = 0.0; y[64 + lane] = 0.0;
-    double gram = 0.0;                               // (Y^T Y)(j, lane)
-    auto gram_add = [&](int buf) {                   // += sum_r Y_stage(r, j) Y_stage(r, lane), columns of the other warps from shared memory
-        if (lane < Dsep) {
-            const double* mine = y + buf * 32;
-            const double* other = ybase + (size_t)lane * 128 + buf * 32;
-            double a = 0.0;
-#pragma unroll 8
-            for (int r = 0; r < 32; r++) a += mine[r] * other[r];      // rows >= d of a stage vector are zero
-            gram += a;
-        }
-    };
-    for (int i = i0; i < i1; i++) {
-        msw_cp_wait<MSP_R - 2>();
-        __syncthreads();                             // packet i landed for every thread; every warp finished stage i - 1
-        if (i + MSP_R - 1 < i1) issue(i + MSP_R - 1);
-        msw_cp_commit();
-        const int t = i - i0, cur = (t % 3) * 32, prev = ((t + 2) % 3) * 32, nxt = ((t + 1) % 3) * 32;
-        if (t > 0) gram_add((t + 2) % 3);
-        const int d = s.diag[i], D = s.cls[i];
-        const int PD = t > 0 ? s.cls[i - 1] : 0;
-        const double* pkt = ring + (size_t)(t % MSP_R) * slot_doubles;
-        if (D == 16) msw_fwd_stage<16>(pkt, PD, y, cur, prev, d, 0, tmp, nullptr, lane);
-        else if (D == 8) msw_fwd_stage<8>(pkt, PD, y, cur, prev, d, 0, tmp, nullptr, lane);
-        else msw_fwd_stage<32>(pkt, PD, y, cur, prev, d, 0, tmp, nullptr, lane);
-        if (lane >= d) y[cur + lane] = 0.0;          // keep the vector zero-padded (the Gram sums run over 32 rows)
-        // Y into the packets of this stage, both orientations, zero-padded to the class sizes
-        if (j < Dsep && lane < D) {
-            const double v = (lane < d && j < dg) ? y[cur + lane] : 0.0;
-            pk[s.pkB[i] + msp_yB(s.cls, i, N) + lane + j * D] = v;            // Y  [D x Dsep]
-            pk[s.pkF[i] + msp_yF(s.cls, i) + j + lane * Dsep] = v;            // Y^T [Dsep x D]
-        }
-        // the buffer of stage t - 2 becomes the vector of stage t + 1 (zero right-hand side): every warp read it for its Gram row
-        // before the barrier at the top of this iteration
-        y[nxt + lane] = 0.0;
+    for (int q = 0; q < MSP_PF; q++) { if (q < NS) issue(q); msw_cp_commit(); }
+    // first stage: V = K[first stage, g] = B(g): rows = the first og variables of the run, columns = the dg variables of the separator
+    for (int e = lane; e < 32 * MSP_LDY; e += 32) { Yp[e] = 0.0; Yc[e] = 0.0; Vs[e] = 0.0; }
+    __syncwarp();
+    for (int e = lane; e < og * dg; e += 32) { const int r = e % og, j = e / og; Vs[r * MSP_LDY + j] = __ldg(fac + M.offB(g) + e); }
+    double G[4][4][2];
+    msp_zero(G);
+    for (int t = 0; t < NS; t++) {
+        const int i = i0 + t, d = M.diag(i), D = M.cls(i), nr = D / 8;
+        const int PD = t > 0 ? M.cls(i - 1) : 0;
+        msw_cp_wait<MSP_PF - 1>();
         __syncwarp();
+        const double* pkt = ring + (size_t)(t % MSP_PF) * slot_doubles;
+        double acc[4][4][2];
+        if (t > 0) {                                 // V = -(B L^-T)(i-1) Y(i-1)
+            msp_zero(acc);
+            msp_mma(acc, pkt + D * D, D, Yp, MSP_LDY, PD, nr, nc, lane);
+#pragma unroll
+            for (int ri = 0; ri < 4; ri++)
+#pragma unroll
+                for (int ci = 0; ci < 4; ci++) if (ri < nr && ci < nc) {
+                    double* v = Vs + (ri * 8 + gq) * MSP_LDY + ci * 8 + 2 * tq;
+                    v[0] = -acc[ri][ci][0]; v[1] = -acc[ri][ci][1];
+                }
+        }
+        __syncwarp();
+        msp_zero(acc);                               // Y(i) = inv(L_i) V   (rows >= d of the packet's inverse are zero)
+        msp_mma(acc, pkt, D, Vs, MSP_LDY, D, nr, nc, lane);
+        double* Yb = pk + M.pkB(i) + M.yB(i, N);     // Y   [D x Dsep], column-major
+        double* YTb = pk + M.pkF(i) + M.yF(i);       // Y^T [Dsep x D]
+#pragma unroll
+        for (int ri = 0; ri < 4; ri++)
+#pragma unroll
+            for (int ci = 0; ci < 4; ci++) if (ri < nr && ci < nc) {
+                const int r = ri * 8 + gq, c = ci * 8 + 2 * tq;
+                double* y = Yc + r * MSP_LDY + c;
+                y[0] = acc[ri][ci][0]; y[1] = acc[ri][ci][1];
+                Yb[r + c * D] = acc[ri][ci][0]; Yb[r + (c + 1) * D] = acc[ri][ci][1];
+                *reinterpret_cast<double2*>(YTb + c + r * Dsep) = make_double2(acc[ri][ci][0], acc[ri][ci][1]);
+            }
+        __syncwarp();
+        msp_mma(G, Yc, MSP_LDY, Yc, MSP_LDY, D, nc, nc, lane);          // G += Y(i)^T Y(i): A(j1, r) = Yc[r][j1]
+        { const int tn = t + MSP_PF; if (tn < NS) issue(tn); msw_cp_commit(); }
+        double* tmpp = Yp; Yp = Yc; Yc = tmpp;       // Y(i) becomes the previous stage's spike
+        (void)d;
     }
     msw_cp_wait<0>();
-    __syncthreads();
-    const int tl = i1 - 1 - i0, lastbuf = tl % 3;
-    gram_add(lastbuf);
-    // ---- reduced blocks of separator k (lower triangle of D~, upper part zero like the assembled blocks of the chain)
+    __syncwarp();
+    // ---- reduced blocks of separator k (lower triangle of D~; the upper part stays zero like in the assembled blocks of the chain)
     double* rfac = rfac_all + (size_t)b * P.rtotal;
-    if (j < dg) {
-        const int ol = s.off[g - 1];
+    {
+        const int ol_ok = s.off[g - 1];             // coupling rows of the last stage of the run on the left (outside the run-local meta copy)
         const double* carry = carry_all + ((size_t)b * P.K + k) * 1024;      // Schur complement the run on the LEFT left on its coupling rows
-        if (lane < dg) {
-            double v = 0.0;
-            if (j >= lane) {                         // row j, column lane
-                v = fac[s.offD[g] + j + (size_t)lane * dg];
-                if (j < ol) v += carry[j + 32 * lane];
-                v -= gram;
-            }
-            rfac[P.roffD[k] + j + lane * dg] = v;
-        }
-        if (k + 1 < P.K - 1) {                       // B~_k(:, j) = -(B L^-T)(last stage) Y_last(:, j)
-            const int il = i1 - 1, o2 = s.off[il], D = s.cls[il], dl = s.diag[il];
-            const double* BT = pk + s.pkB[il] + D * D;                        // B^T [D x ND]: BT[q + r2 * D], written by the chain kernel
-            const double* yl = y + lastbuf * 32;
-            if (lane < o2) {
-                double a = 0.0;
-                for (int q = 0; q < dl; q++) a += BT[q + lane * D] * yl[q];
-                rfac[P.roffB[k] + lane + j * o2] = -a;
-            }
-        }
+#pragma unroll
+        for (int ri = 0; ri < 4; ri++)
+#pragma unroll
+            for (int ci = 0; ci < 4; ci++) if (ri < nc && ci < nc)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int r = ri * 8 + gq, c = ci * 8 + 2 * tq + e;
+                    if (r < dg && c < dg) {
+                        double v = 0.0;
+                        if (r >= c) {
+                            v = fac[M.offD(g) + r + (size_t)c * dg];
+                            if (r < ol_ok) v += carry[r + 32 * c];
+                            v -= G[ri][ci][e];
+                        }
+                        rfac[P.roffD[k] + r + c * dg] = v;
+                    }
+                }
+    }
+    if (k + 1 < P.K - 1) {                           // B~_k = -(B L^-T)(last stage) Y(last): the separator on the right holds (B L^-T)(il) in its forward packet
+        const int il = i1 - 1, gn = i1, o2 = M.off(il), Dl = M.cls(il), Dn = M.cls(gn);
+        const double* Bh = pk + M.pkF(gn) + Dn * Dn;                         // [Dn x Dl] column-major, rows >= o2 zero (written by the chain kernel of this run)
+        double acc[4][4][2];
+        msp_zero(acc);
+        msp_mma(acc, Bh, Dn, Yp, MSP_LDY, Dl, Dn / 8, nc, lane);             // Yp = Y(last) after the final swap
+#pragma unroll
+        for (int ri = 0; ri < 4; ri++)
+#pragma unroll
+            for (int ci = 0; ci < 4; ci++) if (ri < Dn / 8 && ci < nc)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int r = ri * 8 + gq, c = ci * 8 + 2 * tq + e;
+                    if (r < o2 && c < dg) rfac[P.roffB[k] + r + c * o2] = -acc[ri][ci][e];
+                }
     }
 }
 
@@ -150,28 +222,29 @@ __global__ void __launch_bounds__(32) msp_fwd_kernel(MsDev s, MsPart P, int slot
     const int i0 = P.seg_bounds[2 * run], i1 = P.seg_bounds[2 * run + 1], NS = i1 - i0;
     double* tmp = xs + seg_len_max + 96;
     double* z = tmp + 32;
-    double* ring = z + 32;
-    const int* meta = s.start;
-    const int *m_start = meta, *m_diag = meta + N, *m_cls = meta + 7 * N, *m_pkF = meta + 8 * N, *m_szF = meta + 9 * N;
+    int* metab = reinterpret_cast<int*>(z + 32);
+    double* ring = z + 32 + (MS_META * MSP_META_MAX + 1) / 2;
+    const MspMeta M = msp_load_meta(metab, s, i0, i1, lane, 32);
+    __syncwarp();
     const double* pk = pk_all + (size_t)b * pk_stride;
-    const int base = m_start[i0], len = m_start[i1 - 1] + m_diag[i1 - 1] - base;
+    const int base = M.start(i0), len = M.start(i1 - 1) + M.diag(i1 - 1) - base;
     double* x = X + (size_t)b * s.n + base;
-    const int Dsep = run > 0 ? m_cls[i0 - 1] : 0;
-    for (int q = 0; q < MSP_PF; q++) { if (q < NS) msw_issue(pk + m_pkF[i0 + q], m_szF[i0 + q], ring + (size_t)(q % MSP_PF) * slot_doubles, lane); msw_cp_commit(); }
+    const int Dsep = run > 0 ? M.cls(i0 - 1) : 0;
+    for (int q = 0; q < MSP_PF; q++) { if (q < NS) msw_issue(pk + M.pkF(i0 + q), M.szF(i0 + q), ring + (size_t)(q % MSP_PF) * slot_doubles, lane); msw_cp_commit(); }
     for (int e = lane; e < seg_len_max + 96; e += 32) xs[e] = e < len ? x[e] : 0.0;
     z[lane] = 0.0;
     for (int t = 0; t < NS; t++) {
         const int i = i0 + t;
         msw_cp_wait<MSP_PF - 1>();
         __syncwarp();
-        const int d = m_diag[i], st = m_start[i] - base, D = m_cls[i];
-        const int PD = t > 0 ? m_cls[i - 1] : 0, pst = t > 0 ? m_start[i - 1] - base : 0;
+        const int d = M.diag(i), st = M.start(i) - base, D = M.cls(i);
+        const int PD = t > 0 ? M.cls(i - 1) : 0, pst = t > 0 ? M.start(i - 1) - base : 0;
         const double* pkt = ring + (size_t)(t % MSP_PF) * slot_doubles;
         if (D == 16) msw_fwd_stage<16>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
         else if (D == 8) msw_fwd_stage<8>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
         else msw_fwd_stage<32>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
         if (run > 0) {                               // z += Y_i^T y_i (off the dependent chain)
-            const double* YT = pkt + msp_yF(m_cls, i);
+            const double* YT = pkt + M.yF(i);
             if (lane < 32) tmp[lane] = lane < d ? xs[st + lane] : 0.0;       // zero-padded copy: the padded columns of Y^T are zero, the entries of xs behind the stage are not
             __syncwarp();
             double acc;
@@ -181,7 +254,7 @@ __global__ void __launch_bounds__(32) msp_fwd_kernel(MsDev s, MsPart P, int slot
         }
         __syncwarp();
         const int jn = t + MSP_PF;
-        if (jn < NS) msw_issue(pk + m_pkF[i0 + jn], m_szF[i0 + jn], ring + (size_t)(jn % MSP_PF) * slot_doubles, lane);
+        if (jn < NS) msw_issue(pk + M.pkF(i0 + jn), M.szF(i0 + jn), ring + (size_t)(jn % MSP_PF) * slot_doubles, lane);
         msw_cp_commit();
     }
     msw_cp_wait<0>();
@@ -219,32 +292,33 @@ __global__ void __launch_bounds__(32) msp_bwd_kernel(MsDev s, MsPart P, int slot
     const int i0 = P.seg_bounds[2 * run], i1 = P.seg_bounds[2 * run + 1], NS = i1 - i0;
     double* tmp = xs + seg_len_max + 96;
     double* xl = tmp + 32;
-    double* ring = xl + 32;
-    const int* meta = s.start;
-    const int *m_start = meta, *m_diag = meta + N, *m_cls = meta + 7 * N, *m_pkB = meta + 10 * N, *m_szB = meta + 11 * N;
+    int* metab = reinterpret_cast<int*>(xl + 32);
+    double* ring = xl + 32 + (MS_META * MSP_META_MAX + 1) / 2;
+    const MspMeta M = msp_load_meta(metab, s, i0, i1, lane, 32);
+    __syncwarp();
     const double* pk = pk_all + (size_t)b * pk_stride;
     const double* xr = xr_all + (size_t)b * P.rn;
-    const int base = m_start[i0], len = m_start[i1 - 1] + m_diag[i1 - 1] - base;
+    const int base = M.start(i0), len = M.start(i1 - 1) + M.diag(i1 - 1) - base;
     double* x = X + (size_t)b * s.n + base;
-    const int Dsep = run > 0 ? m_cls[i0 - 1] : 0;
-    for (int q = 0; q < MSP_PF; q++) { const int t = NS - 1 - q; if (t >= 0) msw_issue(pk + m_pkB[i0 + t], m_szB[i0 + t], ring + (size_t)(t % MSP_PF) * slot_doubles, lane); msw_cp_commit(); }
+    const int Dsep = run > 0 ? M.cls(i0 - 1) : 0;
+    for (int q = 0; q < MSP_PF; q++) { const int t = NS - 1 - q; if (t >= 0) msw_issue(pk + M.pkB(i0 + t), M.szB(i0 + t), ring + (size_t)(t % MSP_PF) * slot_doubles, lane); msw_cp_commit(); }
     for (int e = lane; e < seg_len_max + 96; e += 32) xs[e] = e < len ? x[e] : 0.0;
     __syncwarp();
     if (run + 1 < P.K) {                              // solution of the separator on the right sits where the next stage's x is read; it also goes back to X
-        const int g = P.sep[run], d = m_diag[g];
-        if (lane < d) { const double v = xr[P.rstart[run] + lane]; xs[len + lane] = v; X[(size_t)b * s.n + m_start[g] + lane] = v; }
+        const int g = P.sep[run], d = M.diag(g);
+        if (lane < d) { const double v = xr[P.rstart[run] + lane]; xs[len + lane] = v; X[(size_t)b * s.n + M.start(g) + lane] = v; }
     }
-    { const int dl = run > 0 ? m_diag[i0 - 1] : 0; xl[lane] = lane < dl ? xr[P.rstart[run - (run > 0)] + lane] : 0.0; }
+    { const int dl = run > 0 ? M.diag(i0 - 1) : 0; xl[lane] = lane < dl ? xr[P.rstart[run - (run > 0)] + lane] : 0.0; }
     __syncwarp();
     for (int t = NS - 1; t >= 0; t--) {
         const int i = i0 + t;
         msw_cp_wait<MSP_PF - 1>();
         __syncwarp();
-        const int d = m_diag[i], st = m_start[i] - base, D = m_cls[i];
-        const int ND = (i + 2 < N) ? m_cls[i + 1] : 0, nst = st + d;
+        const int d = M.diag(i), st = M.start(i) - base, D = M.cls(i);
+        const int ND = (i + 2 < N) ? M.cls(i + 1) : 0, nst = st + d;
         const double* pkt = ring + (size_t)(t % MSP_PF) * slot_doubles;
         if (run > 0) {                               // y_i -= Y_i x(separator on the left)
-            const double* Y = pkt + msp_yB(m_cls, i, N);
+            const double* Y = pkt + M.yB(i, N);
             double acc;
             if (D == 16) { acc = msw_matvec_dyn<16>(Y, xl, Dsep, lane % 16, lane / 16); acc = msw_reduce_h<16>(acc); if (lane < 16 && lane < d) xs[st + lane] -= acc; }
             else if (D == 8) { acc = msw_matvec_dyn<8>(Y, xl, Dsep, lane % 8, lane / 8); acc = msw_reduce_h<8>(acc); if (lane < 8 && lane < d) xs[st + lane] -= acc; }
@@ -255,7 +329,7 @@ __global__ void __launch_bounds__(32) msp_bwd_kernel(MsDev s, MsPart P, int slot
         else if (D == 8) msw_bwd_stage<8>(pkt, ND, xs, st, nst, d, 0, s.n, tmp, lane);
         else msw_bwd_stage<32>(pkt, ND, xs, st, nst, d, 0, s.n, tmp, lane);
         const int jn = t - MSP_PF;
-        if (jn >= 0) msw_issue(pk + m_pkB[i0 + jn], m_szB[i0 + jn], ring + (size_t)(jn % MSP_PF) * slot_doubles, lane);
+        if (jn >= 0) msw_issue(pk + M.pkB(i0 + jn), M.szB(i0 + jn), ring + (size_t)(jn % MSP_PF) * slot_doubles, lane);
         msw_cp_commit();
     }
     msw_cp_wait<0>();
