@@ -439,7 +439,7 @@ MultistageBatchedKKT::MultistageBatchedKKT(SparseData* data, cudaStream_t st) : 
         packets.alloc((size_t)batch * pk_stride);
         packets.zero(st);
         B200_CUDA(cudaFuncSetAttribute(msw_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(chain_solve_smem, 48 * 1024)));
-        const int csm = (int)(sizeof(MswChainSmem) + sizeof(int) * MS_META * S.N);
+        const int csm = (int)(sizeof(MswChainSmem) + sizeof(int) * MS_META * std::max(S.N, MSP_META_MAX));      // segment mode stages MSP_META_MAX entries per array
         B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
         B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
         B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));

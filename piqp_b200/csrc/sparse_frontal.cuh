@@ -27,6 +27,7 @@ struct MfDev {
     int nsup, nk, n, p, m, front_smem_rows, fmax;
     long long upd_total;
     size_t nnzL, nnzPK;
+    int big_right_looking; // 1: fronts beyond shared memory use the right-looking blocked elimination (B200_MF_BIG=right), 0: the left-looking one
     long long* prof;       // optional [8] phase clocks of CTA 0 (B200_MF_PROF=1): zero+scatter, extend-add, eliminate (smem), eliminate (HBM), Schur store
 };
 
@@ -167,6 +168,113 @@ __device__ void mf_eliminate_big(double* __restrict__ F, int f, int ws, int j0, 
     }
 }
 
+// ---- LEFT-LOOKING blocked elimination of a front held in HBM/L2 (default for fronts beyond shared memory).  The assembled front F
+// is only READ: for every block of <= 32 columns, one thread per row accumulates  F(row, block) - sum_{k < kmax} L(row, k) D_k L(block, k)
+// in 32 registers (L from the CSC storage of L, coalesced over rows; the D L rows of the block staged in shared memory, 64 pivots at
+// a time), then either finishes the block's pivots (LDL^T of the 32 x 32 diagonal block by one warp, every row solved against it in
+// registers) and writes L / D, or -- for the columns behind the supernode -- writes the Schur complement straight onto the update
+// stack.  Compared with the right-looking variant above, the front is never read-modified-written (ws / 32 sweeps over f^2 / 2
+// entries saved) and the inner loop is pure register arithmetic: one load per 32 multiply-subtract pairs.  Sums run over k in
+// increasing order with products and differences rounded separately: the reference's own order (sparse/ldlt.hpp:139-158).
+// sm: >= MFL_KC * 32 + 32 * 33 + 32 doubles.
+constexpr int MFL_KC = 64;
+__device__ void mf_eliminate_left(const double* __restrict__ F, int f, int ws, int us, int j0, int lp0, double* sm, double* __restrict__ Lx,
+                                  double* __restrict__ Dv, double* __restrict__ Dinv, int* failb, double* __restrict__ U) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double* Wt = sm;                                    // [MFL_KC][32]: Wt[k][j] = D_k L(c0 + j, k)
+    double* A11 = Wt + MFL_KC * 32;                     // [32][33]
+    double* dd = A11 + 32 * 33;                         // [32]
+    constexpr int LDA = 33;
+    auto colbase = [&](int k) { return (size_t)((long long)lp0 + (long long)k * (f - 1) - ((long long)k * (k - 1)) / 2 - (k + 1)); };
+    int c0 = 0;
+    while (c0 < f) {
+        const bool panel = c0 < ws;
+        const int nb = panel ? min(32, ws - c0) : min(32, f - c0);
+        const int kmax = min(c0, ws);
+        for (int r0 = c0; r0 < f; r0 += MF_T) {
+            const int row = r0 + tid;
+            const bool live = row < f;
+            double acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc[j] = (live && j < nb && row >= c0 + j) ? F[(size_t)row + (size_t)(c0 + j) * f] : 0.0;
+            for (int k0 = 0; k0 < kmax; k0 += MFL_KC) {
+                const int kc = min(MFL_KC, kmax - k0);
+                __syncthreads();                                   // previous chunk consumed
+                for (int e = tid; e < kc * 32; e += MF_T) {
+                    const int k = e >> 5, j = e & 31;
+                    Wt[e] = j < nb ? Dv[j0 + k0 + k] * Lx[colbase(k0 + k) + (c0 + j)] : 0.0;
+                }
+                __syncthreads();
+                if (live) {
+                    for (int k = 0; k < kc; k++) {
+                        const double a = Lx[colbase(k0 + k) + row];
+                        const double2* w2 = reinterpret_cast<const double2*>(Wt + k * 32);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const double2 w = w2[j];
+                            acc[2 * j] = __dsub_rn(acc[2 * j], __dmul_rn(a, w.x));
+                            acc[2 * j + 1] = __dsub_rn(acc[2 * j + 1], __dmul_rn(a, w.y));
+                        }
+                    }
+                }
+            }
+            if (!panel) {                                          // Schur complement block -> update stack (lower part)
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) if (j < nb && row >= c0 + j) U[(size_t)(row - ws) + (size_t)(c0 + j - ws) * us] = acc[j];
+                }
+                continue;
+            }
+            if (r0 == c0) {                                        // first row tile: holds the rows of the diagonal block
+                __syncthreads();
+                if (tid < nb) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) if (j < nb) A11[tid + j * LDA] = (j <= tid) ? acc[j] : 0.0;
+                }
+                __syncthreads();
+                if (wid == 0) {                                    // LDL^T of the nb x nb block, right-looking, one warp (same arithmetic as mf_eliminate_big)
+                    for (int k = 0; k < nb; k++) {
+                        const double d = A11[k + k * LDA];
+                        const double wi = (lane > k && lane < nb) ? A11[lane + k * LDA] : 0.0;
+                        const double li = wi / d;
+                        __syncwarp();
+                        if (lane > k && lane < nb) A11[lane + k * LDA] = li;
+                        __syncwarp();
+                        if (lane > k && lane < nb) for (int c = k + 1; c <= lane; c++) A11[lane + c * LDA] = __dsub_rn(A11[lane + c * LDA], __dmul_rn(wi, A11[c + k * LDA]));
+                        if (lane == 0) dd[k] = d;
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+                for (int k = tid; k < nb; k += MF_T) {
+                    const double d = dd[k];
+                    if (d == 0.0 && *failb == 0) *failb = j0 + c0 + k + 1;       // ldlt.hpp:161
+                    Dv[j0 + c0 + k] = d; Dinv[j0 + c0 + k] = 1.0 / d;
+                }
+                for (int e = tid; e < nb * nb; e += MF_T) {
+                    const int i = e % nb, c = e / nb;
+                    if (i > c) Lx[colbase(c0 + c) + (c0 + i)] = A11[i + c * LDA];
+                }
+            }
+            if (live && row >= c0 + nb) {                          // rows below the block: w = a L11^-T, l = w / d
+#pragma unroll
+                for (int k = 0; k < 32; k++) {
+                    if (k < nb) {
+                        double a = acc[k];
+#pragma unroll
+                        for (int q = 0; q < k; q++) a = __dsub_rn(a, __dmul_rn(acc[q], A11[k + q * LDA]));
+                        acc[k] = a;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 32; k++) if (k < nb) Lx[colbase(c0 + k) + row] = acc[k] / dd[k];
+            }
+        }
+        __syncthreads();                                           // L / D of this block visible to the next block's Wt staging (same CTA: global writes + barrier)
+        c0 += nb;
+    }
+}
+
 // PKasm: the permuted KKT values in ASSEMBLY order (grouped by supernode, see LdltSymbolic::asm_*), so that a front's
 // original entries are one contiguous, coalesced read.
 __global__ void __launch_bounds__(MF_T) mf_factor_kernel(MfDev M, const double* __restrict__ PKasm_all, double* __restrict__ Lx_all, double* __restrict__ Dv_all,
@@ -242,9 +350,10 @@ __global__ void __launch_bounds__(MF_T) mf_factor_kernel(MfDev M, const double* 
         MF_LAP(1);
         // ---- eliminate the ws pivots of the supernode
         if (in_smem) { mf_eliminate_smem(Fs, f, ws, j0, lp0, lcol, Lx, Dv, Dinv, fail + b); MF_LAP(2); }
-        else { mf_eliminate_big(big, f, ws, j0, lp0, Fs, Wg, Lg, Lx, Dv, Dinv, fail + b); __syncthreads(); MF_LAP(3); }
+        else if (M.big_right_looking) { mf_eliminate_big(big, f, ws, j0, lp0, Fs, Wg, Lg, Lx, Dv, Dinv, fail + b); __syncthreads(); MF_LAP(3); }
+        else { mf_eliminate_left(big, f, ws, us, j0, lp0, Fs, Lx, Dv, Dinv, fail + b, upd + my_off); __syncthreads(); MF_LAP(3); }
         // ---- Schur complement -> stack (full us x us square, ld = us; only the lower part is meaningful)
-        if (us > 0) {
+        if (us > 0 && (in_smem || M.big_right_looking)) {       // the left-looking elimination wrote its Schur complement itself
             double* U = upd + my_off;
             for (int col = wid; col < us; col += NW) {
                 const double* Fc = F + (size_t)(ws + col) * f + ws;

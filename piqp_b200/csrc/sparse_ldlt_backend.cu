@@ -756,6 +756,7 @@ static MfDev make_mf(const SparseLdltBatchedKKT& K) {
     M.upd_total = std::max<long long>(K.S.upd_total, 1);
     M.nnzL = std::max<size_t>(K.S.Li.size(), 1); M.nnzPK = K.S.PKi_rows.size();
     M.prof = K.d_prof.n ? K.d_prof.get() : nullptr;
+    { const char* e = getenv("B200_MF_BIG"); M.big_right_looking = (e && std::string(e) == "right") ? 1 : 0; }
     return M;
 }
 
