@@ -623,9 +623,21 @@ void MultistageBatchedKKT::build_partition(const std::vector<int>& cls, cudaStre
     zbuf.alloc((size_t)batch * K * 32); zbuf.zero(st);
     xred.alloc((size_t)batch * std::max(part_rn, 1)); xred.zero(st);
     const size_t meta_d = (size_t)(MS_META * MSP_META_MAX + 1) / 2;
-    part_seg_smem = sizeof(double) * ((size_t)part_seg_len + 96 + 64 + meta_d + (size_t)MSP_PF * chain_slot);
-    part_spike_slot = 2;
-    for (int i = 1; i + 1 < S.N; i++) part_spike_slot = std::max(part_spike_slot, cls[i] * cls[i] + cls[i] * cls[i - 1]);
+    // ring slots are sized for the MOST COMMON packet size; the few larger packets (stages of a bigger class) are read from global memory
+    auto mode_of = [](std::vector<int> v) { std::sort(v.begin(), v.end()); int best = v.empty() ? 2 : v[0], cnt = 0, bc = 0, prev = -1;
+        for (int x : v) { cnt = (x == prev) ? cnt + 1 : 1; prev = x; if (cnt >= bc) { bc = cnt; best = x; } } return best; };
+    std::vector<int> sz_solve, sz_spike;
+    {
+        std::vector<int> szF_(S.N, 0), szB_(S.N, 0);
+        for (int i = 0; i + 1 < S.N; i++) {
+            const int D = cls[i], PD = i > 0 ? cls[i - 1] : 0, ND = (i + 2 < S.N) ? cls[i + 1] : 0;
+            const int y = part_dsep[i] * D;
+            sz_solve.push_back(std::max(D * D + D * PD + y, D * D + D * ND + y));
+            if (i > 0) sz_spike.push_back(D * D + D * PD);
+        }
+    }
+    part_solve_slot = mode_of(sz_solve); part_spike_slot = mode_of(sz_spike);
+    part_seg_smem = sizeof(double) * ((size_t)part_seg_len + 96 + 64 + meta_d + (size_t)MSP_PF * part_solve_slot);
     part_spike_smem = sizeof(double) * ((size_t)3 * 32 * MSP_LDY + meta_d + (size_t)MSP_PF * part_spike_slot);
     for (int r = 0; r < K; r++) if (part_bounds[2 * r + 1] - part_bounds[2 * r] + 2 > MSP_META_MAX) { part_K = 1; return; }      // run-local meta copies
     part_rsolve_smem = sizeof(double) * ((size_t)((part_rn + 1) & ~1) + 96 + (size_t)(((MS_META * NR + 1) / 2 + 1) / 2 * 2) + (size_t)MSW_R * part_rslot);
@@ -704,14 +716,14 @@ void MultistageBatchedKKT::solve_partitioned(double* lx, const int* active) {
     const MsDev dv = make_dev(S, d_meta.get());
     dim3 gseg(batch, K);
     g_ms_timer.mark(0, stream);
-    B200_LAUNCH(msp_fwd_kernel, gseg, 32, part_seg_smem, stream, dv, P, chain_slot, part_seg_len, packets.get(), pk_stride, lx, zbuf.get(), active);
+    B200_LAUNCH(msp_fwd_kernel, gseg, 32, part_seg_smem, stream, dv, P, part_solve_slot, part_seg_len, packets.get(), pk_stride, lx, zbuf.get(), active);
     g_ms_timer.mark(1, stream);
     B200_LAUNCH(msp_gather_kernel, dim3(batch, ceil_div(K - 1, 4)), 128, 0, stream, dv, P, packets.get(), pk_stride, lx, zbuf.get(), xred.get(), active);
     const MsDev rd = make_rdev(d_rmeta.get(), K, part_rn, part_rtotal);
     g_ms_timer.mark(2, stream);
     B200_LAUNCH(msw_solve_kernel, batch, 32, std::max<size_t>(part_rsolve_smem, 1), stream, rd, part_rslot, (const double*)nullptr, rpackets.get(), part_rpk_stride, xred.get(), active);
     g_ms_timer.mark(3, stream);
-    B200_LAUNCH(msp_bwd_kernel, gseg, 32, part_seg_smem, stream, dv, P, chain_slot, part_seg_len, packets.get(), pk_stride, lx, xred.get(), active);
+    B200_LAUNCH(msp_bwd_kernel, gseg, 32, part_seg_smem, stream, dv, P, part_solve_slot, part_seg_len, packets.get(), pk_stride, lx, xred.get(), active);
     g_ms_timer.mark(4, stream);
     g_ms_timer.done(1, 4, stream);
 }

@@ -119,9 +119,13 @@ __global__ void __launch_bounds__(32) msp_spike_kernel(MsDev s, MsPart P, int sl
     const double* fac = fac_all + (size_t)b * s.total;
     double* pk = pk_all + (size_t)b * pk_stride;
     const int dg = M.diag(g), og = M.off(g), Dsep = M.cls(g), nc = Dsep / 8;
+    // A packet larger than a ring slot (a stage of a bigger class than the common one, e.g. the 28-variable last stage of the MPC
+    // problems next to 16-variable stages) is read from global memory instead: sizing the slots for it would halve the number of
+    // resident CTAs for every run.
+    auto psize = [&](int i) { const int D = M.cls(i); return D * D + D * (i > 0 ? M.cls(i - 1) : 0); };
     auto issue = [&](int t) {                        // inv(L_i) | (B L^-T)(i-1) of the forward packet
-        const int i = i0 + t, D = M.cls(i);
-        msw_issue(pk + M.pkF(i), D * D + D * (i > 0 ? M.cls(i - 1) : 0), ring + (size_t)(t % MSP_PF) * slot_doubles, lane);
+        const int i = i0 + t, sz = psize(i);
+        if (sz <= slot_doubles) msw_issue(pk + M.pkF(i), sz, ring + (size_t)(t % MSP_PF) * slot_doubles, lane);
     };
     for (int q = 0; q < MSP_PF; q++) { if (q < NS) issue(q); msw_cp_commit(); }
     // first stage: V = K[first stage, g] = B(g): rows = the first og variables of the run, columns = the dg variables of the separator
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(32) msp_spike_kernel(MsDev s, MsPart P, int sl
         const int PD = t > 0 ? M.cls(i - 1) : 0;
         msw_cp_wait<MSP_PF - 1>();
         __syncwarp();
-        const double* pkt = ring + (size_t)(t % MSP_PF) * slot_doubles;
+        const double* pkt = psize(i) <= slot_doubles ? ring + (size_t)(t % MSP_PF) * slot_doubles : pk + M.pkF(i);
         double acc[4][4][2];
         if (t > 0) {                                 // V = -(B L^-T)(i-1) Y(i-1)
             msp_zero(acc);
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(32) msp_fwd_kernel(MsDev s, MsPart P, int slot
     const int base = M.start(i0), len = M.start(i1 - 1) + M.diag(i1 - 1) - base;
     double* x = X + (size_t)b * s.n + base;
     const int Dsep = run > 0 ? M.cls(i0 - 1) : 0;
-    for (int q = 0; q < MSP_PF; q++) { if (q < NS) msw_issue(pk + M.pkF(i0 + q), M.szF(i0 + q), ring + (size_t)(q % MSP_PF) * slot_doubles, lane); msw_cp_commit(); }
+    for (int q = 0; q < MSP_PF; q++) { if (q < NS && M.szF(i0 + q) <= slot_doubles) msw_issue(pk + M.pkF(i0 + q), M.szF(i0 + q), ring + (size_t)(q % MSP_PF) * slot_doubles, lane); msw_cp_commit(); }
     for (int e = lane; e < seg_len_max + 96; e += 32) xs[e] = e < len ? x[e] : 0.0;
     z[lane] = 0.0;
     for (int t = 0; t < NS; t++) {
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(32) msp_fwd_kernel(MsDev s, MsPart P, int slot
         __syncwarp();
         const int d = M.diag(i), st = M.start(i) - base, D = M.cls(i);
         const int PD = t > 0 ? M.cls(i - 1) : 0, pst = t > 0 ? M.start(i - 1) - base : 0;
-        const double* pkt = ring + (size_t)(t % MSP_PF) * slot_doubles;
+        const double* pkt = M.szF(i) <= slot_doubles ? ring + (size_t)(t % MSP_PF) * slot_doubles : pk + M.pkF(i);      // oversized packet: straight from global memory
         if (D == 16) msw_fwd_stage<16>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
         else if (D == 8) msw_fwd_stage<8>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
         else msw_fwd_stage<32>(pkt, PD, xs, st, pst, d, 0, tmp, nullptr, lane);
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(32) msp_fwd_kernel(MsDev s, MsPart P, int slot
         }
         __syncwarp();
         const int jn = t + MSP_PF;
-        if (jn < NS) msw_issue(pk + M.pkF(i0 + jn), M.szF(i0 + jn), ring + (size_t)(jn % MSP_PF) * slot_doubles, lane);
+        if (jn < NS && M.szF(i0 + jn) <= slot_doubles) msw_issue(pk + M.pkF(i0 + jn), M.szF(i0 + jn), ring + (size_t)(jn % MSP_PF) * slot_doubles, lane);
         msw_cp_commit();
     }
     msw_cp_wait<0>();
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(32) msp_bwd_kernel(MsDev s, MsPart P, int slot
     const int base = M.start(i0), len = M.start(i1 - 1) + M.diag(i1 - 1) - base;
     double* x = X + (size_t)b * s.n + base;
     const int Dsep = run > 0 ? M.cls(i0 - 1) : 0;
-    for (int q = 0; q < MSP_PF; q++) { const int t = NS - 1 - q; if (t >= 0) msw_issue(pk + M.pkB(i0 + t), M.szB(i0 + t), ring + (size_t)(t % MSP_PF) * slot_doubles, lane); msw_cp_commit(); }
+    for (int q = 0; q < MSP_PF; q++) { const int t = NS - 1 - q; if (t >= 0 && M.szB(i0 + t) <= slot_doubles) msw_issue(pk + M.pkB(i0 + t), M.szB(i0 + t), ring + (size_t)(t % MSP_PF) * slot_doubles, lane); msw_cp_commit(); }
     for (int e = lane; e < seg_len_max + 96; e += 32) xs[e] = e < len ? x[e] : 0.0;
     __syncwarp();
     if (run + 1 < P.K) {                              // solution of the separator on the right sits where the next stage's x is read; it also goes back to X
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(32) msp_bwd_kernel(MsDev s, MsPart P, int slot
         __syncwarp();
         const int d = M.diag(i), st = M.start(i) - base, D = M.cls(i);
         const int ND = (i + 2 < N) ? M.cls(i + 1) : 0, nst = st + d;
-        const double* pkt = ring + (size_t)(t % MSP_PF) * slot_doubles;
+        const double* pkt = M.szB(i) <= slot_doubles ? ring + (size_t)(t % MSP_PF) * slot_doubles : pk + M.pkB(i);
         if (run > 0) {                               // y_i -= Y_i x(separator on the left)
             const double* Y = pkt + M.yB(i, N);
             double acc;
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(32) msp_bwd_kernel(MsDev s, MsPart P, int slot
         else if (D == 8) msw_bwd_stage<8>(pkt, ND, xs, st, nst, d, 0, s.n, tmp, lane);
         else msw_bwd_stage<32>(pkt, ND, xs, st, nst, d, 0, s.n, tmp, lane);
         const int jn = t - MSP_PF;
-        if (jn >= 0) msw_issue(pk + M.pkB(i0 + jn), M.szB(i0 + jn), ring + (size_t)(jn % MSP_PF) * slot_doubles, lane);
+        if (jn >= 0 && M.szB(i0 + jn) <= slot_doubles) msw_issue(pk + M.pkB(i0 + jn), M.szB(i0 + jn), ring + (size_t)(jn % MSP_PF) * slot_doubles, lane);
         msw_cp_commit();
     }
     msw_cp_wait<0>();

@@ -206,15 +206,28 @@ __device__ void mf_eliminate_left(const double* __restrict__ F, int f, int ws, i
                 }
                 __syncthreads();
                 if (live) {
-                    for (int k = 0; k < kc; k++) {
-                        const double a = Lx[colbase(k0 + k) + row];
-                        const double2* w2 = reinterpret_cast<const double2*>(Wt + k * 32);
+                    // L(row, k) comes from L2 (~0.5 us round trip): eight loads are kept in flight one group ahead of the arithmetic
+                    constexpr int PFK = 8;
+                    double a[PFK], an[PFK];
 #pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const double2 w = w2[j];
-                            acc[2 * j] = __dsub_rn(acc[2 * j], __dmul_rn(a, w.x));
-                            acc[2 * j + 1] = __dsub_rn(acc[2 * j + 1], __dmul_rn(a, w.y));
+                    for (int u = 0; u < PFK; u++) a[u] = u < kc ? Lx[colbase(k0 + u) + row] : 0.0;
+                    for (int k = 0; k < kc; k += PFK) {
+#pragma unroll
+                        for (int u = 0; u < PFK; u++) an[u] = (k + PFK + u < kc) ? Lx[colbase(k0 + k + PFK + u) + row] : 0.0;
+#pragma unroll
+                        for (int u = 0; u < PFK; u++) {
+                            if (k + u < kc) {
+                                const double2* w2 = reinterpret_cast<const double2*>(Wt + (k + u) * 32);
+#pragma unroll
+                                for (int j = 0; j < 16; j++) {
+                                    const double2 w = w2[j];
+                                    acc[2 * j] = __dsub_rn(acc[2 * j], __dmul_rn(a[u], w.x));
+                                    acc[2 * j + 1] = __dsub_rn(acc[2 * j + 1], __dmul_rn(a[u], w.y));
+                                }
+                            }
                         }
+#pragma unroll
+                        for (int u = 0; u < PFK; u++) a[u] = an[u];
                     }
                 }
             }
@@ -295,8 +308,8 @@ __global__ void __launch_bounds__(MF_T) mf_factor_kernel(MfDev M, const double* 
     double* Lg = Wg ? Wg + (size_t)M.fmax * MF_NB : nullptr;
     const int fpad = (M.fmax + 1) & ~1;
     double* lcol = mf_sm;                                  // fmax doubles
-    int* relbuf = reinterpret_cast<int*>(mf_sm + fpad);    // fmax ints
-    double* Fs = mf_sm + ((fpad + fpad / 2 + 3) & ~3);
+    int* relbuf = reinterpret_cast<int*>(mf_sm + fpad);    // 2 x fmax ints (double buffer of the extend-add)
+    double* Fs = mf_sm + ((2 * fpad + 3) & ~3);
     if (tid == 0) fail[b] = 0;
     const int4* hdr4 = reinterpret_cast<const int4*>(M.hdr);
     int4 nh0 = hdr4[0], nh1 = hdr4[1];
@@ -324,24 +337,25 @@ __global__ void __launch_bounds__(MF_T) mf_factor_kernel(MfDev M, const double* 
         for (int u = 0; u < 2; u++) if (tid + u * MF_T < an) F[ap[u]] = av[u];
         for (int t = tid + 2 * MF_T; t < an; t += MF_T) F[M.asm_pos[ab + t]] = PK[ab + t];
         MF_LAP(0);
-        for (int c = 0; c < cn; c++) {                       // extend-add, one child at a time (fixed order)
-            const int4 cr = reinterpret_cast<const int4*>(M.crec)[cb + c];
-            const int uc = cr.x;
-            const double* U = upd + (((long long)cr.w << 32) | (unsigned)cr.z);
-            for (int t = tid; t < uc; t += MF_T) relbuf[t] = M.rel_idx[cr.y + t];
-            __syncthreads();                                  // relbuf ready; scatter of the original entries done
-            const int total = uc * uc;
-            for (int e0 = tid; e0 < total; e0 += 4 * MF_T) {
-                double uv[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) { const int e = e0 + u * MF_T; uv[u] = e < total ? U[e] : 0.0; }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int e = e0 + u * MF_T;
-                    if (e < total) {
-                        const int col = e / uc, a = e - col * uc;
-                        if (a >= col) { const size_t pos = (size_t)relbuf[a] + (size_t)relbuf[col] * f; if (in_smem) Fs[pos] += uv[u]; else big[pos] += uv[u]; }
-                    }
+        // extend-add, one child at a time in the fixed (postorder) order: deterministic, no atomics.  The next child's record and
+        // relative indices are fetched while the current child's update matrix is added (double-buffered relbuf, one barrier per
+        // child); only the lower triangle of an update matrix is read, one warp per column.
+        if (cn > 0) {
+            int4 crn = reinterpret_cast<const int4*>(M.crec)[cb];
+            for (int t = tid; t < crn.x; t += MF_T) relbuf[t] = M.rel_idx[crn.y + t];
+            for (int c = 0; c < cn; c++) {
+                const int4 cr = crn;
+                int* rel = relbuf + (c & 1) * M.fmax;
+                int* reln = relbuf + ((c + 1) & 1) * M.fmax;
+                if (c + 1 < cn) crn = reinterpret_cast<const int4*>(M.crec)[cb + c + 1];
+                __syncthreads();                              // rel ready; the previous child's additions (and the scatter of the original entries) are done
+                if (c + 1 < cn) for (int t = tid; t < crn.x; t += MF_T) reln[t] = M.rel_idx[crn.y + t];
+                const int uc = cr.x;
+                const double* U = upd + (((long long)cr.w << 32) | (unsigned)cr.z);
+                for (int col = wid; col < uc; col += NW) {
+                    const size_t cbase = (size_t)rel[col] * f;
+                    const double* Uc = U + (size_t)col * uc;
+                    for (int a = col + lane; a < uc; a += 32) { const size_t pos = (size_t)rel[a] + cbase; if (in_smem) Fs[pos] += Uc[a]; else big[pos] += Uc[a]; }
                 }
             }
             __syncthreads();

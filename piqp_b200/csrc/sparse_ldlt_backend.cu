@@ -1071,7 +1071,7 @@ SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_per
         if (const char* e = getenv("B200_LDLT_WIDE")) wide = atoi(e) != 0;
         if (!wide) upd.alloc(B * (size_t)std::max<long long>(S.upd_total, 1));
         const size_t fpad = (size_t)((S.fmax + 1) & ~1);
-        const size_t smem_cap = 200 * 1024, lcol_bytes = sizeof(double) * ((fpad + fpad / 2 + 3) & ~(size_t)3);      // lcol (doubles) + relbuf (ints)
+        const size_t smem_cap = 200 * 1024, lcol_bytes = sizeof(double) * ((2 * fpad + 3) & ~(size_t)3);      // lcol (doubles) + relbuf (2 x fmax ints: mf_factor_kernel double-buffers it)
         const size_t big_scratch = sizeof(double) * (size_t)(2 * MF_TS * MF_NB + MF_NB * (MF_NB + 2));
         if (!wide && lcol_bytes + big_scratch > smem_cap) throw std::runtime_error("sparse_ldlt: a front of this size is not supported by this build");
         int fs = S.fmax;
