@@ -356,12 +356,15 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
     zinv.alloc((size_t)batch * m); delta.alloc(batch); fail.alloc(batch); fail.zero(st);
     set_smem(gemm_nt_tile_kernel<EPI_ASSEMBLE, true>, GEMM_SMEM);
     set_smem(gemm_nt_t64_kernel<EPI_ASSEMBLE, true>, T64_SMEM);
+    set_smem(gemm_nt_t64_kernel<EPI_SUB, false>, T64_SMEM);
+    chol_split = !(getenv("B200_CHOL_SPLIT") && getenv("B200_CHOL_SPLIT")[0] == '0');      // 0 = the fused round-1 panel kernel
     gemm_t64 = !(getenv("B200_GEMM_T64") && getenv("B200_GEMM_T64")[0] == '0');      // 128 x 64 tiles, two CTAs per SM (default); 0 = the 128 x 128 kernel
     set_smem(gemm_nt_tile_kernel<EPI_ASSEMBLE, false>, GEMM_SMEM);
     set_smem(gemm_nt_tile_kernel<EPI_SUB, false>, GEMM_SMEM);
     set_smem(gemm_nt_tile_kernel<EPI_STORE, false>, GEMM_SMEM);
     set_smem(chol_diag_kernel, CHOL_DIAG_SMEM);
-    set_smem(chol_panel_kernel, CHOL_PANEL_SMEM);
+    set_smem(chol_panel_kernel<true>, CHOL_PANEL_SMEM);
+    set_smem(chol_panel_kernel<false>, CHOL_PANEL_SMEM);
     Linv_stride = (long long)ceil_div(std::max(n, 1), TILE) * 4 * LB_SZ;
     Linv.alloc((size_t)batch * Linv_stride); Linv.zero(st);
     set_smem(trsv_kernel, (size_t)(n + 32) * sizeof(double) > 48 * 1024 ? (size_t)(n + 32) * sizeof(double) : 48 * 1024);
@@ -500,11 +503,25 @@ void DenseBatchedKKT::cholesky(const int* active) {   // Eigen::LLT<Lower>::comp
     B200_LAUNCH(clear_fail_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, batch);
     for (int jb = 0; jb < nt; jb++) {
         const int j0 = jb * TILE;
-        B200_LAUNCH(chol_diag_kernel, batch, CHOL_THREADS, CHOL_DIAG_SMEM, stream, K.get(), D->sP(), D->ld, n, j0, Linv.get(), Linv_stride, fail.get(), active);
         const int rt = nt - jb - 1;
-        if (rt > 0)
-            B200_LAUNCH(chol_panel_kernel, (unsigned)(rt * batch), CHOL_THREADS, CHOL_PANEL_SMEM, stream, K.get(), D->sP(), D->ld, n, jb, rt,
-                        Linv.get(), Linv_stride, fail.get(), active);
+        if (chol_split && jb > 0) {
+            // left-looking update of block column jb, diagonal tile included:  K(:, jb) -= L(:, 0:j0) L(jb, 0:j0)^T  on the two-CTA-per-SM
+            // DMMA tile kernel (contraction depth j0 = 128 .. n - 128)
+            GemmArgs g{};
+            g.A = K.get(); g.strideA = D->sP(); g.lda = D->ld;
+            g.B = g.A; g.strideB = g.strideA; g.ldb = g.lda;
+            g.C = K.get(); g.strideC = D->sP(); g.ldc = D->ld;
+            g.n = n; g.rows_valid = D->ld; g.K = j0; g.nt = nt; g.tj_fixed = -1; g.tj_start = jb; g.tiles = 2 * (nt - jb);
+            g.active = active; g.fail = fail.get();
+            B200_LAUNCH((gemm_nt_t64_kernel<EPI_SUB, false>), (unsigned)((size_t)g.tiles * batch), GEMM_THREADS, T64_SMEM, stream, g);
+        }
+        B200_LAUNCH(chol_diag_kernel, batch, CHOL_THREADS, CHOL_DIAG_SMEM, stream, K.get(), D->sP(), D->ld, n, j0, Linv.get(), Linv_stride, fail.get(), active);
+        if (rt > 0) {
+            if (chol_split) B200_LAUNCH(chol_panel_kernel<false>, (unsigned)(rt * batch), CHOL_THREADS, CHOL_PANEL_SMEM, stream, K.get(), D->sP(), D->ld, n, jb, rt,
+                                        Linv.get(), Linv_stride, fail.get(), active);
+            else B200_LAUNCH(chol_panel_kernel<true>, (unsigned)(rt * batch), CHOL_THREADS, CHOL_PANEL_SMEM, stream, K.get(), D->sP(), D->ld, n, jb, rt,
+                             Linv.get(), Linv_stride, fail.get(), active);
+        }
     }
 }
 

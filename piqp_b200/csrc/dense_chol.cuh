@@ -163,6 +163,10 @@ chol_diag_kernel(double* Kmat, long long strideK, int ld, int n, int j0, double*
 }
 
 // ---------------------------------------------------------------------------------------------------
+// FUSED = true: the round-1 kernel (left-looking mainloop + solve + look-ahead update of the own diagonal tile in one CTA that holds a
+// whole SM).  FUSED = false (default since round 2): solve only -- the left-looking update of the whole block column (diagonal tile
+// included) is done beforehand by gemm_nt_t64_kernel<EPI_SUB> (two CTAs per SM, no serial tail behind its mainloop).
+template <bool FUSED>
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
 chol_panel_kernel(double* Kmat, long long strideK, int ld, int n, int jb, int row_tiles, const double* Linv, long long strideLinv, const int* fail, const int* active) {
     extern __shared__ __align__(16) double smem[];
@@ -192,15 +196,19 @@ chol_panel_kernel(double* Kmat, long long strideK, int ld, int n, int jb, int ro
 
     // ---- left-looking update: acc = sum_{k < j0} L(ti,k) L(jb,k)^T
     double acc[8][4][2];
+    if (FUSED) {
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+        for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-    if (j0 > 0) {
-        gemm_mainloop<false>(acc, smem, K, ld, rows0, K, ld, j0, ld, j0, nullptr, false);
-        __syncthreads();
+            for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        if (j0 > 0) {
+            gemm_mainloop<false>(acc, smem, K, ld, rows0, K, ld, j0, ld, j0, nullptr, false);
+            __syncthreads();
+        }
+        acc_to_smem(acc, Ts, -1.0);
+    } else {
+        for (int e = tid; e < TILE * TS_LD; e += CHOL_THREADS) Ts[e] = 0.0;
     }
-    acc_to_smem(acc, Ts, -1.0);
     cp_async_wait<0>();
     __syncthreads();
     // ---- T = A - acc: all 32 16-byte loads of this thread are in flight before the first use
@@ -257,7 +265,7 @@ chol_panel_kernel(double* Kmat, long long strideK, int ld, int n, int jb, int ro
     }
     // ---- look-ahead: this row tile's own diagonal tile (ti,ti) gets its rank-128 contribution of block column jb now
     //      (D -= X X^T, lower part), so chol_diag_kernel never needs a mainloop and the work is spread over all panel CTAs
-    {
+    if (FUSED) {
 #pragma unroll
         for (int i = 0; i < 8; i++)
 #pragma unroll
