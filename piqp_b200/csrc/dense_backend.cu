@@ -358,6 +358,13 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
     set_smem(gemm_nt_t64_kernel<EPI_ASSEMBLE, true>, T64_SMEM);
     set_smem(gemm_nt_t64_kernel<EPI_SUB, false>, T64_SMEM);
     chol_split = !(getenv("B200_CHOL_SPLIT") && getenv("B200_CHOL_SPLIT")[0] == '0');      // 0 = the fused round-1 panel kernel
+    if (chol_split && !(getenv("B200_CHOL_AUX") && getenv("B200_CHOL_AUX")[0] == '0')) {
+        int lo = 0, hi = 0;
+        B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        B200_CUDA(cudaStreamCreateWithPriority(&chol_aux, cudaStreamNonBlocking, hi));
+        chol_ev.resize(2 * (size_t)ceil_div(std::max(n, 1), TILE) + 2);
+        for (auto& e : chol_ev) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     gemm_t64 = !(getenv("B200_GEMM_T64") && getenv("B200_GEMM_T64")[0] == '0');      // 128 x 64 tiles, two CTAs per SM (default); 0 = the 128 x 128 kernel
     set_smem(gemm_nt_tile_kernel<EPI_ASSEMBLE, false>, GEMM_SMEM);
     set_smem(gemm_nt_tile_kernel<EPI_SUB, false>, GEMM_SMEM);
@@ -501,27 +508,43 @@ void DenseBatchedKKT::cholesky(const int* active) {   // Eigen::LLT<Lower>::comp
     if (n == 0) return;
     const int nt = ceil_div(n, TILE);
     B200_LAUNCH(clear_fail_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, batch);
+    auto update = [&](int jb, int t0, int tiles, cudaStream_t st) {
+        // left-looking update of (part of) block column jb:  K(:, jb) -= L(:, 0:j0) L(jb, 0:j0)^T  on the two-CTA-per-SM DMMA tile kernel
+        // (contraction depth j0 = 128 .. n - 128); tiles t0 .. t0 + tiles - 1 of the column (two 64-column halves per 128-row tile)
+        GemmArgs g{};
+        g.A = K.get(); g.strideA = D->sP(); g.lda = D->ld;
+        g.B = g.A; g.strideB = g.strideA; g.ldb = g.lda;
+        g.C = K.get(); g.strideC = D->sP(); g.ldc = D->ld;
+        g.n = n; g.rows_valid = D->ld; g.K = jb * TILE; g.nt = nt; g.tj_fixed = -1; g.tj_start = jb; g.tiles = tiles; g.t0 = t0;
+        g.active = active; g.fail = fail.get();
+        B200_LAUNCH((gemm_nt_t64_kernel<EPI_SUB, false>), (unsigned)((size_t)tiles * batch), GEMM_THREADS, T64_SMEM, st, g);
+    };
     for (int jb = 0; jb < nt; jb++) {
         const int j0 = jb * TILE;
         const int rt = nt - jb - 1;
-        if (chol_split && jb > 0) {
-            // left-looking update of block column jb, diagonal tile included:  K(:, jb) -= L(:, 0:j0) L(jb, 0:j0)^T  on the two-CTA-per-SM
-            // DMMA tile kernel (contraction depth j0 = 128 .. n - 128)
-            GemmArgs g{};
-            g.A = K.get(); g.strideA = D->sP(); g.lda = D->ld;
-            g.B = g.A; g.strideB = g.strideA; g.ldb = g.lda;
-            g.C = K.get(); g.strideC = D->sP(); g.ldc = D->ld;
-            g.n = n; g.rows_valid = D->ld; g.K = j0; g.nt = nt; g.tj_fixed = -1; g.tj_start = jb; g.tiles = 2 * (nt - jb);
-            g.active = active; g.fail = fail.get();
-            B200_LAUNCH((gemm_nt_t64_kernel<EPI_SUB, false>), (unsigned)((size_t)g.tiles * batch), GEMM_THREADS, T64_SMEM, stream, g);
+        if (!chol_split) {
+            B200_LAUNCH(chol_diag_kernel, batch, CHOL_THREADS, CHOL_DIAG_SMEM, stream, K.get(), D->sP(), D->ld, n, j0, Linv.get(), Linv_stride, fail.get(), active);
+            if (rt > 0) B200_LAUNCH(chol_panel_kernel<true>, (unsigned)(rt * batch), CHOL_THREADS, CHOL_PANEL_SMEM, stream, K.get(), D->sP(), D->ld, n, jb, rt,
+                                    Linv.get(), Linv_stride, fail.get(), active);
+            continue;
         }
-        B200_LAUNCH(chol_diag_kernel, batch, CHOL_THREADS, CHOL_DIAG_SMEM, stream, K.get(), D->sP(), D->ld, n, j0, Linv.get(), Linv_stride, fail.get(), active);
-        if (rt > 0) {
-            if (chol_split) B200_LAUNCH(chol_panel_kernel<false>, (unsigned)(rt * batch), CHOL_THREADS, CHOL_PANEL_SMEM, stream, K.get(), D->sP(), D->ld, n, jb, rt,
-                                        Linv.get(), Linv_stride, fail.get(), active);
-            else B200_LAUNCH(chol_panel_kernel<true>, (unsigned)(rt * batch), CHOL_THREADS, CHOL_PANEL_SMEM, stream, K.get(), D->sP(), D->ld, n, jb, rt,
-                             Linv.get(), Linv_stride, fail.get(), active);
+        // The factorisation of the diagonal tile is a latency chain (one busy warp per instance, ~65 us): it runs on an auxiliary
+        // high-priority stream BESIDE the update of the tiles below it -- a diag CTA (144 KB, 128 registers) leaves room for one
+        // tile-kernel CTA on its SM -- and the panel solve joins both.
+        const bool fork = chol_aux && jb > 0 && rt > 0;
+        if (jb > 0) update(jb, 0, 2, stream);                         // the diagonal tile first
+        cudaStream_t ds = stream;
+        if (fork) {
+            B200_CUDA(cudaEventRecord(chol_ev[2 * jb], stream));
+            B200_CUDA(cudaStreamWaitEvent(chol_aux, chol_ev[2 * jb], 0));
+            ds = chol_aux;
         }
+        B200_LAUNCH(chol_diag_kernel, batch, CHOL_THREADS, CHOL_DIAG_SMEM, ds, K.get(), D->sP(), D->ld, n, j0, Linv.get(), Linv_stride, fail.get(), active);
+        if (fork) B200_CUDA(cudaEventRecord(chol_ev[2 * jb + 1], chol_aux));
+        if (jb > 0 && rt > 0) update(jb, 2, 2 * rt, stream);          // the tiles below, concurrently with the diag factorisation
+        if (fork) B200_CUDA(cudaStreamWaitEvent(stream, chol_ev[2 * jb + 1], 0));
+        if (rt > 0) B200_LAUNCH(chol_panel_kernel<false>, (unsigned)(rt * batch), CHOL_THREADS, CHOL_PANEL_SMEM, stream, K.get(), D->sP(), D->ld, n, jb, rt,
+                                Linv.get(), Linv_stride, fail.get(), active);
     }
 }
 

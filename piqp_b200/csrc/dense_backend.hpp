@@ -75,6 +75,9 @@ public:
     DevBuf<double> Linv;     // [batch][n/32 (padded to whole tiles)][32 x 36] inverses of the 32 x 32 diagonal blocks of L
     long long Linv_stride = 0;
     // Ozaki / tcgen05 assembly path (dense_ozaki.cuh)
+    cudaStream_t chol_aux = nullptr;           // diag-tile factorisations run here, beside the block-column update on `stream`
+    std::vector<cudaEvent_t> chol_ev;
+    ~DenseBatchedKKT() override { for (auto e : chol_ev) cudaEventDestroy(e); if (chol_aux) cudaStreamDestroy(chol_aux); }
     bool chol_split = true;  // Cholesky: block-column update on the two-CTA-per-SM tile kernel + solve-only panel kernel (B200_CHOL_SPLIT=0: fused panel kernel)
     bool gemm_t64 = true;    // assembly with gemm_nt_t64_kernel (two CTAs per SM) instead of gemm_nt_tile_kernel
     bool ozaki = false;

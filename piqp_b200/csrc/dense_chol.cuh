@@ -15,7 +15,7 @@
 constexpr int CB = 32;                 // inner block
 constexpr int LB_LD = CB + 4;          // leading dim of a 32 x 32 block in smem: Bs[k * LB_LD + n]
 constexpr int LB_SZ = CB * LB_LD;      // doubles per block
-constexpr size_t CHOL_DIAG_SMEM = TILE_SMEM + 4 * LB_SZ * sizeof(double);
+constexpr size_t CHOL_DIAG_SMEM = TILE_SMEM + 1 * LB_SZ * sizeof(double);      // 144 KB: one gemm_nt_t64 CTA (77 KB) still fits beside a diag CTA
 constexpr size_t CHOL_PANEL_SMEM = TILE_SMEM + 10 * LB_SZ * sizeof(double);
 constexpr int CHOL_THREADS = 256;
 
@@ -103,11 +103,11 @@ __device__ __noinline__ int warp_potf2_32(double* T, double* inv) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CHOL_THREADS, 1)
+__global__ void __launch_bounds__(CHOL_THREADS, 2)      // <= 128 registers: a gemm_nt_t64 CTA (122 registers x 256 threads, 77 KB) can share the SM with a diag CTA
 chol_diag_kernel(double* Kmat, long long strideK, int ld, int n, int j0, double* Linv, long long strideLinv, int* fail, const int* active) {
     extern __shared__ __align__(16) double smem[];
     double* Ts = smem;
-    double* inv = smem + TILE * TS_LD;          // 4 blocks
+    double* inv = smem + TILE * TS_LD;          // ONE 32 x 32 inverse block at a time (written to global memory as soon as the rows below have used it)
     __shared__ int s_fail;
     const int b = blockIdx.x;
     if (active && !active[b]) return;
@@ -123,7 +123,7 @@ chol_diag_kernel(double* Kmat, long long strideK, int ld, int n, int j0, double*
             if (r < nb && c < nb) v = (r >= c) ? K[(size_t)(j0 + c) * ld + j0 + r] : 0.0;
             Ts[c * TS_LD + r] = v;
         }
-    for (int i = tid; i < 4 * LB_SZ; i += CHOL_THREADS) inv[i] = 0.0;
+    double* ib = Linv + (size_t)b * strideLinv + (size_t)(j0 / CB) * LB_SZ;   // blocks j0/32 .. j0/32 + 3 (allocation is padded to whole tiles)
     __syncthreads();
     const int nblk = (nb + CB - 1) / CB;
     const int row0 = warp * 16;                 // this warp's 16-row strip
@@ -137,10 +137,11 @@ chol_diag_kernel(double* Kmat, long long strideK, int ld, int n, int j0, double*
             __syncwarp();
             cfrag_store(acc, Ts + (CB * s) * TS_LD + row0);
         }
+        for (int i = tid; i < LB_SZ; i += CHOL_THREADS) inv[i] = 0.0;      // the previous block's inverse went to global memory before the last barrier
         __syncthreads();
         // (2) pivot block + its inverse
         if (warp == 0) {
-            const int f = warp_potf2_32(Ts + (CB * s) * TS_LD + CB * s, inv + s * LB_SZ);
+            const int f = warp_potf2_32(Ts + (CB * s) * TS_LD + CB * s, inv);
             if (f && (tid == 0)) s_fail = j0 + CB * s + f;
         }
         __syncthreads();
@@ -149,17 +150,17 @@ chol_diag_kernel(double* Kmat, long long strideK, int ld, int n, int j0, double*
         if (row0 >= CB * (s + 1)) {
             double acc[2][4][2];
             cfrag_zero(acc);
-            warp_mma_16x32(acc, Ts + (CB * s) * TS_LD + row0, TS_LD, inv + s * LB_SZ, LB_LD, CB, false);
+            warp_mma_16x32(acc, Ts + (CB * s) * TS_LD + row0, TS_LD, inv, LB_LD, CB, false);
             __syncwarp();
             cfrag_store(acc, Ts + (CB * s) * TS_LD + row0);
         }
+        for (int i = tid; i < LB_SZ; i += CHOL_THREADS) ib[(size_t)s * LB_SZ + i] = inv[i];
         __syncthreads();
     }
     if (s_fail) { if (tid == 0) fail[b] = s_fail; return; }
+    for (int s = nblk; s < 4; s++) for (int i = tid; i < LB_SZ; i += CHOL_THREADS) ib[(size_t)s * LB_SZ + i] = 0.0;
     for (int c = warp; c < nb; c += CHOL_THREADS / 32)
         for (int r = c + (tid & 31); r < nb; r += 32) K[(size_t)(j0 + c) * ld + j0 + r] = Ts[c * TS_LD + r];
-    double* ib = Linv + (size_t)b * strideLinv + (size_t)(j0 / CB) * LB_SZ;   // blocks j0/32 .. j0/32 + 3 (allocation is padded to whole tiles)
-    for (int i = tid; i < 4 * LB_SZ; i += CHOL_THREADS) ib[i] = inv[i];
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -46,6 +46,7 @@ struct GemmArgs {
     int tj_start;
     int ncol;         // > 0: only columns < ncol of C are stored (narrow window updates); 0: all n
     int tiles;        // tiles per instance
+    int t0;           // gemm_nt_t64_kernel: index of the first tile of this launch within the enumeration (skip the diagonal tile: t0 = 2)
     // EPI_ASSEMBLE extras
     const double* Pf; long long strideP;     // full symmetric P, ld = ldc
     const double* AtA; long long strideAtA;  // nullable
@@ -268,7 +269,7 @@ template <int EPI, bool HAS_W>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_kernel(GemmArgs g) {
     extern __shared__ __align__(16) double smem[];
     const int b = blockIdx.x / g.tiles;
-    int t = blockIdx.x % g.tiles;
+    int t = blockIdx.x % g.tiles + g.t0;
     if (g.active && !g.active[b]) return;
     if (g.fail && g.fail[b]) return;
     int tj = g.tj_start;
