@@ -372,6 +372,8 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
     set_smem(chol_diag_kernel, CHOL_DIAG_SMEM);
     set_smem(chol_panel_kernel<true>, CHOL_PANEL_SMEM);
     set_smem(chol_panel_kernel<false>, CHOL_PANEL_SMEM);
+    set_smem(chol_solve64_kernel, CHOL_SOLVE64_SMEM);
+    chol_solve64 = !(getenv("B200_CHOL_SOLVE64") && getenv("B200_CHOL_SOLVE64")[0] == '0');
     Linv_stride = (long long)ceil_div(std::max(n, 1), TILE) * 4 * LB_SZ;
     Linv.alloc((size_t)batch * Linv_stride); Linv.zero(st);
     set_smem(trsv_kernel, (size_t)(n + 32) * sizeof(double) > 48 * 1024 ? (size_t)(n + 32) * sizeof(double) : 48 * 1024);
@@ -543,8 +545,10 @@ void DenseBatchedKKT::cholesky(const int* active) {   // Eigen::LLT<Lower>::comp
         if (fork) B200_CUDA(cudaEventRecord(chol_ev[2 * jb + 1], chol_aux));
         if (jb > 0 && rt > 0) update(jb, 2, 2 * rt, stream);          // the tiles below, concurrently with the diag factorisation
         if (fork) B200_CUDA(cudaStreamWaitEvent(stream, chol_ev[2 * jb + 1], 0));
-        if (rt > 0) B200_LAUNCH(chol_panel_kernel<false>, (unsigned)(rt * batch), CHOL_THREADS, CHOL_PANEL_SMEM, stream, K.get(), D->sP(), D->ld, n, jb, rt,
-                                Linv.get(), Linv_stride, fail.get(), active);
+        if (rt > 0 && chol_solve64) B200_LAUNCH(chol_solve64_kernel, (unsigned)(2 * rt * batch), CS_THREADS, CHOL_SOLVE64_SMEM, stream, K.get(), D->sP(), D->ld, n, jb, 2 * rt,
+                                                Linv.get(), Linv_stride, fail.get(), active);
+        else if (rt > 0) B200_LAUNCH(chol_panel_kernel<false>, (unsigned)(rt * batch), CHOL_THREADS, CHOL_PANEL_SMEM, stream, K.get(), D->sP(), D->ld, n, jb, rt,
+                                     Linv.get(), Linv_stride, fail.get(), active);
     }
 }
 

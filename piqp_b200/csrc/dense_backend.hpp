@@ -78,6 +78,7 @@ public:
     cudaStream_t chol_aux = nullptr;           // diag-tile factorisations run here, beside the block-column update on `stream`
     std::vector<cudaEvent_t> chol_ev;
     ~DenseBatchedKKT() override { for (auto e : chol_ev) cudaEventDestroy(e); if (chol_aux) cudaStreamDestroy(chol_aux); }
+    bool chol_solve64 = true;  // panel solve on 64-row half tiles with L11 read from global memory (three CTAs per SM)
     bool chol_split = true;  // Cholesky: block-column update on the two-CTA-per-SM tile kernel + solve-only panel kernel (B200_CHOL_SPLIT=0: fused panel kernel)
     bool gemm_t64 = true;    // assembly with gemm_nt_t64_kernel (two CTAs per SM) instead of gemm_nt_tile_kernel
     bool ozaki = false;

@@ -310,3 +310,86 @@ chol_panel_kernel(double* Kmat, long long strideK, int ld, int n, int jb, int ro
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Panel solve on 64-row half tiles (default): X L11^T = T for rows [rows0, rows0 + 64) of block column jb.  Only the T tile lives in
+// shared memory (68 KB): the off-diagonal 32 x 32 blocks of L11 and the inverted diagonal blocks are read as DMMA B operands straight
+// from global memory (they are shared by every CTA of the instance and L2-hot), so three CTAs fit one SM -- or one beside a
+// tile-kernel CTA -- instead of one CTA holding a whole SM behind a latency-bound substitution.  4 warps, one 16-row strip each.
+constexpr int CS_ROWS = 64;
+constexpr int CS_THREADS = 128;
+constexpr int CS_LD = CS_ROWS + 4;
+constexpr size_t CHOL_SOLVE64_SMEM = (size_t)TILE * CS_LD * sizeof(double);
+__device__ __forceinline__ void cfrag_load_ld(double (&acc)[2][4][2], const double* Ts, int ldt) {
+    const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) acc[i][j][e] = Ts[(j * 8 + tq * 2 + e) * ldt + i * 8 + gq];
+}
+__device__ __forceinline__ void cfrag_store_ld(const double (&acc)[2][4][2], double* Ts, int ldt) {
+    const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) Ts[(j * 8 + tq * 2 + e) * ldt + i * 8 + gq] = acc[i][j][e];
+}
+__global__ void __launch_bounds__(CS_THREADS, 3)
+chol_solve64_kernel(double* Kmat, long long strideK, int ld, int n, int jb, int half_tiles, const double* Linv, long long strideLinv, const int* fail, const int* active) {
+    extern __shared__ __align__(16) double smem[];
+    double* Ts = smem;                          // Ts[col * CS_LD + row], 128 columns x 64 rows
+    const int b = blockIdx.x / half_tiles, t = blockIdx.x % half_tiles;
+    if (active && !active[b]) return;
+    if (fail[b]) return;
+    double* K = Kmat + (size_t)b * strideK;
+    const int j0 = jb * TILE, rows0 = (jb + 1) * TILE + t * CS_ROWS;
+    if (rows0 >= n) return;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = (tid & 31) * 2, cg = tid >> 5;                 // two rows per thread, 4 column groups
+    {
+        const bool rok = rows0 + r + 1 < ld;
+        double2 a[TILE / 4];
+#pragma unroll
+        for (int it = 0; it < TILE / 4; it++) {
+            const int c = it * 4 + cg;
+            a[it] = make_double2(0.0, 0.0);
+            if (rok) a[it] = *reinterpret_cast<const double2*>(K + (size_t)(j0 + c) * ld + rows0 + r);
+        }
+#pragma unroll
+        for (int it = 0; it < TILE / 4; it++) { const int c = it * 4 + cg; *reinterpret_cast<double2*>(Ts + c * CS_LD + r) = a[it]; }
+    }
+    __syncthreads();
+    {
+        const int row0 = warp * 16;
+        const double* L11 = K + (size_t)j0 * ld + j0;                                   // L11(i, k) at L11[k * ld + i]
+        const double* inv = Linv + (size_t)b * strideLinv + (size_t)(j0 / CB) * LB_SZ;  // block s: inv[s * LB_SZ + k * LB_LD + nn] = Linv_ss(nn, k)
+        for (int s = 0; s < 4; s++) {
+            double c2[2][4][2];
+            if (s > 0) {
+                cfrag_load_ld(c2, Ts + (CB * s) * CS_LD + row0, CS_LD);
+                for (int k = 0; k < s; k++)      // B(kk, nn) = L11(32 s + nn, 32 k + kk)
+                    warp_mma_16x32(c2, Ts + (CB * k) * CS_LD + row0, CS_LD, L11 + (size_t)(CB * k) * ld + CB * s, ld, CB, true);
+                __syncwarp();
+                cfrag_store_ld(c2, Ts + (CB * s) * CS_LD + row0, CS_LD);
+                __syncwarp();
+            }
+            cfrag_zero(c2);
+            warp_mma_16x32(c2, Ts + (CB * s) * CS_LD + row0, CS_LD, inv + (size_t)s * LB_SZ, LB_LD, CB, false);
+            __syncwarp();
+            cfrag_store_ld(c2, Ts + (CB * s) * CS_LD + row0, CS_LD);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int it = 0; it < TILE / 4; it++) {
+        const int c = it * 4 + cg;
+        const double2 v = *reinterpret_cast<const double2*>(Ts + c * CS_LD + r);
+        double* dst = K + (size_t)(j0 + c) * ld + rows0 + r;
+        if (rows0 + r + 1 < n) *reinterpret_cast<double2*>(dst) = v;
+        else if (rows0 + r < n) dst[0] = v.x;
+    }
+}
