@@ -146,8 +146,11 @@ class DenseWorkload:
         return {k: v.cpu().pin_memory() for k, v in data.items()}
 
     def h2d_bytes(self, host):
-        keys = ["P", "c", "x_l", "x_u"] + (["A", "b"] if self.p else []) + (["G", "h_l", "h_u"] if self.m else [])
-        return sum(host[k].numel() * 8 for k in keys)
+        keys = ["c", "x_l", "x_u"] + (["A", "b"] if self.p else []) + (["G", "h_l", "h_u"] if self.m else [])
+        n, B = self.n, host["P"].shape[0]
+        # P: only the upper triangle crosses PCIe, as trapezoids of 128 rows (b200qp_setup_dense, capi.cu: load_problem)
+        p_elems = sum((n - r0) * min(128, n - r0) for r0 in range(0, n, 128)) if n >= 256 else n * n
+        return sum(host[k].numel() * 8 for k in keys) + B * p_elems * 8
 
     def cpu_solvers(self, n_qp, seed0, native):
         from oracle import pyoracle

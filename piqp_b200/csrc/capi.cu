@@ -405,7 +405,25 @@ void load_problem(b200qp_handle* h, bool first, const double* P, const double* c
     // from different host threads, and the H2D copies of one then overlap the kernels of the others
     {
         Staged s;
-        if (P && n > 0) { const double* src = s.get(P, (size_t)B * n * n, on_device, st); dense_pack_sym_upper(src, (long long)n * n, n, 1, h->dd, st); s.buf.release_on(st); }
+        if (P && n > 0) {
+            const double* src = nullptr;
+            if (!on_device && n >= 256) {
+                // Only the upper triangle of P is read (piqp_typedef.h:44, dense/data.hpp): upload it as trapezoids of 128 rows
+                // (columns r0 .. n-1 of rows r0 .. r0+127) -- 56 % of the bytes of the full matrices at n = 1024, and P is two thirds
+                // of what config 2 sends over PCIe.  The lower part of the staging buffer stays untouched and is never read.
+                s.buf.alloc((size_t)B * n * n);
+                for (int b2 = 0; b2 < B; b2++)
+                    for (int r0 = 0; r0 < n; r0 += 128) {
+                        const int rows = std::min(128, n - r0);
+                        const size_t off = (size_t)b2 * n * n + (size_t)r0 * n + r0;
+                        B200_CUDA(cudaMemcpy2DAsync(s.buf.get() + off, (size_t)n * sizeof(double), P + off, (size_t)n * sizeof(double), (size_t)(n - r0) * sizeof(double), rows,
+                                                    cudaMemcpyHostToDevice, st));
+                    }
+                src = s.buf.get();
+            } else src = s.get(P, (size_t)B * n * n, on_device, st);
+            dense_pack_sym_upper(src, (long long)n * n, n, 1, h->dd, st);
+            s.buf.release_on(st);
+        }
     }
     {
         Staged s;

@@ -781,6 +781,7 @@ BatchedIPSolver::BatchedIPSolver(int batch_, int n_, int p_, int m_, const b200q
     d.trace = nullptr; d.trace_rows = 0;
     if (st.verbose >= 2) { d.trace_rows = st.max_iter + 1; d.trace = alloc_d(B * d.trace_rows * 10); }
     B200_CUDA(cudaMallocHost(&h_flags_, sizeof(int) * std::max<size_t>(3 * B, 3)));
+    for (int k = 0; k < 2; k++) { B200_CUDA(cudaMallocHost(&h_flags2_[k], sizeof(int) * std::max<size_t>(3 * B, 3))); B200_CUDA(cudaEventCreateWithFlags(&flag_ev_[k], cudaEventDisableTiming)); }
     for (auto& e : ev_) B200_CUDA(cudaEventCreate(&e));
     // threads per instance CTA of the O(n+m) kernels: few large instances want more memory-level parallelism per CTA
     ipt_ = ((size_t)batch <= 296 && (size_t)n + m >= 1536) ? 512 : IPT;
@@ -789,6 +790,7 @@ BatchedIPSolver::BatchedIPSolver(int batch_, int n_, int p_, int m_, const b200q
 }
 BatchedIPSolver::~BatchedIPSolver() {
     if (h_flags_) cudaFreeHost(h_flags_);
+    for (int k = 0; k < 2; k++) { if (h_flags2_[k]) cudaFreeHost(h_flags2_[k]); if (flag_ev_[k]) cudaEventDestroy(flag_ev_[k]); }
     if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
     for (auto& e : ev_) cudaEventDestroy(e);
     for (auto& e : iter_ev_) cudaEventDestroy(e);
@@ -964,6 +966,43 @@ void BatchedIPSolver::solve() {
     while (active > 0) {
         const bool last = L + 1 >= st.max_iter;
         if (want_graph && !any_ir_ && !last && ensure_graph()) {
+            if (be_->factor_never_fails()) {
+                // The backend never reports a failed factorisation (multistage, like the reference's, multistage_kkt.hpp:218), so nothing
+                // the host reads back can change what the NEXT replay does for an active instance: replay L + 1 is enqueued before the
+                // flags of replay L are inspected (double-buffered read-back), and the GPU no longer idles for a host round trip per
+                // iteration.  A replay that follows the last iteration finds every instance inactive and does nothing.
+                int launched = 0, inspected = 0, stop = 0;
+                while (!stop) {
+                    while (launched - inspected < 2 && L + launched + 1 < st.max_iter) {
+                        B200_CUDA(cudaGraphLaunch(graph_exec_, stream));
+                        g_launches.fetch_add(graph_launches_, std::memory_order_relaxed);
+                        B200_CUDA(cudaMemcpyAsync(h_flags2_[launched & 1], d_.need_factor, sizeof(int) * 3 * batch, cudaMemcpyDeviceToHost, stream));
+                        B200_CUDA(cudaEventRecord(flag_ev_[launched & 1], stream));
+                        launched++;
+                    }
+                    if (launched == inspected) break;             // max_iter reached: the stepwise tail below finishes
+                    B200_CUDA(cudaEventSynchronize(flag_ev_[inspected & 1]));
+                    const int* f = h_flags2_[inspected & 1];
+                    int pending = 0; active = 0; bool ir = false;
+                    for (int i = 0; i < batch; i++) { pending += f[i] != 0; ir |= f[batch + i] != 0; active += f[2 * batch + i] != 0; }
+                    inspected++;
+                    if (active == 0 || pending > 0 || ir) stop = 1;
+                }
+                L += inspected;
+                if (launched > inspected) {                       // a speculative replay is in flight: let it drain, its flags are the current ones
+                    B200_CUDA(cudaEventSynchronize(flag_ev_[(launched - 1) & 1]));
+                    if (active > 0) {                             // stopped for another reason than convergence: the extra replay was a real iteration
+                        const int* f = h_flags2_[(launched - 1) & 1];
+                        active = 0; any_ir_ = false;
+                        for (int i = 0; i < batch; i++) { any_ir_ |= f[batch + i] != 0; active += f[2 * batch + i] != 0; }
+                        L += launched - inspected;
+                        active = factor_with_retry(true);
+                    }
+                }
+                else if (active > 0 && stop) active = factor_with_retry(true);      // (unreachable for a backend that never fails: pending rounds / refinement)
+                if (active == 0) break;
+                continue;                                         // max_iter - 1 replays done: the stepwise last iteration follows on the next pass
+            }
             B200_CUDA(cudaGraphLaunch(graph_exec_, stream));
             g_launches.fetch_add(graph_launches_, std::memory_order_relaxed);
             L++;

@@ -84,6 +84,8 @@ private:
     std::vector<DevBuf<int>> ipool_;
     DevBuf<IpScalars> sc_;
     int* h_flags_ = nullptr;   // pinned
+    int* h_flags2_[2] = {nullptr, nullptr};      // pinned, double-buffered read-back of pipelined graph replays
+    cudaEvent_t flag_ev_[2] = {nullptr, nullptr};
     b200qp_stats stats_{};
     cudaEvent_t ev_[6];
     int ipt_ = 256;

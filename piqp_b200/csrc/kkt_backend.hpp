@@ -33,6 +33,9 @@ struct BatchedKKT {
     // true if factor / solve / eval_* only enqueue work on `stream` (no host synchronisation, no other streams): the IP driver
     // may then capture a whole iteration into a CUDA graph
     virtual bool graph_capturable() const { return false; }
+    // true if factor() reports ok = 1 for every active instance, whatever the data (the IP driver may then enqueue the next iteration
+    // before it has read the flags of the current one)
+    virtual bool factor_never_fails() const { return false; }
     // algorithmic work per call and instance, for GFLOP/s and roofline reporting
     virtual double factor_flops() const = 0;
     virtual double factor_bytes() const = 0;

@@ -47,6 +47,7 @@ public:
     void extract_P_diag(double* P_diag) override;
     void print_info() const override;
     bool graph_capturable() const override;
+    bool factor_never_fails() const override { return true; }      // multistage_kkt.hpp:218: update_scalings_and_factor always returns true
     double factor_flops() const override { return S.factor_flops(); }
     double factor_bytes() const override { return S.factor_bytes(); }
     double solve_flops() const override { return S.solve_flops(); }
