@@ -15,7 +15,6 @@
 constexpr int CB = 32;                 // inner block
 constexpr int LB_LD = CB + 4;          // leading dim of a 32 x 32 block in smem: Bs[k * LB_LD + n]
 constexpr int LB_SZ = CB * LB_LD;      // doubles per block
-constexpr size_t CHOL_DIAG_SMEM = TILE_SMEM + 1 * LB_SZ * sizeof(double);      // 144 KB: one gemm_nt_t64 CTA (77 KB) still fits beside a diag CTA
 constexpr size_t CHOL_PANEL_SMEM = TILE_SMEM + 10 * LB_SZ * sizeof(double);
 constexpr int CHOL_THREADS = 256;
 
@@ -103,64 +102,123 @@ __device__ __noinline__ int warp_potf2_32(double* T, double* inv) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CHOL_THREADS, 2)      // <= 128 registers: a gemm_nt_t64 CTA (122 registers x 256 threads, 77 KB) can share the SM with a diag CTA
+// The 128 x 128 diagonal tile is held as its 10 lower 32 x 32 BLOCKS (block (bi, bk), bk <= bi, at index bi (bi + 1) / 2 + bk, element
+// (r, c) at [c * LB_LD + r]): 92 KB + one inverse block = 101 KB and <= 128 registers, so TWO diag CTAs share an SM and the 256
+// instances of BASELINE config 2 are one wave on 148 SMs instead of two (the kernel is a latency chain with one busy warp).
+constexpr size_t CHOL_DIAG_SMEM = (size_t)11 * LB_SZ * sizeof(double);
+__device__ __forceinline__ double* cd_blk(double* Tb, int bi, int bk) { return Tb + (size_t)(bi * (bi + 1) / 2 + bk) * LB_SZ; }
+__device__ __forceinline__ void cfrag_load_ld(double (&acc)[2][4][2], const double* Ts, int ldt);
+__device__ __forceinline__ void cfrag_store_ld(const double (&acc)[2][4][2], double* Ts, int ldt);
+// one warp: Cholesky of a 32 x 32 block stored with leading dimension LB_LD (wrapper around warp_potf2_32's TS_LD layout is avoided
+// by templating the leading dimension)
+template <int LDT>
+__device__ __noinline__ int warp_potf2_32_ld(double* T, double* inv) {
+    const int lane = threadIdx.x & 31;
+    double a[CB];
+#pragma unroll
+    for (int c = 0; c < CB; c++) a[c] = (c <= lane) ? T[c * LDT + lane] : 0.0;
+    int failed = 0;
+    double my_rinv = 1.0;
+#pragma unroll
+    for (int k = 0; k < CB; k++) {
+        double dk = __shfl_sync(0xffffffffu, a[k], k);
+        if (!(dk > 0.0)) { if (!failed) failed = k + 1; dk = 1.0; }
+        const double rinv = rsqrt(dk);
+        const double lkk = dk * rinv;
+        const double lrk = a[k] * rinv;
+        a[k] = (lane == k) ? lkk : lrk;
+        if (lane == k) my_rinv = rinv;
+#pragma unroll
+        for (int j = k + 1; j < CB; j++) {
+            const double ljk = __shfl_sync(0xffffffffu, lrk, j);
+            if (lane >= j) a[j] -= lrk * ljk;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CB; c++) if (c <= lane) T[c * LDT + lane] = a[c];
+    __syncwarp();
+    double x[CB];
+#pragma unroll
+    for (int i = 0; i < CB; i++) {
+        double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; k++) s -= T[k * LDT + i] * x[k];
+        x[i] = s * __shfl_sync(0xffffffffu, my_rinv, i);
+    }
+#pragma unroll
+    for (int i = 0; i < CB; i++) inv[lane * LB_LD + i] = x[i];
+    return failed;
+}
+__global__ void __launch_bounds__(CHOL_THREADS, 2)
 chol_diag_kernel(double* Kmat, long long strideK, int ld, int n, int j0, double* Linv, long long strideLinv, int* fail, const int* active) {
     extern __shared__ __align__(16) double smem[];
-    double* Ts = smem;
-    double* inv = smem + TILE * TS_LD;          // ONE 32 x 32 inverse block at a time (written to global memory as soon as the rows below have used it)
+    double* Tb = smem;                          // 10 lower blocks of the tile
+    double* inv = smem + 10 * LB_SZ;            // ONE 32 x 32 inverse block at a time (written to global memory as soon as the rows below have used it)
     __shared__ int s_fail;
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     if (fail[b]) return;
     double* K = Kmat + (size_t)b * strideK;
     const int nb = min(TILE, n - j0);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s_fail = 0;
     // lower triangle of the tile; identity on the padding so that partial tiles factor trivially there
-    for (int c = warp; c < TILE; c += CHOL_THREADS / 32)
-        for (int r = tid & 31; r < TILE; r += 32) {
-            double v = (r == c) ? 1.0 : 0.0;
-            if (r < nb && c < nb) v = (r >= c) ? K[(size_t)(j0 + c) * ld + j0 + r] : 0.0;
-            Ts[c * TS_LD + r] = v;
+    for (int blk = 0; blk < 10; blk++) {
+        int bi = 0; while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
+        const int bk = blk - bi * (bi + 1) / 2;
+        double* B = Tb + (size_t)blk * LB_SZ;
+        for (int c = warp; c < CB; c += CHOL_THREADS / 32) {
+            const int gr = bi * CB + lane, gc = bk * CB + c;
+            double v = (gr == gc) ? 1.0 : 0.0;
+            if (gr < nb && gc < nb) v = (gr >= gc) ? K[(size_t)(j0 + gc) * ld + j0 + gr] : 0.0;
+            B[c * LB_LD + lane] = v;
         }
+    }
     double* ib = Linv + (size_t)b * strideLinv + (size_t)(j0 / CB) * LB_SZ;   // blocks j0/32 .. j0/32 + 3 (allocation is padded to whole tiles)
     __syncthreads();
     const int nblk = (nb + CB - 1) / CB;
-    const int row0 = warp * 16;                 // this warp's 16-row strip
+    const int bi_w = warp >> 1, ro = (warp & 1) * 16;      // this warp's 16-row strip: block row bi_w, rows ro .. ro + 15 inside the block
     for (int s = 0; s < nblk; s++) {
         // (1) left-looking update of block column s with block columns < s, rows >= 32 s
-        if (s > 0 && row0 >= CB * s) {
+        if (s > 0 && bi_w >= s) {
             double acc[2][4][2];
-            cfrag_load(acc, Ts + (CB * s) * TS_LD + row0);
-            for (int k = 0; k < s; k++)
-                warp_mma_16x32(acc, Ts + (CB * k) * TS_LD + row0, TS_LD, Ts + (CB * k) * TS_LD + CB * s, TS_LD, CB, true);
+            cfrag_load_ld(acc, cd_blk(Tb, bi_w, s) + ro, LB_LD);
+            for (int k = 0; k < s; k++)      // A = T(strip, block column k); B(kk, nn) = T(32 s + nn, 32 k + kk) = block (s, k) [kk * LB_LD + nn]
+                warp_mma_16x32(acc, cd_blk(Tb, bi_w, k) + ro, LB_LD, cd_blk(Tb, s, k), LB_LD, CB, true);
             __syncwarp();
-            cfrag_store(acc, Ts + (CB * s) * TS_LD + row0);
+            cfrag_store_ld(acc, cd_blk(Tb, bi_w, s) + ro, LB_LD);
         }
         for (int i = tid; i < LB_SZ; i += CHOL_THREADS) inv[i] = 0.0;      // the previous block's inverse went to global memory before the last barrier
         __syncthreads();
         // (2) pivot block + its inverse
         if (warp == 0) {
-            const int f = warp_potf2_32(Ts + (CB * s) * TS_LD + CB * s, inv);
+            const int f = warp_potf2_32_ld<LB_LD>(cd_blk(Tb, s, s), inv);
             if (f && (tid == 0)) s_fail = j0 + CB * s + f;
         }
         __syncthreads();
         if (s_fail) break;
         // (3) rows below: X = T * L_ss^{-T}
-        if (row0 >= CB * (s + 1)) {
+        if (bi_w >= s + 1) {
             double acc[2][4][2];
             cfrag_zero(acc);
-            warp_mma_16x32(acc, Ts + (CB * s) * TS_LD + row0, TS_LD, inv, LB_LD, CB, false);
+            warp_mma_16x32(acc, cd_blk(Tb, bi_w, s) + ro, LB_LD, inv, LB_LD, CB, false);
             __syncwarp();
-            cfrag_store(acc, Ts + (CB * s) * TS_LD + row0);
+            cfrag_store_ld(acc, cd_blk(Tb, bi_w, s) + ro, LB_LD);
         }
         for (int i = tid; i < LB_SZ; i += CHOL_THREADS) ib[(size_t)s * LB_SZ + i] = inv[i];
         __syncthreads();
     }
     if (s_fail) { if (tid == 0) fail[b] = s_fail; return; }
     for (int s = nblk; s < 4; s++) for (int i = tid; i < LB_SZ; i += CHOL_THREADS) ib[(size_t)s * LB_SZ + i] = 0.0;
-    for (int c = warp; c < nb; c += CHOL_THREADS / 32)
-        for (int r = c + (tid & 31); r < nb; r += 32) K[(size_t)(j0 + c) * ld + j0 + r] = Ts[c * TS_LD + r];
+    for (int blk = 0; blk < 10; blk++) {
+        int bi = 0; while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
+        const int bk = blk - bi * (bi + 1) / 2;
+        const double* B = Tb + (size_t)blk * LB_SZ;
+        for (int c = warp; c < CB; c += CHOL_THREADS / 32) {
+            const int gr = bi * CB + lane, gc = bk * CB + c;
+            if (gr < nb && gc < nb && gr >= gc) K[(size_t)(j0 + gc) * ld + j0 + gr] = B[c * LB_LD + lane];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
