@@ -234,7 +234,7 @@ class MultistageWorkload:
             self._work = (f, 2.0 * n * 16)     # solve flops only used on the reference arm when no GPU ran: coarse
         return out
 
-    roofline_kernel = "msw_factor_chain_kernel (block-tridiagonal Cholesky chain, one warp per QP, fronts in registers)"
+    roofline_kernel = "partitioned block-tridiagonal Cholesky: msw_factor_chain_kernel on K runs per QP (one warp per run, fronts in registers) + msp_spike_kernel (DMMA) + reduced chain; one launch group = one factorisation of the batch"
 
 
 class SparseWorkload(MultistageWorkload):
@@ -300,7 +300,7 @@ class SparseWorkload(MultistageWorkload):
             self._work = (float(flops), 4.0 * nnzL + self.n + self.p + self.m)
         return out
 
-    roofline_kernel = "mf_factor_kernel (supernodal multifrontal sparse LDL^T, one CTA per QP, fronts in shared memory)"
+    roofline_kernel = "mf_factor_kernel (supernodal multifrontal sparse LDL^T, one CTA per QP, fronts in shared memory, left-looking blocked elimination of the fronts beyond it)"
 
 
 class SparseC3Workload(SparseWorkload):
@@ -685,7 +685,7 @@ def measure(args, wl, ctx):
         roofline = {"kernel": wl.roofline_kernel, "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": achieved / fp64_peak if fp64_peak else None,
                     "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json carries no fp64 figure; DMMA.8x8x4 probe: 37.1 TFLOP/s, profiles/dmma_probe_b200.txt)",
-                    "flops_per_launch": fl_launch, "ms_per_launch": ms_launch, "traffic": traffic,
+                    "flops_per_launch": fl_launch, "ms_per_launch": ms_launch, "traffic": traffic, "traffic_source": "profiles/traffic.json (one ncu --set full capture, not measured in this run)",
                     "cholesky_tflops": (agg["factor_calls"] * n ** 3 / 3.0) / (agg["cholesky_ms"] * 1e-3) * 1e-12 if agg["cholesky_ms"] else None,
                     "backend_solve_gbs": (agg["backend_solves"] * 8.0 * (n * n + 2 * n * m + 2 * n * p)) / (agg["backend_solve_ms"] * 1e-3) * 1e-9 if agg["backend_solve_ms"] else None,
                     "hbm_peak_gbs": hbm_peak}
@@ -729,7 +729,7 @@ def measure(args, wl, ctx):
         except Exception:
             pass
         roofline = {"kernel": wl.roofline_kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "peak_source": hbm_src, "bytes_per_launch": by_launch, "ms_per_launch": ms_launch, "traffic": traffic,
+                    "peak_source": hbm_src, "bytes_per_launch": by_launch, "ms_per_launch": ms_launch, "traffic": traffic, "traffic_source": "profiles/traffic.json (one ncu --set full capture, not measured in this run)",
                     "note": ("latency-bound chain of N dependent 16x16 block steps per QP; algorithmic bytes = blocks read + factor written and read once" if wl.name == "multistage"
                              else "one launch = one numeric factorisation of every QP of the batch; algorithmic bytes = 12 nnz(L) written + 12 nnz(KKT) read per QP (SURVEY 8d); latency-bound walk over the supernodes"),
                     "factor_gflops": (agg["factor_calls"] * ff) / (agg["cholesky_ms"] * 1e-3) * 1e-9 if agg["cholesky_ms"] else None,
