@@ -49,6 +49,10 @@ extern "C" {
 const char* b200_last_error(void);
 /* number of kernels launched by this library in this process so far (bench.py reports the delta) */
 unsigned long long b200_kernel_launch_count(void);
+/* debugging aid: with B200_TIMELINE=1 in the environment every kernel launch is followed by a one-thread kernel that stamps
+ * %globaltimer; this writes "index <TAB> kernel <TAB> ns" per stamp in execution order (graph replays included), starts a new
+ * timeline and returns the number of stamps written, 0 when the timeline is off, -1 on error                                  */
+int b200_timeline_dump(const char* path);
 int b200_device_count(void);
 
 /* ------------------------------------------------------------------------------------------------

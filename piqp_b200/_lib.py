@@ -62,7 +62,7 @@ class Stats(C.Structure):
 
 # every symbol include/piqp_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "b200_last_error", "b200_kernel_launch_count", "b200_device_count",
+    "b200_last_error", "b200_kernel_launch_count", "b200_timeline_dump", "b200_device_count",
     "b200kkt_dense_create", "b200kkt_sparse_create", "b200kkt_sparse_info", "b200_sparse_ldlt_symbolic", "b200_sparse_ldlt_symbolic_mode", "b200kkt_multistage_create", "b200kkt_update_data",
     "b200kkt_factor", "b200kkt_solve", "b200kkt_eval_P_x", "b200kkt_eval_A_xn_and_AT_xt", "b200kkt_eval_G_xn_and_GT_xt",
     "b200kkt_clone", "b200kkt_print_info", "b200kkt_destroy", "b200kkt_dense_get_kkt",

@@ -78,6 +78,7 @@ extern "C" {
 
 const char* b200_last_error(void) { return g_err.c_str(); }
 unsigned long long b200_kernel_launch_count(void) { return g_launches.load(); }
+int b200_timeline_dump(const char* path) { try { return b200::timeline_dump(path); } catch (...) { return -1; } }
 int b200_device_count(void) { int c = 0; if (cudaGetDeviceCount(&c) != cudaSuccess) return 0; return c; }
 
 int b200kkt_dense_create(b200kkt_handle** out, int n, int p, int m, const double* P_utri, const double* AT, const double* GT, int device) {

@@ -24,11 +24,19 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 #define B200_CUDA(x) ::b200::cuda_check((x), #x, __FILE__, __LINE__)
 
 extern std::atomic<unsigned long long> g_launches;  // counted at every kernel launch (b200_kernel_launch_count); handles may be driven from several host threads
+// Device timeline (debugging aid, B200_TIMELINE=1; off: one predictable branch per launch).  There is no nsys in the image and ncu
+// serialises launches, so the only way to see where a captured IP iteration spends its time is to stamp it on the device: after every
+// launch a one-thread kernel appends (%globaltimer, kernel name id) to a device buffer.  Stamps captured into a CUDA graph are replayed
+// with it.  b200_timeline_dump() writes the stamps in execution order and starts over.  stamp i - stamp i-1 = kernel i + its launch gap (+ ~1 us stamp).
+extern bool g_timeline_on;
+void timeline_stamp(const char* name, cudaStream_t stream);
+int timeline_dump(const char* path);
 #define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                         \
     do {                                                                            \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                 \
         ::b200::g_launches.fetch_add(1, std::memory_order_relaxed);                 \
         B200_CUDA(cudaPeekAtLastError());                                           \
+        if (::b200::g_timeline_on) ::b200::timeline_stamp(#kernel, (stream));       \
     } while (0)
 
 // NVTX ranges named after the reference's Tracy zones (include/piqp/utils/tracy.hpp:11-25, PIQP_TRACY_ZoneScopedN("piqp::...")): a
@@ -48,6 +56,22 @@ struct NvtxZone {
 // (~0.2 ms, once per handle), device-wide synchronisations hold it shared.
 inline std::shared_mutex& capture_mutex() { static std::shared_mutex m; return m; }
 inline cudaError_t device_synchronize_shared() { std::shared_lock<std::shared_mutex> lk(capture_mutex()); return cudaDeviceSynchronize(); }
+
+// Opt a kernel in to large dynamic shared memory.  cudaFuncAttributeMaxDynamicSharedMemorySize is per FUNCTION (and device), not per handle or
+// launch: handles of different shapes are set up and driven from different host threads (bench.py, tools/mm_suite.py), so a per-handle value
+// would race (one handle lowers the limit another is about to launch with: "invalid argument").  Every call therefore sets the same value,
+// the device's opt-in maximum minus the kernel's static shared memory; `needed` is only checked against it.
+template <class Kern>
+inline void allow_dynamic_smem(Kern kern, size_t needed) {
+    int dev = 0, optin = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cudaFuncAttributes a;
+    B200_CUDA(cudaFuncGetAttributes(&a, kern));
+    const size_t limit = (size_t)optin - a.sharedSizeBytes;
+    if (needed > limit) { char buf[160]; snprintf(buf, sizeof buf, "kernel needs %zu bytes of dynamic shared memory, the device allows %zu", needed, limit); throw CudaError(buf); }
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+}
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

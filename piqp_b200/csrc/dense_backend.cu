@@ -2,11 +2,54 @@
 #include "dense_backend.hpp"
 #include <string>
 #include <cstdlib>
+#include <algorithm>
+#include <mutex>
+#include <vector>
+#include <cstdio>
 #include "dense_kernels.cuh"
 
 namespace b200 {
 
 std::atomic<unsigned long long> g_launches{0};
+
+// ---- device timeline (common.cuh)
+bool g_timeline_on = getenv("B200_TIMELINE") != nullptr;
+namespace {
+constexpr unsigned long long TIMELINE_CAP = 1ull << 20;
+std::mutex tl_mutex;
+unsigned long long* tl_buf = nullptr;          // [0] = number of stamps so far; then (time, name id) pairs in execution order
+std::vector<const char*> tl_names;
+__global__ void timeline_stamp_kernel(unsigned long long* buf, unsigned long long id, unsigned long long cap) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long slot = atomicAdd(buf, 1ull);
+    if (slot < cap) { buf[2 + 2 * slot] = t; buf[3 + 2 * slot] = id; }
+}
+}  // namespace
+void timeline_stamp(const char* name, cudaStream_t stream) {      // the id travels as a kernel argument, so a stamp captured into a graph keeps its name at every replay
+    std::lock_guard<std::mutex> lk(tl_mutex);
+    if (!tl_buf) { B200_CUDA(cudaMalloc(&tl_buf, 16 * (TIMELINE_CAP + 1))); B200_CUDA(cudaMemset(tl_buf, 0, 16 * (TIMELINE_CAP + 1))); }
+    size_t id = 0;
+    while (id < tl_names.size() && tl_names[id] != name) id++;     // string literals of one B200_LAUNCH site share an address
+    if (id == tl_names.size()) tl_names.push_back(name);
+    timeline_stamp_kernel<<<1, 1, 0, stream>>>(tl_buf, id, TIMELINE_CAP);
+}
+int timeline_dump(const char* path) {
+    std::lock_guard<std::mutex> lk(tl_mutex);
+    if (!tl_buf) return 0;
+    B200_CUDA(device_synchronize_shared());
+    unsigned long long cnt = 0;
+    B200_CUDA(cudaMemcpy(&cnt, tl_buf, sizeof cnt, cudaMemcpyDeviceToHost));
+    cnt = std::min(cnt, TIMELINE_CAP);
+    std::vector<unsigned long long> h(2 * cnt);
+    if (cnt) B200_CUDA(cudaMemcpy(h.data(), tl_buf + 2, 16 * cnt, cudaMemcpyDeviceToHost));
+    FILE* f = fopen(path, "w");
+    if (!f) return -1;
+    for (unsigned long long i = 0; i < cnt; i++) fprintf(f, "%llu\t%s\t%llu\n", i, h[2 * i + 1] < tl_names.size() ? tl_names[h[2 * i + 1]] : "?", h[2 * i]);
+    fclose(f);
+    B200_CUDA(cudaMemset(tl_buf, 0, sizeof cnt));      // start over
+    return (int)cnt;
+}
 
 void BatchedKKT::tic(int kind) {
     if (!profile) return;
@@ -347,7 +390,7 @@ __global__ void extract_diag_kernel(const double* Pf, long long sP, int ld, int 
 
 template <class Kern>
 static void set_smem(Kern k, size_t bytes) {
-    B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    allow_dynamic_smem(k, (size_t)((int)bytes));
 }
 
 DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {

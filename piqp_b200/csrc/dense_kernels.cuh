@@ -66,6 +66,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
 }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_tile_kernel(GemmArgs 
 // ---------------------------------------------------------------------------------------------------
 constexpr int T64_N = 64;
 constexpr int LDS_B64 = T64_N + 4;
-constexpr size_t T64_STAGE_SMEM = (size_t)STAGES * KB * (LDS_T + LDS_B64) * sizeof(double);
+constexpr size_t T64_STAGE_SMEM = (size_t)STAGES * KB * (LDS_T + LDS_B64 + 1) * sizeof(double);     // + the stage's KB weights
 constexpr size_t T64_TILE_SMEM = (size_t)T64_N * TS_LD * sizeof(double);
 constexpr size_t T64_SMEM = T64_TILE_SMEM > T64_STAGE_SMEM ? T64_TILE_SMEM : T64_STAGE_SMEM;
 
@@ -284,6 +288,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_kernel(GemmArgs g
 
     double* As = smem;                                   // [STAGES][KB][LDS_T]
     double* Bs = smem + STAGES * KB * LDS_T;             // [STAGES][KB][LDS_B64]
+    double* Ws = Bs + STAGES * KB * LDS_B64;             // [STAGES][KB]: the weights of the stage ride the same cp.async groups (a global load per
+                                                         // k-block sat on the DMUL -> DMMA chain: ncu source view, 4 % of the stall samples in long scoreboard)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = warp >> 1, wn = warp & 1;
     const int gq = lane >> 2, tq = lane & 3;
@@ -298,15 +304,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_kernel(GemmArgs g
         if (s < nkb) {
             load_panel(As + s * KB * LDS_T, A, g.lda, rowA0, rows_valid, s * KB, K);
             if (!diag) load_panel64(Bs + s * KB * LDS_B64, B, g.ldb, rowB0, rows_valid, s * KB, K);
+            if (HAS_W && threadIdx.x < KB) { const int gk = s * KB + threadIdx.x; cp_async8(Ws + s * KB + threadIdx.x, gk < K ? w + gk : w, gk < K ? 8 : 0); }
         }
         cp_async_commit();
-    }
-    double wcur[KB / 4], wnext[KB / 4];
-#pragma unroll
-    for (int kk = 0; kk < KB / 4; kk++) { wcur[kk] = 1.0; wnext[kk] = 1.0; }
-    if (HAS_W) {
-#pragma unroll
-        for (int kk = 0; kk < KB / 4; kk++) { const int gk = kk * 4 + tq; wcur[kk] = gk < K ? w[gk] : 0.0; }
     }
     const int ldsb = diag ? LDS_T : LDS_B64;
     // warp tiles of a diagonal block that lie strictly above the diagonal are never stored: their warps skip the DMMAs (they
@@ -321,14 +321,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_kernel(GemmArgs g
                 const int s = nx % STAGES;
                 load_panel(As + s * KB * LDS_T, A, g.lda, rowA0, rows_valid, nx * KB, K);
                 if (!diag) load_panel64(Bs + s * KB * LDS_B64, B, g.ldb, rowB0, rows_valid, nx * KB, K);
+                if (HAS_W && threadIdx.x < KB) { const int gk = nx * KB + threadIdx.x; cp_async8(Ws + s * KB + threadIdx.x, gk < K ? w + gk : w, gk < K ? 8 : 0); }
             }
             cp_async_commit();
         }
+        const int s = kb % STAGES;
+        double wcur[KB / 4];
         if (HAS_W) {
 #pragma unroll
-            for (int kk = 0; kk < KB / 4; kk++) { const int gk = (kb + 1) * KB + kk * 4 + tq; wnext[kk] = gk < K ? w[gk] : 0.0; }
+            for (int kk = 0; kk < KB / 4; kk++) wcur[kk] = Ws[s * KB + kk * 4 + tq];
         }
-        const int s = kb % STAGES;
         const double* as = As + s * KB * LDS_T;
         const double* bs = diag ? (as + half * T64_N) : (Bs + s * KB * LDS_B64);
         if (!skip_mma) {
@@ -345,10 +347,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_kernel(GemmArgs g
 #pragma unroll
                 for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
-        }
-        if (HAS_W) {
-#pragma unroll
-            for (int kk = 0; kk < KB / 4; kk++) wcur[kk] = wnext[kk];
         }
     }
     cp_async_wait<0>();

@@ -104,10 +104,12 @@ __global__ void k_prepare_factor(IpDev d) {
     double v[2] = {0.0, 0.0};
     FOR_T(i, d.n) {
         double xv = rho;
-        if (q.hxl[i]) { ksbl[i] = it.s_bl[i]; kzbl[i] = 1.0 / it.z_bl[i]; xv += q.xbs[i] * q.xbs[i] / (kzbl[i] * ksbl[i] + delta); }
-        if (q.hxu[i]) { ksbu[i] = it.s_bu[i]; kzbu[i] = 1.0 / it.z_bu[i]; xv += q.xbs[i] * q.xbs[i] / (kzbu[i] * ksbu[i] + delta); }
+        const int fl = q.hxl[i], fu = q.hxu[i];
+        const double sl = it.s_bl[i], zl = it.z_bl[i], su = it.s_bu[i], zu = it.z_bu[i], xb = q.xbs[i], pdi = pdg[i];
+        if (fl) { const double kz = 1.0 / zl; ksbl[i] = sl; kzbl[i] = kz; xv += xb * xb / (kz * sl + delta); }
+        if (fu) { const double kz = 1.0 / zu; ksbu[i] = su; kzbu[i] = kz; xv += xb * xb / (kz * su + delta); }
         xr[i] = xv;
-        v[0] = fmax(v[0], fabs(pdg[i] + xv));
+        v[0] = fmax(v[0], fabs(pdi + xv));
     }
     FOR_T(i, d.m) {
         ksl[i] = it.s_l[i]; ksu[i] = it.s_u[i]; kzl[i] = 1.0 / it.z_l[i]; kzu[i] = 1.0 / it.z_u[i];
@@ -177,8 +179,10 @@ __global__ void k_solve_pre(IpDev d, Vars rhsv, const int* mask) {
     }
     FOR_T(i, d.n) {
         double v = rhs.x[i];
-        if (q.hxl[i]) v -= q.xbs[i] * (rhs.z_bl[i] - kzbl[i] * rhs.s_bl[i]) / (ksbl[i] * kzbl[i] + delta);
-        if (q.hxu[i]) v += q.xbs[i] * (rhs.z_bu[i] - kzbu[i] * rhs.s_bu[i]) / (ksbu[i] * kzbu[i] + delta);
+        const int fl = q.hxl[i], fu = q.hxu[i];
+        const double xb = q.xbs[i], rzl = rhs.z_bl[i], rsl = rhs.s_bl[i], kzl_ = kzbl[i], ksl_ = ksbl[i], rzu = rhs.z_bu[i], rsu = rhs.s_bu[i], kzu_ = kzbu[i], ksu_ = ksbu[i];
+        if (fl) v -= xb * (rzl - kzl_ * rsl) / (ksl_ * kzl_ + delta);
+        if (fu) v += xb * (rzu - kzu_ * rsu) / (ksu_ * kzu_ + delta);
         rxb[i] = v;
     }
     if (threadIdx.x == 0) { d.sc[b].n_solve++; d.sc[b].n_backend_solve++; }
@@ -218,13 +222,15 @@ __global__ void k_solve_post(IpDev d, Vars rhsv, Vars lhsv, const int* mask) {
         }
     }
     FOR_T(i, d.n) {
-        if (q.hxl[i]) {
-            const double z = (-q.xbs[i] * lhs.x[i] - rhs.z_bl[i] + kzbl[i] * rhs.s_bl[i]) / (ksbl[i] * kzbl[i] + delta);
-            lhs.z_bl[i] = z; lhs.s_bl[i] = kzbl[i] * (rhs.s_bl[i] - ksbl[i] * z);
+        const int fl = q.hxl[i], fu = q.hxu[i];
+        const double xb = q.xbs[i], lx = lhs.x[i], rzl = rhs.z_bl[i], rsl = rhs.s_bl[i], kzl_ = kzbl[i], ksl_ = ksbl[i], rzu = rhs.z_bu[i], rsu = rhs.s_bu[i], kzu_ = kzbu[i], ksu_ = ksbu[i];
+        if (fl) {
+            const double z = (-xb * lx - rzl + kzl_ * rsl) / (ksl_ * kzl_ + delta);
+            lhs.z_bl[i] = z; lhs.s_bl[i] = kzl_ * (rsl - ksl_ * z);
         }
-        if (q.hxu[i]) {
-            const double z = (q.xbs[i] * lhs.x[i] - rhs.z_bu[i] + kzbu[i] * rhs.s_bu[i]) / (ksbu[i] * kzbu[i] + delta);
-            lhs.z_bu[i] = z; lhs.s_bu[i] = kzbu[i] * (rhs.s_bu[i] - ksbu[i] * z);
+        if (fu) {
+            const double z = (xb * lx - rzu + kzu_ * rsu) / (ksu_ * kzu_ + delta);
+            lhs.z_bu[i] = z; lhs.s_bu[i] = kzu_ * (rsu - ksu_ * z);
         }
     }
 }
@@ -319,7 +325,12 @@ __global__ void k_copy_int(const int* src, int* dst, int n) {
 __device__ double calc_mu(const IpDev& d, const InstPtr& q, const VarsB& it, double n_fin) {   // solver.hpp:884-891
     double v[4] = {0, 0, 0, 0};
     FOR_T(i, d.m) { v[0] += it.s_l[i] * it.z_l[i]; v[1] += it.s_u[i] * it.z_u[i]; }
-    FOR_T(i, d.n) { if (q.hxl[i]) v[2] += it.s_bl[i] * it.z_bl[i]; if (q.hxu[i]) v[3] += it.s_bu[i] * it.z_bu[i]; }
+    FOR_T(i, d.n) {      // loads first, flags second: a load behind a data-dependent branch costs one L2 round trip per level (see the note at FOR_T)
+        const int fl = q.hxl[i], fu = q.hxu[i];
+        const double sl = it.s_bl[i], zl = it.z_bl[i], su = it.s_bu[i], zu = it.z_bu[i];
+        if (fl) v[2] += sl * zl;
+        if (fu) v[3] += su * zu;
+    }
     const int op[4] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM};
     block_reduce<4>(v, op, g_red);
     return (v[0] + v[1] + v[2] + v[3]) / n_fin;
@@ -328,14 +339,19 @@ __device__ double calc_mu(const IpDev& d, const InstPtr& q, const VarsB& it, dou
 __device__ void calc_step(const IpDev& d, const InstPtr& q, const VarsB& it, const VarsB& st, double& as, double& az) {   // solver.hpp:893-958
     double v[2] = {1.0, 1.0};
     FOR_T(i, d.m) {
-        if (st.s_l[i] < 0) v[0] = fmin(v[0], -it.s_l[i] / st.s_l[i]);
-        if (st.s_u[i] < 0) v[0] = fmin(v[0], -it.s_u[i] / st.s_u[i]);
-        if (st.z_l[i] < 0) v[1] = fmin(v[1], -it.z_l[i] / st.z_l[i]);
-        if (st.z_u[i] < 0) v[1] = fmin(v[1], -it.z_u[i] / st.z_u[i]);
+        const double dsl = st.s_l[i], dsu = st.s_u[i], dzl = st.z_l[i], dzu = st.z_u[i];
+        const double sl = it.s_l[i], su = it.s_u[i], zl = it.z_l[i], zu = it.z_u[i];
+        if (dsl < 0) v[0] = fmin(v[0], -sl / dsl);
+        if (dsu < 0) v[0] = fmin(v[0], -su / dsu);
+        if (dzl < 0) v[1] = fmin(v[1], -zl / dzl);
+        if (dzu < 0) v[1] = fmin(v[1], -zu / dzu);
     }
     FOR_T(i, d.n) {
-        if (q.hxl[i]) { if (st.s_bl[i] < 0) v[0] = fmin(v[0], -it.s_bl[i] / st.s_bl[i]); if (st.z_bl[i] < 0) v[1] = fmin(v[1], -it.z_bl[i] / st.z_bl[i]); }
-        if (q.hxu[i]) { if (st.s_bu[i] < 0) v[0] = fmin(v[0], -it.s_bu[i] / st.s_bu[i]); if (st.z_bu[i] < 0) v[1] = fmin(v[1], -it.z_bu[i] / st.z_bu[i]); }
+        const int fl = q.hxl[i], fu = q.hxu[i];
+        const double dsl = st.s_bl[i], dsu = st.s_bu[i], dzl = st.z_bl[i], dzu = st.z_bu[i];
+        const double sl = it.s_bl[i], su = it.s_bu[i], zl = it.z_bl[i], zu = it.z_bu[i];
+        if (fl) { if (dsl < 0) v[0] = fmin(v[0], -sl / dsl); if (dzl < 0) v[1] = fmin(v[1], -zl / dzl); }
+        if (fu) { if (dsu < 0) v[0] = fmin(v[0], -su / dsu); if (dzu < 0) v[1] = fmin(v[1], -zu / dzu); }
     }
     const int op[2] = {RED_MIN, RED_MIN};
     block_reduce<2>(v, op, g_red);
@@ -365,10 +381,13 @@ __device__ ResR residuals_r(const IpDev& d, int b, const InstPtr& q, double rho,
         v[2] = fmax(v[2], fmax(fabs(US_DUAL_INEQ(px.z_l[i] - it.z_l[i], i)), fabs(US_DUAL_INEQ(px.z_u[i] - it.z_u[i], i))));
     }
     FOR_T(i, d.n) {   // signed (no abs) for the box terms, as in the reference
-        if (q.hxl[i]) { const double rb = rnr.z_bl[i] - delta * (px.z_bl[i] - it.z_bl[i]); r.z_bl[i] = rb;
-            v[0] = fmax(v[0], US_PRES_B(rb, i)); v[2] = fmax(v[2], US_DUAL_B(px.z_bl[i] - it.z_bl[i], i)); }
-        if (q.hxu[i]) { const double rb = rnr.z_bu[i] - delta * (px.z_bu[i] - it.z_bu[i]); r.z_bu[i] = rb;
-            v[0] = fmax(v[0], US_PRES_B(rb, i)); v[2] = fmax(v[2], US_DUAL_B(px.z_bu[i] - it.z_bu[i], i)); }
+        const int fl = q.hxl[i], fu = q.hxu[i];
+        const double nl = rnr.z_bl[i], pl = px.z_bl[i], zl = it.z_bl[i], nu = rnr.z_bu[i], pu = px.z_bu[i], zu = it.z_bu[i];
+        const double pbi = q.pdb_inv[i], pb = q.pdb[i];
+        if (fl) { const double rb = nl - delta * (pl - zl); r.z_bl[i] = rb;
+            v[0] = fmax(v[0], rb * pbi); v[2] = fmax(v[2], (pl - zl) * q.pc_inv * pb); }
+        if (fu) { const double rb = nu - delta * (pu - zu); r.z_bu[i] = rb;
+            v[0] = fmax(v[0], rb * pbi); v[2] = fmax(v[2], (pu - zu) * q.pc_inv * pb); }
     }
     const int op[4] = {RED_MAX, RED_MAX, RED_MAX, RED_MAX};
     block_reduce<4>(v, op, g_red);
@@ -467,7 +486,12 @@ __global__ void k_head(IpDev d) {
         if (q.hhl[i] && it.z_l[i] < eps) { it.z_l[i] += eps; v[0] = 1.0; }
         if (q.hhu[i] && it.z_u[i] < eps) { it.z_u[i] += eps; v[0] = 1.0; }
     }
-    FOR_T(i, d.n) { if (q.hxl[i]) v[1] = fmin(v[1], it.z_bl[i]); if (q.hxu[i]) v[2] = fmin(v[2], it.z_bu[i]); }
+    FOR_T(i, d.n) {
+        const int fl = q.hxl[i], fu = q.hxu[i];
+        const double zl = it.z_bl[i], zu = it.z_bu[i];
+        if (fl) v[1] = fmin(v[1], zl);
+        if (fu) v[2] = fmin(v[2], zu);
+    }
     const int op[3] = {RED_MAX, RED_MIN, RED_MIN};
     block_reduce<3>(v, op, g_red);
     bool shifted = v[0] > 0.0;
@@ -503,7 +527,12 @@ __global__ void k_predictor(IpDev d) {
     }
     if (s.has_ineq) {
         FOR_T(i, d.m) { r.s_l[i] = -it.s_l[i] * it.z_l[i]; r.s_u[i] = -it.s_u[i] * it.z_u[i]; }
-        FOR_T(i, d.n) { if (q.hxl[i]) r.s_bl[i] = -it.s_bl[i] * it.z_bl[i]; if (q.hxu[i]) r.s_bu[i] = -it.s_bu[i] * it.z_bu[i]; }
+        FOR_T(i, d.n) {
+            const int fl = q.hxl[i], fu = q.hxu[i];
+            const double sl = it.s_bl[i], zl = it.z_bl[i], su = it.s_bu[i], zu = it.z_bu[i];
+            if (fl) r.s_bl[i] = -sl * zl;
+            if (fu) r.s_bu[i] = -su * zu;
+        }
     }
 }
 
@@ -531,8 +560,10 @@ __global__ void k_corrector(IpDev d) {
         v[1] += (it.s_u[i] + as * sp.s_u[i]) * (it.z_u[i] + az * sp.z_u[i]);
     }
     FOR_T(i, d.n) {
-        if (q.hxl[i]) v[2] += (it.s_bl[i] + as * sp.s_bl[i]) * (it.z_bl[i] + az * sp.z_bl[i]);
-        if (q.hxu[i]) v[3] += (it.s_bu[i] + as * sp.s_bu[i]) * (it.z_bu[i] + az * sp.z_bu[i]);
+        const int fl = q.hxl[i], fu = q.hxu[i];
+        const double sl = it.s_bl[i], dsl = sp.s_bl[i], zl = it.z_bl[i], dzl = sp.z_bl[i], su = it.s_bu[i], dsu = sp.s_bu[i], zu = it.z_bu[i], dzu = sp.z_bu[i];
+        if (fl) v[2] += (sl + as * dsl) * (zl + az * dzl);
+        if (fu) v[3] += (su + as * dsu) * (zu + az * dzu);
     }
     const int op[4] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM};
     block_reduce<4>(v, op, g_red);
@@ -542,7 +573,12 @@ __global__ void k_corrector(IpDev d) {
     const double sigma = sgm * sgm * sgm;
     const double sm = sigma * mu;
     FOR_T(i, d.m) { r.s_l[i] += -sp.s_l[i] * sp.z_l[i] + sm; r.s_u[i] += -sp.s_u[i] * sp.z_u[i] + sm; }
-    FOR_T(i, d.n) { if (q.hxl[i]) r.s_bl[i] += -sp.s_bl[i] * sp.z_bl[i] + sm; if (q.hxu[i]) r.s_bu[i] += -sp.s_bu[i] * sp.z_bu[i] + sm; }
+    FOR_T(i, d.n) {
+        const int fl = q.hxl[i], fu = q.hxu[i];
+        const double rl = r.s_bl[i], dsl = sp.s_bl[i], dzl = sp.z_bl[i], ru = r.s_bu[i], dsu = sp.s_bu[i], dzu = sp.z_bu[i];
+        if (fl) r.s_bl[i] = rl + (-dsl * dzl + sm);
+        if (fu) r.s_bu[i] = ru + (-dsu * dzu + sm);
+    }
     if (threadIdx.x == 0) { sg.sigma = sigma; d.act2[b] = 1; }
 }
 
@@ -558,9 +594,11 @@ __global__ void k_update(IpDev d) {
     calc_step(d, q, it, sp, as, az);
     const double ps = as * d.st.tau, dsz = az * d.st.tau;
     FOR_T(i, d.n) {
+        const int fl = q.hxl[i], fu = q.hxu[i];
+        const double zl = it.z_bl[i], dzl = sp.z_bl[i], sl = it.s_bl[i], dsl = sp.s_bl[i], zu = it.z_bu[i], dzu = sp.z_bu[i], su = it.s_bu[i], dsu = sp.s_bu[i];
         it.x[i] += ps * sp.x[i];
-        if (q.hxl[i]) { it.z_bl[i] += dsz * sp.z_bl[i]; it.s_bl[i] += ps * sp.s_bl[i]; }
-        if (q.hxu[i]) { it.z_bu[i] += dsz * sp.z_bu[i]; it.s_bu[i] += ps * sp.s_bu[i]; }
+        if (fl) { it.z_bl[i] = zl + dsz * dzl; it.s_bl[i] = sl + ps * dsl; }
+        if (fu) { it.z_bu[i] = zu + dsz * dzu; it.s_bu[i] = su + ps * dsu; }
     }
     FOR_T(i, d.p) it.y[i] += dsz * sp.y[i];
     FOR_T(i, d.m) {
@@ -592,31 +630,36 @@ __global__ void k_resid_nr(IpDev d, const int* mask, int first) {
     // 11: non-finite flag (fmax drops NaNs, so a NaN iterate would otherwise report residuals of 0)
     double v[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     FOR_T(i, d.n) {
-        double wxi = wx[i] + wx2[i];
-        const double mPx = rnr.x[i];
-        v[7] = fmax(v[7], fabs(US_DRES(mPx, i)));
-        v[0] += it.x[i] * mPx;            // tmp = -x.(-Px) handled below
-        v[1] += q.c[i] * it.x[i];
-        double rx = mPx - q.c[i];
-        v[7] = fmax(v[7], fabs(US_DRES(q.c[i], i)));
-        if (q.hxl[i]) { wxi -= q.xbs[i] * it.z_bl[i]; v[5] += q.x_l[i] * it.z_bl[i]; }
-        if (q.hxu[i]) { wxi += q.xbs[i] * it.z_bu[i]; v[6] += q.x_u[i] * it.z_bu[i]; }
-        v[7] = fmax(v[7], fabs(US_DRES(wxi, i)));
+        // every load of the iteration up front (the values behind the flags are only USED under them): a load issued inside a
+        // data-dependent branch waits for the flag's own round trip first, and this kernel is nothing but such round trips
+        const int fl = q.hxl[i], fu = q.hxu[i];
+        const double wa = wx[i], wb = wx2[i], mPx = rnr.x[i], xi = it.x[i], ci = q.c[i], xb = q.xbs[i];
+        const double zbl = it.z_bl[i], zbu = it.z_bu[i], sbl = it.s_bl[i], sbu = it.s_bu[i], xl = q.x_l[i], xu = q.x_u[i];
+        const double pdi = q.pd_inv[i], pbi = q.pdb_inv[i];      // US_DRES(v, i) = (v * pc_inv) * pd_inv[i], in this order
+        double wxi = wa + wb;
+        v[7] = fmax(v[7], fabs(mPx * q.pc_inv * pdi));
+        v[0] += xi * mPx;            // tmp = -x.(-Px) handled below
+        v[1] += ci * xi;
+        double rx = mPx - ci;
+        v[7] = fmax(v[7], fabs(ci * q.pc_inv * pdi));
+        if (fl) { wxi -= xb * zbl; v[5] += xl * zbl; }
+        if (fu) { wxi += xb * zbu; v[6] += xu * zbu; }
+        v[7] = fmax(v[7], fabs(wxi * q.pc_inv * pdi));
         rx -= wxi;
         rnr.x[i] = rx;
-        v[10] = fmax(v[10], fabs(US_DRES(rx, i)));
+        v[10] = fmax(v[10], fabs(rx * q.pc_inv * pdi));
         if (!isfinite(rx)) v[11] = 1.0;
         // box primal residuals (signed maxima, solver.hpp:1077-1095, 1137-1144)
-        if (q.hxl[i]) {
-            const double t = q.xbs[i] * it.x[i];
-            v[8] = fmax(v[8], US_PRES_B(t, i)); v[8] = fmax(v[8], US_PRES_B(q.x_l[i], i)); v[8] = fmax(v[8], US_PRES_B(it.s_bl[i], i));
-            const double rb = t + (-q.x_l[i] - it.s_bl[i]);
+        if (fl) {
+            const double t = xb * xi;
+            v[8] = fmax(v[8], t * pbi); v[8] = fmax(v[8], xl * pbi); v[8] = fmax(v[8], sbl * pbi);
+            const double rb = t + (-xl - sbl);
             rnr.z_bl[i] = rb;
         }
-        if (q.hxu[i]) {
-            const double t = -q.xbs[i] * it.x[i];
-            v[8] = fmax(v[8], US_PRES_B(t, i)); v[8] = fmax(v[8], US_PRES_B(q.x_u[i], i)); v[8] = fmax(v[8], US_PRES_B(it.s_bu[i], i));
-            const double rb = t + (q.x_u[i] - it.s_bu[i]);
+        if (fu) {
+            const double t = -xb * xi;
+            v[8] = fmax(v[8], t * pbi); v[8] = fmax(v[8], xu * pbi); v[8] = fmax(v[8], sbu * pbi);
+            const double rb = t + (xu - sbu);
             rnr.z_bu[i] = rb;
         }
     }
@@ -716,7 +759,7 @@ __global__ void k_reg_update(IpDev d) {
         FOR_T(i, d.p) px.y[i] = it.y[i];
         if (s.has_ineq) {
             FOR_T(i, d.m) { px.z_l[i] = it.z_l[i]; px.z_u[i] = it.z_u[i]; }
-            FOR_T(i, d.n) { if (q.hxl[i]) px.z_bl[i] = it.z_bl[i]; if (q.hxu[i]) px.z_bu[i] = it.z_bu[i]; }
+            FOR_T(i, d.n) { const int fl = q.hxl[i], fu = q.hxu[i]; const double zl = it.z_bl[i], zu = it.z_bu[i]; if (fl) px.z_bl[i] = zl; if (fu) px.z_bu[i] = zu; }
         }
     }
     if (threadIdx.x == 0) sg = s;

@@ -438,13 +438,13 @@ MultistageBatchedKKT::MultistageBatchedKKT(SparseData* data, cudaStream_t st) : 
     if (warp_chain) {
         packets.alloc((size_t)batch * pk_stride);
         packets.zero(st);
-        B200_CUDA(cudaFuncSetAttribute(msw_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(chain_solve_smem, 48 * 1024)));
+        allow_dynamic_smem(msw_solve_kernel, (size_t)((int)std::max<size_t>(chain_solve_smem, 48 * 1024)));
         const int csm = (int)(sizeof(MswChainSmem) + sizeof(int) * MS_META * std::max(S.N, MSP_META_MAX));      // segment mode stages MSP_META_MAX entries per array
-        B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
-        B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
-        B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
-        B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
-        B200_CUDA(cudaFuncSetAttribute(msw_factor_chain_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, csm));
+        allow_dynamic_smem(msw_factor_chain_kernel<4>, (size_t)(csm));
+        allow_dynamic_smem(msw_factor_chain_kernel<8>, (size_t)(csm));
+        allow_dynamic_smem(msw_factor_chain_kernel<12>, (size_t)(csm));
+        allow_dynamic_smem(msw_factor_chain_kernel<14>, (size_t)(csm));
+        allow_dynamic_smem(msw_factor_chain_kernel<16>, (size_t)(csm));
     }
     upload(d_P_slot, S.P_slot);
     std::vector<int> diag_var(S.total, -1);
@@ -461,8 +461,8 @@ MultistageBatchedKKT::MultistageBatchedKKT(SparseData* data, cudaStream_t st) : 
     factor_smem = sizeof(double) * ((size_t)2 * dm * dm + 2 * (size_t)om * dm + 2 * (size_t)w * dm + (size_t)w * w + (size_t)std::max(om, w) * dm + std::max(dm, w) + 8);
     solve_smem = sizeof(double) * ((size_t)n + std::max(dm, w) + 8);
     if (factor_smem > 227 * 1024 || solve_smem > 227 * 1024) throw std::runtime_error("multistage: blocks too large for shared memory");
-    B200_CUDA(cudaFuncSetAttribute(ms_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(factor_smem, 48 * 1024)));
-    B200_CUDA(cudaFuncSetAttribute(ms_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(solve_smem, 48 * 1024)));
+    allow_dynamic_smem(ms_factor_kernel, (size_t)((int)std::max<size_t>(factor_smem, 48 * 1024)));
+    allow_dynamic_smem(ms_solve_kernel, (size_t)((int)std::max<size_t>(solve_smem, 48 * 1024)));
     load_P();
     compute_AtA();
 }
@@ -642,9 +642,9 @@ void MultistageBatchedKKT::build_partition(const std::vector<int>& cls, cudaStre
     for (int r = 0; r < K; r++) if (part_bounds[2 * r + 1] - part_bounds[2 * r] + 2 > MSP_META_MAX) { part_K = 1; return; }      // run-local meta copies
     part_rsolve_smem = sizeof(double) * ((size_t)((part_rn + 1) & ~1) + 96 + (size_t)(((MS_META * NR + 1) / 2 + 1) / 2 * 2) + (size_t)MSW_R * part_rslot);
     if (part_seg_smem > 227 * 1024 || part_spike_smem > 227 * 1024 || part_rsolve_smem > 227 * 1024) { part_K = 1; return; }
-    B200_CUDA(cudaFuncSetAttribute(msp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(part_seg_smem, 48 * 1024)));
-    B200_CUDA(cudaFuncSetAttribute(msp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(part_seg_smem, 48 * 1024)));
-    B200_CUDA(cudaFuncSetAttribute(msp_spike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(part_spike_smem, 48 * 1024)));
+    allow_dynamic_smem(msp_fwd_kernel, (size_t)((int)std::max<size_t>(part_seg_smem, 48 * 1024)));
+    allow_dynamic_smem(msp_bwd_kernel, (size_t)((int)std::max<size_t>(part_seg_smem, 48 * 1024)));
+    allow_dynamic_smem(msp_spike_kernel, (size_t)((int)std::max<size_t>(part_spike_smem, 48 * 1024)));
 }
 
 static MsDev make_rdev(const int* meta, int NR, int rn, int rtotal) {

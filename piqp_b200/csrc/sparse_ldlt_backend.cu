@@ -873,9 +873,9 @@ void SparseLdltBatchedKKT::build_wide() {
     Tcm.alloc(std::max<size_t>((size_t)batch * (size_t)tinv_stride, 1)); Trm.alloc(std::max<size_t>((size_t)batch * (size_t)tinv_stride, 1));
     B200_CUDA(cudaMemset(wcounter.get(), 0, sizeof(unsigned) * batch));
     const size_t sbs = (size_t)wide_sb;
-    B200_CUDA(cudaFuncSetAttribute(mfw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(small_smem_max, 48 * 1024)));
-    B200_CUDA(cudaFuncSetAttribute(mfw_block_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sizeof(double) * sbs * (sbs + 1), 48 * 1024)));
-    B200_CUDA(cudaFuncSetAttribute(mfw_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MW_PANEL_SMEM));
+    allow_dynamic_smem(mfw_small_kernel, (size_t)((int)std::max<size_t>(small_smem_max, 48 * 1024)));
+    allow_dynamic_smem(mfw_block_inverse_kernel, (size_t)((int)std::max<size_t>(sizeof(double) * sbs * (sbs + 1), 48 * 1024)));
+    allow_dynamic_smem(mfw_panel_kernel, (size_t)((int)MW_PANEL_SMEM));
     if (getenv("B200_DEBUG_SYMBOLIC"))
         fprintf(stderr, "[sparse_ldlt wide] levels=%d factor steps=%zu (HBM fronts %zu) solve steps=%zu upd_total=%lld front_stride=%lld\n", maxl + 1, wf_steps.size(),
                 wfronts.size(), ws_steps.size(), upd_total_w, front_stride);
@@ -1088,8 +1088,8 @@ SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_per
         solve_x_in_smem = (size_t)S.nk * sizeof(double) <= smem_cap;
         solve_smem = solve_x_in_smem ? (size_t)S.nk * sizeof(double) : 0;
         if (!wide) {
-            B200_CUDA(cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(factor_smem, 48 * 1024)));
-            B200_CUDA(cudaFuncSetAttribute(mf_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(solve_smem, 48 * 1024)));
+            allow_dynamic_smem(mf_factor_kernel, (size_t)((int)std::max<size_t>(factor_smem, 48 * 1024)));
+            allow_dynamic_smem(mf_solve_kernel, (size_t)((int)std::max<size_t>(solve_smem, 48 * 1024)));
         }
         // streamed solve (mf_solve_ring_kernel): x + a double-buffered panel + row indices in shared memory
         ring_solve = false;
@@ -1119,7 +1119,7 @@ SparseLdltBatchedKKT::SparseLdltBatchedKKT(SparseData* data, const int* user_per
                 ring_nblk = (int)sh.size() / 8; ring_pb = (int)pb; ring_rb = (int)rb;
                 upload(d_shdr, sh);
                 ring_smem = xbytes + 2 * pb * sizeof(double) + 2 * rb * sizeof(int);
-                B200_CUDA(cudaFuncSetAttribute(mf_solve_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ring_smem, 48 * 1024)));
+                allow_dynamic_smem(mf_solve_ring_kernel, (size_t)((int)std::max<size_t>(ring_smem, 48 * 1024)));
                 ring_solve = true;
             }
         }
