@@ -645,6 +645,22 @@ void MultistageBatchedKKT::build_partition(const std::vector<int>& cls, cudaStre
     allow_dynamic_smem(msp_fwd_kernel, (size_t)((int)std::max<size_t>(part_seg_smem, 48 * 1024)));
     allow_dynamic_smem(msp_bwd_kernel, (size_t)((int)std::max<size_t>(part_seg_smem, 48 * 1024)));
     allow_dynamic_smem(msp_spike_kernel, (size_t)((int)std::max<size_t>(part_spike_smem, 48 * 1024)));
+    // fused solve (one CTA per QP, 2K warps): worth it while the QPs of the batch are resident together
+    part_fused_smem = 0;
+    {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        part_fused_slot = part_spike_slot;              // chain part of the packets: inv(L) | (B L^-T), the same mode as the spike kernel's
+        size_t run_d = (size_t)part_seg_len + 96 + 96 + (size_t)MSF_PF * part_fused_slot + (MS_META * MSP_META_MAX + 2 + 1) / 2;
+        run_d = (run_d + 1) & ~(size_t)1;
+        const size_t total = sizeof(double) * (K * run_d) + part_rsolve_smem;
+        const char* e = getenv("B200_MS_FUSED_SOLVE");
+        const bool want = e ? e[0] == '1' : batch <= 2 * sms;
+        if (want && 2 * K * 32 <= 512 && total <= 200 * 1024) {
+            part_fused_smem = total; part_fused_run = (int)run_d;
+            allow_dynamic_smem(msp_solve_fused_kernel, total);
+        }
+    }
 }
 
 static MsDev make_rdev(const int* meta, int NR, int rn, int rtotal) {
@@ -715,6 +731,12 @@ void MultistageBatchedKKT::solve_partitioned(double* lx, const int* active) {
     const MsPart P = make_part();
     const MsDev dv = make_dev(S, d_meta.get());
     dim3 gseg(batch, K);
+    if (part_fused_smem > 0 && !g_ms_timer.on) {
+        const MsDev rd = make_rdev(d_rmeta.get(), K, part_rn, part_rtotal);
+        B200_LAUNCH(msp_solve_fused_kernel, batch, 64 * K, part_fused_smem, stream, dv, P, rd, part_fused_slot, part_seg_len, part_fused_run, part_rslot, packets.get(), pk_stride,
+                    rpackets.get(), part_rpk_stride, lx, zbuf.get(), xred.get(), active);
+        return;
+    }
     g_ms_timer.mark(0, stream);
     B200_LAUNCH(msp_fwd_kernel, gseg, 32, part_seg_smem, stream, dv, P, part_solve_slot, part_seg_len, packets.get(), pk_stride, lx, zbuf.get(), active);
     g_ms_timer.mark(1, stream);

@@ -70,7 +70,8 @@ public:
     int part_K = 1;                     // 1 = off
     std::vector<int> part_bounds, part_sep, part_dsep;     // [2K] stage ranges of the runs; separator stages; per stage: class of the separator on the left of its run (0: none)
     int part_rn = 0, part_rtotal = 0, part_rslot = 0, part_rrp = 16, part_seg_len = 0, part_dsep_max = 8, part_spike_slot = 2, part_solve_slot = 2;
-    size_t part_rpk_stride = 0, part_seg_smem = 0, part_spike_smem = 0, part_rsolve_smem = 0;
+    size_t part_rpk_stride = 0, part_seg_smem = 0, part_spike_smem = 0, part_rsolve_smem = 0, part_fused_smem = 0;      // part_fused_smem > 0: one launch per solve (msp_solve_fused_kernel)
+    int part_fused_run = 0, part_fused_slot = 0;
     DevBuf<int> d_rmeta, d_part;
     DevBuf<double> rfac, rpackets, carry, zbuf, xred;
 private:

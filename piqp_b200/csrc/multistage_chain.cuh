@@ -431,15 +431,11 @@ __device__ __forceinline__ void msw_bwd_stage(const double* pkt, int ND, double*
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32) msw_solve_kernel(MsDev s, int slot_doubles, const double* __restrict__ inv_all, const double* __restrict__ pk_all,
-                                                       size_t pk_stride, double* __restrict__ X, const int* __restrict__ active) {
-    extern __shared__ __align__(16) double xs[];
-    const int b = blockIdx.x;
-    if (active && !active[b]) return;
-    const double* Linv = inv_all + (size_t)b * s.total_inv;
-    const double* pk = pk_all + (size_t)b * pk_stride;
-    double* x = X + (size_t)b * s.n;
-    const int lane = threadIdx.x, N = s.N, w = s.w, n = s.n;
+// one warp, one QP: x <- L^-T L^-1 x.  `xs` is this warp's shared-memory workspace (layout above); also called by the fused
+// parallel-in-horizon solve (multistage_partition.cuh) for the reduced chain.
+__device__ __forceinline__ void msw_solve_body(const MsDev& s, int slot_doubles, const double* __restrict__ Linv, const double* __restrict__ pk,
+                                               double* __restrict__ x, double* xs, int lane) {
+    const int N = s.N, w = s.w, n = s.n;
     const int NS = N - 1;                          // regular stages
     double* tmp = xs + ((n + 1) & ~1) + 32;        // 32 doubles of slack after xs: padded rows/columns read (and ignore) them
     double* accN = tmp + 32;
@@ -501,6 +497,14 @@ __global__ void __launch_bounds__(32) msw_solve_kernel(MsDev s, int slot_doubles
     msw_cp_wait<0>();
     __syncwarp();
     for (int i = lane; i < n; i += 32) x[i] = xs[i];
+}
+
+__global__ void __launch_bounds__(32) msw_solve_kernel(MsDev s, int slot_doubles, const double* __restrict__ inv_all, const double* __restrict__ pk_all,
+                                                       size_t pk_stride, double* __restrict__ X, const int* __restrict__ active) {
+    extern __shared__ __align__(16) double msw_solve_smem[];
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    msw_solve_body(s, slot_doubles, inv_all ? inv_all + (size_t)b * s.total_inv : nullptr, pk_all + (size_t)b * pk_stride, X + (size_t)b * s.n, msw_solve_smem, threadIdx.x);
 }
 
 }  // namespace b200
