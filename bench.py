@@ -603,7 +603,7 @@ def measure(args, wl, ctx):
             # interior-point solve of a sub-batch starts as soon as its own setup is done and overlaps the copies of the next ones.
             # Same inputs (slices of the same pinned buffers), same outputs (slices of hx), every QP solved.
             from concurrent.futures import ThreadPoolExecutor
-            nchunk = 4
+            nchunk = max(2, int(os.environ.get("B200_E2E_CHUNKS", "4")))
             bounds = [(B * c // nchunk, B * (c + 1) // nchunk) for c in range(nchunk)]
             chunks = [{k: v[lo:hi] for k, v in host.items()} for lo, hi in bounds]
             turn = [threading.Event() for _ in range(nchunk + 1)]
@@ -637,11 +637,11 @@ def measure(args, wl, ctx):
                     assert all(r[1] for r in res)
                     if rep > 0:
                         ptimes.append(dt); pfl.append(sum(r[0] for r in res))
-            print("e2e repetitions, 4 pipelined sub-batches (s): %s" % ["%.4f" % t for t in ptimes], file=sys.stderr)
+            print("e2e repetitions, %d pipelined sub-batches (s): %s" % (nchunk, ["%.4f" % t for t in ptimes]), file=sys.stderr)
             if max(ptimes) < max(times):
                 times, fl = ptimes, pfl
-                what = ("b200qp_setup_dense(host pinned buffers) + b200qp_solve + b200qp_get_result(x -> host) on 4 sub-batches of the per-GPU batch, one handle / "
-                        "stream / host thread each: setups in turn, each solve overlapping the H2D copies of the following sub-batches")
+                what = ("b200qp_setup_dense(host pinned buffers) + b200qp_solve + b200qp_get_result(x -> host) on %d sub-batches of the per-GPU batch, one handle / "
+                        "stream / host thread each: setups in turn, each solve overlapping the H2D copies of the following sub-batches" % nchunk)
         tmax = torch.tensor([max(times)], dtype=torch.float64, device=dev)      # conservative: slowest repetition
         fsum = torch.tensor([sum(fl) / len(fl)], dtype=torch.float64, device=dev)
         tsingle = torch.tensor([max(single_times)], dtype=torch.float64, device=dev)

@@ -305,7 +305,13 @@ b200kkt_handle* b200kkt_clone(const b200kkt_handle* src) {
     } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
 }
 void b200kkt_print_info(const b200kkt_handle* h) { if (h && h->be) h->be->print_info(); }
-void b200kkt_destroy(b200kkt_handle* h) { if (h) { cudaSetDevice(h->device); delete h; } }
+void b200kkt_destroy(b200kkt_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    ReleaseScope scope;
+    delete h;
+}
 
 int b200kkt_dense_get_kkt(b200kkt_handle* h, double* kkt_lower, double* chol_lower) {
     if (!h || !h->dense) return fail(B200_E_INVALID, "not a dense handle");
@@ -495,8 +501,7 @@ int b200qp_setup_dense(b200qp_handle** out, int batch, int n, int p, int m, cons
         const bool verbose_timing = getenv("B200_TIMING") != nullptr;
         auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         double t_0 = now();
-        h->dd.alloc(batch, n, p, m);
-        B200_CUDA(device_synchronize_shared());
+        h->dd.alloc(batch, n, p, m, h->stream);          // zero-fill on the handle's stream: no device-wide synchronisation in the setup of a pipelined sub-batch
         B200_CUDA(cudaEventRecord(e0, h->stream));
         h->ip = std::make_unique<BatchedIPSolver>(batch, n, p, m, h->st, h->stream);
         h->ruiz.alloc(batch, n, p, m);
@@ -808,7 +813,15 @@ int b200qp_get_trace(b200qp_handle* h, int b, double* rows, int max_rows) {
     )
     return nrows;
 }
-void b200qp_cleanup(b200qp_handle* h) { if (h) { cudaSetDevice(h->device); delete h; } }
+void b200qp_cleanup(b200qp_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    // every API call returns with the handle's stream drained (its side streams join it before that), so nothing that touches the
+    // handle's buffers is in flight after this one synchronisation
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    ReleaseScope scope;
+    delete h;
+}
 
 int b200qp_bench_factor_solve(b200qp_handle* h, int reps, int nsolve, double* factor_ms, double* solve_ms) {
     if (!h || reps <= 0) return fail(B200_E_INVALID, "bad arguments");

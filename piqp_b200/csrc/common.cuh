@@ -92,6 +92,15 @@ inline void pool_setup_once() {
     }
     configured_dev = dev;
 }
+// Inside a ReleaseScope (b200qp_cleanup / b200kkt_destroy, after the handle's own stream has been synchronised) DevBuf::release() skips its
+// device-wide synchronisation: a handle owns ~100 buffers, and every one of them would otherwise wait for the in-flight work of all the other
+// handles of the process (4 pipelined sub-batches in bench.py, 12 handles in flight in tools/mm_suite.py).
+struct ReleaseScope {
+    ReleaseScope() { depth()++; }
+    ~ReleaseScope() { depth()--; }
+    ReleaseScope(const ReleaseScope&) = delete;
+    static int& depth() { static thread_local int d = 0; return d; }
+};
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -114,7 +123,7 @@ struct DevBuf {
     }
     void zero(cudaStream_t s = 0) { if (n) B200_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
     void release() {
-        if (p) { device_synchronize_shared(); cudaFreeAsync(p, cudaStreamPerThread); }
+        if (p) { if (ReleaseScope::depth() == 0) device_synchronize_shared(); cudaFreeAsync(p, cudaStreamPerThread); }
         p = nullptr; n = 0;
     }
     // stream-ordered release: the memory goes back to the pool once `s` has passed this point -- no device-wide synchronisation

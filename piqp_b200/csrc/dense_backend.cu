@@ -79,10 +79,10 @@ void BatchedKKT::reset_profile() { collect(); for (int i = 0; i < T_COUNT; i++) 
 // =====================================================================================================
 // data packing
 // =====================================================================================================
-void DenseData::alloc(int batch_, int n_, int p_, int m_) {
+void DenseData::alloc(int batch_, int n_, int p_, int m_, cudaStream_t zero_stream) {
     batch = batch_; n = n_; p = p_; m = m_; ld = round_up(n > 0 ? n : 1, 8);
     Pf.alloc((size_t)batch * ld * n); AT.alloc((size_t)batch * ld * p); GT.alloc((size_t)batch * ld * m);
-    Pf.zero(); AT.zero(); GT.zero();
+    Pf.zero(zero_stream); AT.zero(zero_stream); GT.zero(zero_stream);
 }
 
 __global__ void pack_sym_upper_kernel(const double* src, long long sb, long long rs, long long cs, double* Pf, long long sP, int ld, int n) {

@@ -16,7 +16,7 @@ struct DenseData {
     long long sP() const { return (long long)ld * n; }
     long long sA() const { return (long long)ld * p; }
     long long sG() const { return (long long)ld * m; }
-    void alloc(int batch_, int n_, int p_, int m_);
+    void alloc(int batch_, int n_, int p_, int m_, cudaStream_t zero_stream = 0);      // the zero-fill runs on zero_stream (0: legacy default stream, callers synchronise)
 };
 
 // element (i, j) of source instance b is src[b*sb + i*rs + j*cs]
