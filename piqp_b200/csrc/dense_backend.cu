@@ -2,6 +2,7 @@
 #include "dense_backend.hpp"
 #include <string>
 #include <cstdlib>
+#include <cstdint>
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -400,6 +401,8 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
     set_smem(gemm_nt_tile_kernel<EPI_ASSEMBLE, true>, GEMM_SMEM);
     set_smem(gemm_nt_t64_kernel<EPI_ASSEMBLE, true>, T64_SMEM);
     set_smem(gemm_nt_t64_kernel<EPI_SUB, false>, T64_SMEM);
+    set_smem(gemm_nt_t64_bulk_kernel<EPI_ASSEMBLE, true>, T64_BULK_SMEM);
+    set_smem(gemm_nt_t64_bulk_kernel<EPI_SUB, false>, T64_BULK_SMEM);
     chol_split = !(getenv("B200_CHOL_SPLIT") && getenv("B200_CHOL_SPLIT")[0] == '0');      // 0 = the fused round-1 panel kernel
     if (chol_split && !(getenv("B200_CHOL_AUX") && getenv("B200_CHOL_AUX")[0] == '0')) {
         int lo = 0, hi = 0;
@@ -531,6 +534,15 @@ void DenseBatchedKKT::assemble_ozaki(const double* x_reg, const int* active) {  
                      *reinterpret_cast<const CUtensorMap*>(oz_mapB), a);
 }
 
+// gemm_nt_t64_bulk_kernel (TMA bulk copies + mbarrier ring, no CTA barrier in the main loop) needs whole k-blocks, whole tiles in memory and
+// 16-byte aligned rows; everything else runs the cp.async kernel.  B200_GEMM_BULK=0 switches it off.
+static bool bulk_gemm_enabled() { const char* e = getenv("B200_GEMM_BULK"); return !(e && e[0] == '0'); }      // read per call: the tests switch it
+static bool bulk_gemm_ok(const GemmArgs& g, bool has_w) {
+    return bulk_gemm_enabled() && g.K >= 64 && g.K % KB == 0 && g.nt * TILE <= g.rows_valid && g.lda % 2 == 0 && g.ldb % 2 == 0 && g.strideA % 2 == 0 && g.strideB % 2 == 0 &&
+           (!has_w || g.stridew % 2 == 0) && (reinterpret_cast<uintptr_t>(g.A) % 16 == 0) && (reinterpret_cast<uintptr_t>(g.B) % 16 == 0) &&
+           (!has_w || reinterpret_cast<uintptr_t>(g.w) % 16 == 0);
+}
+
 void DenseBatchedKKT::assemble(const double* x_reg, const int* active) {   // dense/kkt.hpp:140-160
     if (n == 0) return;
     if (ozaki) { assemble_ozaki(x_reg, active); return; }
@@ -543,7 +555,8 @@ void DenseBatchedKKT::assemble(const double* x_reg, const int* active) {   // de
     g.Pf = D->Pf.get(); g.strideP = D->sP();
     g.AtA = p > 0 ? AtA.get() : nullptr; g.strideAtA = D->sP();
     g.xreg = x_reg; g.stridex = n; g.delta = delta.get(); g.active = active; g.fail = nullptr;
-    if (m > 0 && gemm_t64) { g.tiles *= 2; B200_LAUNCH((gemm_nt_t64_kernel<EPI_ASSEMBLE, true>), (unsigned)(g.tiles * batch), GEMM_THREADS, T64_SMEM, stream, g); }
+    if (m > 0 && gemm_t64 && bulk_gemm_ok(g, true)) { g.tiles *= 2; B200_LAUNCH((gemm_nt_t64_bulk_kernel<EPI_ASSEMBLE, true>), (unsigned)(g.tiles * batch), GEMM_THREADS, T64_BULK_SMEM, stream, g); }
+    else if (m > 0 && gemm_t64) { g.tiles *= 2; B200_LAUNCH((gemm_nt_t64_kernel<EPI_ASSEMBLE, true>), (unsigned)(g.tiles * batch), GEMM_THREADS, T64_SMEM, stream, g); }
     else if (m > 0) B200_LAUNCH((gemm_nt_tile_kernel<EPI_ASSEMBLE, true>), (unsigned)(g.tiles * batch), GEMM_THREADS, GEMM_SMEM, stream, g);
     else { g.A = D->Pf.get(); g.B = g.A; g.K = 0; g.w = nullptr;
            B200_LAUNCH((gemm_nt_tile_kernel<EPI_ASSEMBLE, false>), (unsigned)(g.tiles * batch), GEMM_THREADS, GEMM_SMEM, stream, g); }
@@ -562,7 +575,8 @@ void DenseBatchedKKT::cholesky(const int* active) {   // Eigen::LLT<Lower>::comp
         g.C = K.get(); g.strideC = D->sP(); g.ldc = D->ld;
         g.n = n; g.rows_valid = D->ld; g.K = jb * TILE; g.nt = nt; g.tj_fixed = -1; g.tj_start = jb; g.tiles = tiles; g.t0 = t0;
         g.active = active; g.fail = fail.get();
-        B200_LAUNCH((gemm_nt_t64_kernel<EPI_SUB, false>), (unsigned)((size_t)tiles * batch), GEMM_THREADS, T64_SMEM, st, g);
+        if (bulk_gemm_ok(g, false)) B200_LAUNCH((gemm_nt_t64_bulk_kernel<EPI_SUB, false>), (unsigned)((size_t)tiles * batch), GEMM_THREADS, T64_BULK_SMEM, st, g);
+        else B200_LAUNCH((gemm_nt_t64_kernel<EPI_SUB, false>), (unsigned)((size_t)tiles * batch), GEMM_THREADS, T64_SMEM, st, g);
     };
     for (int jb = 0; jb < nt; jb++) {
         const int j0 = jb * TILE;

@@ -405,6 +405,177 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_kernel(GemmArgs g
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// gemm_nt_t64_bulk_kernel: the same 128 x 64 tile kernel with the operand panels staged by the TMA engine's bulk copies
+// (cp.async.bulk.shared.global, one 1 KB / 512 B row of the panel per copy, 32 copies per stage issued by the lanes of warp 0)
+// into a 4-stage ring guarded by mbarriers: full[s] (expect_tx = the stage's bytes) releases the consumers, empty[s] (one arrival per
+// warp) releases the slot.  There is NO CTA-wide barrier in the main loop: the source view of the cp.async kernel
+// (profiles/r02d_ncu_source_stalls.txt) had 13 % of its stall samples on the per-k-block __syncthreads, because eight warps that
+// drift apart on the DMMA pipe were re-aligned 32 times per tile.  A slot is refilled two k-blocks after its consumption, so warp 0
+// (a consumer like the others) practically never waits for the empty barrier.  The padded rows of the cp.async layout are kept
+// (conflict-free fragment loads): that is why the copies are 1-D bulk copies per panel row and not one tensor-map box per panel.
+// Preconditions (host-checked, else the cp.async kernel runs): K % 16 == 0, tile rows inside rows_valid, 16-byte aligned bases / strides.
+// ---------------------------------------------------------------------------------------------------
+constexpr int BULK_STAGES = 4;
+constexpr int BULK_STAGE_DOUBLES = KB * (LDS_T + LDS_B64) + KB;          // A panel | B panel | weights
+constexpr size_t T64_BULK_SMEM_RING = (size_t)BULK_STAGES * BULK_STAGE_DOUBLES * sizeof(double);
+constexpr size_t T64_BULK_SMEM = (T64_TILE_SMEM > T64_BULK_SMEM_RING ? T64_TILE_SMEM : T64_BULK_SMEM_RING) + 2 * BULK_STAGES * sizeof(unsigned long long);
+
+__device__ __forceinline__ unsigned bk_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bk_mbar_init(unsigned long long* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bk_smem(bar)), "r"(count)); }
+__device__ __forceinline__ void bk_mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bk_smem(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bk_expect_tx(unsigned long long* bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bk_smem(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bk_arrive(unsigned long long* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bk_smem(bar)) : "memory"); }
+__device__ __forceinline__ void bk_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bk_smem(dst)), "l"(src), "r"(bytes), "r"(bk_smem(bar)) : "memory");
+}
+
+template <int EPI, bool HAS_W>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_bulk_kernel(GemmArgs g) {
+    extern __shared__ __align__(128) double smem[];
+    const int b = blockIdx.x / g.tiles;
+    int t = blockIdx.x % g.tiles + g.t0;
+    if (g.active && !g.active[b]) return;
+    if (g.fail && g.fail[b]) return;
+    int tj = g.tj_start;
+    while (t >= 2 * (g.nt - tj)) { t -= 2 * (g.nt - tj); tj++; }
+    const int ti = tj + (t >> 1), half = t & 1;
+    const bool diag = (ti == tj) && (g.A == g.B);          // the B rows are a 64-row slice of the A panel: read it from there
+    const double* A = g.A + (size_t)b * g.strideA;
+    const double* B = g.B + (size_t)b * g.strideB;
+    const double* w = HAS_W ? g.w + (size_t)b * g.stridew : nullptr;
+    const int rowA0 = ti * TILE, rowB0 = tj * TILE + half * T64_N;
+    const int K = g.K;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(smem) + (T64_BULK_SMEM - 2 * BULK_STAGES * sizeof(unsigned long long)));
+    unsigned long long* empty = full + BULK_STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int nkb = K / KB;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < BULK_STAGES; s++) { bk_mbar_init(&full[s], 1); bk_mbar_init(&empty[s], GEMM_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned stage_bytes = (unsigned)(sizeof(double) * KB * (TILE + (diag ? 0 : T64_N) + (HAS_W ? 1 : 0)));
+    // fill slot (kb % BULK_STAGES) with k-block kb: lanes 0..15 copy the A rows, 16..31 the B rows, lane 0 also the 16 weights
+    auto fill = [&](int kb) {
+        const int s = kb % BULK_STAGES;
+        double* as = smem + (size_t)s * BULK_STAGE_DOUBLES;
+        double* bs = as + KB * LDS_T;
+        double* ws = bs + KB * LDS_B64;
+        if (lane == 0) bk_expect_tx(&full[s], stage_bytes);
+        __syncwarp();
+        const int k = lane & 15;
+        if (lane < 16) bk_bulk_g2s(as + k * LDS_T, A + (size_t)(kb * KB + k) * g.lda + rowA0, TILE * sizeof(double), &full[s]);
+        else if (!diag) bk_bulk_g2s(bs + k * LDS_B64, B + (size_t)(kb * KB + k) * g.ldb + rowB0, T64_N * sizeof(double), &full[s]);
+        if (HAS_W && lane == 0) bk_bulk_g2s(ws, w + kb * KB, KB * sizeof(double), &full[s]);
+    };
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    if (warp == 0) { for (int kb = 0; kb < BULK_STAGES - 2 && kb < nkb; kb++) fill(kb); }
+    const int ldsb = diag ? LDS_T : LDS_B64;
+    const bool skip_mma = (ti == tj) && (half * T64_N + wn * 32 >= wm * 32 + 32);
+    for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % BULK_STAGES;
+        if (warp == 0) {                              // refill the slot consumed two k-blocks ago with k-block kb + BULK_STAGES - 2
+            const int nx = kb + BULK_STAGES - 2;
+            if (nx < nkb) {
+                if (nx >= BULK_STAGES) bk_mbar_wait(&empty[nx % BULK_STAGES], ((nx / BULK_STAGES) - 1) & 1);
+                fill(nx);
+            }
+        }
+        bk_mbar_wait(&full[s], (kb / BULK_STAGES) & 1);
+        const double* as = smem + (size_t)s * BULK_STAGE_DOUBLES;
+        const double* bs = diag ? (as + half * T64_N) : (as + KB * LDS_T);
+        const double* ws = as + KB * (LDS_T + LDS_B64);
+        if (!skip_mma) {
+            double wcur[KB / 4];
+            if (HAS_W) {
+#pragma unroll
+                for (int kk = 0; kk < KB / 4; kk++) wcur[kk] = ws[kk * 4 + tq];
+            }
+#pragma unroll
+            for (int kk = 0; kk < KB / 4; kk++) {
+                double af[4], bf[4];
+                const int krow = kk * 4 + tq;
+#pragma unroll
+                for (int i = 0; i < 4; i++) af[i] = as[krow * LDS_T + wm * 32 + i * 8 + gq];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { bf[j] = bs[krow * ldsb + wn * 32 + j * 8 + gq]; if (HAS_W) bf[j] *= wcur[kk]; }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) bk_arrive(&empty[s]);
+    }
+    const int rows_valid = g.rows_valid;
+    // ---- epilogue through shared memory (Cs[col * TS_LD + row], 64 columns): coalesced 16-byte global accesses
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) smem[(wn * 32 + j * 8 + tq * 2 + e) * TS_LD + wm * 32 + i * 8 + gq] = acc[i][j][e];
+    __syncthreads();
+    double* __restrict__ C = g.C + (size_t)b * g.strideC;
+    const double dinv = (EPI == EPI_ASSEMBLE) ? 1.0 / g.delta[b] : 0.0;
+    const double* __restrict__ Pf = (EPI == EPI_ASSEMBLE) ? g.Pf + (size_t)b * g.strideP : nullptr;
+    const double* __restrict__ AtA = (EPI == EPI_ASSEMBLE && g.AtA) ? g.AtA + (size_t)b * g.strideAtA : nullptr;
+    const double* __restrict__ xr = (EPI == EPI_ASSEMBLE) ? g.xreg + (size_t)b * g.stridex : nullptr;
+    const int ncol = g.ncol > 0 ? g.ncol : g.n;
+    const int r = rowA0 + (threadIdx.x & 63) * 2;
+    constexpr int U = 4;
+#pragma unroll 1
+    for (int it0 = 0; it0 < T64_N / 4; it0 += U) {
+        double2 base[U], extra[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int cl = (it0 + u) * 4 + (threadIdx.x >> 6);
+            const int c = rowB0 + cl;
+            ok[u] = (r + 1 < g.rows_valid) && (c < ncol) && (r < g.n) && (r + 1 >= c);
+            base[u] = make_double2(0.0, 0.0); extra[u] = make_double2(0.0, 0.0);
+            if (ok[u]) {
+                const size_t idx = (size_t)c * g.ldc + r;
+                if (EPI == EPI_SUB) base[u] = *reinterpret_cast<const double2*>(C + idx);
+                if (EPI == EPI_ASSEMBLE) { base[u] = *reinterpret_cast<const double2*>(Pf + idx); if (AtA) extra[u] = *reinterpret_cast<const double2*>(AtA + idx); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!ok[u]) continue;
+            const int cl = (it0 + u) * 4 + (threadIdx.x >> 6);
+            const int c = rowB0 + cl;
+            const double2 a = *reinterpret_cast<const double2*>(smem + cl * TS_LD + (threadIdx.x & 63) * 2);
+            double v0 = a.x, v1 = a.y;
+            if (EPI == EPI_SUB) { v0 = base[u].x - v0; v1 = base[u].y - v1; }
+            if (EPI == EPI_ASSEMBLE) {
+                double b0 = base[u].x, b1 = base[u].y;
+                if (r == c) b0 += xr[r];
+                if (r + 1 == c) b1 += xr[r + 1];
+                if (AtA) { b0 += dinv * extra[u].x; b1 += dinv * extra[u].y; }
+                v0 = b0 + v0; v1 = b1 + v1;
+            }
+            const size_t idx = (size_t)c * g.ldc + r;
+            if (r >= c && r + 1 < g.n) *reinterpret_cast<double2*>(C + idx) = make_double2(v0, v1);
+            else { if (r >= c && r < g.n) C[idx] = v0; if (r + 1 >= c && r + 1 < g.n) C[idx + 1] = v1; }
+        }
+    }
+}
+
 #include "dense_chol.cuh"
 #include "dense_ozaki.cuh"
 

@@ -20,13 +20,15 @@ def _rel(a, b):
     return np.abs(a - b).max() / max(1.0, np.abs(b).max())
 
 
-@pytest.fixture(params=["dmma", "dmma_tile128", "ozaki"])
+@pytest.fixture(params=["dmma", "dmma_cp_async", "dmma_tile128", "ozaki"])
 def assemble_mode(request, monkeypatch):
     """All assembly kernels for K = P + diag + AtA/delta + G^T Z^-1 G: the FP64 DMMA kernel with 128 x 64 tiles and two CTAs per
-    SM (default), the 128 x 128-tile DMMA kernel (B200_GEMM_T64=0) and the Ozaki-split tcgen05 (s8 tensor core + TMEM + TMA)
+    SM (default; its operand panels staged by TMA bulk copies + mbarriers where the shape allows, by cp.async otherwise or with
+    B200_GEMM_BULK=0), the 128 x 128-tile DMMA kernel (B200_GEMM_T64=0) and the Ozaki-split tcgen05 (s8 tensor core + TMEM + TMA)
     kernel, forced through B200_DENSE_ASSEMBLE (read when a backend is constructed)."""
     monkeypatch.setenv("B200_DENSE_ASSEMBLE", "ozaki" if request.param == "ozaki" else "dmma")
     monkeypatch.setenv("B200_GEMM_T64", "0" if request.param == "dmma_tile128" else "1")
+    monkeypatch.setenv("B200_GEMM_BULK", "0" if request.param == "dmma_cp_async" else "1")
     return request.param
 
 
@@ -36,7 +38,7 @@ def _oracle_backend(oracle, dims, seed):
     return q, s, s.scaled_matrices()
 
 
-@pytest.mark.parametrize("dims", [(20, 8, 9), (128, 32, 64), (200, 0, 300), (260, 30, 0), (300, 17, 45), (5, 0, 0)])
+@pytest.mark.parametrize("dims", [(20, 8, 9), (128, 32, 64), (200, 0, 300), (260, 30, 0), (300, 17, 45), (5, 0, 0), (256, 0, 128), (384, 16, 208)])
 def test_backend_factor_solve_eval_parity(oracle, b200, dims, assemble_mode):
     n, p, m = dims
     q, s, (P, AT, GT) = _oracle_backend(oracle, dims, seed=11)
