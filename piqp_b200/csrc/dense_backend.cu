@@ -555,7 +555,7 @@ void DenseBatchedKKT::assemble(const double* x_reg, const int* active) {   // de
     g.Pf = D->Pf.get(); g.strideP = D->sP();
     g.AtA = p > 0 ? AtA.get() : nullptr; g.strideAtA = D->sP();
     g.xreg = x_reg; g.stridex = n; g.delta = delta.get(); g.active = active; g.fail = nullptr;
-    if (m > 0 && gemm_t64 && bulk_gemm_ok(g, true)) { g.tiles *= 2; B200_LAUNCH((gemm_nt_t64_bulk_kernel<EPI_ASSEMBLE, true>), (unsigned)(g.tiles * batch), GEMM_THREADS, T64_BULK_SMEM, stream, g); }
+    if (m > 0 && gemm_t64 && bulk_gemm_ok(g, true)) { g.tiles *= 2; B200_LAUNCH((gemm_nt_t64_bulk_kernel<EPI_ASSEMBLE, true>), (unsigned)(g.tiles * batch), GEMM_THREADS + BULK_PRODUCER_THREADS, T64_BULK_SMEM, stream, g); }
     else if (m > 0 && gemm_t64) { g.tiles *= 2; B200_LAUNCH((gemm_nt_t64_kernel<EPI_ASSEMBLE, true>), (unsigned)(g.tiles * batch), GEMM_THREADS, T64_SMEM, stream, g); }
     else if (m > 0) B200_LAUNCH((gemm_nt_tile_kernel<EPI_ASSEMBLE, true>), (unsigned)(g.tiles * batch), GEMM_THREADS, GEMM_SMEM, stream, g);
     else { g.A = D->Pf.get(); g.B = g.A; g.K = 0; g.w = nullptr;
@@ -575,7 +575,7 @@ void DenseBatchedKKT::cholesky(const int* active) {   // Eigen::LLT<Lower>::comp
         g.C = K.get(); g.strideC = D->sP(); g.ldc = D->ld;
         g.n = n; g.rows_valid = D->ld; g.K = jb * TILE; g.nt = nt; g.tj_fixed = -1; g.tj_start = jb; g.tiles = tiles; g.t0 = t0;
         g.active = active; g.fail = fail.get();
-        if (bulk_gemm_ok(g, false)) B200_LAUNCH((gemm_nt_t64_bulk_kernel<EPI_SUB, false>), (unsigned)((size_t)tiles * batch), GEMM_THREADS, T64_BULK_SMEM, st, g);
+        if (bulk_gemm_ok(g, false)) B200_LAUNCH((gemm_nt_t64_bulk_kernel<EPI_SUB, false>), (unsigned)((size_t)tiles * batch), GEMM_THREADS + BULK_PRODUCER_THREADS, T64_BULK_SMEM, st, g);
         else B200_LAUNCH((gemm_nt_t64_kernel<EPI_SUB, false>), (unsigned)((size_t)tiles * batch), GEMM_THREADS, T64_SMEM, st, g);
     };
     for (int jb = 0; jb < nt; jb++) {

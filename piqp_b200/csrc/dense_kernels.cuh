@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_kernel(GemmArgs g
 // Preconditions (host-checked, else the cp.async kernel runs): K % 16 == 0, tile rows inside rows_valid, 16-byte aligned bases / strides.
 // ---------------------------------------------------------------------------------------------------
 constexpr int BULK_STAGES = 4;
+constexpr int BULK_PRODUCER_THREADS = 32;      // 32: a ninth, producer-only warp; 0: warp 0 doubles as the producer
 constexpr int BULK_STAGE_DOUBLES = KB * (LDS_T + LDS_B64) + KB;          // A panel | B panel | weights
 constexpr size_t T64_BULK_SMEM_RING = (size_t)BULK_STAGES * BULK_STAGE_DOUBLES * sizeof(double);
 constexpr size_t T64_BULK_SMEM = (T64_TILE_SMEM > T64_BULK_SMEM_RING ? T64_TILE_SMEM : T64_BULK_SMEM_RING) + 2 * BULK_STAGES * sizeof(unsigned long long);
@@ -436,7 +437,7 @@ __device__ __forceinline__ void bk_bulk_g2s(void* dst, const void* src, unsigned
 }
 
 template <int EPI, bool HAS_W>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_bulk_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(GEMM_THREADS + BULK_PRODUCER_THREADS, 2) gemm_nt_t64_bulk_kernel(GemmArgs g) {
     extern __shared__ __align__(128) double smem[];
     const int b = blockIdx.x / g.tiles;
     int t = blockIdx.x % g.tiles + g.t0;
@@ -481,12 +482,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_bulk_kernel(GemmA
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-    if (warp == 0) { for (int kb = 0; kb < BULK_STAGES - 2 && kb < nkb; kb++) fill(kb); }
+    if (BULK_PRODUCER_THREADS > 0 && warp == GEMM_THREADS / 32) {      // dedicated producer warp: runs ahead of the consumers by the whole ring
+        for (int kb = 0; kb < nkb; kb++) {
+            if (kb >= BULK_STAGES) bk_mbar_wait(&empty[kb % BULK_STAGES], ((kb / BULK_STAGES) - 1) & 1);
+            fill(kb);
+        }
+    }
+    if (BULK_PRODUCER_THREADS == 0 && warp == 0) { for (int kb = 0; kb < BULK_STAGES - 2 && kb < nkb; kb++) fill(kb); }
     const int ldsb = diag ? LDS_T : LDS_B64;
     const bool skip_mma = (ti == tj) && (half * T64_N + wn * 32 >= wm * 32 + 32);
-    for (int kb = 0; kb < nkb; kb++) {
+    for (int kb = 0; kb < nkb && warp < GEMM_THREADS / 32; kb++) {
         const int s = kb % BULK_STAGES;
-        if (warp == 0) {                              // refill the slot consumed two k-blocks ago with k-block kb + BULK_STAGES - 2
+        if (BULK_PRODUCER_THREADS == 0 && warp == 0) {      // refill the slot consumed two k-blocks ago with k-block kb + BULK_STAGES - 2
             const int nx = kb + BULK_STAGES - 2;
             if (nx < nkb) {
                 if (nx >= BULK_STAGES) bk_mbar_wait(&empty[nx % BULK_STAGES], ((nx / BULK_STAGES) - 1) & 1);
@@ -523,13 +530,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_bulk_kernel(GemmA
     const int rows_valid = g.rows_valid;
     // ---- epilogue through shared memory (Cs[col * TS_LD + row], 64 columns): coalesced 16-byte global accesses
     __syncthreads();
+    if (warp < GEMM_THREADS / 32) {
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
             for (int e = 0; e < 2; e++) smem[(wn * 32 + j * 8 + tq * 2 + e) * TS_LD + wm * 32 + i * 8 + gq] = acc[i][j][e];
+    }
     __syncthreads();
+    if (warp >= GEMM_THREADS / 32) return;          // the producer warp has no part in the epilogue (no barrier follows)
     double* __restrict__ C = g.C + (size_t)b * g.strideC;
     const double dinv = (EPI == EPI_ASSEMBLE) ? 1.0 / g.delta[b] : 0.0;
     const double* __restrict__ Pf = (EPI == EPI_ASSEMBLE) ? g.Pf + (size_t)b * g.strideP : nullptr;
