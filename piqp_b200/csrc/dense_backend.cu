@@ -468,6 +468,15 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
     }
 }
 
+// gemm_nt_t64_bulk_kernel (TMA bulk copies + mbarrier ring, no CTA barrier in the main loop) needs whole k-blocks and 16-byte aligned
+// rows (an even number of them in memory); everything else runs the cp.async kernel.  B200_GEMM_BULK=0 switches it off.
+static bool bulk_gemm_enabled() { const char* e = getenv("B200_GEMM_BULK"); return !(e && e[0] == '0'); }      // read per call: the tests switch it
+static bool bulk_gemm_ok(const GemmArgs& g, bool has_w) {
+    return bulk_gemm_enabled() && g.K >= 64 && g.K % KB == 0 && g.rows_valid % 2 == 0 && g.lda % 2 == 0 && g.ldb % 2 == 0 && g.strideA % 2 == 0 && g.strideB % 2 == 0 &&
+           (!has_w || g.stridew % 2 == 0) && (reinterpret_cast<uintptr_t>(g.A) % 16 == 0) && (reinterpret_cast<uintptr_t>(g.B) % 16 == 0) &&
+           (!has_w || reinterpret_cast<uintptr_t>(g.w) % 16 == 0);
+}
+
 void dense_syrk_sub_scaled(const double* A, long long strideA, int lda, const double* w, long long stridew, double* C, long long strideC, int ldc,
                            int n, int K, int batch, const int* active, cudaStream_t st, int tj_start, int tj_end, int ncol) {
     if (n <= 0 || K <= 0 || batch <= 0) return;
@@ -475,7 +484,7 @@ void dense_syrk_sub_scaled(const double* A, long long strideA, int lda, const do
     int dev = 0;
     B200_CUDA(cudaGetDevice(&dev));
     static const bool use_t64 = !(getenv("B200_GEMM_T64") && getenv("B200_GEMM_T64")[0] == '0');      // 128 x 64 tiles, two CTAs per SM (default)
-    if (dev != configured_dev) { set_smem(gemm_nt_tile_kernel<EPI_SUB, true>, GEMM_SMEM); set_smem(gemm_nt_t64_kernel<EPI_SUB, true>, T64_SMEM); configured_dev = dev; }
+    if (dev != configured_dev) { set_smem(gemm_nt_tile_kernel<EPI_SUB, true>, GEMM_SMEM); set_smem(gemm_nt_t64_kernel<EPI_SUB, true>, T64_SMEM); set_smem(gemm_nt_t64_bulk_kernel<EPI_SUB, true>, T64_BULK_SMEM); configured_dev = dev; }
     GemmArgs g{};
     g.A = A; g.strideA = strideA; g.lda = lda;
     g.B = A; g.strideB = strideA; g.ldb = lda;
@@ -488,6 +497,11 @@ void dense_syrk_sub_scaled(const double* A, long long strideA, int lda, const do
     for (int tj = tj_start; tj < tj_end; tj++) g.tiles += g.nt - tj;
     g.active = active;
     if (g.tiles <= 0) return;
+    if (use_t64 && K >= 64 && bulk_gemm_ok(g, true)) {
+        g.tiles *= 2;
+        B200_LAUNCH((gemm_nt_t64_bulk_kernel<EPI_SUB, true>), (unsigned)((size_t)g.tiles * batch), GEMM_THREADS + BULK_PRODUCER_THREADS, T64_BULK_SMEM, st, g);
+        return;
+    }
     if (use_t64 && K >= 128) { g.tiles *= 2; B200_LAUNCH((gemm_nt_t64_kernel<EPI_SUB, true>), (unsigned)((size_t)g.tiles * batch), GEMM_THREADS, T64_SMEM, st, g); return; }
     B200_LAUNCH((gemm_nt_tile_kernel<EPI_SUB, true>), (unsigned)((size_t)g.tiles * batch), GEMM_THREADS, GEMM_SMEM, st, g);
 }
@@ -532,15 +546,6 @@ void DenseBatchedKKT::assemble_ozaki(const double* x_reg, const int* active) {  
                                  *reinterpret_cast<const CUtensorMap*>(oz_mapB), a);
     else B200_LAUNCH((oz_gemm_kernel<32, 4>), (unsigned)((size_t)oz_ntiles * batch), 128, OZ_GEMM_SMEM, stream, *reinterpret_cast<const CUtensorMap*>(oz_mapA),
                      *reinterpret_cast<const CUtensorMap*>(oz_mapB), a);
-}
-
-// gemm_nt_t64_bulk_kernel (TMA bulk copies + mbarrier ring, no CTA barrier in the main loop) needs whole k-blocks, whole tiles in memory and
-// 16-byte aligned rows; everything else runs the cp.async kernel.  B200_GEMM_BULK=0 switches it off.
-static bool bulk_gemm_enabled() { const char* e = getenv("B200_GEMM_BULK"); return !(e && e[0] == '0'); }      // read per call: the tests switch it
-static bool bulk_gemm_ok(const GemmArgs& g, bool has_w) {
-    return bulk_gemm_enabled() && g.K >= 64 && g.K % KB == 0 && g.nt * TILE <= g.rows_valid && g.lda % 2 == 0 && g.ldb % 2 == 0 && g.strideA % 2 == 0 && g.strideB % 2 == 0 &&
-           (!has_w || g.stridew % 2 == 0) && (reinterpret_cast<uintptr_t>(g.A) % 16 == 0) && (reinterpret_cast<uintptr_t>(g.B) % 16 == 0) &&
-           (!has_w || reinterpret_cast<uintptr_t>(g.w) % 16 == 0);
 }
 
 void DenseBatchedKKT::assemble(const double* x_reg, const int* active) {   // dense/kkt.hpp:140-160

@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_kernel(GemmArgs g
 // drift apart on the DMMA pipe were re-aligned 32 times per tile.  A slot is refilled two k-blocks after its consumption, so warp 0
 // (a consumer like the others) practically never waits for the empty barrier.  The padded rows of the cp.async layout are kept
 // (conflict-free fragment loads): that is why the copies are 1-D bulk copies per panel row and not one tensor-map box per panel.
-// Preconditions (host-checked, else the cp.async kernel runs): K % 16 == 0, tile rows inside rows_valid, 16-byte aligned bases / strides.
+// Preconditions (host-checked, else the cp.async kernel runs): K % 16 == 0, an even number of rows in memory, 16-byte aligned bases / strides.
 // ---------------------------------------------------------------------------------------------------
 constexpr int BULK_STAGES = 4;
 constexpr int BULK_PRODUCER_THREADS = 32;      // 32: a ninth, producer-only warp; 0: warp 0 doubles as the producer
@@ -463,7 +463,10 @@ __global__ void __launch_bounds__(GEMM_THREADS + BULK_PRODUCER_THREADS, 2) gemm_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const unsigned stage_bytes = (unsigned)(sizeof(double) * KB * (TILE + (diag ? 0 : T64_N) + (HAS_W ? 1 : 0)));
+    // rows of the tile that exist in memory (even counts: 16-byte copies); the rows behind them keep whatever the slot held -- they only feed
+    // accumulator rows / columns >= n, which the epilogue never stores
+    const int ra = min(TILE, g.rows_valid - rowA0), rb = diag ? 0 : max(0, min(T64_N, g.rows_valid - rowB0));
+    const unsigned stage_bytes = (unsigned)(sizeof(double) * KB * (ra + rb + (HAS_W ? 1 : 0)));
     // fill slot (kb % BULK_STAGES) with k-block kb: lanes 0..15 copy the A rows, 16..31 the B rows, lane 0 also the 16 weights
     auto fill = [&](int kb) {
         const int s = kb % BULK_STAGES;
@@ -473,8 +476,8 @@ __global__ void __launch_bounds__(GEMM_THREADS + BULK_PRODUCER_THREADS, 2) gemm_
         if (lane == 0) bk_expect_tx(&full[s], stage_bytes);
         __syncwarp();
         const int k = lane & 15;
-        if (lane < 16) bk_bulk_g2s(as + k * LDS_T, A + (size_t)(kb * KB + k) * g.lda + rowA0, TILE * sizeof(double), &full[s]);
-        else if (!diag) bk_bulk_g2s(bs + k * LDS_B64, B + (size_t)(kb * KB + k) * g.ldb + rowB0, T64_N * sizeof(double), &full[s]);
+        if (lane < 16) bk_bulk_g2s(as + k * LDS_T, A + (size_t)(kb * KB + k) * g.lda + rowA0, ra * sizeof(double), &full[s]);
+        else if (rb > 0) bk_bulk_g2s(bs + k * LDS_B64, B + (size_t)(kb * KB + k) * g.ldb + rowB0, rb * sizeof(double), &full[s]);
         if (HAS_W && lane == 0) bk_bulk_g2s(ws, w + kb * KB, KB * sizeof(double), &full[s]);
     };
     double acc[4][4][2];
