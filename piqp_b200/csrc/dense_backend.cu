@@ -410,6 +410,10 @@ DenseBatchedKKT::DenseBatchedKKT(DenseData* data, cudaStream_t st) : D(data) {
         B200_CUDA(cudaStreamCreateWithPriority(&chol_aux, cudaStreamNonBlocking, hi));
         chol_ev.resize(2 * (size_t)ceil_div(std::max(n, 1), TILE) + 2);
         for (auto& e : chol_ev) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        B200_CUDA(cudaStreamCreateWithFlags(&chol_aux2, cudaStreamNonBlocking));
+        chol_ev2.resize(chol_ev.size());
+        for (auto& e : chol_ev2) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        chol_lookahead = !(getenv("B200_CHOL_LOOKAHEAD") && getenv("B200_CHOL_LOOKAHEAD")[0] == '0');
     }
     gemm_t64 = !(getenv("B200_GEMM_T64") && getenv("B200_GEMM_T64")[0] == '0');      // 128 x 64 tiles, two CTAs per SM (default); 0 = the 128 x 128 kernel
     set_smem(gemm_nt_tile_kernel<EPI_ASSEMBLE, false>, GEMM_SMEM);
@@ -571,14 +575,14 @@ void DenseBatchedKKT::cholesky(const int* active) {   // Eigen::LLT<Lower>::comp
     if (n == 0) return;
     const int nt = ceil_div(n, TILE);
     B200_LAUNCH(clear_fail_kernel, ceil_div(batch, 256), 256, 0, stream, fail.get(), active, batch);
-    auto update = [&](int jb, int t0, int tiles, cudaStream_t st) {
-        // left-looking update of (part of) block column jb:  K(:, jb) -= L(:, 0:j0) L(jb, 0:j0)^T  on the two-CTA-per-SM DMMA tile kernel
-        // (contraction depth j0 = 128 .. n - 128); tiles t0 .. t0 + tiles - 1 of the column (two 64-column halves per 128-row tile)
+    auto update = [&](int jb, int t0, int tiles, cudaStream_t st, int k_lo = 0, int k_len = -1) {
+        // left-looking update of (part of) block column jb:  K(:, jb) -= L(:, k_lo : k_lo + k_len) L(jb, same)^T  on the two-CTA-per-SM DMMA tile
+        // kernel (default: the whole contraction 0 : j0, j0 = 128 .. n - 128); tiles t0 .. t0 + tiles - 1 of the column (two 64-column halves per 128-row tile)
         GemmArgs g{};
-        g.A = K.get(); g.strideA = D->sP(); g.lda = D->ld;
+        g.A = K.get() + (size_t)k_lo * D->ld; g.strideA = D->sP(); g.lda = D->ld;
         g.B = g.A; g.strideB = g.strideA; g.ldb = g.lda;
         g.C = K.get(); g.strideC = D->sP(); g.ldc = D->ld;
-        g.n = n; g.rows_valid = D->ld; g.K = jb * TILE; g.nt = nt; g.tj_fixed = -1; g.tj_start = jb; g.tiles = tiles; g.t0 = t0;
+        g.n = n; g.rows_valid = D->ld; g.K = k_len >= 0 ? k_len : jb * TILE; g.nt = nt; g.tj_fixed = -1; g.tj_start = jb; g.tiles = tiles; g.t0 = t0;
         g.active = active; g.fail = fail.get();
         if (bulk_gemm_ok(g, false)) B200_LAUNCH((gemm_nt_t64_bulk_kernel<EPI_SUB, false>), (unsigned)((size_t)tiles * batch), GEMM_THREADS + BULK_PRODUCER_THREADS, T64_BULK_SMEM, st, g);
         else B200_LAUNCH((gemm_nt_t64_kernel<EPI_SUB, false>), (unsigned)((size_t)tiles * batch), GEMM_THREADS, T64_SMEM, st, g);
@@ -596,7 +600,21 @@ void DenseBatchedKKT::cholesky(const int* active) {   // Eigen::LLT<Lower>::comp
         // high-priority stream BESIDE the update of the tiles below it -- a diag CTA (144 KB, 128 registers) leaves room for one
         // tile-kernel CTA on its SM -- and the panel solve joins both.
         const bool fork = chol_aux && jb > 0 && rt > 0;
-        if (jb > 0) update(jb, 0, 2, stream);                         // the diagonal tile first
+        // Look-ahead of the diagonal-tile update.  The two half tiles of the diagonal block are 512 CTAs for a 256-QP batch (1.7 waves) with
+        // a contraction that grows to K = n - 128, and they sit alone on the critical path in front of the diag factorisation.  All but the
+        // last 128 columns of that contraction are final one block column EARLIER, so that part runs on a second side stream beside block
+        // column jb - 1 and only the K = 128 remainder stays in front of the diag kernel.
+        const bool la = chol_aux2 && chol_lookahead;
+        if (la && jb >= 1 && jb + 1 < nt) {                           // early part of the NEXT diagonal tile: columns 0 : j0 of L are final here
+            B200_CUDA(cudaEventRecord(chol_ev2[2 * jb], stream));
+            B200_CUDA(cudaStreamWaitEvent(chol_aux2, chol_ev2[2 * jb], 0));
+            update(jb + 1, 0, 2, chol_aux2, 0, j0);
+            B200_CUDA(cudaEventRecord(chol_ev2[2 * jb + 1], chol_aux2));
+        }
+        if (la && jb >= 2) {                                          // this diagonal tile: join its early part, then the last 128 columns
+            B200_CUDA(cudaStreamWaitEvent(stream, chol_ev2[2 * (jb - 1) + 1], 0));
+            update(jb, 0, 2, stream, j0 - TILE, TILE);
+        } else if (jb > 0) update(jb, 0, 2, stream);                  // the diagonal tile first
         cudaStream_t ds = stream;
         if (fork) {
             B200_CUDA(cudaEventRecord(chol_ev[2 * jb], stream));

@@ -77,7 +77,15 @@ public:
     // Ozaki / tcgen05 assembly path (dense_ozaki.cuh)
     cudaStream_t chol_aux = nullptr;           // diag-tile factorisations run here, beside the block-column update on `stream`
     std::vector<cudaEvent_t> chol_ev;
-    ~DenseBatchedKKT() override { for (auto e : chol_ev) cudaEventDestroy(e); if (chol_aux) cudaStreamDestroy(chol_aux); }
+    cudaStream_t chol_aux2 = nullptr;          // early part of the next diagonal tile's update (look-ahead), beside the current block column
+    std::vector<cudaEvent_t> chol_ev2;
+    bool chol_lookahead = true;
+    ~DenseBatchedKKT() override {
+        for (auto e : chol_ev) cudaEventDestroy(e);
+        for (auto e : chol_ev2) cudaEventDestroy(e);
+        if (chol_aux) cudaStreamDestroy(chol_aux);
+        if (chol_aux2) cudaStreamDestroy(chol_aux2);
+    }
     bool chol_solve64 = true;  // panel solve on 64-row half tiles with L11 read from global memory (three CTAs per SM)
     bool chol_split = true;  // Cholesky: block-column update on the two-CTA-per-SM tile kernel + solve-only panel kernel (B200_CHOL_SPLIT=0: fused panel kernel)
     bool gemm_t64 = true;    // assembly with gemm_nt_t64_kernel (two CTAs per SM) instead of gemm_nt_tile_kernel

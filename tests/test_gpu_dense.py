@@ -249,7 +249,7 @@ def test_batched_trace_matches_oracle(oracle, b200):
 
 def test_batched_full_size_properties(oracle, b200, assemble_mode):
     """BASELINE config 2 shape (n=1024, m=512) at a small batch: every instance solves, satisfies the KKT conditions,
-    and instance 0 matches the oracle's iteration count and solution."""
+    and matches the oracle's iteration count and solution."""
     qs = [dense_strongly_convex_qp(1024, 0, 512, seed=42 + b) for b in range(3)]
     s, r = _solve_batch(b200, qs)
     assert [i.status for i in r.info] == [1, 1, 1]
@@ -261,7 +261,33 @@ def test_batched_full_size_properties(oracle, b200, assemble_mode):
         for k in ("x", "y", "z_l", "z_u", "z_bl", "z_bu"):
             setattr(rr, k, getattr(r, k)[b])
         assert kkt_residuals(q, rr) < 1e-5
-    o = oracle.DenseSolver(); o.setup(*setup_args(qs[0])); assert o.solve() == 1
-    ro = o.result()
-    assert r.info[0].iter == ro.info.iter
-    assert np.abs(r.x[0] - ro.x).max() <= 1e-8 * max(1.0, np.abs(ro.x).max())
+    for b, q in enumerate(qs):      # every instance: the oracle's iteration count and solution
+        o = oracle.DenseSolver(); o.setup(*setup_args(q)); assert o.solve() == 1
+        ro = o.result()
+        assert r.info[b].iter == ro.info.iter
+        assert np.abs(r.x[b] - ro.x).max() <= 1e-8 * max(1.0, np.abs(ro.x).max())
+
+
+def test_batched_full_size_iteration_statistics(oracle, b200):
+    """BASELINE config 2's shape, 12 instances: the termination tests of the IP loop compare residuals of ~1e-9 with eps = 1e-8 on a
+    KKT system whose condition number has grown to ~1e8 by then, so a different (blocked, tensor-pipe) summation order inside the
+    Cholesky factor flips the last iteration of a few instances in either direction -- measured on 32 instances: 30 identical, 2 off
+    by one (profiles/r02d_dense_iter_parity.txt; the oracle against Eigen's own blocked LLT would show the same).  The bar here is
+    what holds: every instance solved, never more than one iteration apart, at least 5 in 6 identical, x within 1e-8 where the counts
+    agree and within 2e-7 (one IP step at the tolerance) where they do not."""
+    B = 12
+    qs = [dense_strongly_convex_qp(1024, 0, 512, seed=52 + b) for b in range(B)]
+    s, r = _solve_batch(b200, qs)
+    same = 0
+    for b, q in enumerate(qs):
+        o = oracle.DenseSolver(); o.setup(*setup_args(q)); assert o.solve() == 1
+        ro = o.result()
+        assert r.info[b].status == 1
+        assert abs(r.info[b].iter - ro.info.iter) <= 1, (b, r.info[b].iter, ro.info.iter)
+        dx = np.abs(r.x[b] - ro.x).max() / max(1.0, np.abs(ro.x).max())
+        if r.info[b].iter == ro.info.iter:
+            same += 1
+            assert dx <= 1e-8, (b, dx)
+        else:
+            assert dx <= 2e-7, (b, dx)
+    assert same >= (5 * B) // 6, same
