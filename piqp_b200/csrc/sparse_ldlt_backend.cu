@@ -772,6 +772,9 @@ SparseLdltBatchedKKT::~SparseLdltBatchedKKT() {
     if (ev_col) cudaEventDestroy(ev_col);
     if (ev_panel) cudaEventDestroy(ev_panel);
     if (aux_stream) cudaStreamDestroy(aux_stream);
+    if (ev_p2) cudaEventDestroy(ev_p2);
+    if (ev_r2) cudaEventDestroy(ev_r2);
+    if (aux2_stream) cudaStreamDestroy(aux2_stream);
 }
 
 void SparseLdltBatchedKKT::build_wide() {
@@ -781,6 +784,11 @@ void SparseLdltBatchedKKT::build_wide() {
         B200_CUDA(cudaStreamCreateWithPriority(&aux_stream, cudaStreamNonBlocking, prio_hi));      // panel CTAs go first when SMs free up
         B200_CUDA(cudaEventCreateWithFlags(&ev_col, cudaEventDisableTiming));
         B200_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
+        if (!getenv("B200_WIDE_NO_WINDOW_SPLIT")) {
+            B200_CUDA(cudaStreamCreateWithPriority(&aux2_stream, cudaStreamNonBlocking, prio_hi));
+            B200_CUDA(cudaEventCreateWithFlags(&ev_p2, cudaEventDisableTiming));
+            B200_CUDA(cudaEventCreateWithFlags(&ev_r2, cudaEventDisableTiming));
+        }
     }
     const int nsup = S.nsup, nk = S.nk;
     auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
@@ -925,13 +933,32 @@ void SparseLdltBatchedKKT::factor_wide(const int* active) {
         const int npan = 1 + (w.ws - nb0) / MW_NB;
         auto pstart = [&](int j) { return j == 0 ? 0 : nb0 + (j - 1) * MW_NB; };
         auto pwidth = [&](int j) { return j == 0 ? nb0 : MW_NB; };
+        // The launch-by-launch timeline of config 3 (profiles/r02d_timeline_sparse_c3.txt) shows the factorisation bound by THIS chain (panel 75 us +
+        // window update 50 us, 158 times = 20 ms; the far updates are shorter and hide behind it).  Panel j + 1 only needs its own columns
+        // updated, so the window update is split: those columns first on the chain's stream, the columns of the later panels of the group on a
+        // second stream beside panel j + 1.  Two updates that subtract into the same columns stay ordered: rest(j) runs after rest(j - 1)
+        // (same stream) and first(j) waits for rest(j - 1).
         auto chain = [&](int ja, int jb, cudaStream_t st) {      // panels [ja, jb) of one group with their window updates
             const int gend = pstart(jb - 1) + pwidth(jb - 1);
+            bool rest_pending = false;
             for (int j = ja; j < jb; j++) {
                 panel(pstart(j), pwidth(j), st);
                 const int r0 = pstart(j) + pwidth(j);
-                if (j + 1 < jb) update(pstart(j), pwidth(j), r0, st, 0, ceil_div(gend - r0, 128), gend - r0);      // 128 = tile width of the DMMA kernel
+                if (j + 1 >= jb) continue;
+                if (!aux2_stream) { update(pstart(j), pwidth(j), r0, st, 0, ceil_div(gend - r0, 128), gend - r0); continue; }      // 128 = tile width of the DMMA kernel
+                const int w1 = pwidth(j + 1), c1 = r0 + w1;
+                B200_CUDA(cudaEventRecord(ev_p2, st));
+                B200_CUDA(cudaStreamWaitEvent(aux2_stream, ev_p2, 0));
+                if (rest_pending) B200_CUDA(cudaStreamWaitEvent(st, ev_r2, 0));
+                update(pstart(j), pwidth(j), r0, st, 0, 1, w1);                                                  // first(j): the columns of panel j + 1
+                rest_pending = false;
+                if (gend > c1) {
+                    update(pstart(j), pwidth(j), c1, aux2_stream, 0, ceil_div(gend - c1, 128), gend - c1);       // rest(j): the later panels of the group
+                    B200_CUDA(cudaEventRecord(ev_r2, aux2_stream));
+                    rest_pending = true;
+                }
             }
+            if (rest_pending) B200_CUDA(cudaStreamWaitEvent(st, ev_r2, 0));
         };
         const int G = wide_group;
         chain(0, std::min(G, npan), stream);

@@ -123,6 +123,8 @@ public:
     long long upd_total_w = 0, front_stride = 0;
     cudaStream_t aux_stream = nullptr;        // look-ahead: panel k+1 runs here while the rest of trailing update k runs on `stream`
     cudaEvent_t ev_col = nullptr, ev_panel = nullptr;
+    cudaStream_t aux2_stream = nullptr;       // the part of a window update that the next panel does not need runs here, beside that panel
+    cudaEvent_t ev_p2 = nullptr, ev_r2 = nullptr;
 private:
     void build_wide();
     void factor_wide(const int* active);
