@@ -792,8 +792,20 @@ __global__ void k_finish(IpDev d) {
 // =====================================================================================================
 // host side
 // =====================================================================================================
-double* BatchedIPSolver::alloc_d(size_t cnt) { pool_.emplace_back(std::max<size_t>(cnt, 1)); pool_.back().zero(stream); return pool_.back().get(); }
-int* BatchedIPSolver::alloc_i(size_t cnt) { ipool_.emplace_back(std::max<size_t>(cnt, 1)); ipool_.back().zero(stream); return ipool_.back().get(); }
+// The ~90 vectors of the IP loop are carved out of a few zero-filled slabs: every DevBuf::alloc is a cudaMallocAsync plus a stream
+// synchronisation (~50 us), which made "allocate the solver" 5-7 ms of a 13 ms end-to-end step of BASELINE config 4.
+double* BatchedIPSolver::alloc_d(size_t cnt) {
+    const size_t need = (std::max<size_t>(cnt, 1) + 31) & ~(size_t)31;          // 256-byte granules
+    if (arena_left_ < need) {
+        const size_t chunk = std::max(need, (size_t)24 * (size_t)batch * (size_t)(n + p + m + 8));
+        pool_.emplace_back(chunk); pool_.back().zero(stream);
+        arena_ptr_ = pool_.back().get(); arena_left_ = chunk;
+    }
+    double* r = arena_ptr_;
+    arena_ptr_ += need; arena_left_ -= need;
+    return r;
+}
+int* BatchedIPSolver::alloc_i(size_t cnt) { return reinterpret_cast<int*>(alloc_d((std::max<size_t>(cnt, 1) + 1) / 2)); }
 Vars BatchedIPSolver::alloc_vars() {
     Vars v;
     const size_t B = batch;

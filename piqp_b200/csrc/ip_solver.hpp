@@ -82,6 +82,8 @@ private:
     BatchedKKT* be_ = nullptr;
     std::vector<DevBuf<double>> pool_;
     std::vector<DevBuf<int>> ipool_;
+    double* arena_ptr_ = nullptr;      // bump allocator over the last slab of pool_ (alloc_d / alloc_i)
+    size_t arena_left_ = 0;
     DevBuf<IpScalars> sc_;
     int* h_flags_ = nullptr;   // pinned
     int* h_flags2_[2] = {nullptr, nullptr};      // pinned, double-buffered read-back of pipelined graph replays
