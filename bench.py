@@ -608,9 +608,12 @@ def measure(args, wl, ctx):
             chunks = [{k: v[lo:hi] for k, v in host.items()} for lo, hi in bounds]
             turn = [threading.Event() for _ in range(nchunk + 1)]
 
+            use_turns = os.environ.get("B200_E2E_TURNS", "0") == "1"      # 1: bench-side turns (setups one after the other), 0: the library's H2D turnstile
+
             def run_chunk(ci):
                 torch.cuda.set_device(local)
-                turn[ci].wait()
+                if use_turns:
+                    turn[ci].wait()
                 try:
                     sc = wl.make_solver(local, chunks[ci], on_host=True)
                 finally:
@@ -641,7 +644,7 @@ def measure(args, wl, ctx):
             if max(ptimes) < max(times):
                 times, fl = ptimes, pfl
                 what = ("b200qp_setup_dense(host pinned buffers) + b200qp_solve + b200qp_get_result(x -> host) on %d sub-batches of the per-GPU batch, one handle / "
-                        "stream / host thread each: setups in turn, each solve overlapping the H2D copies of the following sub-batches" % nchunk)
+                        "stream / host thread each; the library's H2D turnstile gives the copies of one sub-batch the whole link while the previous ones equilibrate and solve" % nchunk)
         tmax = torch.tensor([max(times)], dtype=torch.float64, device=dev)      # conservative: slowest repetition
         fsum = torch.tensor([sum(fl) / len(fl)], dtype=torch.float64, device=dev)
         tsingle = torch.tensor([max(single_times)], dtype=torch.float64, device=dev)

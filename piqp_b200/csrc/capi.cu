@@ -11,6 +11,7 @@
 #include <memory>
 #include <string>
 #include <vector>
+#include <mutex>
 
 using namespace b200;
 
@@ -408,6 +409,12 @@ void load_problem(b200qp_handle* h, bool first, const double* P, const double* c
     const int B = h->batch, n = h->n, p = h->p, m = h->m;
     cudaStream_t st = h->stream;
     IpDev& d = h->ip->dev();
+    // Host buffers: the H2D phases of handles that are set up concurrently from several host threads take turns (one process-wide
+    // turnstile held until this handle's copies have landed), so each gets the whole PCIe link and the NEXT handle's copies overlap this
+    // handle's Ruiz sweeps and solve -- the pipelining of sub-batches that bench.py used to arrange with its own events.
+    static std::mutex h2d_turnstile;
+    std::unique_lock<std::mutex> turn(h2d_turnstile, std::defer_lock);
+    if (!on_device) turn.lock();
     // staging buffers are released in stream order (no device-wide wait): several handles may be set up and solved concurrently
     // from different host threads, and the H2D copies of one then overlap the kernels of the others
     {
