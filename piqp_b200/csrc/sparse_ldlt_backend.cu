@@ -793,6 +793,7 @@ void SparseLdltBatchedKKT::build_wide() {
     const int nsup = S.nsup, nk = S.nk;
     auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
     wide_group = std::min(8, std::max(1, knob("B200_WIDE_GROUP", 4)));
+
     wide_sb = 128;
     { const int v = knob("B200_WIDE_SB", 128); for (int c : {8, 16, 32, 64, 128}) if (v == c) wide_sb = c; }     // power of two <= 128
     const int ws_min = std::max(2, knob("B200_WIDE_WS", 64));          // supernodes at least this wide are solved blocked over the GPU
@@ -884,6 +885,7 @@ void SparseLdltBatchedKKT::build_wide() {
     allow_dynamic_smem(mfw_small_kernel, (size_t)((int)std::max<size_t>(small_smem_max, 48 * 1024)));
     allow_dynamic_smem(mfw_block_inverse_kernel, (size_t)((int)std::max<size_t>(sizeof(double) * sbs * (sbs + 1), 48 * 1024)));
     allow_dynamic_smem(mfw_panel_kernel, (size_t)((int)MW_PANEL_SMEM));
+    { const char* e = getenv("B200_WIDE_GRAPH"); wide_graph = e ? e[0] == '1' : wfronts.size() > 4; }
     if (getenv("B200_DEBUG_SYMBOLIC"))
         fprintf(stderr, "[sparse_ldlt wide] levels=%d factor steps=%zu (HBM fronts %zu) solve steps=%zu upd_total=%lld front_stride=%lld\n", maxl + 1, wf_steps.size(),
                 wfronts.size(), ws_steps.size(), upd_total_w, front_stride);

@@ -73,7 +73,11 @@ public:
     void eval_G(double an, double at, const double* xn, const double* xt, double* zn, double* zt, const int* active) override;
     void extract_P_diag(double* P_diag) override;
     void print_info() const override;
-    bool graph_capturable() const override { return !wide; }      // the whole-GPU schedule forks onto an auxiliary stream (look-ahead)
+    // the whole-GPU schedule forks onto auxiliary streams (look-ahead) and joins them again before every factor / solve returns, so it can be
+    // captured like the dense Cholesky's side streams; its thousands of launches per iteration are what a graph replay is for (B200_WIDE_NO_GRAPH=1: stepwise)
+    bool graph_capturable() const override { return !wide || wide_graph; }
+    bool wide_graph = false;      // set by build_wide(): schedules with many HBM fronts (thousands of short dependent launches per iteration) replay as a graph;
+                                  // one or two huge fronts (config 3) run 3 % faster stepwise (stream priorities of the look-ahead chain)
     double factor_flops() const override { return S.factor_flops(); }
     double factor_bytes() const override { return 12.0 * S.nnzL() + 12.0 * (double)S.PKi_rows.size(); }
     double solve_flops() const override { return 4.0 * S.nnzL() + S.nk; }
