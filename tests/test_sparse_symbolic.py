@@ -130,3 +130,23 @@ def test_approximate_degree_ordering_is_as_good_as_exact_and_scales(monkeypatch)
     big = sparse_ldlt_symbolic(q["P"], q["A"], q["G"])
     assert time.time() - t0 < 30.0
     assert sorted(big["perm"].tolist()) == list(range(6000))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_fast_column_counts_equal_the_reference_walk(monkeypatch, mode):
+    """The O(nnz(K) alpha) elimination tree + skeleton column counts (Liu / Gilbert-Ng-Peyton) against the reference's O(nnz(L))
+    row-subtree walk (sparse/ldlt.hpp:42-99, kept under B200_SYMBOLIC_WALK=1): identical permutation, nnz(L), flops, supernodes,
+    largest front and level count on random KKT patterns of every KKTMode (the amalgamation pass runs on top of both)."""
+    import piqp_b200
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        n = int(rng.integers(30, 400)); p = int(rng.integers(0, n // 2)); m = int(rng.integers(0, n))
+        q = sparse_strongly_convex_qp(n, p, m, float(rng.uniform(0.01, 0.15)), seed=100 + trial, eig_shift="gershgorin")
+        P, A, G = sp.csc_matrix(q["P"]), (sp.csc_matrix(q["A"]) if p else None), (sp.csc_matrix(q["G"]) if m else None)
+        monkeypatch.delenv("B200_SYMBOLIC_WALK", raising=False)
+        fast = piqp_b200.sparse_ldlt_symbolic(P, A, G, mode=mode)
+        monkeypatch.setenv("B200_SYMBOLIC_WALK", "1")
+        walk = piqp_b200.sparse_ldlt_symbolic(P, A, G, mode=mode)
+        for k in ("nnz_kkt", "nnz_L", "levels", "flops", "supernodes", "largest_front"):
+            assert fast[k] == walk[k], (trial, mode, k, fast[k], walk[k])
+        assert np.array_equal(fast["perm"], walk["perm"])
