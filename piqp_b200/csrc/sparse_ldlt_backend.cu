@@ -94,6 +94,7 @@ std::vector<int> minimum_degree_ordering(int n, const std::vector<int>& cp, cons
     for (auto& v : avar) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
     std::vector<int> deg(n), mark(n, -1), head(n + 1, -1), nxt(n, -1), prv(n, -1);
     std::vector<long long> w(n, 0);
+    std::vector<int> msize(n, 0);
     long long wflg = 1;
     const int n_all = n;
     n -= (int)dense_nodes.size();          // the elimination below runs on the n sparse nodes (bucket indices / clique tests use this count)
@@ -129,7 +130,7 @@ std::vector<int> minimum_degree_ordering(int n, const std::vector<int>& cp, cons
         std::vector<int>().swap(avar[pv]); std::vector<int>().swap(aelem[pv]);
         const int lp = (int)Lp.size();
         // |L_e \ L_p| for every element adjacent to L_p: w[e] - wflg
-        for (int i : Lp) for (int e : aelem[i]) { if (!elem_alive[e]) continue; if (w[e] < wflg) w[e] = (long long)members[e].size() + wflg; w[e]--; }
+        for (int i : Lp) for (int e : aelem[i]) { if (!elem_alive[e]) continue; if (w[e] < wflg) w[e] = (long long)msize[e] + wflg; w[e]--; }      // msize: |L_e| without touching the vector's header
         for (int i : Lp) {
             auto& av = avar[i];
             size_t o = 0;
@@ -155,7 +156,7 @@ std::vector<int> minimum_degree_ordering(int n, const std::vector<int>& cp, cons
             bucket_insert(i);
             if (deg[i] < mindeg) mindeg = deg[i];
         }
-        members[pv] = Lp; elem_alive[pv] = lp > 0;
+        members[pv] = Lp; msize[pv] = lp; elem_alive[pv] = lp > 0;
         wflg += (long long)n_all + 1;
     }
     std::stable_sort(dense_nodes.begin(), dense_nodes.end(), [&](int a, int b) { return deg0[a] < deg0[b]; });
