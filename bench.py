@@ -167,7 +167,7 @@ class DenseWorkload:
             out.append(make)
         return out
 
-    roofline_kernel = "gemm_nt_t64_kernel<EPI_ASSEMBLE,true> (K = P + diag + G^T Z^-1 G, DMMA m8n8k4 fp64, 128x64 tiles, two CTAs per SM)"
+    roofline_kernel = "gemm_nt_t64_bulk_kernel<EPI_ASSEMBLE,true> (K = P + diag + G^T Z^-1 G, DMMA m8n8k4 fp64, 128x64 tiles, operands by TMA bulk copies into an mbarrier ring, two CTAs per SM)"
 
 
 class MultistageWorkload:
@@ -365,7 +365,7 @@ class SparseC3Workload(SparseWorkload):
     def cpu_sample_note(self):
         return "same family at n=%d, p=m=%d (one factorisation at n=%d takes minutes on one core)" % (self.CPU_N, self.CPU_N // 2, self.n)
 
-    roofline_kernel = "gemm_nt_t64_kernel<EPI_SUB,true> (far updates F22 -= L21 D L21^T of the two-level blocked LDL^T of the root front, DMMA m8n8k4 fp64, K = 256; window updates K = 64)"
+    roofline_kernel = "gemm_nt_t64_bulk_kernel<EPI_SUB,true> (far updates F22 -= L21 D L21^T of the two-level blocked LDL^T of the root front, DMMA m8n8k4 fp64, K = 256; window updates K = 64)"
 
 
 def cpu_oracle_sample(wl, n_qp, threads, seed0=1042):
@@ -682,7 +682,7 @@ def measure(args, wl, ctx):
         achieved = fl_launch / (ms_launch * 1e-3) * 1e-12 if ms_launch > 0 else 0.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("gemm_nt_t64_kernel_assemble_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("gemm_nt_t64_bulk_kernel_assemble_bytes_per_launch")
         except Exception:
             pass
         roofline = {"kernel": wl.roofline_kernel, "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
