@@ -407,13 +407,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_nt_t64_kernel(GemmArgs g
 
 // ---------------------------------------------------------------------------------------------------
 // gemm_nt_t64_bulk_kernel: the same 128 x 64 tile kernel with the operand panels staged by the TMA engine's bulk copies
-// (cp.async.bulk.shared.global, one 1 KB / 512 B row of the panel per copy, 32 copies per stage issued by the lanes of warp 0)
-// into a 4-stage ring guarded by mbarriers: full[s] (expect_tx = the stage's bytes) releases the consumers, empty[s] (one arrival per
-// warp) releases the slot.  There is NO CTA-wide barrier in the main loop: the source view of the cp.async kernel
-// (profiles/r02d_ncu_source_stalls.txt) had 13 % of its stall samples on the per-k-block __syncthreads, because eight warps that
-// drift apart on the DMMA pipe were re-aligned 32 times per tile.  A slot is refilled two k-blocks after its consumption, so warp 0
-// (a consumer like the others) practically never waits for the empty barrier.  The padded rows of the cp.async layout are kept
-// (conflict-free fragment loads): that is why the copies are 1-D bulk copies per panel row and not one tensor-map box per panel.
+// (cp.async.bulk.shared.global, one 1 KB / 512 B row of the panel per copy: 32 copies + the 16 weights per stage) into a 4-stage ring
+// guarded by mbarriers: full[s] (expect_tx = the stage's bytes) releases the consumers, empty[s] (one arrival per consumer warp)
+// releases the slot.  A NINTH, PRODUCER-ONLY WARP issues the copies and runs the whole ring ahead of the eight consumer warps
+// (288 threads at 96 registers: still two CTAs per SM); with BULK_PRODUCER_THREADS = 0 warp 0 doubles as the producer and refills a
+// slot two k-blocks after its consumption (measured: assembly 68.6 instead of 62.6 ms per step of config 2).
+// There is NO CTA-wide barrier in the main loop: the source view of the cp.async kernel (profiles/r02d_ncu_source_stalls.txt) had
+// 13 % of its stall samples on the per-k-block __syncthreads, because eight warps that drift apart on the DMMA pipe were re-aligned
+// 32 times per tile.  The padded rows of the cp.async layout are kept (conflict-free fragment loads): that is why the copies are 1-D
+// bulk copies per panel row and not one tensor-map box per panel.  Rows of a partial tile that do not exist in memory are not copied;
+// what the slot holds there only feeds accumulator rows / columns that the epilogue never stores.
 // Preconditions (host-checked, else the cp.async kernel runs): K % 16 == 0, an even number of rows in memory, 16-byte aligned bases / strides.
 // ---------------------------------------------------------------------------------------------------
 constexpr int BULK_STAGES = 4;
